@@ -1,0 +1,222 @@
+/*
+ * streammos_b200.h — C-ABI of the B200 (sm_100a) StreamMOS hot-path library.
+ *
+ * Drop-in boundary for the per-scan data-parallel hot path of StreamMOS:
+ *   (A) point -> BEV / range-view scatter-max pooling and bilinear gather-back,
+ *   (B) multi-scale deformable-attention sampling (forward / backward),
+ *   (C) long-term-memory voxel voting and per-instance vote counting.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - strides are in ELEMENTS, not bytes;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no allocation, no synchronisation, no host<->device copy happens inside
+ *     the library: the caller owns all buffers including scratch (`plan`,
+ *     `workspace`), whose sizes come from the *_bytes() functions;
+ *   - return value: 0 on success, a negative SMOS_E* code for bad arguments,
+ *     or a positive cudaError_t if a launch failed. smos_error_string() maps
+ *     either to text. The Python shims raise RuntimeError on non-zero.
+ *
+ * Each entry point cites the reference interface (file:line under the
+ * StreamMOS tree) it replaces.
+ */
+#ifndef STREAMMOS_B200_H_
+#define STREAMMOS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMOS_OK 0
+#define SMOS_EINVAL (-1)       /* bad shape / null pointer / misaligned */
+#define SMOS_EUNSUPPORTED (-2) /* valid request the library does not implement */
+
+#define SMOS_ABI_VERSION 1
+
+int smos_abi_version(void);
+const char* smos_error_string(int code);
+
+/* ------------------------------------------------------------------------- */
+/* (A1) VoxelMaxPool — scatter-max of point features into a dense 2-D grid.   */
+/* Replaces point_deep.cuda_kernel.voxel_maxpooling_forward/backward          */
+/* (deep_point/src/point_deep_cuda.cpp:22-62,                                  */
+/*  deep_point/src/point_deep_cuda_kernel.cu:24-186) and the allocation +     */
+/* metadata upload in deep_point/__init__.py:17-44.                            */
+/* ------------------------------------------------------------------------- */
+
+/* Tile shape the library will use for an (H, W) grid with C channels.
+ * Pure host function; deterministic. Writes tile_h, tile_w, chan_chunk. */
+int smos_pool_tile_shape(int32_t B, int32_t C, int32_t H, int32_t W,
+                         int32_t* tile_h_host, int32_t* tile_w_host,
+                         int32_t* chan_chunk_host);
+
+/* Bytes of scratch a pooling plan needs for B x N points on an (H, W) grid. */
+int64_t smos_pool_plan_bytes(int64_t B, int64_t N, int32_t H, int32_t W);
+
+/* Build the pooling plan for one coordinate array:
+ *   cell(b,n) = trunc(float(ind[b,n,0]) * scale_h) * W + trunc(ind[b,n,1] * scale_w)
+ *   valid iff 0 <= idx_d < size_d for both d (C cast = truncation toward zero,
+ *   point_deep_cuda_kernel.cu:40-46); invalid points get cell = -1.
+ * Then points are bucketed by output tile (stable within a thread block) so the
+ * pooling kernel can own each output tile in shared memory.
+ *   pcds_ind       : (B, N, 2) float32, element strides ind_sb / ind_sn / ind_sd
+ *   voxel_max_idx  : optional (B, N) int64 out — the reference's side product:
+ *                    b*C*H*W + h*W + w (flat NCHW offset of the c=0 plane) or -1
+ *                    (point_deep_cuda_kernel.cu:36,50; deep_point/__init__.py:27).
+ *                    `idx_batch_stride` = C*H*W. May be NULL.
+ *   plan           : scratch of smos_pool_plan_bytes(), 16-byte aligned.
+ */
+int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N,
+                         int64_t ind_sb, int64_t ind_sn, int64_t ind_sd,
+                         int32_t H, int32_t W, float scale_h, float scale_w,
+                         int64_t* voxel_max_idx, int64_t idx_batch_stride,
+                         void* plan, void* stream);
+
+/* Forward: voxel_out[b,c,h,w] = max over points of the cell, 0 for empty cells
+ * (true max even if negative: point_deep_cuda_kernel.cu:56-99).
+ *   pcds_feat : (B, C, N) float32, element strides f_sb / f_sc / f_sn
+ *               (channel-major N-fastest and point-major C-fastest both run
+ *               at full coalescing).
+ *   voxel_out : (B, C, H, W) float32 NCHW-contiguous; EVERY element is written
+ *               (no pre-zeroing needed).
+ */
+int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int64_t N,
+                               int64_t f_sb, int64_t f_sc, int64_t f_sn,
+                               int32_t H, int32_t W, const void* plan,
+                               float* voxel_out, void* stream);
+
+/* Backward: grad_feat[b,c,n] = grad_out[b,c,cell] if voxel_out[b,c,cell] == feat[b,c,n]
+ * else 0 — every tied point receives the gradient (point_deep_cuda_kernel.cu:109-132).
+ *   grad_feat : (B, C, N) float32 with strides g_sb / g_sc / g_sn; every element written.
+ */
+int smos_voxel_maxpool_backward(const float* pcds_feat, int64_t B, int64_t C, int64_t N,
+                                int64_t f_sb, int64_t f_sc, int64_t f_sn,
+                                int32_t H, int32_t W, const void* plan,
+                                const float* voxel_out, const float* grad_voxel_out,
+                                float* grad_feat, int64_t g_sb, int64_t g_sc, int64_t g_sn,
+                                void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* (A3) BilinearSample — bilinear gather of grid features back to points.     */
+/* Replaces networks/backbone.py:458-475 (normalise, F.grid_sample bilinear,   */
+/* zeros padding, align_corners=True). The float sequence of the reference is  */
+/* replayed: g = 2*c*s/(size-1) - 1 ; pix = ((g+1)/2)*(size-1).               */
+/* ------------------------------------------------------------------------- */
+
+/*   grid  : (B, C, H, W) float32, element strides gr_sb / gr_sc / gr_sh / gr_sw
+ *           (NCHW and channels-last both supported)
+ *   coord : (B, N, 2) float32, strides co_sb / co_sn / co_sd ; d=0 -> row (H), d=1 -> col (W)
+ *   out   : (B, C, N) float32, strides o_sb / o_sc / o_sn
+ */
+int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W,
+                                 int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
+                                 const float* coord, int64_t N,
+                                 int64_t co_sb, int64_t co_sn, int64_t co_sd,
+                                 float scale_h, float scale_w,
+                                 float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
+                                 void* stream);
+
+/* grad_grid (B, C, H, W) NCHW-contiguous must be ZERO-FILLED by the caller;
+ * contributions are accumulated with fp32 atomics (grid_sampler backward). */
+int smos_bilinear_gather_backward(const float* grad_out, int64_t B, int64_t C, int64_t N,
+                                  int64_t go_sb, int64_t go_sc, int64_t go_sn,
+                                  const float* coord,
+                                  int64_t co_sb, int64_t co_sn, int64_t co_sd,
+                                  float scale_h, float scale_w,
+                                  int32_t H, int32_t W, float* grad_grid, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* (B) MSDeformAttn sampling core.                                            */
+/* Replaces MultiScaleDeformableAttention.ms_deform_attn_forward/backward      */
+/* (deformattn/src/vision.cpp:13-16, src/ms_deform_attn.h:20-61,               */
+/*  src/cuda/ms_deform_attn_cuda.cu:20-153, src/cuda/ms_deform_im2col_cuda.cuh */
+/*  :237-299 forward, :301-403 backward).                                      */
+/*   value            : (B, S, M, D) contiguous                                */
+/*   spatial_shapes   : (L, 2) int64 DEVICE [(H_l, W_l)]                       */
+/*   level_start_index: (L,) int64 DEVICE                                      */
+/*   sampling_loc     : (B, Q, M, L, P, 2) contiguous, (x, y) normalised       */
+/*   attn_weight      : (B, Q, M, L, P) contiguous                             */
+/*   output           : (B, Q, M*D); every element written                     */
+/* dtype: 0 = float32, 1 = float64 (the reference dispatches both).            */
+/* ------------------------------------------------------------------------- */
+#define SMOS_F32 0
+#define SMOS_F64 1
+
+int smos_ms_deform_attn_forward(int32_t dtype, const void* value,
+                                const int64_t* spatial_shapes,
+                                const int64_t* level_start_index,
+                                const void* sampling_loc, const void* attn_weight,
+                                int32_t B, int32_t S, int32_t M, int32_t D,
+                                int32_t L, int32_t Q, int32_t P,
+                                void* output, void* stream);
+
+/* grad_value must be ZERO-FILLED by the caller (atomic accumulation);
+ * grad_sampling_loc and grad_attn_weight are fully written. */
+int smos_ms_deform_attn_backward(int32_t dtype, const void* value,
+                                 const int64_t* spatial_shapes,
+                                 const int64_t* level_start_index,
+                                 const void* sampling_loc, const void* attn_weight,
+                                 const void* grad_output,
+                                 int32_t B, int32_t S, int32_t M, int32_t D,
+                                 int32_t L, int32_t Q, int32_t P,
+                                 void* grad_value, void* grad_sampling_loc,
+                                 void* grad_attn_weight, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* (C) Long-term-memory voting.                                               */
+/* ------------------------------------------------------------------------- */
+
+/* Quantize (voxel_voting.py:77-91; voxel_instance_voting.py:117-135):
+ *   out[p,d] = (pcds[p,d] - min_d) / delta_d   in float32, IEEE division.
+ *   pcds : (P, row_stride>=3) float32 ; out : (P, 3) float32 contiguous. */
+int smos_quantize(const float* pcds, int64_t P, int64_t row_stride,
+                  float min_x, float min_y, float min_z,
+                  float dx, float dy, float dz, float* out, void* stream);
+
+/* Bytes of scratch for smos_vote_voxel_labels. */
+int64_t smos_vote_workspace_bytes(int64_t P, int32_t X, int32_t Y, int32_t Z, int32_t num_classes);
+
+/* determine_voxel_labels (voxel_voting.py:55-75): per-voxel class histogram over
+ * the local map, argmax with ties -> lowest class, empty voxel -> 0.
+ *   voxel_coords : (P, 3) int64 contiguous ; semantic_labels : (P,) int64
+ *   voxel_labels : (X, Y, Z) int64 contiguous; every element written.
+ * Points whose coordinates fall outside the grid or whose label is outside
+ * [0, num_classes) are ignored (the reference assumes pre-cropped input). */
+int smos_vote_voxel_labels(const int64_t* voxel_coords, const int64_t* semantic_labels,
+                           int64_t P, int32_t X, int32_t Y, int32_t Z, int32_t num_classes,
+                           void* workspace, int64_t* voxel_labels, void* stream);
+
+/* get_point_labels_from_voxel_labels (voxel_voting.py:38-53): bounds mask +
+ * gather; out-of-range points get 0.  (sx, sy, sz) are the label grid dims. */
+int smos_vote_point_labels(const int64_t* new_voxel_coords, int64_t Pc,
+                           const int64_t* voxel_labels, int32_t X, int32_t Y, int32_t Z,
+                           int64_t* point_labels, void* stream);
+
+/* Fused long-term voting for the streaming path (same results
+ * as Quantize -> .to(int64) -> determine_voxel_labels -> get_point_labels...):
+ *   points (P, row_stride) float32, labels (P,) uint8, the LAST `Pc` rows are the
+ *   current scan. Writes voxel_labels_u8 (X*Y*Z) and point_labels (Pc,) int64. */
+int smos_vote_fused(const float* points, int64_t P, int64_t row_stride,
+                    const uint8_t* labels, int64_t Pc,
+                    float min_x, float min_y, float min_z, float dx, float dy, float dz,
+                    int32_t X, int32_t Y, int32_t Z, int32_t num_classes,
+                    void* workspace, uint8_t* voxel_labels_u8, int64_t* point_labels,
+                    void* stream);
+
+/* Per-instance vote count (voxel_instance_voting.py:169-187, in_hull :62-76):
+ * for each of K axis-aligned boxes count local-map points inside (inclusive
+ * lo <= p <= hi) with prediction 1 (weight 1) and prediction 2 (weight 2).
+ *   points : (P, row_stride>=3) float32 ; pred : (P,) int64
+ *   box_lo, box_hi : (K, 3) float32
+ *   sums   : (K, 2) int64 ZERO-FILLED by the caller -> [static_sum, dynamic_sum]
+ * The cluster label is 2 if dynamic_sum > static_sum else 1 (:184-187). */
+int smos_instance_vote(const float* points, int64_t P, int64_t row_stride,
+                       const int64_t* pred, const float* box_lo, const float* box_hi,
+                       int32_t K, int64_t* sums, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMMOS_B200_H_ */

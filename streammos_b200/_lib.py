@@ -1,0 +1,70 @@
+"""ctypes binding of libstreammos_b200.so (include/streammos_b200.h).
+
+The library is the ONLY compute path: if it is missing, loading raises — there is no CPU or
+PyTorch fallback (BASELINE.json north_star: "no CPU fallback").
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libstreammos_b200.so")
+
+_i32, _i64, _f32, _vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/streammos_b200.h one to one
+SIGNATURES = {
+    "smos_abi_version": (ctypes.c_int, []),
+    "smos_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "smos_pool_tile_shape": (ctypes.c_int, [_i32, _i32, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32),
+                                            ctypes.POINTER(_i32)]),
+    "smos_pool_plan_bytes": (_i64, [_i64, _i64, _i32, _i32]),
+    "smos_pool_plan_build": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _f32, _f32, _vp, _i64,
+                                            _vp, _vp]),
+    "smos_voxel_maxpool_forward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp,
+                                                  _vp]),
+    "smos_voxel_maxpool_backward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp,
+                                                   _vp, _vp, _i64, _i64, _i64, _vp]),
+    "smos_bilinear_gather_forward": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _i64,
+                                                    _i64, _i64, _i64, _f32, _f32, _vp, _i64, _i64, _i64, _vp]),
+    "smos_bilinear_gather_backward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
+                                                     _f32, _f32, _i32, _i32, _vp, _vp]),
+    "smos_ms_deform_attn_forward": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
+                                                   _i32, _i32, _vp, _vp]),
+    "smos_ms_deform_attn_backward": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                                    _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "smos_quantize": (ctypes.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
+    "smos_vote_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32]),
+    "smos_vote_voxel_labels": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "smos_vote_point_labels": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "smos_vote_fused": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _i32,
+                                       _i32, _i32, _vp, _vp, _vp, _vp]),
+    "smos_instance_vote": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once). Raises RuntimeError if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "streammos_b200: %s not found — build it with `python -m streammos_b200.build` "
+            "(there is no CPU/PyTorch fallback for the hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.smos_abi_version() != 1:
+        raise RuntimeError("streammos_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().smos_error_string(int(code))
+        raise RuntimeError("%s failed: %s (code %d)" % (what, msg.decode() if msg else "?", code))

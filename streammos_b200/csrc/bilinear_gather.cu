@@ -1,0 +1,219 @@
+// BilinearSample for sm_100a: bilinear gather of 2-D grid features back to points.
+//
+// Replaces networks/backbone.py:458-475, i.e. four elementwise prep kernels + torch.stack +
+// F.grid_sample(bilinear, zeros, align_corners=True). One kernel: the sampling position and
+// the four tap weights are computed once per point and reused for every channel; the
+// reference's float sequence (normalise then un-normalise) is replayed with explicitly
+// rounded fp32 operations so results stay within 1e-5 of grid_sample.
+#include "common.cuh"
+
+namespace {
+
+struct Taps {
+  int32_t x0, y0;        // north-west integer pixel
+  float w_nw, w_ne, w_sw, w_se;
+  bool in_nw, in_ne, in_sw, in_se;
+};
+
+// pix = ((g + 1) / 2) * (size - 1), g = 2 * c * s / (size - 1) - 1   (backbone.py:469-470 + ATen
+// grid_sampler_unnormalize with align_corners=True). Every step individually rounded.
+__device__ __forceinline__ float replay_pixel(float c, float s, int32_t size) {
+  const float sm1 = static_cast<float>(size - 1);
+  float g = __fmul_rn(__fmul_rn(2.0f, c), s);
+  g = __fdiv_rn(g, sm1);
+  g = __fsub_rn(g, 1.0f);
+  float p = __fadd_rn(g, 1.0f);
+  p = __fmul_rn(p, 0.5f);
+  return __fmul_rn(p, sm1);
+}
+
+__device__ __forceinline__ Taps make_taps(float cy, float cx, float sh, float sw, int32_t H, int32_t W) {
+  Taps t;
+  const float ix = replay_pixel(cx, sw, W);
+  const float iy = replay_pixel(cy, sh, H);
+  const float fx = floorf(ix), fy = floorf(iy);
+  // weights as in ATen grid_sampler_2d: nw = (x_se - x)(y_se - y) ...
+  const float x1 = __fadd_rn(fx, 1.0f), y1 = __fadd_rn(fy, 1.0f);
+  t.w_nw = __fmul_rn(__fsub_rn(x1, ix), __fsub_rn(y1, iy));
+  t.w_ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(y1, iy));
+  t.w_sw = __fmul_rn(__fsub_rn(x1, ix), __fsub_rn(iy, fy));
+  t.w_se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
+  // clamp before the int cast so far-away pads (and NaN) become plain out-of-bounds
+  const float cxl = fminf(fmaxf(fx, -2.0f), static_cast<float>(W) + 1.0f);
+  const float cyl = fminf(fmaxf(fy, -2.0f), static_cast<float>(H) + 1.0f);
+  t.x0 = (fx == fx) ? static_cast<int32_t>(cxl) : -2;
+  t.y0 = (fy == fy) ? static_cast<int32_t>(cyl) : -2;
+  const bool xl = t.x0 >= 0 && t.x0 < W, xh = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  const bool yl = t.y0 >= 0 && t.y0 < H, yh = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  t.in_nw = xl && yl; t.in_ne = xh && yl; t.in_sw = xl && yh; t.in_se = xh && yh;
+  return t;
+}
+
+constexpr int kGatherThreads = 128;
+constexpr int kCPT = 8;  // channels per thread per step in the planar kernel
+
+// Planar (NCHW-like: arbitrary channel stride) grid; lanes run over points, so the taps of
+// neighbouring points in scan order share sectors. Each thread produces kCPT consecutive
+// channels per step: 4*kCPT independent loads in flight, and for point-major outputs one
+// full 32-byte sector per store.
+__global__ void __launch_bounds__(kGatherThreads)
+gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
+                             int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
+                             const float* __restrict__ coord, int32_t N,
+                             int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
+                             float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
+                             int32_t c_per_block) {
+  const int32_t n = blockIdx.x * kGatherThreads + threadIdx.x;
+  const int32_t b = blockIdx.z;
+  if (n >= N) return;
+  const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
+  const Taps t = make_taps(cp[0], cp[co_sd], sh, sw, H, W);
+  const int64_t o_nw = static_cast<int64_t>(t.y0) * gr_sh + static_cast<int64_t>(t.x0) * gr_sw;
+  const float* g = grid + b * gr_sb;
+  float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn;
+  const int32_t c_begin = blockIdx.y * c_per_block;
+  const int32_t c_end = min(C, c_begin + c_per_block);
+  const bool vec_out = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (int32_t c0 = c_begin; c0 < c_end; c0 += kCPT) {
+    float acc[kCPT];
+#pragma unroll
+    for (int k = 0; k < kCPT; ++k) {
+      const int32_t c = c0 + k;
+      float a = 0.f;
+      if (c < c_end) {
+        const float* gc = g + static_cast<int64_t>(c) * gr_sc + o_nw;
+        const float v_nw = t.in_nw ? __ldg(gc) : 0.f;
+        const float v_ne = t.in_ne ? __ldg(gc + gr_sw) : 0.f;
+        const float v_sw = t.in_sw ? __ldg(gc + gr_sh) : 0.f;
+        const float v_se = t.in_se ? __ldg(gc + gr_sh + gr_sw) : 0.f;
+        a = fmaf(v_nw, t.w_nw, a);
+        a = fmaf(v_ne, t.w_ne, a);
+        a = fmaf(v_sw, t.w_sw, a);
+        a = fmaf(v_se, t.w_se, a);
+      }
+      acc[k] = a;
+    }
+    if (vec_out && c0 + kCPT <= c_end && (c0 & 3) == 0) {
+      *reinterpret_cast<float4*>(o + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(o + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kCPT; ++k)
+        if (c0 + k < c_end) o[static_cast<int64_t>(c0 + k) * o_sc] = acc[k];
+    }
+  }
+}
+
+// Channels-last grid (gr_sc == 1, C % 4 == 0): lanes run over channel quads, every tap is a
+// contiguous 16-byte load and a point's taps are four contiguous C*4-byte rows.
+__global__ void __launch_bounds__(kGatherThreads)
+gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
+                           int64_t gr_sb, int64_t gr_sh, int64_t gr_sw,
+                           const float* __restrict__ coord, int32_t N,
+                           int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
+                           float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn) {
+  const int32_t q = C >> 2;  // channel quads per point
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * kGatherThreads + threadIdx.x;
+  const int32_t n = static_cast<int32_t>(gid / q);
+  const int32_t cq = static_cast<int32_t>(gid - static_cast<int64_t>(n) * q);
+  const int32_t b = blockIdx.z;
+  if (n >= N) return;
+  const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
+  const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
+  const float* g = grid + b * gr_sb + static_cast<int64_t>(t.y0) * gr_sh +
+                   static_cast<int64_t>(t.x0) * gr_sw + (cq << 2);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 v_nw = t.in_nw ? __ldg(reinterpret_cast<const float4*>(g)) : z;
+  const float4 v_ne = t.in_ne ? __ldg(reinterpret_cast<const float4*>(g + gr_sw)) : z;
+  const float4 v_sw = t.in_sw ? __ldg(reinterpret_cast<const float4*>(g + gr_sh)) : z;
+  const float4 v_se = t.in_se ? __ldg(reinterpret_cast<const float4*>(g + gr_sh + gr_sw)) : z;
+  float4 a;
+  a.x = fmaf(v_se.x, t.w_se, fmaf(v_sw.x, t.w_sw, fmaf(v_ne.x, t.w_ne, fmaf(v_nw.x, t.w_nw, 0.f))));
+  a.y = fmaf(v_se.y, t.w_se, fmaf(v_sw.y, t.w_sw, fmaf(v_ne.y, t.w_ne, fmaf(v_nw.y, t.w_nw, 0.f))));
+  a.z = fmaf(v_se.z, t.w_se, fmaf(v_sw.z, t.w_sw, fmaf(v_ne.z, t.w_ne, fmaf(v_nw.z, t.w_nw, 0.f))));
+  a.w = fmaf(v_se.w, t.w_se, fmaf(v_sw.w, t.w_sw, fmaf(v_ne.w, t.w_ne, fmaf(v_nw.w, t.w_nw, 0.f))));
+  float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(cq << 2) * o_sc;
+  if (o_sc == 1 && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+    *reinterpret_cast<float4*>(o) = a;
+  } else {
+    o[0] = a.x; o[o_sc] = a.y; o[2 * o_sc] = a.z; o[3 * o_sc] = a.w;
+  }
+}
+
+// Backward wrt the grid (grid_sampler_2d backward, input gradient only: coordinates are data).
+__global__ void __launch_bounds__(256)
+gather_backward_kernel(const float* __restrict__ gout, int32_t C, int32_t N, int64_t total,
+                       int64_t go_sb, int64_t go_sc, int64_t go_sn, const float* __restrict__ coord,
+                       int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
+                       int32_t H, int32_t W, float* __restrict__ ggrid, int fast_n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t cn = static_cast<int64_t>(C) * N;
+  const int32_t b = static_cast<int32_t>(i / cn);
+  const int64_t r = i - b * cn;
+  int32_t c, n;
+  if (fast_n) { c = static_cast<int32_t>(r / N); n = static_cast<int32_t>(r - static_cast<int64_t>(c) * N); }
+  else        { n = static_cast<int32_t>(r / C); c = static_cast<int32_t>(r - static_cast<int64_t>(n) * C); }
+  const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
+  const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
+  const float go = gout[b * go_sb + c * go_sc + n * go_sn];
+  float* g = ggrid + ((static_cast<int64_t>(b) * C + c) * H + t.y0) * W + t.x0;
+  if (t.in_nw) atomicAdd(g, go * t.w_nw);
+  if (t.in_ne) atomicAdd(g + 1, go * t.w_ne);
+  if (t.in_sw) atomicAdd(g + W, go * t.w_sw);
+  if (t.in_se) atomicAdd(g + W + 1, go * t.w_se);
+}
+
+}  // namespace
+
+extern "C" {
+
+int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W, int64_t gr_sb,
+                                 int64_t gr_sc, int64_t gr_sh, int64_t gr_sw, const float* coord, int64_t N,
+                                 int64_t co_sb, int64_t co_sn, int64_t co_sd, float scale_h, float scale_w,
+                                 float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, void* stream) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || N < 0) return SMOS_EINVAL;
+  if (N == 0) return SMOS_OK;
+  if (!grid || !coord || !out) return SMOS_EINVAL;
+  if (B > 65535 || N >= (int64_t(1) << 31) || C >= (1 << 24)) return SMOS_EUNSUPPORTED;
+  cudaStream_t st = smos_stream(stream);
+  const bool nhwc = (gr_sc == 1) && ((C & 3) == 0) && ((gr_sw & 3) == 0) && ((gr_sh & 3) == 0) &&
+                    ((gr_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+  if (nhwc) {
+    const int64_t threads = N * (C >> 2);
+    dim3 g(smos_ceil_div(threads, kGatherThreads), 1, static_cast<unsigned>(B));
+    gather_forward_nhwc_kernel<<<g, kGatherThreads, 0, st>>>(
+        grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb, co_sn,
+        co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn);
+  } else {
+    const int32_t nblk = smos_ceil_div(N, kGatherThreads);
+    // split channels across blockIdx.y until the grid covers the SMs ~4x
+    int32_t c_per_block = static_cast<int32_t>(C);
+    while (c_per_block > kCPT && (c_per_block % (2 * kCPT)) == 0 &&
+           static_cast<int64_t>(nblk) * B * (C / c_per_block) < 4 * SMOS_SM_COUNT)
+      c_per_block >>= 1;
+    dim3 g(nblk, smos_ceil_div(C, c_per_block), static_cast<unsigned>(B));
+    gather_forward_planar_kernel<<<g, kGatherThreads, 0, st>>>(
+        grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb,
+        co_sn, co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn, c_per_block);
+  }
+  return smos_launch_status();
+}
+
+int smos_bilinear_gather_backward(const float* grad_out, int64_t B, int64_t C, int64_t N, int64_t go_sb,
+                                  int64_t go_sc, int64_t go_sn, const float* coord, int64_t co_sb,
+                                  int64_t co_sn, int64_t co_sd, float scale_h, float scale_w, int32_t H,
+                                  int32_t W, float* grad_grid, void* stream) {
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || N < 0) return SMOS_EINVAL;
+  if (N == 0) return SMOS_OK;
+  if (!grad_out || !coord || !grad_grid) return SMOS_EINVAL;
+  const int64_t total = B * C * N;
+  const int fast_n = (go_sc == 1 && C > 1) ? 0 : 1;
+  gather_backward_kernel<<<smos_ceil_div(total, 256), 256, 0, smos_stream(stream)>>>(
+      grad_out, static_cast<int32_t>(C), static_cast<int32_t>(N), total, go_sb, go_sc, go_sn, coord, co_sb, co_sn,
+      co_sd, scale_h, scale_w, H, W, grad_grid, fast_n);
+  return smos_launch_status();
+}
+
+}  // extern "C"

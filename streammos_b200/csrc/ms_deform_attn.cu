@@ -1,0 +1,264 @@
+// Multi-scale deformable-attention sampling core for sm_100a (forward + backward).
+//
+// Replaces deformattn/src/cuda/ms_deform_im2col_cuda.cuh:237-299 (forward, one thread per
+// output scalar) and :301-403 (backward for D=32: one 32-thread block per (b,q,m), serial
+// shared-memory reduction by thread 0, scalar atomics). Here a group of D/4 lanes owns one
+// (b, q, m): every tap is a 16-byte load per lane (a full 128-byte line per group at D=32),
+// the per-sample gradients are reduced with warp shuffles, and sampling locations/weights are
+// loaded once per group. Semantics are the reference's: pixel = loc * size - 0.5, a sample
+// contributes iff -1 < pixel < size in both axes, per-tap zero padding.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMsdaThreads = 256;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+template <typename T>
+struct Bilinear {
+  int h_low, w_low;
+  T lh, lw, hh, hw;
+  bool in1, in2, in3, in4;  // (low,low) (low,high) (high,low) (high,high)
+};
+
+template <typename T>
+__device__ __forceinline__ Bilinear<T> make_bilinear(T h, T w, int H, int W) {
+  Bilinear<T> s;
+  s.h_low = static_cast<int>(floor(h));
+  s.w_low = static_cast<int>(floor(w));
+  s.lh = h - s.h_low;
+  s.lw = w - s.w_low;
+  s.hh = 1 - s.lh;
+  s.hw = 1 - s.lw;
+  const bool hl = s.h_low >= 0, wl = s.w_low >= 0;
+  const bool hh_ok = s.h_low + 1 <= H - 1, wh_ok = s.w_low + 1 <= W - 1;
+  s.in1 = hl && wl; s.in2 = hl && wh_ok; s.in3 = hh_ok && wl; s.in4 = hh_ok && wh_ok;
+  return s;
+}
+
+// ------------------------------- forward -----------------------------------------------
+// VEC channels per lane (4 when D % 4 == 0, else 1); LPG lanes per (b,q,m) group (power of 2).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kMsdaThreads)
+msda_forward_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lsi, const T* __restrict__ loc,
+                    const T* __restrict__ attn, int32_t S, int32_t M, int32_t D, int32_t L,
+                    int32_t Q, int32_t P, int64_t n_groups, int32_t lpg, T* __restrict__ out) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * kMsdaThreads + threadIdx.x;
+  const int64_t grp = tid / lpg;  // (b*Q + q)*M + m
+  const int32_t gl = static_cast<int32_t>(tid - grp * lpg);
+  if (grp >= n_groups) return;
+  const int32_t m = static_cast<int32_t>(grp % M);
+  const int64_t bq = grp / M;
+  const int32_t b = static_cast<int32_t>(bq / Q);
+  const int64_t row = static_cast<int64_t>(M) * D;  // elements per spatial position
+  const T* vb = value + static_cast<int64_t>(b) * S * row + static_cast<int64_t>(m) * D;
+  const T* lp = loc + grp * L * P * 2;
+  const T* ap = attn + grp * L * P;
+  const int32_t dvec = D / VEC;
+  for (int32_t dv = gl; dv < dvec; dv += lpg) {
+    const int32_t d0 = dv * VEC;
+    T acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0;
+    for (int32_t l = 0; l < L; ++l) {
+      const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+      const T* vl = vb + lsi[l] * row + d0;
+      for (int32_t p = 0; p < P; ++p) {
+        const T loc_w = lp[(l * P + p) * 2], loc_h = lp[(l * P + p) * 2 + 1];
+        const T wgt = ap[l * P + p];
+        const T h_im = loc_h * H - T(0.5);
+        const T w_im = loc_w * W - T(0.5);
+        if (h_im > -1 && w_im > -1 && h_im < H && w_im < W) {
+          const Bilinear<T> s = make_bilinear<T>(h_im, w_im, H, W);
+          const T w1 = s.hh * s.hw, w2 = s.hh * s.lw, w3 = s.lh * s.hw, w4 = s.lh * s.lw;
+          const T* v1 = vl + (static_cast<int64_t>(s.h_low) * W + s.w_low) * row;
+          if constexpr (VEC == 4) {
+            using V = typename Vec4<T>::type;
+            V z; z.x = z.y = z.z = z.w = 0;
+            const V a1 = s.in1 ? *reinterpret_cast<const V*>(v1) : z;
+            const V a2 = s.in2 ? *reinterpret_cast<const V*>(v1 + row) : z;
+            const V a3 = s.in3 ? *reinterpret_cast<const V*>(v1 + static_cast<int64_t>(W) * row) : z;
+            const V a4 = s.in4 ? *reinterpret_cast<const V*>(v1 + static_cast<int64_t>(W) * row + row) : z;
+            acc[0] += (w1 * a1.x + w2 * a2.x + w3 * a3.x + w4 * a4.x) * wgt;
+            acc[1] += (w1 * a1.y + w2 * a2.y + w3 * a3.y + w4 * a4.y) * wgt;
+            acc[2] += (w1 * a1.z + w2 * a2.z + w3 * a3.z + w4 * a4.z) * wgt;
+            acc[3] += (w1 * a1.w + w2 * a2.w + w3 * a3.w + w4 * a4.w) * wgt;
+          } else {
+            const T a1 = s.in1 ? v1[0] : T(0);
+            const T a2 = s.in2 ? v1[row] : T(0);
+            const T a3 = s.in3 ? v1[static_cast<int64_t>(W) * row] : T(0);
+            const T a4 = s.in4 ? v1[static_cast<int64_t>(W) * row + row] : T(0);
+            acc[0] += (w1 * a1 + w2 * a2 + w3 * a3 + w4 * a4) * wgt;
+          }
+        }
+      }
+    }
+    T* o = out + grp * D + d0;
+    if constexpr (VEC == 4) {
+      using V = typename Vec4<T>::type;
+      V r; r.x = acc[0]; r.y = acc[1]; r.z = acc[2]; r.w = acc[3];
+      *reinterpret_cast<V*>(o) = r;
+    } else {
+      o[0] = acc[0];
+    }
+  }
+}
+
+// ------------------------------- backward ----------------------------------------------
+// One warp-aligned group of `lpg` lanes per (b,q,m); lanes stride over channels. For every
+// sample the group reduces d/d(loc) and d/d(attn) with shuffles; lane 0 stores them (each
+// (b,q,m,l,p) is owned by exactly one group, so plain stores). grad_value uses atomics.
+template <typename T>
+__global__ void __launch_bounds__(kMsdaThreads)
+msda_backward_kernel(const T* __restrict__ gout, const T* __restrict__ value,
+                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+                     const T* __restrict__ loc, const T* __restrict__ attn, int32_t S, int32_t M,
+                     int32_t D, int32_t L, int32_t Q, int32_t P, int64_t n_groups, int32_t lpg,
+                     T* __restrict__ gvalue, T* __restrict__ gloc, T* __restrict__ gattn) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * kMsdaThreads + threadIdx.x;
+  const int64_t grp = tid / lpg;
+  const int32_t gl = static_cast<int32_t>(tid - grp * lpg);
+  const bool active = grp < n_groups;
+  const int64_t g = active ? grp : 0;
+  const int32_t m = static_cast<int32_t>(g % M);
+  const int32_t b = static_cast<int32_t>((g / M) / Q);
+  const int64_t row = static_cast<int64_t>(M) * D;
+  const int64_t voff = static_cast<int64_t>(b) * S * row + static_cast<int64_t>(m) * D;
+  const T* lp = loc + g * L * P * 2;
+  const T* ap = attn + g * L * P;
+  const T* go = gout + g * D;
+  for (int32_t l = 0; l < L; ++l) {
+    const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
+    const int64_t loff = voff + lsi[l] * row;
+    for (int32_t p = 0; p < P; ++p) {
+      const T loc_w = lp[(l * P + p) * 2], loc_h = lp[(l * P + p) * 2 + 1];
+      const T wgt = ap[l * P + p];
+      const T h_im = loc_h * H - T(0.5);
+      const T w_im = loc_w * W - T(0.5);
+      T g_w = 0, g_h = 0, g_a = 0;
+      if (active && h_im > -1 && w_im > -1 && h_im < H && w_im < W) {
+        const Bilinear<T> s = make_bilinear<T>(h_im, w_im, H, W);
+        const T w1 = s.hh * s.hw, w2 = s.hh * s.lw, w3 = s.lh * s.hw, w4 = s.lh * s.lw;
+        const int64_t o1 = loff + (static_cast<int64_t>(s.h_low) * W + s.w_low) * row;
+        const int64_t o2 = o1 + row, o3 = o1 + static_cast<int64_t>(W) * row, o4 = o3 + row;
+        for (int32_t d = gl; d < D; d += lpg) {
+          const T top = go[d];
+          const T tgv = top * wgt;
+          T gh = 0, gw = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+          if (s.in1) { v1 = value[o1 + d]; gh -= s.hw * v1; gw -= s.hh * v1; atomicAdd(gvalue + o1 + d, w1 * tgv); }
+          if (s.in2) { v2 = value[o2 + d]; gh -= s.lw * v2; gw += s.hh * v2; atomicAdd(gvalue + o2 + d, w2 * tgv); }
+          if (s.in3) { v3 = value[o3 + d]; gh += s.hw * v3; gw -= s.lh * v3; atomicAdd(gvalue + o3 + d, w3 * tgv); }
+          if (s.in4) { v4 = value[o4 + d]; gh += s.lw * v4; gw += s.lh * v4; atomicAdd(gvalue + o4 + d, w4 * tgv); }
+          const T val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
+          g_a += top * val;
+          g_w += W * gw * tgv;
+          g_h += H * gh * tgv;
+        }
+      }
+      // group reduction (lpg is a power of two <= 32 and groups are lane-aligned)
+      for (int o = lpg >> 1; o > 0; o >>= 1) {
+        g_w += __shfl_xor_sync(0xffffffffu, g_w, o);
+        g_h += __shfl_xor_sync(0xffffffffu, g_h, o);
+        g_a += __shfl_xor_sync(0xffffffffu, g_a, o);
+      }
+      if (active && gl == 0) {
+        gloc[(g * L * P + l * P + p) * 2] = g_w;
+        gloc[(g * L * P + l * P + p) * 2 + 1] = g_h;
+        gattn[g * L * P + l * P + p] = g_a;
+      }
+    }
+  }
+}
+
+int32_t pick_lpg(int32_t dvec) {
+  int32_t lpg = 1;
+  while (lpg < dvec && lpg < 32) lpg <<= 1;
+  return lpg;
+}
+
+template <typename T>
+int forward_impl(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc, const void* attn,
+                 int32_t B, int32_t S, int32_t M, int32_t D, int32_t L, int32_t Q, int32_t P, void* out,
+                 cudaStream_t st) {
+  const int64_t n_groups = static_cast<int64_t>(B) * Q * M;
+  const size_t vbytes = 4 * sizeof(T);
+  const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(value) % vbytes == 0) &&
+                   (reinterpret_cast<uintptr_t>(out) % vbytes == 0);
+  const int32_t lpg = pick_lpg(vec ? D / 4 : D);
+  const int64_t threads = n_groups * lpg;
+  const int grid = smos_ceil_div(threads, kMsdaThreads);
+  if (vec)
+    msda_forward_kernel<T, 4><<<grid, kMsdaThreads, 0, st>>>(
+        static_cast<const T*>(value), shapes, lsi, static_cast<const T*>(loc), static_cast<const T*>(attn), S, M, D,
+        L, Q, P, n_groups, lpg, static_cast<T*>(out));
+  else
+    msda_forward_kernel<T, 1><<<grid, kMsdaThreads, 0, st>>>(
+        static_cast<const T*>(value), shapes, lsi, static_cast<const T*>(loc), static_cast<const T*>(attn), S, M, D,
+        L, Q, P, n_groups, lpg, static_cast<T*>(out));
+  return smos_launch_status();
+}
+
+template <typename T>
+int backward_impl(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc, const void* attn,
+                  const void* gout, int32_t B, int32_t S, int32_t M, int32_t D, int32_t L, int32_t Q, int32_t P,
+                  void* gvalue, void* gloc, void* gattn, cudaStream_t st) {
+  const int64_t n_groups = static_cast<int64_t>(B) * Q * M;
+  const int32_t lpg = pick_lpg(D);
+  const int64_t threads = n_groups * lpg;
+  msda_backward_kernel<T><<<smos_ceil_div(threads, kMsdaThreads), kMsdaThreads, 0, st>>>(
+      static_cast<const T*>(gout), static_cast<const T*>(value), shapes, lsi, static_cast<const T*>(loc),
+      static_cast<const T*>(attn), S, M, D, L, Q, P, n_groups, lpg, static_cast<T*>(gvalue), static_cast<T*>(gloc),
+      static_cast<T*>(gattn));
+  return smos_launch_status();
+}
+
+bool bad_dims(int32_t B, int32_t S, int32_t M, int32_t D, int32_t L, int32_t Q, int32_t P) {
+  return B <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Q <= 0 || P <= 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smos_ms_deform_attn_forward(int32_t dtype, const void* value, const int64_t* spatial_shapes,
+                                const int64_t* level_start_index, const void* sampling_loc,
+                                const void* attn_weight, int32_t B, int32_t S, int32_t M, int32_t D, int32_t L,
+                                int32_t Q, int32_t P, void* output, void* stream) {
+  if (bad_dims(B, S, M, D, L, Q, P)) return SMOS_EINVAL;
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output)
+    return SMOS_EINVAL;
+  if (static_cast<int64_t>(B) * S * M * D >= (int64_t(1) << 40)) return SMOS_EUNSUPPORTED;
+  cudaStream_t st = smos_stream(stream);
+  if (dtype == SMOS_F32)
+    return forward_impl<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, B, S, M, D, L,
+                               Q, P, output, st);
+  if (dtype == SMOS_F64)
+    return forward_impl<double>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, B, S, M, D, L,
+                                Q, P, output, st);
+  return SMOS_EUNSUPPORTED;
+}
+
+int smos_ms_deform_attn_backward(int32_t dtype, const void* value, const int64_t* spatial_shapes,
+                                 const int64_t* level_start_index, const void* sampling_loc,
+                                 const void* attn_weight, const void* grad_output, int32_t B, int32_t S,
+                                 int32_t M, int32_t D, int32_t L, int32_t Q, int32_t P, void* grad_value,
+                                 void* grad_sampling_loc, void* grad_attn_weight, void* stream) {
+  if (bad_dims(B, S, M, D, L, Q, P)) return SMOS_EINVAL;
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
+      !grad_value || !grad_sampling_loc || !grad_attn_weight)
+    return SMOS_EINVAL;
+  cudaStream_t st = smos_stream(stream);
+  if (dtype == SMOS_F32)
+    return backward_impl<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                                B, S, M, D, L, Q, P, grad_value, grad_sampling_loc, grad_attn_weight, st);
+  if (dtype == SMOS_F64)
+    return backward_impl<double>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                                 B, S, M, D, L, Q, P, grad_value, grad_sampling_loc, grad_attn_weight, st);
+  return SMOS_EUNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+// Long-term-memory voting for sm_100a.
+//
+// Replaces determine_voxel_labels / get_point_labels_from_voxel_labels / Quantize
+// (voxel_voting.py:38-91) and the in-box vote count of cluster()
+// (voxel_instance_voting.py:169-187). The reference materialises a dense
+// (X*Y*Z, num_classes) int64 vote tensor (188 MB), a (P, num_classes) int64 one-hot and runs a
+// generic scatter_add + argmax, with a device sync to find num_classes. Here the class counts
+// of a voxel are bit-packed into one 64-bit word (21 bits per class, <= 3 classes) so a vote is
+// a single 8-byte L2 atomic and the argmax reads 8 bytes per voxel; more classes fall back to
+// one 32-bit counter per (voxel, class).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kVoteThreads = 256;
+constexpr int kPackBits = 21;
+constexpr unsigned long long kPackMask = (1ull << kPackBits) - 1ull;
+constexpr int64_t kPackMaxPoints = (int64_t(1) << kPackBits) - 1;
+constexpr int kMaxClasses = 64;
+
+bool use_packed(int64_t P, int32_t num_classes) { return num_classes <= 3 && P <= kPackMaxPoints; }
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kVoteThreads)
+vote_i64_kernel(const int64_t* __restrict__ coords, const int64_t* __restrict__ labels, int64_t P,
+                int32_t X, int32_t Y, int32_t Z, int32_t C, int packed, void* __restrict__ ws) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= P) return;
+  const int64_t x = coords[i * 3], y = coords[i * 3 + 1], z = coords[i * 3 + 2];
+  const int64_t lab = labels[i];
+  if (x < 0 || x >= X || y < 0 || y >= Y || z < 0 || z >= Z || lab < 0 || lab >= C) return;
+  const int64_t lin = (x * Y + y) * Z + z;
+  if (packed)
+    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << (kPackBits * static_cast<int>(lab)));
+  else
+    atomicAdd(static_cast<unsigned int*>(ws) + lin * C + lab, 1u);
+}
+
+__device__ __forceinline__ float quant(float v, float lo, float d) { return __fdiv_rn(__fsub_rn(v, lo), d); }
+
+// float xyz -> voxel index with the reference's arithmetic: fp32 (x - min) / d, then .to(int64)
+// truncation (voxel_voting.py:86-88,240). Returns false if outside the grid.
+__device__ __forceinline__ bool quant_voxel(const float* p, float mx, float my, float mz, float dx, float dy,
+                                            float dz, int32_t X, int32_t Y, int32_t Z, int64_t* lin) {
+  const long long x = static_cast<long long>(quant(p[0], mx, dx));
+  const long long y = static_cast<long long>(quant(p[1], my, dy));
+  const long long z = static_cast<long long>(quant(p[2], mz, dz));
+  if (x < 0 || x >= X || y < 0 || y >= Y || z < 0 || z >= Z) return false;
+  *lin = (static_cast<int64_t>(x) * Y + y) * Z + z;
+  return true;
+}
+
+__global__ void __launch_bounds__(kVoteThreads)
+vote_fused_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const uint8_t* __restrict__ labels,
+                  float mx, float my, float mz, float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z,
+                  int32_t C, int packed, void* __restrict__ ws) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= P) return;
+  const int lab = labels[i];
+  int64_t lin;
+  if (lab >= C || !quant_voxel(pts + i * rs, mx, my, mz, dx, dy, dz, X, Y, Z, &lin)) return;
+  if (packed)
+    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << (kPackBits * lab));
+  else
+    atomicAdd(static_cast<unsigned int*>(ws) + lin * C + lab, 1u);
+}
+
+// argmax with ties -> lowest class, empty voxel -> 0 (torch.argmax on an all-zero row)
+template <typename OutT>
+__global__ void __launch_bounds__(kVoteThreads)
+vote_argmax_kernel(const void* __restrict__ ws, int64_t V, int32_t C, int packed, OutT* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= V) return;
+  int best = 0;
+  if (packed) {
+    const unsigned long long w = static_cast<const unsigned long long*>(ws)[i];
+    if (w != 0ull) {
+      const unsigned c0 = static_cast<unsigned>(w & kPackMask);
+      const unsigned c1 = static_cast<unsigned>((w >> kPackBits) & kPackMask);
+      const unsigned c2 = static_cast<unsigned>((w >> (2 * kPackBits)) & kPackMask);
+      unsigned bv = c0;
+      if (c1 > bv) { bv = c1; best = 1; }
+      if (c2 > bv) { bv = c2; best = 2; }
+    }
+  } else {
+    const unsigned int* r = static_cast<const unsigned int*>(ws) + i * C;
+    unsigned bv = r[0];
+    for (int c = 1; c < C; ++c) {
+      const unsigned v = r[c];
+      if (v > bv) { bv = v; best = c; }
+    }
+  }
+  out[i] = static_cast<OutT>(best);
+}
+
+__global__ void __launch_bounds__(kVoteThreads)
+point_labels_i64_kernel(const int64_t* __restrict__ coords, int64_t Pc, const int64_t* __restrict__ vlabels,
+                        int32_t X, int32_t Y, int32_t Z, int64_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= Pc) return;
+  const int64_t x = coords[i * 3], y = coords[i * 3 + 1], z = coords[i * 3 + 2];
+  int64_t r = 0;
+  if (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) r = __ldg(vlabels + (x * Y + y) * Z + z);
+  out[i] = r;
+}
+
+__global__ void __launch_bounds__(kVoteThreads)
+point_labels_fused_kernel(const float* __restrict__ pts, int64_t Pc, int64_t rs, float mx, float my, float mz,
+                          float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z,
+                          const uint8_t* __restrict__ vlabels, int64_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= Pc) return;
+  int64_t lin;
+  int64_t r = 0;
+  if (quant_voxel(pts + i * rs, mx, my, mz, dx, dy, dz, X, Y, Z, &lin)) r = vlabels[lin];
+  out[i] = r;
+}
+
+__global__ void __launch_bounds__(kVoteThreads)
+quantize_kernel(const float* __restrict__ pcds, int64_t P, int64_t rs, float mx, float my, float mz, float dx,
+                float dy, float dz, float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= P) return;
+  const float* p = pcds + i * rs;
+  out[i * 3] = quant(p[0], mx, dx);
+  out[i * 3 + 1] = quant(p[1], my, dy);
+  out[i * 3 + 2] = quant(p[2], mz, dz);
+}
+
+// Instance vote: boxes of one chunk live in shared memory together with their counters;
+// a point that falls in a box bumps a shared counter, the block flushes once at the end.
+constexpr int kBoxChunk = 256;
+
+__global__ void __launch_bounds__(kVoteThreads)
+instance_vote_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const int64_t* __restrict__ pred,
+                     const float* __restrict__ lo, const float* __restrict__ hi, int32_t K,
+                     unsigned long long* __restrict__ sums) {
+  __shared__ float s_lo[kBoxChunk * 3];
+  __shared__ float s_hi[kBoxChunk * 3];
+  __shared__ unsigned int s_cnt[kBoxChunk * 2];
+  const int32_t k0 = blockIdx.y * kBoxChunk;
+  const int32_t kn = min(kBoxChunk, K - k0);
+  for (int i = threadIdx.x; i < kn * 3; i += kVoteThreads) {
+    s_lo[i] = lo[k0 * 3 + i];
+    s_hi[i] = hi[k0 * 3 + i];
+  }
+  for (int i = threadIdx.x; i < kn * 2; i += kVoteThreads) s_cnt[i] = 0u;
+  __syncthreads();
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x; i < P;
+       i += static_cast<int64_t>(gridDim.x) * kVoteThreads) {
+    const int64_t pr = pred[i];
+    if (pr != 1 && pr != 2) continue;
+    const float* p = pts + i * rs;
+    const float x = p[0], y = p[1], z = p[2];
+    for (int k = 0; k < kn; ++k) {
+      const bool in = x >= s_lo[k * 3] && x <= s_hi[k * 3] && y >= s_lo[k * 3 + 1] && y <= s_hi[k * 3 + 1] &&
+                      z >= s_lo[k * 3 + 2] && z <= s_hi[k * 3 + 2];
+      if (in) atomicAdd(&s_cnt[k * 2 + (pr - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kn * 2; i += kVoteThreads) {
+    const unsigned int c = s_cnt[i];
+    // sum(pred[pred==2]) counts 2 per dynamic point (voxel_instance_voting.py:182-184)
+    if (c) atomicAdd(&sums[k0 * 2 + i], static_cast<unsigned long long>(c) * ((i & 1) ? 2ull : 1ull));
+  }
+}
+
+int64_t ws_bytes(int64_t P, int64_t V, int32_t C) {
+  return use_packed(P, C) ? V * 8 : V * static_cast<int64_t>(C) * 4;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smos_quantize(const float* pcds, int64_t P, int64_t row_stride, float min_x, float min_y, float min_z,
+                  float dx, float dy, float dz, float* out, void* stream) {
+  if (P < 0 || row_stride < 3) return SMOS_EINVAL;
+  if (P == 0) return SMOS_OK;
+  if (!pcds || !out) return SMOS_EINVAL;
+  quantize_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, smos_stream(stream)>>>(
+      pcds, P, row_stride, min_x, min_y, min_z, dx, dy, dz, out);
+  return smos_launch_status();
+}
+
+int64_t smos_vote_workspace_bytes(int64_t P, int32_t X, int32_t Y, int32_t Z, int32_t num_classes) {
+  if (P < 0 || X <= 0 || Y <= 0 || Z <= 0 || num_classes <= 0 || num_classes > kMaxClasses) return SMOS_EINVAL;
+  return ws_bytes(P, static_cast<int64_t>(X) * Y * Z, num_classes);
+}
+
+int smos_vote_voxel_labels(const int64_t* voxel_coords, const int64_t* semantic_labels, int64_t P, int32_t X,
+                           int32_t Y, int32_t Z, int32_t num_classes, void* workspace, int64_t* voxel_labels,
+                           void* stream) {
+  if (P < 0 || X <= 0 || Y <= 0 || Z <= 0 || num_classes <= 0 || num_classes > kMaxClasses) return SMOS_EINVAL;
+  if (!workspace || !voxel_labels || (P > 0 && (!voxel_coords || !semantic_labels))) return SMOS_EINVAL;
+  const int64_t V = static_cast<int64_t>(X) * Y * Z;
+  const int packed = use_packed(P, num_classes) ? 1 : 0;
+  cudaStream_t st = smos_stream(stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws_bytes(P, V, num_classes)), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (P > 0)
+    vote_i64_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st>>>(voxel_coords, semantic_labels, P, X, Y,
+                                                                             Z, num_classes, packed, workspace);
+  vote_argmax_kernel<int64_t><<<smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st>>>(workspace, V, num_classes,
+                                                                                       packed, voxel_labels);
+  return smos_launch_status();
+}
+
+int smos_vote_point_labels(const int64_t* new_voxel_coords, int64_t Pc, const int64_t* voxel_labels, int32_t X,
+                           int32_t Y, int32_t Z, int64_t* point_labels, void* stream) {
+  if (Pc < 0 || X <= 0 || Y <= 0 || Z <= 0) return SMOS_EINVAL;
+  if (Pc == 0) return SMOS_OK;
+  if (!new_voxel_coords || !voxel_labels || !point_labels) return SMOS_EINVAL;
+  point_labels_i64_kernel<<<smos_ceil_div(Pc, kVoteThreads), kVoteThreads, 0, smos_stream(stream)>>>(
+      new_voxel_coords, Pc, voxel_labels, X, Y, Z, point_labels);
+  return smos_launch_status();
+}
+
+int smos_vote_fused(const float* points, int64_t P, int64_t row_stride, const uint8_t* labels, int64_t Pc,
+                    float min_x, float min_y, float min_z, float dx, float dy, float dz, int32_t X, int32_t Y,
+                    int32_t Z, int32_t num_classes, void* workspace, uint8_t* voxel_labels_u8,
+                    int64_t* point_labels, void* stream) {
+  if (P < 0 || Pc < 0 || Pc > P || row_stride < 3 || X <= 0 || Y <= 0 || Z <= 0 || num_classes <= 0 ||
+      num_classes > kMaxClasses)
+    return SMOS_EINVAL;
+  if (!workspace || !voxel_labels_u8 || (P > 0 && (!points || !labels)) || (Pc > 0 && !point_labels))
+    return SMOS_EINVAL;
+  const int64_t V = static_cast<int64_t>(X) * Y * Z;
+  const int packed = use_packed(P, num_classes) ? 1 : 0;
+  cudaStream_t st = smos_stream(stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws_bytes(P, V, num_classes)), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (P > 0)
+    vote_fused_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st>>>(
+        points, P, row_stride, labels, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, num_classes, packed, workspace);
+  vote_argmax_kernel<uint8_t><<<smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st>>>(workspace, V, num_classes,
+                                                                                       packed, voxel_labels_u8);
+  if (Pc > 0)
+    point_labels_fused_kernel<<<smos_ceil_div(Pc, kVoteThreads), kVoteThreads, 0, st>>>(
+        points + (P - Pc) * row_stride, Pc, row_stride, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, voxel_labels_u8,
+        point_labels);
+  return smos_launch_status();
+}
+
+int smos_instance_vote(const float* points, int64_t P, int64_t row_stride, const int64_t* pred,
+                       const float* box_lo, const float* box_hi, int32_t K, int64_t* sums, void* stream) {
+  if (P < 0 || K < 0 || row_stride < 3) return SMOS_EINVAL;
+  if (K == 0 || P == 0) return SMOS_OK;
+  if (!points || !pred || !box_lo || !box_hi || !sums) return SMOS_EINVAL;
+  int gx = smos_ceil_div(P, kVoteThreads);
+  if (gx > 4 * SMOS_SM_COUNT) gx = 4 * SMOS_SM_COUNT;  // persistent-style grid-stride loop
+  dim3 grid(gx, smos_ceil_div(K, kBoxChunk));
+  instance_vote_kernel<<<grid, kVoteThreads, 0, smos_stream(stream)>>>(
+      points, P, row_stride, pred, box_lo, box_hi, K, reinterpret_cast<unsigned long long*>(sums));
+  return smos_launch_status();
+}
+
+}  // extern "C"

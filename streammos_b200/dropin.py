@@ -1,0 +1,33 @@
+"""Install the sm_100a implementations under the names the reference imports, so that
+models/StreamMOS.py, networks/multi_view_encoder.py and deformattn/ run unmodified:
+
+    import streammos_b200.dropin as dropin; dropin.install()
+    # then:  import deep_point; import MultiScaleDeformableAttention; from networks import backbone
+
+(The reference has no plugin registry; its modules are found through sys.modules.)"""
+import sys
+
+
+def install(point_major_points=False):
+    from . import MultiScaleDeformableAttention as msda
+    from . import backbone as b200_backbone
+    from . import deep_point as b200_deep_point
+    from . import point_deep as b200_point_deep
+
+    sys.modules["point_deep"] = b200_point_deep
+    sys.modules["point_deep.cuda_kernel"] = b200_point_deep.cuda_kernel
+    sys.modules["point_deep.cpu_kernel"] = b200_point_deep.cpu_kernel
+    sys.modules["deep_point"] = b200_deep_point
+    sys.modules["MultiScaleDeformableAttention"] = msda
+    b200_backbone.BilinearSample.point_major_out = bool(point_major_points)
+    # networks.backbone.BilinearSample is looked up by name at model build time (backbone.py:37-43,
+    # multi_view_encoder.py:377-378): replace the class if the reference package is importable.
+    ref_backbone = sys.modules.get("networks.backbone")
+    if ref_backbone is None:
+        try:
+            import networks.backbone as ref_backbone  # noqa: F811
+        except Exception:
+            ref_backbone = None
+    if ref_backbone is not None:
+        ref_backbone.BilinearSample = b200_backbone.BilinearSample
+    return True

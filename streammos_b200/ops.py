@@ -1,0 +1,326 @@
+"""Torch-tensor front end of the C-ABI: allocates outputs, passes raw pointers/strides and the
+current CUDA stream. Nothing here computes — every function ends in a kernel launch inside
+libstreammos_b200.so and raises if the tensors are not on a CUDA device."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (streammos_b200 has no CPU path)" % name)
+
+
+def _need_f32(t, name):
+    if t.dtype != torch.float32:
+        raise NotImplementedError("%s: only float32 is implemented on the B200 path (got %s)" % (name, t.dtype))
+
+
+# ----------------------------------------------------------------------------------------------
+# VoxelMaxPool
+# ----------------------------------------------------------------------------------------------
+class PoolPlan:
+    """Per-(coordinate array, grid, scale) bucketing of points by output tile.
+
+    Re-usable across every pooling call that shares the coordinates (forward and backward)."""
+
+    __slots__ = ("buf", "B", "N", "H", "W", "voxel_max_idx")
+
+    def __init__(self, buf, B, N, H, W, voxel_max_idx):
+        self.buf, self.B, self.N, self.H, self.W, self.voxel_max_idx = buf, B, N, H, W, voxel_max_idx
+
+
+def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=0):
+    """pcds_ind (B, N, 2[, 1]) float32 -> PoolPlan. `idx_out` (B, N) int64 receives the reference's
+    voxel_max_idx side product if given (deep_point/__init__.py:27)."""
+    _need_cuda(pcds_ind, "pcds_ind")
+    _need_f32(pcds_ind, "pcds_ind")
+    if pcds_ind.dim() == 4:
+        if pcds_ind.size(3) != 1:
+            raise RuntimeError("pcds_ind last dimension must be 1")
+        ind = pcds_ind[..., 0]
+    else:
+        ind = pcds_ind
+    if ind.dim() != 3 or ind.size(2) != 2 or len(output_size) != 2 or len(scale_rate) != 2:
+        raise NotImplementedError("only 2-D grids (D == 2) are implemented — the shapes StreamMOS uses")
+    B, N = int(ind.size(0)), int(ind.size(1))
+    H, W = int(output_size[0]), int(output_size[1])
+    lib = _lib.load()
+    nbytes = lib.smos_pool_plan_bytes(B, N, H, W)
+    if nbytes < 0:
+        _lib.check(int(nbytes), "smos_pool_plan_bytes")
+    buf = torch.empty(int(nbytes), dtype=torch.uint8, device=ind.device)
+    if idx_out is not None:
+        _need_cuda(idx_out, "voxel_max_idx")
+        assert idx_out.dtype == torch.int64 and idx_out.is_contiguous() and idx_out.numel() == B * N
+    with torch.cuda.device(ind.device):
+        rc = lib.smos_pool_plan_build(_ptr(ind), B, N, ind.stride(0), ind.stride(1), ind.stride(2), H, W,
+                                      float(scale_rate[0]), float(scale_rate[1]), _ptr(idx_out),
+                                      int(idx_batch_stride), _ptr(buf), _stream())
+    _lib.check(rc, "smos_pool_plan_build")
+    return PoolPlan(buf, B, N, H, W, idx_out)
+
+
+def _feat3(pcds_feat):
+    if pcds_feat.dim() == 4:
+        if pcds_feat.size(3) != 1:
+            raise RuntimeError("pcds_feat last dimension must be 1")
+        return pcds_feat[..., 0]
+    return pcds_feat
+
+
+def voxel_maxpool_forward(pcds_feat, plan, out=None):
+    """pcds_feat (B, C, N[, 1]) float32, any strides -> (B, C, H, W) NCHW-contiguous."""
+    _need_cuda(pcds_feat, "pcds_feat")
+    _need_f32(pcds_feat, "pcds_feat")
+    f = _feat3(pcds_feat)
+    B, C, N = (int(s) for s in f.shape)
+    if B != plan.B or N != plan.N:
+        raise RuntimeError("pcds_feat (B=%d, N=%d) does not match the plan (B=%d, N=%d)" % (B, N, plan.B, plan.N))
+    if out is None:
+        out = torch.empty((B, C, plan.H, plan.W), dtype=torch.float32, device=f.device)
+    else:
+        assert out.is_contiguous() and out.shape == (B, C, plan.H, plan.W) and out.dtype == torch.float32
+    with torch.cuda.device(f.device):
+        rc = _lib.load().smos_voxel_maxpool_forward(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2),
+                                                    plan.H, plan.W, _ptr(plan.buf), _ptr(out), _stream())
+    _lib.check(rc, "smos_voxel_maxpool_forward")
+    return out
+
+
+def voxel_maxpool_backward(pcds_feat, plan, voxel_out, grad_voxel_out, grad_feat=None):
+    _need_cuda(pcds_feat, "pcds_feat")
+    _need_f32(pcds_feat, "pcds_feat")
+    f = _feat3(pcds_feat)
+    B, C, N = (int(s) for s in f.shape)
+    grad_voxel_out = grad_voxel_out.contiguous()
+    assert voxel_out.is_contiguous()
+    if grad_feat is None:
+        grad_feat = torch.empty(pcds_feat.shape, dtype=torch.float32, device=f.device)
+    g = _feat3(grad_feat)
+    with torch.cuda.device(f.device):
+        rc = _lib.load().smos_voxel_maxpool_backward(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2),
+                                                     plan.H, plan.W, _ptr(plan.buf), _ptr(voxel_out),
+                                                     _ptr(grad_voxel_out), _ptr(g), g.stride(0), g.stride(1),
+                                                     g.stride(2), _stream())
+    _lib.check(rc, "smos_voxel_maxpool_backward")
+    return grad_feat
+
+
+# ----------------------------------------------------------------------------------------------
+# BilinearSample
+# ----------------------------------------------------------------------------------------------
+def bilinear_gather_forward(grid_feat, grid_coord, scale_rate, point_major_out=False):
+    """grid_feat (B, C, H, W) float32 (NCHW or channels_last), grid_coord (B, N, 2, S) float32
+    -> (B, C, N, S). With point_major_out the result is channels_last-strided (each point's C
+    features contiguous), the layout the pooling kernel reads fastest."""
+    _need_cuda(grid_feat, "grid_feat")
+    _need_cuda(grid_coord, "grid_coord")
+    _need_f32(grid_feat, "grid_feat")
+    _need_f32(grid_coord, "grid_coord")
+    B, C, H, W = (int(s) for s in grid_feat.shape)
+    if grid_coord.dim() != 4 or grid_coord.size(0) != B or grid_coord.size(2) != 2:
+        raise RuntimeError("grid_coord must be (B, N, 2, S)")
+    N, S = int(grid_coord.size(1)), int(grid_coord.size(3))
+    if S == 1:
+        co = grid_coord[..., 0]  # (B, N, 2)
+    else:
+        co = grid_coord.permute(0, 1, 3, 2).reshape(B, N * S, 2)
+    NP = N * S
+    if point_major_out:
+        out = torch.empty((B, N, S, C), dtype=torch.float32, device=grid_feat.device).permute(0, 3, 1, 2)
+    else:
+        out = torch.empty((B, C, N, S), dtype=torch.float32, device=grid_feat.device)
+    o_sb, o_sc = out.stride(0), out.stride(1)
+    o_sn = out.stride(3)  # flattened (n, s) index advances by the stride of s
+    with torch.cuda.device(grid_feat.device):
+        rc = _lib.load().smos_bilinear_gather_forward(
+            _ptr(grid_feat), B, C, H, W, grid_feat.stride(0), grid_feat.stride(1), grid_feat.stride(2),
+            grid_feat.stride(3), _ptr(co), NP, co.stride(0), co.stride(1), co.stride(2), float(scale_rate[0]),
+            float(scale_rate[1]), _ptr(out), o_sb, o_sc, o_sn, _stream())
+    _lib.check(rc, "smos_bilinear_gather_forward")
+    return out
+
+
+def bilinear_gather_backward(grad_out, grid_coord, scale_rate, H, W):
+    """grad_out (B, C, N, S) -> grad wrt grid_feat (B, C, H, W)."""
+    _need_cuda(grad_out, "grad_out")
+    _need_f32(grad_out, "grad_out")
+    B, C, N, S = (int(s) for s in grad_out.shape)
+    if S == 1:
+        co = grid_coord[..., 0]
+        go = grad_out[..., 0]
+    else:
+        co = grid_coord.permute(0, 1, 3, 2).reshape(B, N * S, 2)
+        go = grad_out.reshape(B, C, N * S)
+    grad_grid = torch.zeros((B, C, H, W), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        rc = _lib.load().smos_bilinear_gather_backward(
+            _ptr(go), B, C, N * S, go.stride(0), go.stride(1), go.stride(2), _ptr(co), co.stride(0), co.stride(1),
+            co.stride(2), float(scale_rate[0]), float(scale_rate[1]), int(H), int(W), _ptr(grad_grid), _stream())
+    _lib.check(rc, "smos_bilinear_gather_backward")
+    return grad_grid
+
+
+# ----------------------------------------------------------------------------------------------
+# MSDeformAttn
+# ----------------------------------------------------------------------------------------------
+_DT = {torch.float32: 0, torch.float64: 1}
+
+
+def _msda_check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, extra=()):
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)] + list(extra)
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError("%s tensor has to be contiguous" % name)  # ms_deform_attn_cuda.cu:28-32
+    for name, t in named:
+        if not t.is_cuda:
+            raise RuntimeError("%s must be a CUDA tensor (Not implemented on the CPU)" % name)  # :34-38
+    if value.dtype not in _DT:
+        raise RuntimeError("ms_deform_attn: only float32/float64 are dispatched (got %s)" % value.dtype)
+    if sampling_loc.dtype != value.dtype or attn_weight.dtype != value.dtype:
+        raise RuntimeError("ms_deform_attn: value, sampling_loc and attn_weight must share a dtype")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("ms_deform_attn: spatial_shapes / level_start_index must be int64")
+    B, S, M, D = (int(s) for s in value.shape)
+    L = int(spatial_shapes.size(0))
+    Q, P = int(sampling_loc.size(1)), int(sampling_loc.size(4))
+    return B, S, M, D, L, Q, P
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    B, S, M, D, L, Q, P = _msda_check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    out = torch.empty((B, Q, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.load().smos_ms_deform_attn_forward(_DT[value.dtype], _ptr(value), _ptr(spatial_shapes),
+                                                     _ptr(level_start_index), _ptr(sampling_loc),
+                                                     _ptr(attn_weight), B, S, M, D, L, Q, P, _ptr(out), _stream())
+    _lib.check(rc, "smos_ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output):
+    B, S, M, D, L, Q, P = _msda_check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                      extra=[("grad_output", grad_output)])
+    grad_value = torch.zeros_like(value)
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    with torch.cuda.device(value.device):
+        rc = _lib.load().smos_ms_deform_attn_backward(
+            _DT[value.dtype], _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
+            _ptr(attn_weight), _ptr(grad_output), B, S, M, D, L, Q, P, _ptr(grad_value), _ptr(grad_loc),
+            _ptr(grad_attn), _stream())
+    _lib.check(rc, "smos_ms_deform_attn_backward")
+    return grad_value, grad_loc, grad_attn
+
+
+# ----------------------------------------------------------------------------------------------
+# Voting
+# ----------------------------------------------------------------------------------------------
+def quantize(pcds, mins, deltas):
+    _need_cuda(pcds, "pcds")
+    _need_f32(pcds, "pcds")
+    assert pcds.dim() == 2 and pcds.size(1) >= 3 and pcds.stride(1) == 1
+    P = int(pcds.size(0))
+    out = torch.empty((P, 3), dtype=torch.float32, device=pcds.device)
+    with torch.cuda.device(pcds.device):
+        rc = _lib.load().smos_quantize(_ptr(pcds), P, pcds.stride(0) if P > 1 else pcds.size(1), float(mins[0]),
+                                       float(mins[1]), float(mins[2]), float(deltas[0]), float(deltas[1]),
+                                       float(deltas[2]), _ptr(out), _stream())
+    _lib.check(rc, "smos_quantize")
+    return out
+
+
+def _vote_ws(P, X, Y, Z, C, device):
+    n = _lib.load().smos_vote_workspace_bytes(P, X, Y, Z, C)
+    if n < 0:
+        _lib.check(int(n), "smos_vote_workspace_bytes")
+    return torch.empty(int(n), dtype=torch.uint8, device=device)
+
+
+def vote_voxel_labels(voxel_coords, semantic_labels, dims, num_classes):
+    _need_cuda(voxel_coords, "voxel_coords")
+    _need_cuda(semantic_labels, "semantic_labels")
+    if voxel_coords.dtype != torch.int64 or semantic_labels.dtype != torch.int64:
+        raise RuntimeError("voxel_coords / semantic_labels must be int64 (the reference API dtype)")
+    voxel_coords = voxel_coords.contiguous()
+    semantic_labels = semantic_labels.contiguous()
+    P = int(voxel_coords.size(0))
+    X, Y, Z = (int(d) for d in dims)
+    ws = _vote_ws(P, X, Y, Z, int(num_classes), voxel_coords.device)
+    out = torch.empty((X, Y, Z), dtype=torch.int64, device=voxel_coords.device)
+    with torch.cuda.device(voxel_coords.device):
+        rc = _lib.load().smos_vote_voxel_labels(_ptr(voxel_coords), _ptr(semantic_labels), P, X, Y, Z,
+                                                int(num_classes), _ptr(ws), _ptr(out), _stream())
+    _lib.check(rc, "smos_vote_voxel_labels")
+    return out
+
+
+def vote_point_labels(new_voxel_coords, voxel_labels, dims):
+    _need_cuda(new_voxel_coords, "new_voxel_coords")
+    _need_cuda(voxel_labels, "voxel_labels")
+    if new_voxel_coords.dtype != torch.int64 or voxel_labels.dtype != torch.int64:
+        raise RuntimeError("new_voxel_coords / voxel_labels must be int64 (the reference API dtype)")
+    new_voxel_coords = new_voxel_coords.contiguous()
+    voxel_labels = voxel_labels.contiguous()
+    Pc = int(new_voxel_coords.size(0))
+    X, Y, Z = (int(d) for d in dims)
+    out = torch.empty((Pc,), dtype=torch.int64, device=new_voxel_coords.device)
+    with torch.cuda.device(new_voxel_coords.device):
+        rc = _lib.load().smos_vote_point_labels(_ptr(new_voxel_coords), Pc, _ptr(voxel_labels), X, Y, Z, _ptr(out),
+                                                _stream())
+    _lib.check(rc, "smos_vote_point_labels")
+    return out
+
+
+def vote_fused(points, labels_u8, num_current, mins, deltas, dims, num_classes=3):
+    """Streaming-path voting straight from float xyz + uint8 labels (no int64 staging).
+    Returns (voxel_labels uint8 (X,Y,Z), point_labels int64 (num_current,))."""
+    _need_cuda(points, "points")
+    _need_cuda(labels_u8, "labels")
+    _need_f32(points, "points")
+    assert labels_u8.dtype == torch.uint8 and labels_u8.is_contiguous()
+    assert points.dim() == 2 and points.size(1) >= 3 and points.stride(1) == 1
+    P = int(points.size(0))
+    X, Y, Z = (int(d) for d in dims)
+    ws = _vote_ws(P, X, Y, Z, int(num_classes), points.device)
+    vl = torch.empty((X, Y, Z), dtype=torch.uint8, device=points.device)
+    pl = torch.empty((int(num_current),), dtype=torch.int64, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = _lib.load().smos_vote_fused(_ptr(points), P, points.stride(0) if P > 1 else points.size(1),
+                                         _ptr(labels_u8), int(num_current), float(mins[0]), float(mins[1]),
+                                         float(mins[2]), float(deltas[0]), float(deltas[1]), float(deltas[2]), X, Y,
+                                         Z, int(num_classes), _ptr(ws), _ptr(vl), _ptr(pl), _stream())
+    _lib.check(rc, "smos_vote_fused")
+    return vl, pl
+
+
+def instance_vote(points, pred, box_lo, box_hi):
+    """points (P, >=3) f32, pred (P,) int64, box_lo/box_hi (K, 3) f32 -> sums (K, 2) int64
+    [static_sum, dynamic_sum] with dynamic points weighted 2."""
+    _need_cuda(points, "points")
+    _need_f32(points, "points")
+    if pred.dtype != torch.int64:
+        raise RuntimeError("pred must be int64")
+    pred = pred.contiguous()
+    box_lo = box_lo.to(torch.float32).contiguous()
+    box_hi = box_hi.to(torch.float32).contiguous()
+    assert points.dim() == 2 and points.size(1) >= 3 and points.stride(1) == 1
+    P, K = int(points.size(0)), int(box_lo.size(0))
+    sums = torch.zeros((K, 2), dtype=torch.int64, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = _lib.load().smos_instance_vote(_ptr(points), P, points.stride(0) if P > 1 else points.size(1),
+                                            _ptr(pred), _ptr(box_lo), _ptr(box_hi), K, _ptr(sums), _stream())
+    _lib.check(rc, "smos_instance_vote")
+    return sums
