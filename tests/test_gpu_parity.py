@@ -1,0 +1,404 @@
+"""Parity of the sm_100a kernels (through the reference-shaped Python API -> ctypes -> C-ABI) against
+(1) the committed outputs of the reference itself (tests/golden) and (2) the CPU oracle on seeded
+synthetic inputs, including the BASELINE.json configuration sizes.
+
+Bars (BASELINE.json north_star): voxel indices, scatter winners and vote counts BIT-EXACT; scatter-max
+features bit-exact (max is exact); bilinear gathers and deformable attention within 1e-5 relative in
+fp32 (plus a small atol at zero crossings)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def t(a, dtype=None):
+    x = torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+    return x.to(dtype) if dtype is not None else x
+
+
+def synth_scan(rng, B, N, H, W, scale, n_valid=None):
+    """BEV-like coordinates: valid points span the grid, ~1% in (-1,0) (truncate to cell 0), ~1% beyond the
+    grid, pads at -1000 after n_valid (datasets/data_StreamMOS.py:570-571)."""
+    n_valid = N if n_valid is None else n_valid
+    c = np.stack([rng.uniform(0, H / scale[0], (B, N)), rng.uniform(0, W / scale[1], (B, N))], -1)
+    k = max(1, N // 100)
+    c[:, :k, 0] = rng.uniform(-0.999, 0, (B, k)) / scale[0]
+    c[:, k:2 * k, 1] = W / scale[1] + rng.uniform(0, 2, (B, k))
+    c[:, n_valid:] = -1000.0
+    return c.astype(np.float32)[..., None]
+
+
+# ------------------------------------------------------------------------------------------------
+# VoxelMaxPool
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["pool_a", "pool_b", "pool_c"])
+@pytest.mark.parametrize("layout", ["channel_major", "point_major"])
+def test_pool_golden(golden, name, layout):
+    from streammos_b200 import deep_point
+    g = golden(name)
+    feat = t(g["feat"])
+    if layout == "point_major":
+        feat = feat.contiguous(memory_format=torch.channels_last)
+        assert feat.stride(1) == 1
+    feat.requires_grad_(True)
+    out = deep_point.VoxelMaxPool(feat, t(g["ind"]), (int(g["H"]), int(g["W"])), tuple(float(s) for s in g["scale"]))
+    assert out.is_contiguous()
+    assert np.array_equal(out.detach().cpu().numpy(), g["out"])
+    out.backward(t(g["gout"]))
+    assert np.array_equal(feat.grad.cpu().numpy(), g["gfeat"])  # scatter winners: every tied point
+
+
+def test_pool_lower_boundary_voxel_max_idx(golden):
+    """point_deep.cuda_kernel.* with the reference's 8/10-tensor signature (point_deep_cuda.cpp:22-62)."""
+    from streammos_b200.point_deep import cuda_kernel
+    g = golden("pool_a")
+    feat, ind = t(g["feat"]), t(g["ind"])
+    H, W = int(g["H"]), int(g["W"])
+    B, C, N = feat.shape[:3]
+    voxel_out = torch.zeros((B, C, H, W), device=dev())
+    idx = torch.full((B, N), -1, dtype=torch.int64, device=dev())
+    size_pt = torch.LongTensor([B, C, H, W]).to(dev())
+    stride_pt = torch.LongTensor(list(voxel_out.stride())).to(dev())
+    scale_pt = torch.FloatTensor(g["scale"]).to(dev())
+    cuda_kernel.voxel_maxpooling_forward(feat, ind, voxel_out, idx, size_pt, stride_pt, size_pt[2:], scale_pt)
+    o_ref, i_ref = O.voxel_maxpool_forward(g["feat"], g["ind"], (H, W), g["scale"], want_idx=True)
+    assert np.array_equal(voxel_out.cpu().numpy(), o_ref)
+    assert np.array_equal(idx.cpu().numpy(), i_ref)  # voxel indices bit-exact
+    grad = torch.zeros_like(feat)
+    cuda_kernel.voxel_maxpooling_backward(feat, ind, voxel_out, idx, grad, t(g["gout"]), size_pt, stride_pt,
+                                          size_pt[2:], scale_pt)
+    assert np.array_equal(grad.cpu().numpy(), g["gfeat"])
+    with pytest.raises(RuntimeError):
+        cuda_kernel.voxel_maxpooling_forward(feat.cpu(), ind, voxel_out, idx, size_pt, stride_pt, size_pt[2:],
+                                             scale_pt)
+
+
+POOL_CONFIG = [  # the five call sites per scan at N = 120k valid + pads
+    (3, 64, (512, 512), (1.0, 1.0)),
+    (1, 32, (32, 1024), (0.5, 0.5)),
+    (1, 32, (256, 256), (0.5, 0.5)),
+    (1, 64, (16, 512), (0.25, 0.25)),
+    (1, 64, (128, 128), (0.25, 0.25)),
+]
+
+
+@pytest.mark.parametrize("B,C,size,scale", POOL_CONFIG)
+@pytest.mark.parametrize("layout", ["channel_major", "point_major"])
+def test_pool_config_sizes_vs_oracle(B, C, size, scale, layout):
+    from streammos_b200 import deep_point
+    rng = np.random.default_rng(7 + C + size[0])
+    N, n_valid = 130000, 120000
+    ind = synth_scan(rng, B, N, size[0], size[1], scale, n_valid)
+    feat = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+    ref = O.voxel_maxpool_forward(feat, ind, size, scale)
+    ft = t(feat)
+    if layout == "point_major":
+        ft = ft.contiguous(memory_format=torch.channels_last)
+    ft.requires_grad_(True)
+    out = deep_point.VoxelMaxPool(ft, t(ind), size, scale)
+    assert np.array_equal(out.detach().cpu().numpy(), ref)
+    gout = rng.standard_normal(ref.shape).astype(np.float32)
+    out.backward(t(gout))
+    gref = O.voxel_maxpool_backward(feat, ind, ref, gout, scale)
+    assert np.array_equal(ft.grad.cpu().numpy().reshape(gref.shape), gref)
+
+
+@pytest.mark.parametrize("B,C,N,size,scale", [
+    (1, 1, 1, (4, 4), (1.0, 1.0)),       # single point
+    (2, 3, 31, (5, 7), (1.0, 1.0)),      # ragged: N not a multiple of the warp, odd grid (scalar store path)
+    (1, 7, 1000, (3, 1000), (1.0, 1.0)),  # wide, tile wider than tall
+    (2, 40, 5000, (130, 70), (0.5, 0.5)),  # grid not a multiple of the tile, C not a power of two
+    (1, 4, 2000, (8, 8), (1.0, 1.0)),    # heavy collisions: 2000 points into 64 cells
+])
+def test_pool_edge_shapes(B, C, N, size, scale):
+    from streammos_b200 import deep_point
+    rng = np.random.default_rng(N + C)
+    ind = synth_scan(rng, B, N, size[0], size[1], scale)
+    feat = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+    ref = O.voxel_maxpool_forward(feat, ind, size, scale)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        out = deep_point.VoxelMaxPool(t(feat).contiguous(memory_format=fmt), t(ind), size, scale)
+        assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_pool_all_invalid_and_negative_maxima():
+    from streammos_b200 import deep_point
+    B, C, N = 1, 4, 500
+    ind = np.full((B, N, 2, 1), -1000.0, np.float32)
+    feat = -np.abs(np.random.default_rng(0).standard_normal((B, C, N, 1))).astype(np.float32) - 1
+    out = deep_point.VoxelMaxPool(t(feat), t(ind), (16, 16), (1.0, 1.0))
+    assert float(out.abs().max()) == 0.0  # empty grid is exactly zero
+    ind[:, :, :, 0] = 3.5                 # everything into one cell, all features negative
+    out = deep_point.VoxelMaxPool(t(feat), t(ind), (16, 16), (1.0, 1.0))
+    ref = O.voxel_maxpool_forward(feat, ind, (16, 16), (1.0, 1.0))
+    assert np.array_equal(out.cpu().numpy(), ref) and ref.min() < 0  # true (negative) max survives
+
+
+def test_pool_permutation_invariant():
+    """Size-independent property at the config size: permuting the points does not change the grid."""
+    from streammos_b200 import deep_point
+    rng = np.random.default_rng(11)
+    B, C, N, size, scale = 1, 32, 120000, (256, 256), (0.5, 0.5)
+    ind = synth_scan(rng, B, N, 512, 512, (1.0, 1.0))
+    feat = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+    a = deep_point.VoxelMaxPool(t(feat), t(ind), size, scale)
+    perm = rng.permutation(N)
+    b = deep_point.VoxelMaxPool(t(feat[:, :, perm]), t(ind[:, perm]), size, scale)
+    assert torch.equal(a, b)
+
+
+def test_pool_rejects_cpu_tensors():
+    from streammos_b200 import deep_point
+    with pytest.raises(RuntimeError):
+        deep_point.VoxelMaxPool(torch.zeros(1, 2, 8, 1), torch.zeros(1, 8, 2, 1), (4, 4), (1.0, 1.0))
+
+
+# ------------------------------------------------------------------------------------------------
+# BilinearSample
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["bilinear_a", "bilinear_b"])
+@pytest.mark.parametrize("grid_fmt", ["nchw", "nhwc"])
+@pytest.mark.parametrize("point_major_out", [False, True])
+def test_bilinear_golden(golden, name, grid_fmt, point_major_out):
+    from streammos_b200.backbone import BilinearSample
+    g = golden(name)
+    grid = t(g["grid"])
+    if grid_fmt == "nhwc":
+        grid = grid.contiguous(memory_format=torch.channels_last)
+    grid.requires_grad_(True)
+    m = BilinearSample(in_dim=grid.shape[1], scale_rate=tuple(float(s) for s in g["scale"]))
+    m.point_major_out = point_major_out
+    out = m(grid, t(g["coord"]))
+    assert out.shape == g["out"].shape
+    if point_major_out:
+        assert out.stride(1) == 1
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], rtol=RTOL, atol=ATOL)
+    out.backward(t(g["gout"]))
+    np.testing.assert_allclose(grid.grad.cpu().numpy(), g["ggrid"], rtol=1e-4, atol=1e-4)
+
+
+BILINEAR_CONFIG = [  # the five gathers per scan
+    (32, 256, 256, (0.5, 0.5)), (32, 32, 1024, (0.5, 0.5)), (64, 128, 128, (0.25, 0.25)),
+    (64, 16, 512, (0.25, 0.25)), (64, 256, 256, (0.5, 0.5)),
+]
+
+
+@pytest.mark.parametrize("C,H,W,scale", BILINEAR_CONFIG)
+def test_bilinear_config_sizes_vs_oracle(C, H, W, scale):
+    from streammos_b200 import ops
+    rng = np.random.default_rng(C + H)
+    N = 120000
+    coord = synth_scan(rng, 1, N, H, W, scale, n_valid=118000)
+    grid = rng.standard_normal((1, C, H, W)).astype(np.float32)
+    ref = O.bilinear_sample(grid, coord, scale)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        for pm in (False, True):
+            out = ops.bilinear_gather_forward(t(grid).contiguous(memory_format=fmt), t(coord), scale, pm)
+            np.testing.assert_allclose(out[..., 0].cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    # pads (coord -1000) sample nothing: exact zeros
+    assert float(out[:, :, 118000:].abs().max()) == 0.0
+
+
+def test_bilinear_multi_sample_dim_and_linearity():
+    from streammos_b200 import ops
+    rng = np.random.default_rng(5)
+    B, C, H, W, N, S = 2, 8, 20, 30, 777, 3
+    grid = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    coord = rng.uniform(-2, 32, (B, N, 2, S)).astype(np.float32)
+    out = ops.bilinear_gather_forward(t(grid), t(coord), (1.0, 1.0))
+    assert out.shape == (B, C, N, S)
+    for s in range(S):
+        ref = O.bilinear_sample(grid, coord[..., s], (1.0, 1.0))
+        np.testing.assert_allclose(out[..., s].cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    # linearity in the grid: gather(2a + b) == 2 gather(a) + gather(b)
+    g2 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    lhs = ops.bilinear_gather_forward(t(2 * grid + g2), t(coord), (1.0, 1.0))
+    rhs = 2 * out + ops.bilinear_gather_forward(t(g2), t(coord), (1.0, 1.0))
+    torch.testing.assert_close(lhs, rhs, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# MSDeformAttn
+# ------------------------------------------------------------------------------------------------
+MSDA = ["msda_reftest", "msda_reftest_d30", "msda_reftest_d32", "msda_reftest_d71", "msda_streammos_small"]
+
+
+@pytest.mark.parametrize("name", MSDA)
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_msda_golden(golden, name, dtype):
+    from streammos_b200.functions import MSDeformAttnFunction
+    g = golden(name)
+    value = t(g["value"], dtype).requires_grad_(True)
+    loc = t(g["loc"], dtype).requires_grad_(True)
+    attn = t(g["attn"], dtype).requires_grad_(True)
+    out = MSDeformAttnFunction.apply(value, t(g["shapes"]), t(g["lsi"]), loc, attn, 2)
+    out.backward(t(g["gout"], dtype))
+    scale = np.abs(g["out64"]).max()
+    if dtype == torch.float64:  # deformattn/test.py:41: allclose defaults in double
+        tol = dict(rtol=1e-7, atol=1e-10)
+        gtol = dict(rtol=1e-6, atol=1e-9)
+    else:                       # north_star: 1e-5 relative in fp32
+        tol = dict(rtol=RTOL, atol=1e-6 * max(scale, 1e-3))
+        gtol = dict(rtol=2e-4, atol=2e-5 * max(1.0, np.abs(g["gloc"]).max()))
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out64"], **tol)
+    np.testing.assert_allclose(value.grad.cpu().numpy(), g["gvalue"], **gtol)
+    np.testing.assert_allclose(attn.grad.cpu().numpy(), g["gattn"], **gtol)
+    np.testing.assert_allclose(loc.grad.cpu().numpy(), g["gloc"], **gtol)
+
+
+def _streammos_msda_inputs(rng, B, Hs=64, Ws=64, M=4, D=32, P=4):
+    value = rng.standard_normal((B, Hs * Ws, M, D)).astype(np.float32)
+    ys, xs = np.meshgrid(np.linspace(0.5, Hs - 0.5, Hs), np.linspace(0.5, Ws - 0.5, Ws), indexing="ij")
+    ref_pts = np.stack((xs.reshape(-1) / Ws, ys.reshape(-1) / Hs), -1)
+    loc = ref_pts[None, :, None, None, None, :] + rng.standard_normal((B, Hs * Ws, M, 1, P, 2)) * 3.0 / Hs
+    a = rng.standard_normal((B, Hs * Ws, M, P))
+    attn = np.exp(a) / np.exp(a).sum(-1, keepdims=True)
+    shapes = np.array([[Hs, Ws]], np.int64)
+    lsi = np.array([0], np.int64)
+    return value, shapes, lsi, loc.astype(np.float32), attn.reshape(B, Hs * Ws, M, 1, P).astype(np.float32)
+
+
+@pytest.mark.parametrize("B", [1, 4])
+def test_msda_config_shape_vs_oracle(B):
+    """config #3: value (B,4096,4,32), [[64,64]], 4 points — fwd and bwd against the fp64 oracle."""
+    from streammos_b200 import MultiScaleDeformableAttention as MSDA_mod
+    rng = np.random.default_rng(100 + B)
+    value, shapes, lsi, loc, attn = _streammos_msda_inputs(rng, B)
+    ref = O.ms_deform_attn_forward(value, shapes, lsi, loc, attn)
+    out = MSDA_mod.ms_deform_attn_forward(t(value), t(shapes), t(lsi), t(loc), t(attn), 256)
+    assert out.shape == (B, 4096, 128)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=RTOL, atol=1e-6 * np.abs(ref).max())
+    gout = rng.standard_normal(ref.shape).astype(np.float32)
+    gv, gl, ga = MSDA_mod.ms_deform_attn_backward(t(value), t(shapes), t(lsi), t(loc), t(attn), t(gout), 256)
+    rv, rl, ra = O.ms_deform_attn_backward(value, shapes, lsi, loc, attn, gout)
+    np.testing.assert_allclose(gv.cpu().numpy(), rv, rtol=1e-4, atol=1e-5 * np.abs(rv).max())
+    np.testing.assert_allclose(ga.cpu().numpy(), ra, rtol=1e-4, atol=1e-5 * np.abs(ra).max())
+    np.testing.assert_allclose(gl.cpu().numpy(), rl, rtol=1e-4, atol=1e-5 * np.abs(rl).max())
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71])
+def test_msda_gradcheck_double(channels):
+    """deformattn/test.py:63-78 check_gradient_numerical, same shapes and seed."""
+    from torch.autograd import gradcheck
+    from streammos_b200.functions import MSDeformAttnFunction
+    torch.manual_seed(3)
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=dev())
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = (torch.rand(N, S, M, channels, device=dev()) * 0.01).double().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2, device=dev()).double().requires_grad_(True)
+    attn = torch.rand(N, Lq, M, L, P, device=dev()) + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+    assert gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, attn, 2))
+
+
+def test_msda_error_behaviour():
+    from streammos_b200 import MultiScaleDeformableAttention as MSDA_mod
+    rng = np.random.default_rng(0)
+    value, shapes, lsi, loc, attn = _streammos_msda_inputs(rng, 1, 8, 8)
+    args = [t(value), t(shapes), t(lsi), t(loc), t(attn)]
+    with pytest.raises(RuntimeError, match="contiguous"):
+        MSDA_mod.ms_deform_attn_forward(args[0].transpose(2, 3), *args[1:], 256)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        MSDA_mod.ms_deform_attn_forward(args[0].cpu(), *args[1:], 256)
+    with pytest.raises(RuntimeError):
+        MSDA_mod.ms_deform_attn_forward(args[0].half(), *args[1:], 256)
+
+
+# ------------------------------------------------------------------------------------------------
+# Voting
+# ------------------------------------------------------------------------------------------------
+def test_voting_golden(golden):
+    from streammos_b200 import voting
+    g = golden("voting_a")
+    size = tuple(int(s) for s in g["size"])
+    rx, ry, rz = tuple(g["rx"]), tuple(g["ry"]), tuple(g["rz"])
+    q = voting.Quantize(t(g["pts"]), range_x=rx, range_y=ry, range_z=rz, size=size)
+    assert np.array_equal(q.cpu().numpy(), g["quan"])
+    coords = q.to(torch.int64)
+    assert np.array_equal(coords.cpu().numpy(), g["coords"])          # voxel indices bit-exact
+    vl = voting.determine_voxel_labels(coords, t(g["labels"]), size)  # num_classes via labels.max() like the ref
+    assert vl.dtype == torch.int64 and np.array_equal(vl.cpu().numpy(), g["voxel_labels"])
+    vl3 = voting.determine_voxel_labels(coords, t(g["labels"]), size, num_classes=3)
+    assert torch.equal(vl, vl3)
+    pl = voting.get_point_labels_from_voxel_labels(t(g["cur"]), vl, size)
+    assert np.array_equal(pl.cpu().numpy(), g["point_labels"])
+
+
+@pytest.mark.parametrize("num_classes", [3, 5])
+def test_voting_config_size_vs_oracle(num_classes):
+    """config #1 shape: 8 history + 1 current scans x 120k points into 512 x 512 x 30."""
+    from streammos_b200 import ops, voting
+    rng = np.random.default_rng(42 + num_classes)
+    P, Pc = 9 * 120000, 120000
+    size = (512, 512, 30)
+    rx, ry, rz = (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0)
+    r = np.abs(rng.standard_normal(P)) * 18.0
+    th = rng.uniform(0, 2 * np.pi, P)
+    pts = np.stack([np.clip(r * np.cos(th), -49.99, 49.99), np.clip(r * np.sin(th), -49.99, 49.99),
+                    np.clip(rng.normal(-1.5, 0.6, P), -3.99, 1.99), rng.uniform(0, 1, P)], -1).astype(np.float32)
+    labels = rng.integers(0, num_classes, P).astype(np.int64)
+    q_ref = O.quantize(pts, rx, ry, rz, size)
+    q = voting.Quantize(t(pts), rx, ry, rz, size)
+    assert np.array_equal(q.cpu().numpy(), q_ref)
+    coords = q.to(torch.int64)
+    vl_ref = O.determine_voxel_labels(q_ref.astype(np.int64), labels, size, num_classes)
+    vl = voting.determine_voxel_labels(coords, t(labels), size, num_classes=num_classes)
+    assert np.array_equal(vl.cpu().numpy(), vl_ref)
+    pl = voting.get_point_labels_from_voxel_labels(coords[P - Pc:], vl, size)
+    pl_ref = O.get_point_labels_from_voxel_labels(q_ref.astype(np.int64)[P - Pc:], vl_ref, size)
+    assert np.array_equal(pl.cpu().numpy(), pl_ref)
+    # fused streaming variant: same answers from float xyz + uint8 labels
+    d = [np.float32((rr[1] - rr[0]) / s) for rr, s in zip((rx, ry, rz), size)]
+    vl8, plf = ops.vote_fused(t(pts), t(labels.astype(np.uint8)), Pc, (rx[0], ry[0], rz[0]), d, size, num_classes)
+    assert np.array_equal(vl8.cpu().numpy().astype(np.int64), vl_ref)
+    assert np.array_equal(plf.cpu().numpy(), pl_ref)
+    # checksum of checksums: votes are conserved — every in-range point lands in exactly one voxel
+    assert int((vl > 0).sum()) <= P
+
+
+def test_voting_empty_and_out_of_range():
+    from streammos_b200 import voting
+    size = (8, 8, 4)
+    coords = torch.tensor([[0, 0, 0], [0, 0, 0], [7, 7, 3], [9, 0, 0], [-1, 2, 2]], dtype=torch.int64, device=dev())
+    labels = torch.tensor([2, 2, 1, 2, 2], dtype=torch.int64, device=dev())
+    vl = voting.determine_voxel_labels(coords, labels, size, num_classes=3)
+    assert int(vl[0, 0, 0]) == 2 and int(vl[7, 7, 3]) == 1 and int(vl.sum()) == 3
+    pl = voting.get_point_labels_from_voxel_labels(coords, vl, size)
+    assert pl.tolist() == [2, 2, 1, 0, 0]
+    # tie -> lowest class
+    vl = voting.determine_voxel_labels(coords[:2], torch.tensor([2, 1], device=dev()), size, num_classes=3)
+    assert int(vl[0, 0, 0]) == 1
+
+
+def test_instance_vote_golden(golden):
+    from streammos_b200 import voting
+    g = golden("instance_a")
+    stat, dyn, label = voting.instance_vote_counts(t(g["local_pts"]), t(g["local_pred"]), t(g["corners"]))
+    assert np.array_equal(stat.cpu().numpy(), g["stat"])
+    assert np.array_equal(dyn.cpu().numpy(), g["dyn"])
+    assert np.array_equal(label.cpu().numpy(), g["label"])
+
+
+def test_instance_vote_many_boxes_vs_oracle():
+    from streammos_b200 import ops
+    rng = np.random.default_rng(9)
+    P, K = 300000, 300  # more boxes than one shared-memory chunk
+    pts = np.concatenate([rng.uniform(-50, 50, (P, 2)), rng.uniform(-4, 2, (P, 1)), rng.uniform(0, 1, (P, 1))],
+                         1).astype(np.float32)
+    pred = rng.integers(0, 3, P).astype(np.int64)
+    c = np.concatenate([rng.uniform(-45, 45, (K, 2)), rng.uniform(-3, 1, (K, 1))], 1)
+    half = rng.uniform(0.5, 4, (K, 3))
+    lo, hi = (c - half).astype(np.float32), (c + half).astype(np.float32)
+    sums = ops.instance_vote(t(pts), t(pred), t(lo), t(hi))
+    assert np.array_equal(sums.cpu().numpy(), O.instance_vote(pts, pred, lo, hi))

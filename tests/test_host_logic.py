@@ -1,0 +1,73 @@
+"""Host-side logic of the reference-shaped shims that needs no GPU: argument checks, error behaviour,
+drop-in module registration."""
+import sys
+
+import pytest
+import torch
+
+
+def test_voxel_maxpool_asserts_like_the_reference():
+    from streammos_b200 import deep_point
+    feat = torch.zeros(1, 4, 10, 1)
+    with pytest.raises(AssertionError):  # N mismatch, deep_point/__init__.py:21
+        deep_point.VoxelMaxPool(feat, torch.zeros(1, 9, 2, 1), (4, 4), (1.0, 1.0))
+    with pytest.raises(AssertionError):  # D != len(output_size), :22
+        deep_point.VoxelMaxPool(feat, torch.zeros(1, 10, 2, 1), (4, 4, 4), (1.0, 1.0))
+    with pytest.raises(AssertionError):  # dtype mismatch, :18
+        deep_point.VoxelMaxPool(feat, torch.zeros(1, 10, 2, 1, dtype=torch.float64), (4, 4), (1.0, 1.0))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        deep_point.VoxelMaxPool(feat, torch.zeros(1, 10, 2, 1), (4, 4), (1.0, 1.0))
+
+
+def test_cpu_kernel_stub_raises():
+    from streammos_b200.point_deep import cpu_kernel
+    with pytest.raises(RuntimeError):
+        cpu_kernel.voxel_maxpooling_cpu_forward()
+
+
+def test_msda_rejects_cpu_and_bad_im2col_step():
+    from streammos_b200 import MultiScaleDeformableAttention as M
+    value = torch.zeros(3, 16, 2, 4)
+    shapes = torch.tensor([[4, 4]])
+    lsi = torch.tensor([0])
+    loc = torch.zeros(3, 5, 2, 1, 2, 2)
+    attn = torch.zeros(3, 5, 2, 1, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.ms_deform_attn_forward(value, shapes, lsi, loc, attn, 256)
+    with pytest.raises(AssertionError):  # batch 3 not divisible by min(3, 2): ms_deform_attn_cuda.cu:52
+        M.ms_deform_attn_forward(value, shapes, lsi, loc, attn, 2)
+
+
+def test_voting_rejects_cpu_and_wrong_dtype():
+    from streammos_b200 import voting
+    with pytest.raises(RuntimeError):
+        voting.determine_voxel_labels(torch.zeros(4, 3, dtype=torch.int64), torch.zeros(4, dtype=torch.int64),
+                                      (4, 4, 4), num_classes=3)
+
+
+def test_dropin_registers_reference_module_names():
+    from streammos_b200 import dropin
+    saved = {k: sys.modules.get(k) for k in ("deep_point", "point_deep", "point_deep.cuda_kernel",
+                                             "point_deep.cpu_kernel", "MultiScaleDeformableAttention")}
+    try:
+        dropin.install()
+        import deep_point
+        import point_deep.cuda_kernel as ck
+        import MultiScaleDeformableAttention as MSDA
+        assert hasattr(deep_point, "VoxelMaxPool") and hasattr(deep_point, "VoxelMaxPoolFunction")
+        assert hasattr(ck, "voxel_maxpooling_forward") and hasattr(ck, "voxel_maxpooling_backward")
+        assert hasattr(MSDA, "ms_deform_attn_forward") and hasattr(MSDA, "ms_deform_attn_backward")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_bilinear_sample_signature():
+    from streammos_b200.backbone import BilinearSample
+    m = BilinearSample(in_dim=4, scale_rate=(0.5, 0.5))
+    assert m.scale_rate == (0.5, 0.5)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 2, 4, 4), torch.zeros(1, 3, 2, 1))

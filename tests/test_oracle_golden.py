@@ -1,0 +1,96 @@
+"""Pin the CPU oracle (oracle/smos_oracle.c) against outputs of the reference itself
+(tests/golden/*.npz, made by tools/make_golden.py from /root/reference). Runs anywhere, no GPU."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+POOL = ["pool_a", "pool_b", "pool_c"]
+BILINEAR = ["bilinear_a", "bilinear_b"]
+MSDA = ["msda_reftest", "msda_reftest_d30", "msda_reftest_d32", "msda_reftest_d71", "msda_streammos_small"]
+
+
+@pytest.mark.parametrize("name", POOL)
+def test_pool_forward_bit_exact(golden, name):
+    g = golden(name)
+    out, idx = O.voxel_maxpool_forward(g["feat"], g["ind"], (int(g["H"]), int(g["W"])), g["scale"], want_idx=True)
+    assert np.array_equal(out, g["out"])  # max is exact: bit equality with point_deep.cpp
+    # voxel_max_idx is consistent with the output: valid points never exceed their cell's value
+    B, C, N = g["feat"].shape[:3]
+    flat = out.reshape(-1)
+    feat = g["feat"].reshape(B, C, N)
+    valid = idx >= 0
+    assert valid.any() and (~valid).any()
+    for b in range(B):
+        v = np.nonzero(valid[b])[0]
+        for c in (0, C - 1):
+            assert (flat[idx[b, v] + c * out.shape[2] * out.shape[3]] >= feat[b, c, v]).all()
+
+
+@pytest.mark.parametrize("name", POOL)
+def test_pool_backward_bit_exact(golden, name):
+    g = golden(name)
+    gf = O.voxel_maxpool_backward(g["feat"], g["ind"], g["out"], g["gout"], g["scale"])
+    assert np.array_equal(gf, g["gfeat"].reshape(gf.shape))
+
+
+@pytest.mark.parametrize("name", BILINEAR)
+def test_bilinear_forward(golden, name):
+    g = golden(name)
+    out = O.bilinear_sample(g["grid"], g["coord"], g["scale"])
+    ref = g["out"][..., 0]
+    # north_star tolerance: 1e-5 relative in fp32 (+ small atol near zero crossings)
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out, g["out64"][..., 0], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", BILINEAR)
+def test_bilinear_backward(golden, name):
+    g = golden(name)
+    H, W = g["grid"].shape[2:]
+    gg = O.bilinear_sample_backward(g["gout"], g["coord"], g["scale"], H, W)
+    np.testing.assert_allclose(gg, g["ggrid"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", MSDA)
+def test_msda_forward(golden, name):
+    g = golden(name)
+    out = O.ms_deform_attn_forward(g["value"], g["shapes"], g["lsi"], g["loc"], g["attn"])
+    # deformattn/test.py:41 uses torch.allclose defaults in double
+    np.testing.assert_allclose(out, g["out64"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out, g["out32"], rtol=1e-2, atol=1e-3)  # test.py:56 float tolerance
+
+
+@pytest.mark.parametrize("name", MSDA)
+def test_msda_backward(golden, name):
+    g = golden(name)
+    gv, gl, ga = O.ms_deform_attn_backward(g["value"], g["shapes"], g["lsi"], g["loc"], g["attn"], g["gout"])
+    np.testing.assert_allclose(gv, g["gvalue"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(ga, g["gattn"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(gl, g["gloc"], rtol=1e-7, atol=1e-10)
+
+
+def test_voting_bit_exact(golden):
+    g = golden("voting_a")
+    size = tuple(int(s) for s in g["size"])
+    q = O.quantize(g["pts"], g["rx"], g["ry"], g["rz"], size)
+    assert np.array_equal(q, g["quan"])
+    coords = q.astype(np.int64)  # .to(torch.int64): truncation
+    assert np.array_equal(coords, g["coords"])
+    vl = O.determine_voxel_labels(coords, g["labels"], size)
+    assert np.array_equal(vl, g["voxel_labels"])
+    assert np.array_equal(O.determine_voxel_labels(coords, g["labels"], size, num_classes=3), vl)
+    pl = O.get_point_labels_from_voxel_labels(g["cur"], vl, size)
+    assert np.array_equal(pl, g["point_labels"])
+    assert (vl > 0).any() and (pl == 0).any()
+
+
+def test_instance_vote_bit_exact(golden):
+    g = golden("instance_a")
+    lo, hi = g["corners"].min(1), g["corners"].max(1)
+    sums = O.instance_vote(g["local_pts"], g["local_pred"], lo, hi)
+    assert np.array_equal(sums[:, 0], g["stat"])
+    assert np.array_equal(sums[:, 1], g["dyn"])
+    label = np.where(sums[:, 1] > sums[:, 0], 2, 1)
+    assert np.array_equal(label, g["label"])
+    assert set(label.tolist()) == {1, 2}  # the fixture exercises both outcomes

@@ -1,0 +1,275 @@
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (read-only tree at /root/reference) on
+seeded synthetic inputs, in the build container. The vectors pin oracle/ (and through it the CUDA
+kernels); the reference cannot travel to the GPU box, the vectors do.
+
+What runs, unmodified:
+  * deep_point/__init__.py on top of deep_point/src/point_deep.cpp compiled by oracle/build_ref.py
+  * networks/backbone.py:BilinearSample                       (loaded by file path)
+  * deformattn/functions/ms_deform_attn_func.py:ms_deform_attn_core_pytorch (+ torch autograd for grads)
+  * voxel_voting.py / voxel_instance_voting.py functions, extracted with `ast` because the scripts run
+    argparse at import time (voxel_voting.py:128-136)
+
+    python tools/make_golden.py [--ref /root/reference]
+"""
+import argparse
+import ast
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load_by_path(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def extract_functions(path, names, glob):
+    """exec only the named top-level function definitions of a script."""
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    found = {n.name for n in body}
+    missing = set(names) - found
+    assert not missing, missing
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), glob)
+    return glob
+
+
+def ref_deep_point(ref):
+    from oracle import build_ref
+    build_ref.build(ref)
+    cpu = build_ref.load()
+    assert cpu is not None
+    pkg = types.ModuleType("point_deep")
+    stub = types.ModuleType("point_deep.cuda_kernel")  # never called: CPU tensors only
+    pkg.cpu_kernel, pkg.cuda_kernel = cpu, stub
+    sys.modules["point_deep"] = pkg
+    sys.modules["point_deep.cpu_kernel"] = cpu
+    sys.modules["point_deep.cuda_kernel"] = stub
+    return load_by_path("ref_deep_point", os.path.join(ref, "deep_point", "__init__.py"))
+
+
+def synth_coords(rng, B, N, H, W, scale, frac_edge=0.05):
+    """coords such that coord*scale spans the grid, with a few in (-1,0), >= size and far pads."""
+    c = np.stack([rng.uniform(0, H / scale[0], (B, N)), rng.uniform(0, W / scale[1], (B, N))], -1)
+    k = max(1, int(N * frac_edge))
+    c[:, :k, 0] = rng.uniform(-0.999, 0, (B, k)) / scale[0]            # truncates to cell 0 (valid)
+    c[:, k:2 * k, 1] = W / scale[1] + rng.uniform(0, 3, (B, k))        # out of range high
+    c[:, 2 * k:3 * k] = -1000.0                                        # pads (data_StreamMOS.py:570)
+    c[:, 3 * k:4 * k, 0] = rng.uniform(-5, -1.001, (B, k)) / scale[0]  # out of range low
+    return c.astype(np.float32)
+
+
+def gen_pool(ref, rng):
+    dp = ref_deep_point(ref)
+    cases = {}
+    for name, (B, C, N, H, W, scale) in {
+        "pool_a": (2, 5, 4000, 24, 40, (0.5, 0.25)),
+        "pool_b": (3, 8, 3000, 64, 64, (1.0, 1.0)),
+        "pool_c": (1, 33, 2500, 16, 96, (0.25, 0.5)),
+    }.items():
+        feat = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+        feat[:, :, ::7] = np.round(feat[:, :, ::7], 1)  # force exact ties
+        ind = synth_coords(rng, B, N, H, W, scale)[..., None]
+        tf = torch.from_numpy(feat).requires_grad_(True)
+        out = dp.VoxelMaxPool(tf, torch.from_numpy(ind), (H, W), scale)
+        gout = rng.standard_normal(out.shape).astype(np.float32)
+        out.backward(torch.from_numpy(gout))
+        cases[name] = dict(feat=feat, ind=ind, H=H, W=W, scale=np.array(scale, np.float32),
+                           out=out.detach().numpy(), gout=gout, gfeat=tf.grad.numpy())
+    for k, v in cases.items():
+        np.savez_compressed(os.path.join(GOLD, k + ".npz"), **v)
+    return list(cases)
+
+
+def gen_bilinear(ref, rng):
+    bb = load_by_path("ref_backbone", os.path.join(ref, "networks", "backbone.py"))
+    names = []
+    for name, (B, C, H, W, N, scale) in {
+        "bilinear_a": (2, 6, 16, 24, 3000, (0.5, 0.5)),
+        "bilinear_b": (1, 32, 32, 128, 2000, (0.25, 0.25)),
+    }.items():
+        grid = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        coord = synth_coords(rng, B, N, H, W, scale)[..., None]
+        # push a few points exactly onto / just beyond the last pixel
+        coord[:, -5:, 0, 0] = (H - 1) / scale[0]
+        coord[:, -3:, 1, 0] = (W - 1) / scale[1] + 0.5
+        m = bb.BilinearSample(in_dim=C, scale_rate=scale)
+        tg = torch.from_numpy(grid).requires_grad_(True)
+        out = m(tg, torch.from_numpy(coord))
+        gout = rng.standard_normal(out.shape).astype(np.float32)
+        out.backward(torch.from_numpy(gout))
+        out64 = m(torch.from_numpy(grid).double(), torch.from_numpy(coord).double())
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), grid=grid, coord=coord,
+                            scale=np.array(scale, np.float32), out=out.detach().numpy(), out64=out64.numpy(),
+                            gout=gout, ggrid=tg.grad.numpy())
+        names.append(name)
+    return names
+
+
+def gen_msda(ref, rng):
+    sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+    fn = load_by_path("ref_msda_func", os.path.join(ref, "deformattn", "functions", "ms_deform_attn_func.py"))
+    names = []
+
+    def run(name, value, shapes, loc, attn):
+        lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+        v = value.double().requires_grad_(True)
+        lo = loc.double().requires_grad_(True)
+        a = attn.double().requires_grad_(True)
+        out = fn.ms_deform_attn_core_pytorch(v, shapes, lo, a)
+        gout = torch.from_numpy(rng.standard_normal(tuple(out.shape)))
+        out.backward(gout)
+        out32 = fn.ms_deform_attn_core_pytorch(value.float(), shapes, loc.float(), attn.float())
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), value=value.numpy(), shapes=shapes.numpy(),
+                            lsi=lsi.numpy(), loc=loc.numpy(), attn=attn.numpy(), out64=out.detach().numpy(),
+                            out32=out32.numpy(), gout=gout.numpy(), gvalue=v.grad.numpy(), gloc=lo.grad.numpy(),
+                            gattn=a.grad.numpy())
+        names.append(name)
+
+    # the reference's own test configuration (deformattn/test.py:23-38): seed 3, N,M,D=1,2,2 Lq,L,P=2,2,2
+    torch.manual_seed(3)
+    N, M, D, Lq, L, P = 1, 2, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    value = torch.rand(N, S, M, D) * 0.01
+    loc = torch.rand(N, Lq, M, L, P, 2)
+    attn = torch.rand(N, Lq, M, L, P) + 1e-5
+    attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    run("msda_reftest", value, shapes, loc, attn)
+    # gradcheck channel counts of test.py:85 that are cheap to store
+    for D in (30, 32, 71):
+        value = torch.rand(N, S, M, D) * 0.01
+        loc = torch.rand(N, Lq, M, L, P, 2)
+        attn = torch.rand(N, Lq, M, L, P) + 1e-5
+        attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+        run("msda_reftest_d%d" % D, value, shapes, loc, attn)
+    # StreamMOS configuration in small: 1 level, 4 heads x 32, 4 points, queries = cell centres + offsets
+    Hs = Ws = 16
+    B, M, D, P = 2, 4, 32, 4
+    shapes = torch.as_tensor([(Hs, Ws)], dtype=torch.long)
+    value = torch.randn(B, Hs * Ws, M, D)
+    ys, xs = torch.meshgrid(torch.linspace(0.5, Hs - 0.5, Hs), torch.linspace(0.5, Ws - 0.5, Ws), indexing="ij")
+    ref_pts = torch.stack((xs.reshape(-1) / Ws, ys.reshape(-1) / Hs), -1)  # multi_view_encoder.py:254-266
+    loc = ref_pts[None, :, None, None, None, :] + torch.randn(B, Hs * Ws, M, 1, P, 2) * 2.0 / Hs
+    attn = torch.softmax(torch.randn(B, Hs * Ws, M, 1 * P), -1).view(B, Hs * Ws, M, 1, P)
+    run("msda_streammos_small", value, shapes, loc, attn)
+    return names
+
+
+def gen_voting(ref, rng):
+    g = {"torch": torch, "np": np}
+    extract_functions(os.path.join(ref, "voxel_voting.py"),
+                      ["get_point_labels_from_voxel_labels", "determine_voxel_labels", "Quantize"], g)
+    size = (32, 24, 10)
+    rx, ry, rz = (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0)
+    P, Pc = 20000, 3000
+    pts = np.stack([rng.uniform(rx[0] + 1e-3, rx[1] - 1e-3, P), rng.uniform(ry[0] + 1e-3, ry[1] - 1e-3, P),
+                    rng.uniform(rz[0] + 1e-3, rz[1] - 1e-3, P), rng.uniform(0, 1, P)], -1).astype(np.float32)
+    # concentrate points so that voxels collect several votes and ties occur
+    pts[: P // 2, :3] = (pts[: P // 2, :3] * np.array([0.2, 0.2, 0.5], np.float32))
+    labels = rng.integers(0, 3, P).astype(np.int64)
+    quan = g["Quantize"](torch.from_numpy(pts), range_x=rx, range_y=ry, range_z=rz, size=size)
+    coords = quan.to(torch.int64)
+    vl = g["determine_voxel_labels"](coords, torch.from_numpy(labels), size)
+    cur = coords[P - Pc:].clone()
+    cur[:50, 0] = size[0] + 3     # out-of-range lookups -> 0
+    cur[50:80, 2] = -1
+    pl = g["get_point_labels_from_voxel_labels"](cur, vl, size)
+    np.savez_compressed(os.path.join(GOLD, "voting_a.npz"), pts=pts, labels=labels, size=np.array(size),
+                        rx=np.array(rx), ry=np.array(ry), rz=np.array(rz), quan=quan.numpy(),
+                        coords=coords.numpy(), voxel_labels=vl.numpy(), cur=cur.numpy(), point_labels=pl.numpy())
+
+    # numpy Quantize of voxel_instance_voting.py:117-135 must agree with the torch one on CPU
+    g2 = {"np": np}
+    extract_functions(os.path.join(ref, "voxel_instance_voting.py"), ["Quantize"], g2)
+    q_np = g2["Quantize"](pts, range_x=rx, range_y=ry, range_z=rz, size=size)
+    assert q_np.dtype == np.float32 and np.array_equal(q_np, quan.numpy())
+    return ["voting_a"]
+
+
+def gen_instance(ref, rng):
+    import scipy
+    from scipy.spatial import ConvexHull, Delaunay
+    from sklearn.cluster import DBSCAN
+    g = {"np": np, "scipy": scipy, "Delaunay": Delaunay, "ConvexHull": ConvexHull, "DBSCAN": DBSCAN}
+    extract_functions(os.path.join(ref, "voxel_instance_voting.py"), ["in_hull", "min_bounding_box_3d", "cluster"], g)
+    # local map: background + K object blobs, predictions 0/1/2
+    K = 6
+    centers = np.stack([rng.uniform(-30, 30, K), rng.uniform(-30, 30, K), rng.uniform(-1.5, 0.0, K)], -1)
+    blobs, blob_pred = [], []
+    for k in range(K):
+        n = int(rng.integers(150, 400))
+        blobs.append(centers[k] + rng.uniform(-1, 1, (n, 3)) * np.array([1.5, 0.8, 0.7]))
+        p_dyn = (0.10, 0.60, 0.20, 0.50, 0.30, 0.45)[k]  # 2 votes per dynamic point: threshold is 1/3
+        blob_pred.append(np.where(rng.uniform(0, 1, n) < p_dyn, 2, 1))
+    bg = np.stack([rng.uniform(-50, 50, 30000), rng.uniform(-50, 50, 30000), rng.uniform(-4, 2, 30000)], -1)
+    local_pts = np.concatenate(blobs + [bg]).astype(np.float32)
+    local_pts = np.concatenate([local_pts, rng.uniform(0, 1, (len(local_pts), 1)).astype(np.float32)], 1)
+    local_pred = np.concatenate(blob_pred + [rng.integers(0, 3, 30000)]).astype(np.int64)
+    # AABBs as cluster() builds them: hull corners in float32, z floor lifted by 0.2 (:169-175)
+    corners = []
+    for k in range(K):
+        c = g["min_bounding_box_3d"](blobs[k].astype(np.float32))
+        z_min = np.min(c[:, -1])
+        c[np.where(c[:, -1] == z_min), -1] += 0.2
+        corners.append(c)
+    corners = np.stack(corners)
+    assert corners.dtype == np.float32
+    # put a handful of local-map points EXACTLY on box faces to pin the inclusive comparison
+    for k in range(K):
+        lo, hi = corners[k].min(0), corners[k].max(0)
+        local_pts[30000 + k, :3] = [lo[0], (lo[1] + hi[1]) / 2, (lo[2] + hi[2]) / 2]
+        local_pts[30010 + k, :3] = [(lo[0] + hi[0]) / 2, hi[1], (lo[2] + hi[2]) / 2]
+        local_pred[30000 + k] = 2
+        local_pred[30010 + k] = 1
+    stat, dyn, lab = [], [], []
+    for k in range(K):
+        flag = g["in_hull"](local_pts[:, :3], corners[k])          # voxel_instance_voting.py:177
+        pred_in = local_pred[flag]                                  # :180
+        s = sum(pred_in[pred_in == 1])                              # :182
+        d = sum(pred_in[pred_in == 2])                              # :183
+        stat.append(int(s)); dyn.append(int(d)); lab.append(2 if d > s else 1)  # :184-187
+    # full cluster() run (DBSCAN + hull + vote + relabel) for an end-to-end check of the vote block
+    cur_pts = np.concatenate(blobs + [bg[:5000]]).astype(np.float32)
+    cur_pts = np.concatenate([cur_pts, np.zeros((len(cur_pts), 1), np.float32)], 1)
+    n_obj = sum(len(b) for b in blobs)
+    cur_pred = np.concatenate([np.ones(n_obj, np.int64), rng.integers(0, 3, 5000)])
+    cur_bf = np.concatenate([np.full(n_obj, 2, np.uint32), np.zeros(5000, np.uint32)])
+    out = g["cluster"](cur_pts.copy(), cur_pred.copy(), cur_bf, local_pts, local_pred)
+    np.savez_compressed(os.path.join(GOLD, "instance_a.npz"), local_pts=local_pts, local_pred=local_pred,
+                        corners=corners, stat=np.array(stat), dyn=np.array(dyn), label=np.array(lab),
+                        cur_pts=cur_pts, cur_pred=cur_pred, cur_bf=cur_bf, cluster_out=out)
+    return ["instance_a"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    a = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(20261018)
+    made = []
+    made += gen_pool(a.ref, rng)
+    made += gen_bilinear(a.ref, rng)
+    made += gen_msda(a.ref, rng)
+    made += gen_voting(a.ref, rng)
+    made += gen_instance(a.ref, rng)
+    for m in made:
+        p = os.path.join(GOLD, m + ".npz")
+        print("%-28s %8.1f KB" % (m, os.path.getsize(p) / 1024))
+
+
+if __name__ == "__main__":
+    main()
