@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the StreamMOS hot path on B200 (BASELINE.json metric: scans/s at ~120k points, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a kernels
+    python bench.py --impl reference [...]                          # the reference's CPU path (oracle/cpu_path.py)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                      # one rank per GPU, independent scan streams
+
+One "step" = one synthetic ~120k-point scan through the whole hot path: 5 x VoxelMaxPool + 5 x BilinearSample
+(cascade projection), 2 x MSDeformAttn forward (temporal fusion), voxel voting over 8+1 scans and per-instance
+votes (long-term memory). Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scans/s at ~120k pts (whole hot path: projection + deformable attention + voting)"
+N_SCANS = 8  # distinct synthetic scans cycled through (inputs >> L2: ~100 MB each, ~700 MB touched per step)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=120000)
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--channel-major", action="store_true",
+                    help="keep gathered point features (B,C,N,1)-contiguous instead of point-major")
+    ap.add_argument("--vote-api", default="reference", choices=["reference", "fused"])
+    ap.add_argument("--cpu-scans", type=int, default=6, help="scans timed for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="also print a per-operator table to stderr")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup():
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x, world, device):
+    """Timing plumbing only (no data-path collective): max of a scalar over ranks."""
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_state(hot):
+    return {"x0": hot.x0.cpu(), "x1": hot.x1.cpu(), "dec": hot.dec.cpu(), "memory": hot.memory.cpu().clone(),
+            "local_pts": hot.local_pts.cpu().clone(), "local_pred": hot.local_pred.cpu().clone(),
+            "box_lo": hot.box_lo.cpu(), "box_hi": hot.box_hi.cpu(), "scan_index": 0}
+
+
+def time_cpu_path(state, scans, n_scans, warmup=1):
+    """The reference's CPU path (oracle/cpu_path.py) on the host cores: scans/s over a bounded sample."""
+    import torch
+    from oracle.cpu_path import CpuHotPath
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    path = CpuHotPath(state)
+    with torch.no_grad():
+        for i in range(warmup):
+            path.step(scans[i % len(scans)])
+        t0 = time.perf_counter()
+        for i in range(n_scans):
+            path.step(scans[(warmup + i) % len(scans)])
+        dt = time.perf_counter() - t0
+    return n_scans / dt, dt / n_scans * 1e3, cores
+
+
+def run_reference(args, world, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path. Rank 0 alone runs it."""
+    if rank != 0:
+        return
+    import torch
+    from streammos_b200 import stream
+    hot = stream.HotPath("cpu", n_points=args.points, seed=0)
+    scans = [stream.make_host_scan(i, args.points, pin=False) for i in range(min(N_SCANS, 4))]
+    sps, ms, cores = time_cpu_path(cpu_state(hot), scans, args.steps, warmup=max(1, min(args.warmup, 3)))
+    sample = "%d scans (1 scan per step), torch %s CPU ops on %d threads" % (args.steps, torch.__version__, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "scans/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, graph=False, world=1),
+            "cpu_baseline": {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, graph, world):
+    return {"workload": "BASELINE.json configs[1]+[2]+[0] per scan (5 VoxelMaxPool + 5 BilinearSample + 2 MSDeformAttn fwd "
+                        "+ voxel voting over 8+1 scans + 32 instance votes), B=1, T=3",
+            "points_per_scan": args.points, "bev_shape": [512, 512, 30], "rv_shape": [64, 2048],
+            "memory": [64, 64, 128], "streams": world, "parallelism": "1 independent scan stream per GPU, no collectives",
+            "launch": "cuda-graph replay" if graph else "eager", "vote_api": args.vote_api,
+            "point_feature_layout": "channel-major" if args.channel_major else "point-major (channels_last strides)",
+            "l2": "no explicit flush: %d distinct scans cycled, ~100 MB inputs and ~700 MB touched per step (>126 MB L2)" % N_SCANS}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args, world, rank, local):
+    import torch
+    from streammos_b200 import _lib, ops, stream
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device — the b200 arm has no CPU fallback (use --impl reference)")
+    _lib.load()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    use_graph = not args.no_graph
+    hot = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
+                         vote_api=args.vote_api)
+    host = [stream.make_host_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
+    devb = [h.to(dev) for h in host]
+    torch.cuda.synchronize()
+    cpu_hot_state = cpu_state(hot) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+
+    compute = torch.cuda.Stream(dev)
+    copy = torch.cuda.Stream(dev)
+    outs = [None] * N_SCANS
+    graphs = [None] * N_SCANS
+    launches_per_step = 0
+    with torch.cuda.stream(compute), torch.no_grad():
+        for i in range(N_SCANS):  # eager warm-up: every scan / ring slot once
+            ops.reset_launch_count()
+            outs[i] = hot.step(devb[i])[:2]
+            launches_per_step = ops.launch_count()
+        torch.cuda.synchronize()
+        if use_graph:
+            pool = torch.cuda.graph_pool_handle()
+            for i in range(N_SCANS):
+                hot.scan_index = i
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=compute):
+                    outs[i] = hot.step(devb[i])[:2]
+                graphs[i] = g
+            torch.cuda.synchronize()
+
+        def do_step(i):
+            j = i % N_SCANS
+            if use_graph:
+                graphs[j].replay()
+            else:
+                hot.scan_index = i
+                outs[j] = hot.step(devb[j])[:2]
+            return j
+
+        # ---- device-resident throughput ("value") -------------------------------------------------------
+        for i in range(args.warmup):
+            do_step(i)
+        torch.cuda.synchronize()
+        barrier(world)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(compute)
+        for i in range(args.steps):
+            do_step(i)
+        e1.record(compute)
+        torch.cuda.synchronize()
+        barrier(world)
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
+        ms_step = ms_total / args.steps
+        value = world * 1000.0 / ms_step
+
+        # ---- end to end: host buffers in, labels out, copies inside the timed region --------------------
+        h_labels = [torch.empty(args.points, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
+        h_sums = [torch.empty(stream.N_BOXES, 2, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
+        done = [torch.cuda.Event() for _ in range(N_SCANS)]
+        ready = [torch.cuda.Event() for _ in range(N_SCANS)]
+
+        def e2e_loop(n):
+            for i in range(n):
+                j = i % N_SCANS
+                with torch.cuda.stream(copy):
+                    copy.wait_event(done[j])            # buffer j is free once its previous step finished
+                    devb[j].copy_from(host[j])          # H2D of this scan's inputs (pinned -> HBM)
+                    ready[j].record(copy)
+                compute.wait_event(ready[j])
+                do_step(i)
+                h_labels[j].copy_(outs[j][0], non_blocking=True)   # D2H of the step's result
+                h_sums[j].copy_(outs[j][1], non_blocking=True)
+                done[j].record(compute)
+
+        for j in range(N_SCANS):
+            done[j].record(compute)
+        e2e_loop(max(3, min(args.warmup, N_SCANS)))
+        torch.cuda.synchronize()
+        barrier(world)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(compute)
+        copy.wait_event(f0)
+        e2e_loop(args.steps)
+        f1.record(compute)
+        torch.cuda.synchronize()
+        barrier(world)
+        e2e_ms = max_over_ranks(f0.elapsed_time(f1), world, dev) / args.steps
+        e2e = {"value": world * 1000.0 / e2e_ms, "unit": "scans/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": host[0].nbytes(),
+               "d2h_bytes_per_step": h_labels[0].numel() * 8 + h_sums[0].numel() * 8,
+               "note": "pinned host -> HBM copy of scan i+1 overlaps the kernels of scan i (two streams)"}
+
+        # ---- dominant kernel: VoxelMaxPool #1 forward (3 x 64 x N -> 3 x 64 x 512 x 512) -----------------
+        ab = stream.algorithmic_bytes(args.points)
+        plans = [ops.pool_plan(devb[j].coord_bev, (512, 512), (1.0, 1.0)) for j in range(N_SCANS)]
+        out1 = torch.empty(3, 64, 512, 512, device=dev)
+        k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(3):
+            ops.voxel_maxpool_forward(devb[i].feat, plans[i], out=out1)
+        for i in range(args.steps):
+            j = i % N_SCANS
+            k0[i].record(compute)
+            ops.voxel_maxpool_forward(devb[j].feat, plans[j], out=out1)
+            k1[i].record(compute)
+        torch.cuda.synchronize()
+        kern_ms = sum(a.elapsed_time(b) for a, b in zip(k0, k1)) / args.steps
+        breakdown = op_breakdown(hot, devb, compute, min(args.steps, 50)) if (rank == 0) else None
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = ab["pool"][0] / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "pool_forward_kernel (VoxelMaxPool #1, 3x64xN -> 3x64x512x512)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ab["pool"][0], "kernel_ms": kern_ms, "traffic": None,
+                "whole_path": {"algorithmic_bytes_per_scan": ab["total"],
+                               "achieved": ab["total"] / (ms_step * 1e-3) / 1e9,
+                               "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak}}
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, use_graph, world), "roofline": roofline, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks, "breakdown_ms": breakdown}
+    if cpu_hot_state is not None:
+        scans = [h for h in host[:4]]
+        sps, ms, cores = time_cpu_path(cpu_hot_state, scans, args.cpu_scans)
+        line["cpu_baseline"] = {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port", "ms_per_scan": ms,
+                                "sample": "%d scans of the same workload, oracle/cpu_path.py (torch CPU ops)" % args.cpu_scans}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if args.breakdown and breakdown:
+        for k, v in breakdown.items():
+            sys.stderr.write("%-28s %8.4f ms\n" % (k, v))
+
+
+def op_breakdown(hot, devb, stream_, iters):
+    """CUDA-event time of each operator of the step (eager launches, same inputs) — explains `value`."""
+    import torch
+    from streammos_b200 import MultiScaleDeformableAttention as MSDA
+    from streammos_b200 import deep_point, ops, stream, voting
+    res = {}
+
+    def timeit(name, fn):
+        for _ in range(3):
+            fn(0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream_)
+        for i in range(iters):
+            fn(i)
+        b.record(stream_)
+        torch.cuda.synchronize()
+        res[name] = a.elapsed_time(b) / iters
+
+    B = devb
+    nb = len(B)
+    cur = lambda i: B[i % nb].coord_bev[:1]
+    rv = lambda i: B[i % nb].coord_rv
+    timeit("pool1_bev512_c64x3", lambda i: deep_point.VoxelMaxPool(B[i % nb].feat, B[i % nb].coord_bev, (512, 512), (1.0, 1.0)))
+    x0p = hot.g_half(hot.x0, cur(0))
+    x1p = hot.g_quarter(hot.x1, cur(0))
+    timeit("gather1_x0_256_c32", lambda i: hot.g_half(hot.x0, cur(i)))
+    timeit("pool2_rv32x1024_c32", lambda i: deep_point.VoxelMaxPool(x0p, rv(0), (32, 1024), (0.5, 0.5)))
+    x0rv = deep_point.VoxelMaxPool(x0p, rv(0), (32, 1024), (0.5, 0.5))
+    timeit("gather2_rv32x1024_c32", lambda i: hot.g_half(x0rv, rv(i)))
+    timeit("pool3_bev256_c32", lambda i: deep_point.VoxelMaxPool(x0p, cur(0), (256, 256), (0.5, 0.5)))
+    timeit("gather3_x1_128_c64", lambda i: hot.g_quarter(hot.x1, cur(i)))
+    timeit("pool4_rv16x512_c64", lambda i: deep_point.VoxelMaxPool(x1p, rv(0), (16, 512), (0.25, 0.25)))
+    x1rv = deep_point.VoxelMaxPool(x1p, rv(0), (16, 512), (0.25, 0.25))
+    timeit("gather4_rv16x512_c64", lambda i: hot.g_quarter(x1rv, rv(i)))
+    timeit("pool5_bev128_c64", lambda i: deep_point.VoxelMaxPool(x1p, cur(0), (128, 128), (0.25, 0.25)))
+    timeit("gather5_dec_256_c64", lambda i: hot.g_half(hot.dec, cur(i)))
+    value = hot.memory.view(1, 4096, 4, 32)
+    timeit("msda_fwd_x2", lambda i: (MSDA.ms_deform_attn_forward(value, hot.shapes, hot.lsi, B[i % nb].loc[0], B[i % nb].attn[0], 256),
+                                     MSDA.ms_deform_attn_forward(value, hot.shapes, hot.lsi, B[i % nb].loc[1], B[i % nb].attn[1], 256)))
+    timeit("voting_voxel+instance", lambda i: hot.long_term_voting(B[i % nb]))
+    plan = ops.pool_plan(B[0].coord_bev, (512, 512), (1.0, 1.0))
+    timeit("pool1_plan_only", lambda i: ops.pool_plan(B[i % nb].coord_bev, (512, 512), (1.0, 1.0)))
+    out1 = torch.empty(3, 64, 512, 512, device=hot.device)
+    timeit("pool1_forward_only", lambda i: ops.voxel_maxpool_forward(B[i % nb].feat, plan, out=out1))
+    return res
+
+
+def main():
+    args = parse_args()
+    world, rank, local = dist_setup()
+    try:
+        if args.impl == "reference":
+            run_reference(args, world, rank)
+        else:
+            run_b200(args, world, rank, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

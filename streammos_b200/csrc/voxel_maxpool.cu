@@ -376,16 +376,23 @@ int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int
   // outputs beyond L2 capacity are written with evict-first stores
   const int stream_out = (B * C * static_cast<int64_t>(H) * W * 4 > (int64_t(96) << 20)) ? 1 : 0;
   cudaStream_t st = smos_stream(stream);
-  cudaError_t e;
-  if (point_major) {
-    e = cudaFuncSetAttribute(pool_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+  // opt in to > 48 KB dynamic shared memory once per device (not a stream operation; kept out of the
+  // per-launch path so that launches can be captured into CUDA graphs)
+  static bool smem_opt_in[64] = {};
+  int device = 0;
+  cudaGetDevice(&device);
+  if (device >= 0 && device < 64 && !smem_opt_in[device]) {
+    cudaError_t e = cudaFuncSetAttribute(pool_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(pool_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
+    smem_opt_in[device] = true;
+  }
+  if (point_major) {
     pool_forward_kernel<true><<<static_cast<unsigned>(grid), kPoolThreads, smem, st>>>(
         pcds_feat, static_cast<int32_t>(C), f_sb, f_sc, f_sn, H, W, L.th, L.tw, L.ntx, L.nt, CC, nchunk, start,
         sorted, voxel_out, stream_out);
   } else {
-    e = cudaFuncSetAttribute(pool_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
     pool_forward_kernel<false><<<static_cast<unsigned>(grid), kPoolThreads, smem, st>>>(
         pcds_feat, static_cast<int32_t>(C), f_sb, f_sc, f_sn, H, W, L.th, L.tw, L.ntx, L.nt, CC, nchunk, start,
         sorted, voxel_out, stream_out);

@@ -8,6 +8,22 @@ import torch
 from . import _lib
 
 
+_LAUNCHES = [0]
+
+
+def reset_launch_count():
+    _LAUNCHES[0] = 0
+
+
+def launch_count():
+    """Kernels of libstreammos_b200.so launched through this module since the last reset."""
+    return _LAUNCHES[0]
+
+
+def _count(n):
+    _LAUNCHES[0] += n
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -68,6 +84,7 @@ def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=
                                       float(scale_rate[0]), float(scale_rate[1]), _ptr(idx_out),
                                       int(idx_batch_stride), _ptr(buf), _stream())
     _lib.check(rc, "smos_pool_plan_build")
+    _count(3)  # cell index + tile scan + tile scatter
     return PoolPlan(buf, B, N, H, W, idx_out)
 
 
@@ -95,6 +112,7 @@ def voxel_maxpool_forward(pcds_feat, plan, out=None):
         rc = _lib.load().smos_voxel_maxpool_forward(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2),
                                                     plan.H, plan.W, _ptr(plan.buf), _ptr(out), _stream())
     _lib.check(rc, "smos_voxel_maxpool_forward")
+    _count(1)
     return out
 
 
@@ -114,6 +132,7 @@ def voxel_maxpool_backward(pcds_feat, plan, voxel_out, grad_voxel_out, grad_feat
                                                      _ptr(grad_voxel_out), _ptr(g), g.stride(0), g.stride(1),
                                                      g.stride(2), _stream())
     _lib.check(rc, "smos_voxel_maxpool_backward")
+    _count(1)
     return grad_feat
 
 
@@ -149,6 +168,7 @@ def bilinear_gather_forward(grid_feat, grid_coord, scale_rate, point_major_out=F
             grid_feat.stride(3), _ptr(co), NP, co.stride(0), co.stride(1), co.stride(2), float(scale_rate[0]),
             float(scale_rate[1]), _ptr(out), o_sb, o_sc, o_sn, _stream())
     _lib.check(rc, "smos_bilinear_gather_forward")
+    _count(1)
     return out
 
 
@@ -169,6 +189,7 @@ def bilinear_gather_backward(grad_out, grid_coord, scale_rate, H, W):
             _ptr(go), B, C, N * S, go.stride(0), go.stride(1), go.stride(2), _ptr(co), co.stride(0), co.stride(1),
             co.stride(2), float(scale_rate[0]), float(scale_rate[1]), int(H), int(W), _ptr(grad_grid), _stream())
     _lib.check(rc, "smos_bilinear_gather_backward")
+    _count(1)
     return grad_grid
 
 
@@ -207,6 +228,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
                                                      _ptr(level_start_index), _ptr(sampling_loc),
                                                      _ptr(attn_weight), B, S, M, D, L, Q, P, _ptr(out), _stream())
     _lib.check(rc, "smos_ms_deform_attn_forward")
+    _count(1)
     return out
 
 
@@ -222,6 +244,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
             _ptr(attn_weight), _ptr(grad_output), B, S, M, D, L, Q, P, _ptr(grad_value), _ptr(grad_loc),
             _ptr(grad_attn), _stream())
     _lib.check(rc, "smos_ms_deform_attn_backward")
+    _count(1)
     return grad_value, grad_loc, grad_attn
 
 
@@ -239,6 +262,7 @@ def quantize(pcds, mins, deltas):
                                        float(mins[1]), float(mins[2]), float(deltas[0]), float(deltas[1]),
                                        float(deltas[2]), _ptr(out), _stream())
     _lib.check(rc, "smos_quantize")
+    _count(1)
     return out
 
 
@@ -264,6 +288,7 @@ def vote_voxel_labels(voxel_coords, semantic_labels, dims, num_classes):
         rc = _lib.load().smos_vote_voxel_labels(_ptr(voxel_coords), _ptr(semantic_labels), P, X, Y, Z,
                                                 int(num_classes), _ptr(ws), _ptr(out), _stream())
     _lib.check(rc, "smos_vote_voxel_labels")
+    _count(2)  # vote + argmax
     return out
 
 
@@ -281,6 +306,7 @@ def vote_point_labels(new_voxel_coords, voxel_labels, dims):
         rc = _lib.load().smos_vote_point_labels(_ptr(new_voxel_coords), Pc, _ptr(voxel_labels), X, Y, Z, _ptr(out),
                                                 _stream())
     _lib.check(rc, "smos_vote_point_labels")
+    _count(1)
     return out
 
 
@@ -303,6 +329,7 @@ def vote_fused(points, labels_u8, num_current, mins, deltas, dims, num_classes=3
                                          float(mins[2]), float(deltas[0]), float(deltas[1]), float(deltas[2]), X, Y,
                                          Z, int(num_classes), _ptr(ws), _ptr(vl), _ptr(pl), _stream())
     _lib.check(rc, "smos_vote_fused")
+    _count(3)
     return vl, pl
 
 
@@ -323,4 +350,5 @@ def instance_vote(points, pred, box_lo, box_hi):
         rc = _lib.load().smos_instance_vote(_ptr(points), P, points.stride(0) if P > 1 else points.size(1),
                                             _ptr(pred), _ptr(box_lo), _ptr(box_hi), K, _ptr(sums), _stream())
     _lib.check(rc, "smos_instance_vote")
+    _count(1)
     return sums

@@ -1,0 +1,189 @@
+"""Per-scan streaming harness for the hot path (BASELINE.json configs 2-5).
+
+One `HotPath` object = one independent scan stream on one GPU: it owns the short-term memory (the
+64x64x128 BEV feature carried between scans) and the long-term memory (ring of the last 8 scans'
+points and predictions) in that GPU's HBM. Streams never talk to each other — multi-GPU runs are one
+process per GPU with no collective on the data path.
+
+The step calls the hot-path operators in the order and with the shapes of the reference inference
+(models/StreamMOS.py:86-113, networks/multi_view_encoder.py:390-456, voxel_voting.py:218-243,
+voxel_instance_voting.py:177-187) through the reference-shaped API of this package. The dense CNN
+blocks between the operators are out of scope (cuDNN); where the reference feeds a CNN output into a
+gather, a resident synthetic feature map of the same shape stands in (x0, x1, decoder output), and the
+two range-view CNNs are the identity, so pool -> gather -> pool chains carry real data.
+"""
+import numpy as np
+import torch
+
+from . import MultiScaleDeformableAttention as MSDA
+from . import deep_point, ops, synthetic, voting
+from .backbone import BilinearSample
+
+HISTORY = 8           # frames_num_max, voxel_voting.py:140
+MEM_HW = 64           # query_size, multi_view_encoder.py:326
+N_HEADS, HEAD_DIM, N_POINTS = 4, 32, 4
+N_BOXES = 32
+
+
+class ScanBatch:
+    """Tensors one scan brings into the hot path (host-pinned or device)."""
+
+    FIELDS = ("feat", "coord_bev", "coord_rv", "xyzi", "pred", "loc", "attn")
+
+    def __init__(self, **kw):
+        for f in self.FIELDS:
+            setattr(self, f, kw[f])
+
+    def nbytes(self):
+        return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
+
+    def to(self, device, non_blocking=True):
+        return ScanBatch(**{f: getattr(self, f).to(device, non_blocking=non_blocking) for f in self.FIELDS})
+
+    def copy_from(self, other):
+        for f in self.FIELDS:
+            getattr(self, f).copy_(getattr(other, f), non_blocking=True)
+
+    def empty_like(self, device):
+        return ScanBatch(**{f: torch.empty_like(getattr(self, f), device=device) for f in self.FIELDS})
+
+
+def make_host_scan(seed, n_points=120000, t_frames=3, channels=64, pin=True):
+    """Synthetic inputs of one scan: LiDAR-shaped coordinates, post-ReLU point features (the PointNet
+    output of models/StreamMOS.py:101), predicted labels for the long-term memory and the sampling
+    locations / attention weights the two deformable-attention layers receive."""
+    s = synthetic.make_scan(seed, n_points, t_frames)
+    rng = np.random.default_rng(seed + 7919)
+    feat = np.maximum(rng.standard_normal((t_frames, channels, n_points, 1), dtype=np.float32), 0)
+    coord_bev = np.ascontiguousarray(s["pcds_coord"][:, :, :2])               # (T, N, 2, 1)
+    coord_rv = np.ascontiguousarray(s["pcds_sphere_coord"][:1])              # (1, N, 2, 1)
+    pred = rng.integers(0, 3, n_points).astype(np.uint8)
+    pred[s["n_valid"][0]:] = 0
+    q = MEM_HW * MEM_HW
+    ys, xs = np.meshgrid(np.linspace(0.5, MEM_HW - 0.5, MEM_HW), np.linspace(0.5, MEM_HW - 0.5, MEM_HW),
+                         indexing="ij")
+    ref_pts = np.stack((xs.reshape(-1) / MEM_HW, ys.reshape(-1) / MEM_HW), -1)  # multi_view_encoder.py:254-266
+    loc = ref_pts[None, None, :, None, None, None, :] + \
+        rng.standard_normal((2, 1, q, N_HEADS, 1, N_POINTS, 2)) * (2.0 / MEM_HW)
+    a = rng.standard_normal((2, 1, q, N_HEADS, N_POINTS))
+    attn = (np.exp(a) / np.exp(a).sum(-1, keepdims=True)).reshape(2, 1, q, N_HEADS, 1, N_POINTS)
+    out = ScanBatch(feat=torch.from_numpy(feat), coord_bev=torch.from_numpy(coord_bev),
+                    coord_rv=torch.from_numpy(coord_rv), xyzi=torch.from_numpy(s["xyzi"][0].copy()),
+                    pred=torch.from_numpy(pred), loc=torch.from_numpy(loc.astype(np.float32)),
+                    attn=torch.from_numpy(attn.astype(np.float32)))
+    if pin and torch.cuda.is_available():
+        out = ScanBatch(**{f: getattr(out, f).pin_memory() for f in ScanBatch.FIELDS})
+    return out
+
+
+class HotPath:
+    """One scan stream. `step(batch)` runs the whole hot path for one scan on the current CUDA stream and
+    returns the per-point labels after long-term voting plus the instance votes."""
+
+    def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference"):
+        self.device = torch.device(device)
+        self.n_points = n_points
+        self.point_major = point_major
+        self.vote_api = vote_api
+        g = torch.Generator(device="cpu").manual_seed(seed)
+
+        def rnd(*shape):
+            return torch.randn(*shape, generator=g).relu_().to(self.device)
+
+        # resident stand-ins for CNN activations (shapes: multi_view_encoder.py:393,408,441-448)
+        self.x0 = rnd(1, 32, 256, 256)
+        self.x1 = rnd(1, 64, 128, 128)
+        self.dec = rnd(1, 64, 256, 256)
+        # short-term memory: previous scan's attended BEV feature, (1, 4096, 128) (mve.py:433-439)
+        self.memory = torch.randn(1, MEM_HW * MEM_HW, N_HEADS * HEAD_DIM, generator=g).to(self.device)
+        self.shapes = torch.tensor([[MEM_HW, MEM_HW]], dtype=torch.int64, device=self.device)
+        self.lsi = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # long-term memory: last 8 scans (points + predictions) and the slot of the current scan
+        self.local_pts = torch.empty(HISTORY + 1, n_points, 4, device=self.device)
+        self.local_pred = torch.zeros(HISTORY + 1, n_points, dtype=torch.uint8, device=self.device)
+        for h in range(HISTORY):
+            s = synthetic.make_scan(seed * 1000 + 100 + h, n_points, 1)
+            self.local_pts[h].copy_(torch.from_numpy(s["xyzi"][0]))
+            r = np.random.default_rng(seed * 1000 + 200 + h).integers(0, 3, n_points).astype(np.uint8)
+            self.local_pred[h].copy_(torch.from_numpy(r))
+        lo, hi = synthetic.synthetic_boxes(np.random.default_rng(seed + 31), N_BOXES)
+        self.box_lo, self.box_hi = torch.from_numpy(lo).to(self.device), torch.from_numpy(hi).to(self.device)
+        self.g_half = BilinearSample(in_dim=32, scale_rate=(0.5, 0.5))
+        self.g_quarter = BilinearSample(in_dim=64, scale_rate=(0.25, 0.25))
+        self.g_half.point_major_out = point_major
+        self.g_quarter.point_major_out = point_major
+        self.scan_index = 0
+        self.size = synthetic.BEV_SHAPE
+        self.mins = (synthetic.RANGE_X[0], synthetic.RANGE_Y[0], synthetic.RANGE_Z[0])
+        self.deltas = tuple(float(np.float32((r[1] - r[0]) / s)) for r, s in
+                            zip((synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z), self.size))
+
+    # --- the three pieces of the hot path ----------------------------------------------------------
+    def projection(self, b):
+        """Cascade projection: 5 x VoxelMaxPool + 5 x BilinearSample."""
+        cur_bev, cur_rv = b.coord_bev[:1], b.coord_rv
+        bev_in = deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0))          # StreamMOS.py:102
+        x0_pt = self.g_half(self.x0, cur_bev)                                                   # mve.py:395
+        x0_rv = deep_point.VoxelMaxPool(x0_pt, cur_rv, (32, 1024), (0.5, 0.5))                  # :396
+        x0_pt = self.g_half(x0_rv, cur_rv)                                                      # :400
+        x0_bev = deep_point.VoxelMaxPool(x0_pt, cur_bev, (256, 256), (0.5, 0.5))                # :402
+        x1_pt = self.g_quarter(self.x1, cur_bev)                                                # :410
+        x1_rv = deep_point.VoxelMaxPool(x1_pt, cur_rv, (16, 512), (0.25, 0.25))                 # :411
+        x1_pt = self.g_quarter(x1_rv, cur_rv)                                                   # :415
+        x1_bev = deep_point.VoxelMaxPool(x1_pt, cur_bev, (128, 128), (0.25, 0.25))              # :417
+        pt_bev = self.g_half(self.dec, cur_bev)                                                 # StreamMOS.py:105
+        return bev_in, x0_bev, x1_bev, x1_pt, pt_bev
+
+    def temporal_fusion(self, b):
+        """Two deformable-attention layers sampling the short-term memory (mve.py:268-273, 313-321)."""
+        value = self.memory.view(1, MEM_HW * MEM_HW, N_HEADS, HEAD_DIM)
+        h = MSDA.ms_deform_attn_forward(value, self.shapes, self.lsi, b.loc[0], b.attn[0], 256)
+        value2 = h.view(1, MEM_HW * MEM_HW, N_HEADS, HEAD_DIM)
+        h = MSDA.ms_deform_attn_forward(value2, self.shapes, self.lsi, b.loc[1], b.attn[1], 256)
+        return h
+
+    def long_term_voting(self, b):
+        """Voxel voting over 8 history scans + the current one, then per-instance votes."""
+        cur = HISTORY
+        self.local_pts[cur].copy_(b.xyzi)
+        self.local_pred[cur].copy_(b.pred)
+        pts = self.local_pts.view(-1, 4)
+        n = self.n_points
+        if self.vote_api == "reference":
+            q = voting.Quantize(pts, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, self.size)
+            coords = q.to(torch.int64)                                 # voxel_voting.py:240
+            labels = self.local_pred.view(-1).to(torch.int64)
+            vl = voting.determine_voxel_labels(coords, labels, self.size, num_classes=3)
+            point_labels = voting.get_point_labels_from_voxel_labels(coords[cur * n:], vl, self.size)
+        else:  # fused streaming variant: float xyz + uint8 labels in, no int64 staging
+            _, point_labels = ops.vote_fused(pts, self.local_pred.view(-1), n, self.mins, self.deltas, self.size, 3)
+            labels = self.local_pred.view(-1).to(torch.int64)
+        sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi)
+        # the current scan becomes history (ring slot), as the next frame's window slides
+        slot = self.scan_index % HISTORY
+        self.local_pts[slot].copy_(self.local_pts[cur])
+        self.local_pred[slot].copy_(self.local_pred[cur])
+        return point_labels, sums
+
+    def step(self, b):
+        proj = self.projection(b)
+        fused = self.temporal_fusion(b)
+        self.memory.copy_(fused)  # becomes the next scan's query_embed_store (mve.py:456)
+        point_labels, sums = self.long_term_voting(b)
+        self.scan_index += 1
+        return point_labels, sums, proj
+
+
+def algorithmic_bytes(n_points, t_frames=3):
+    """Compulsory HBM bytes of one scan (SURVEY §8d formulas, fp32, read-once / write-once)."""
+    N = n_points
+    pools = [(t_frames, 64, 512, 512), (1, 32, 32, 1024), (1, 32, 256, 256), (1, 64, 16, 512), (1, 64, 128, 128)]
+    gathers = [(32, 256, 256), (32, 32, 1024), (64, 128, 128), (64, 16, 512), (64, 256, 256)]
+    pool = [4 * B * C * N + 8 * B * N + 4 * B * C * H * W for (B, C, H, W) in pools]
+    gather = [4 * C * H * W + 8 * N + 4 * C * N for (C, H, W) in gathers]
+    S = Q = MEM_HW * MEM_HW
+    msda = 2 * 4 * (S * N_HEADS * HEAD_DIM + 3 * Q * N_HEADS * N_POINTS + Q * N_HEADS * HEAD_DIM)
+    P = (HISTORY + 1) * N
+    vote = 24 * P + 8 * P + 8 * 512 * 512 * 30 + 40 * N
+    return dict(pool=pool, gather=gather, msda=msda, vote=vote,
+                total=sum(pool) + sum(gather) + msda + vote)
