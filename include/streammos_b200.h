@@ -46,21 +46,18 @@ const char* smos_error_string(int code);
 /* metadata upload in deep_point/__init__.py:17-44.                            */
 /* ------------------------------------------------------------------------- */
 
-/* Tile shape the library will use for an (H, W) grid with C channels.
- * Pure host function; deterministic. Writes tile_h, tile_w, chan_chunk. */
-int smos_pool_tile_shape(int32_t B, int32_t C, int32_t H, int32_t W,
-                         int32_t* tile_h_host, int32_t* tile_w_host,
-                         int32_t* chan_chunk_host);
-
 /* Bytes of scratch a pooling plan needs for B x N points on an (H, W) grid. */
 int64_t smos_pool_plan_bytes(int64_t B, int64_t N, int32_t H, int32_t W);
+
+/* Bytes of scratch one forward call needs (piece-maxima rows; touched sparsely). */
+int64_t smos_pool_workspace_bytes(int64_t B, int64_t C, int64_t N);
 
 /* Build the pooling plan for one coordinate array:
  *   cell(b,n) = trunc(float(ind[b,n,0]) * scale_h) * W + trunc(ind[b,n,1] * scale_w)
  *   valid iff 0 <= idx_d < size_d for both d (C cast = truncation toward zero,
  *   point_deep_cuda_kernel.cu:40-46); invalid points get cell = -1.
- * Then points are bucketed by output tile (stable within a thread block) so the
- * pooling kernel can own each output tile in shared memory.
+ * Then the valid points are counting-sorted by cell (per-cell count / start / sorted list), which
+ * both the forward reduction and the dense output writer consume.
  *   pcds_ind       : (B, N, 2) float32, element strides ind_sb / ind_sn / ind_sd
  *   voxel_max_idx  : optional (B, N) int64 out — the reference's side product:
  *                    b*C*H*W + h*W + w (flat NCHW offset of the c=0 plane) or -1
@@ -79,12 +76,13 @@ int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N,
  *   pcds_feat : (B, C, N) float32, element strides f_sb / f_sc / f_sn
  *               (channel-major N-fastest and point-major C-fastest both run
  *               at full coalescing).
+ *   workspace : scratch of smos_pool_workspace_bytes(B, C, N), 256-byte aligned.
  *   voxel_out : (B, C, H, W) float32 NCHW-contiguous; EVERY element is written
  *               (no pre-zeroing needed).
  */
 int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int64_t N,
                                int64_t f_sb, int64_t f_sc, int64_t f_sn,
-                               int32_t H, int32_t W, const void* plan,
+                               int32_t H, int32_t W, const void* plan, void* workspace,
                                float* voxel_out, void* stream);
 
 /* Backward: grad_feat[b,c,n] = grad_out[b,c,cell] if voxel_out[b,c,cell] == feat[b,c,n]

@@ -15,13 +15,12 @@ _i32, _i64, _f32, _vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c
 SIGNATURES = {
     "smos_abi_version": (ctypes.c_int, []),
     "smos_error_string": (ctypes.c_char_p, [ctypes.c_int]),
-    "smos_pool_tile_shape": (ctypes.c_int, [_i32, _i32, _i32, _i32, ctypes.POINTER(_i32), ctypes.POINTER(_i32),
-                                            ctypes.POINTER(_i32)]),
     "smos_pool_plan_bytes": (_i64, [_i64, _i64, _i32, _i32]),
+    "smos_pool_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "smos_pool_plan_build": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _f32, _f32, _vp, _i64,
                                             _vp, _vp]),
     "smos_voxel_maxpool_forward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp,
-                                                  _vp]),
+                                                  _vp, _vp]),
     "smos_voxel_maxpool_backward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp,
                                                    _vp, _vp, _i64, _i64, _i64, _vp]),
     "smos_bilinear_gather_forward": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _i64,

@@ -84,7 +84,7 @@ def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=
                                       float(scale_rate[0]), float(scale_rate[1]), _ptr(idx_out),
                                       int(idx_batch_stride), _ptr(buf), _stream())
     _lib.check(rc, "smos_pool_plan_build")
-    _count(3)  # cell index + tile scan + tile scatter
+    _count(3)  # cell index + cell allocation + scatter
     return PoolPlan(buf, B, N, H, W, idx_out)
 
 
@@ -108,11 +108,13 @@ def voxel_maxpool_forward(pcds_feat, plan, out=None):
         out = torch.empty((B, C, plan.H, plan.W), dtype=torch.float32, device=f.device)
     else:
         assert out.is_contiguous() and out.shape == (B, C, plan.H, plan.W) and out.dtype == torch.float32
+    lib = _lib.load()
+    ws = torch.empty(int(lib.smos_pool_workspace_bytes(B, C, N)), dtype=torch.uint8, device=f.device)
     with torch.cuda.device(f.device):
-        rc = _lib.load().smos_voxel_maxpool_forward(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2),
-                                                    plan.H, plan.W, _ptr(plan.buf), _ptr(out), _stream())
+        rc = lib.smos_voxel_maxpool_forward(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2), plan.H, plan.W,
+                                            _ptr(plan.buf), _ptr(ws), _ptr(out), _stream())
     _lib.check(rc, "smos_voxel_maxpool_forward")
-    _count(1)
+    _count(2)  # piece reduction + dense writer
     return out
 
 

@@ -53,14 +53,10 @@ def test_host_only_entry_points(lib):
     assert lib.smos_abi_version() == 1
     assert lib.smos_error_string(0) == b"ok"
     assert b"invalid" in lib.smos_error_string(-1)
-    th, tw, cc = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
-    for (B, C, H, W) in [(3, 64, 512, 512), (1, 32, 32, 1024), (1, 64, 16, 512), (2, 5, 5, 7)]:
-        assert lib.smos_pool_tile_shape(B, C, H, W, th, tw, cc) == 0
-        assert 1 <= th.value <= max(H, 1) * 2 and tw.value >= 4 and 1 <= cc.value <= 32
-        assert th.value * tw.value * cc.value * 4 <= 64 * 1024  # the smem tile fits three CTAs per SM
-    assert lib.smos_pool_tile_shape(0, 1, 1, 1, th, tw, cc) == -1
     assert lib.smos_pool_plan_bytes(3, 160000, 512, 512) > 3 * 160000 * 16
     assert lib.smos_pool_plan_bytes(0, 10, 4, 4) == -1
+    assert lib.smos_pool_workspace_bytes(3, 64, 120000) >= 3 * 64 * 120000 * 4
+    assert lib.smos_pool_workspace_bytes(3, 0, 120000) == -1
     assert lib.smos_vote_workspace_bytes(1080000, 512, 512, 30, 3) == 512 * 512 * 30 * 8
     assert lib.smos_vote_workspace_bytes(1080000, 512, 512, 30, 5) == 512 * 512 * 30 * 5 * 4
     assert lib.smos_vote_workspace_bytes(10, 0, 1, 1, 3) == -1

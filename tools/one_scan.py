@@ -1,0 +1,26 @@
+"""Run a few eager hot-path steps (for ncu launch lists / single-kernel captures).
+    python tools/one_scan.py [--steps 3] [--channel-major] [--vote-api fused]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from streammos_b200 import stream  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--points", type=int, default=120000)
+ap.add_argument("--channel-major", action="store_true")
+ap.add_argument("--vote-api", default="reference")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+hot = stream.HotPath(dev, a.points, seed=0, point_major=not a.channel_major, vote_api=a.vote_api)
+scans = [stream.make_host_scan(i, a.points).to(dev) for i in range(2)]
+torch.cuda.synchronize()
+with torch.no_grad():
+    for i in range(a.steps):
+        labels, sums, _ = hot.step(scans[i % 2])
+torch.cuda.synchronize()
+print("ok", int(labels.sum()), int(sums.sum()))
