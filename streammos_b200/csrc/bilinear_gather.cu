@@ -50,58 +50,52 @@ __device__ __forceinline__ Taps make_taps(float cy, float cx, float sh, float sw
 }
 
 constexpr int kGatherThreads = 128;
-constexpr int kCPT = 8;  // channels per thread per step in the planar kernel
+constexpr int kCPT = 8;  // channels per thread in the planar kernel
 
-// Planar (NCHW-like: arbitrary channel stride) grid; lanes run over points, so the taps of
-// neighbouring points in scan order share sectors. Each thread produces kCPT consecutive
-// channels per step: 4*kCPT independent loads in flight, and for point-major outputs one
-// full 32-byte sector per store.
+// Planar (NCHW-like: arbitrary channel stride) grid. thread = (point, group of kCPT channels); lanes run
+// over consecutive points, so in scan order the taps of a warp fall into a handful of sectors per
+// channel plane. All 4*kCPT tap loads of a thread are issued before the first use (the kernel is
+// latency bound otherwise), and for point-major outputs the kCPT results leave as one full 32-byte
+// sector per thread.
 __global__ void __launch_bounds__(kGatherThreads)
 gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                              int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
                              const float* __restrict__ coord, int32_t N,
                              int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
-                             float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
-                             int32_t c_per_block) {
+                             float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn) {
   const int32_t n = blockIdx.x * kGatherThreads + threadIdx.x;
   const int32_t b = blockIdx.z;
   if (n >= N) return;
   const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
-  const Taps t = make_taps(cp[0], cp[co_sd], sh, sw, H, W);
-  const int64_t o_nw = static_cast<int64_t>(t.y0) * gr_sh + static_cast<int64_t>(t.x0) * gr_sw;
-  const float* g = grid + b * gr_sb;
-  float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn;
-  const int32_t c_begin = blockIdx.y * c_per_block;
-  const int32_t c_end = min(C, c_begin + c_per_block);
-  const bool vec_out = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
+  const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
+  const int32_t c0 = blockIdx.y * kCPT;
+  const int32_t nch = min(kCPT, C - c0);
+  const float* g = grid + b * gr_sb + static_cast<int64_t>(c0) * gr_sc + static_cast<int64_t>(t.y0) * gr_sh +
+                   static_cast<int64_t>(t.x0) * gr_sw;
+  float v[kCPT][4];
+#pragma unroll
+  for (int k = 0; k < kCPT; ++k) {
+    const float* gc = g + static_cast<int64_t>(k) * gr_sc;
+    const bool ok = k < nch;
+    v[k][0] = (ok && t.in_nw) ? __ldg(gc) : 0.f;
+    v[k][1] = (ok && t.in_ne) ? __ldg(gc + gr_sw) : 0.f;
+    v[k][2] = (ok && t.in_sw) ? __ldg(gc + gr_sh) : 0.f;
+    v[k][3] = (ok && t.in_se) ? __ldg(gc + gr_sh + gr_sw) : 0.f;
+  }
+  float acc[kCPT];
+#pragma unroll
+  for (int k = 0; k < kCPT; ++k)
+    acc[k] = fmaf(v[k][3], t.w_se, fmaf(v[k][2], t.w_sw, fmaf(v[k][1], t.w_ne, fmaf(v[k][0], t.w_nw, 0.f))));
+  float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(c0) * o_sc;
+  const bool vec_out = (o_sc == 1) && (nch == kCPT) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
                        ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  for (int32_t c0 = c_begin; c0 < c_end; c0 += kCPT) {
-    float acc[kCPT];
+  if (vec_out) {
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else {
 #pragma unroll
-    for (int k = 0; k < kCPT; ++k) {
-      const int32_t c = c0 + k;
-      float a = 0.f;
-      if (c < c_end) {
-        const float* gc = g + static_cast<int64_t>(c) * gr_sc + o_nw;
-        const float v_nw = t.in_nw ? __ldg(gc) : 0.f;
-        const float v_ne = t.in_ne ? __ldg(gc + gr_sw) : 0.f;
-        const float v_sw = t.in_sw ? __ldg(gc + gr_sh) : 0.f;
-        const float v_se = t.in_se ? __ldg(gc + gr_sh + gr_sw) : 0.f;
-        a = fmaf(v_nw, t.w_nw, a);
-        a = fmaf(v_ne, t.w_ne, a);
-        a = fmaf(v_sw, t.w_sw, a);
-        a = fmaf(v_se, t.w_se, a);
-      }
-      acc[k] = a;
-    }
-    if (vec_out && c0 + kCPT <= c_end && (c0 & 3) == 0) {
-      *reinterpret_cast<float4*>(o + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(o + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < kCPT; ++k)
-        if (c0 + k < c_end) o[static_cast<int64_t>(c0 + k) * o_sc] = acc[k];
-    }
+    for (int k = 0; k < kCPT; ++k)
+      if (k < nch) o[static_cast<int64_t>(k) * o_sc] = acc[k];
   }
 }
 
@@ -187,16 +181,11 @@ int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_
         grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb, co_sn,
         co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn);
   } else {
-    const int32_t nblk = smos_ceil_div(N, kGatherThreads);
-    // split channels across blockIdx.y until the grid covers the SMs ~4x
-    int32_t c_per_block = static_cast<int32_t>(C);
-    while (c_per_block > kCPT && (c_per_block % (2 * kCPT)) == 0 &&
-           static_cast<int64_t>(nblk) * B * (C / c_per_block) < 4 * SMOS_SM_COUNT)
-      c_per_block >>= 1;
-    dim3 g(nblk, smos_ceil_div(C, c_per_block), static_cast<unsigned>(B));
+    if (C > 65535 * kCPT) return SMOS_EUNSUPPORTED;
+    dim3 g(smos_ceil_div(N, kGatherThreads), smos_ceil_div(C, kCPT), static_cast<unsigned>(B));
     gather_forward_planar_kernel<<<g, kGatherThreads, 0, st>>>(
         grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb,
-        co_sn, co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn, c_per_block);
+        co_sn, co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn);
   }
   return smos_launch_status();
 }

@@ -127,35 +127,82 @@ quantize_kernel(const float* __restrict__ pcds, int64_t P, int64_t rs, float mx,
   out[i * 3 + 2] = quant(p[2], mz, dz);
 }
 
-// Instance vote: boxes of one chunk live in shared memory together with their counters;
-// a point that falls in a box bumps a shared counter, the block flushes once at the end.
+// Instance vote. Testing every point against every box is O(P*K) compares (P ~ 1.08 M); almost all
+// points are near no box. Each CTA therefore first bins the boxes of its chunk into a coarse 16 x 16
+// grid over their common xy extent (a bit mask of boxes per coarse cell, in shared memory); a point
+// looks up its coarse cell — the mapping is monotonic and clamped, so a point inside a box always
+// lands in a cell that lists the box — and runs the exact inclusive test only for the listed boxes.
 constexpr int kBoxChunk = 256;
+constexpr int kIvGrid = 16;
+constexpr int kIvWords = kBoxChunk / 32;
+
+__device__ __forceinline__ int iv_cell(float v, float lo, float inv) {
+  const float f = (v - lo) * inv;
+  return f > 0.f ? (f < static_cast<float>(kIvGrid - 1) ? static_cast<int>(f) : kIvGrid - 1) : 0;
+}
 
 __global__ void __launch_bounds__(kVoteThreads)
 instance_vote_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const int64_t* __restrict__ pred,
                      const float* __restrict__ lo, const float* __restrict__ hi, int32_t K,
                      unsigned long long* __restrict__ sums) {
-  __shared__ float s_lo[kBoxChunk * 3];
-  __shared__ float s_hi[kBoxChunk * 3];
+  __shared__ float4 s_box[kBoxChunk * 2];  // (lo.x, lo.y, lo.z, hi.x) (hi.y, hi.z, -, -)
   __shared__ unsigned int s_cnt[kBoxChunk * 2];
+  __shared__ unsigned int s_mask[kIvGrid * kIvGrid][kIvWords];
+  __shared__ int s_ext[4];  // ordered-int keys of min x, min y, max x, max y
   const int32_t k0 = blockIdx.y * kBoxChunk;
   const int32_t kn = min(kBoxChunk, K - k0);
-  for (int i = threadIdx.x; i < kn * 3; i += kVoteThreads) {
-    s_lo[i] = lo[k0 * 3 + i];
-    s_hi[i] = hi[k0 * 3 + i];
-  }
+  if (threadIdx.x == 0) { s_ext[0] = s_ext[1] = 0x7fffffff; s_ext[2] = s_ext[3] = static_cast<int>(0x80000000u); }
+  for (int i = threadIdx.x; i < kIvGrid * kIvGrid * kIvWords; i += kVoteThreads) (&s_mask[0][0])[i] = 0u;
   for (int i = threadIdx.x; i < kn * 2; i += kVoteThreads) s_cnt[i] = 0u;
   __syncthreads();
+  auto key = [](float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; };  // monotonic
+  auto unkey = [](int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); };
+  for (int i = threadIdx.x; i < kn; i += kVoteThreads) {
+    const float* l = lo + static_cast<int64_t>(k0 + i) * 3;
+    const float* h = hi + static_cast<int64_t>(k0 + i) * 3;
+    s_box[2 * i] = make_float4(l[0], l[1], l[2], h[0]);
+    s_box[2 * i + 1] = make_float4(h[1], h[2], 0.f, 0.f);
+    atomicMin(&s_ext[0], key(l[0])); atomicMin(&s_ext[1], key(l[1]));
+    atomicMax(&s_ext[2], key(h[0])); atomicMax(&s_ext[3], key(h[1]));
+  }
+  __syncthreads();
+  const float gx0 = unkey(s_ext[0]), gy0 = unkey(s_ext[1]);
+  const float ex = unkey(s_ext[2]) - gx0, ey = unkey(s_ext[3]) - gy0;
+  const float invx = ex > 0.f ? static_cast<float>(kIvGrid) / ex : 0.f;
+  const float invy = ey > 0.f ? static_cast<float>(kIvGrid) / ey : 0.f;
+  for (int i = threadIdx.x; i < kn; i += kVoteThreads) {
+    const float4 a = s_box[2 * i], bb = s_box[2 * i + 1];
+    const int x0 = iv_cell(a.x, gx0, invx), x1 = iv_cell(a.w, gx0, invx);
+    const int y0 = iv_cell(a.y, gy0, invy), y1 = iv_cell(bb.x, gy0, invy);
+    for (int y = y0; y <= y1; ++y)
+      for (int x = x0; x <= x1; ++x) atomicOr(&s_mask[y * kIvGrid + x][i >> 5], 1u << (i & 31));
+  }
+  __syncthreads();
+  const int nwords = (kn + 31) >> 5;
+  const bool vec = (rs == 4) && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x; i < P;
        i += static_cast<int64_t>(gridDim.x) * kVoteThreads) {
-    const int64_t pr = pred[i];
+    const int64_t pr = __ldg(pred + i);
     if (pr != 1 && pr != 2) continue;
-    const float* p = pts + i * rs;
-    const float x = p[0], y = p[1], z = p[2];
-    for (int k = 0; k < kn; ++k) {
-      const bool in = x >= s_lo[k * 3] && x <= s_hi[k * 3] && y >= s_lo[k * 3 + 1] && y <= s_hi[k * 3 + 1] &&
-                      z >= s_lo[k * 3 + 2] && z <= s_hi[k * 3 + 2];
-      if (in) atomicAdd(&s_cnt[k * 2 + (pr - 1)], 1u);
+    float x, y, z;
+    if (vec) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(pts) + i);
+      x = q.x; y = q.y; z = q.z;
+    } else {
+      const float* q = pts + i * rs;
+      x = q[0]; y = q[1]; z = q[2];
+    }
+    const unsigned int* m = s_mask[iv_cell(y, gy0, invy) * kIvGrid + iv_cell(x, gx0, invx)];
+    for (int w = 0; w < nwords; ++w) {
+      unsigned int bits = m[w];
+      while (bits) {
+        const int k = (w << 5) + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const float4 a = s_box[2 * k], bb = s_box[2 * k + 1];
+        // inclusive AABB test == in_hull of the 8 corners (voxel_instance_voting.py:62-76,177)
+        if (x >= a.x && x <= a.w && y >= a.y && y <= bb.x && z >= a.z && z <= bb.y)
+          atomicAdd(&s_cnt[k * 2 + static_cast<int>(pr) - 1], 1u);
+      }
     }
   }
   __syncthreads();
@@ -248,8 +295,8 @@ int smos_instance_vote(const float* points, int64_t P, int64_t row_stride, const
   if (P < 0 || K < 0 || row_stride < 3) return SMOS_EINVAL;
   if (K == 0 || P == 0) return SMOS_OK;
   if (!points || !pred || !box_lo || !box_hi || !sums) return SMOS_EINVAL;
-  int gx = smos_ceil_div(P, kVoteThreads);
-  if (gx > 4 * SMOS_SM_COUNT) gx = 4 * SMOS_SM_COUNT;  // persistent-style grid-stride loop
+  int gx = smos_ceil_div(P, kVoteThreads * 4);
+  if (gx > 8 * SMOS_SM_COUNT) gx = 8 * SMOS_SM_COUNT;  // persistent-style grid-stride loop
   dim3 grid(gx, smos_ceil_div(K, kBoxChunk));
   instance_vote_kernel<<<grid, kVoteThreads, 0, smos_stream(stream)>>>(
       points, P, row_stride, pred, box_lo, box_hi, K, reinterpret_cast<unsigned long long*>(sums));

@@ -28,7 +28,7 @@ constexpr int kCG = 8;            // channels per thread in phase B
 
 struct PoolLayout {
   int64_t hw, cells;   // H*W, B*H*W
-  int64_t off_cell, off_rank, off_count, off_start, off_sorted, bytes;
+  int64_t off_cell, off_rank, off_count, off_start, off_sorted, off_multi, bytes;
 };
 
 PoolLayout pool_layout(int64_t B, int64_t N, int32_t H, int32_t W) {
@@ -39,9 +39,11 @@ PoolLayout pool_layout(int64_t B, int64_t N, int32_t H, int32_t W) {
   int64_t off = 0;
   L.off_cell = off;   off += smos_align_up(bn * 4, 256);
   L.off_rank = off;   off += smos_align_up(bn * 4, 256);
-  L.off_count = off;  off += smos_align_up((L.cells + 4) * 4, 256);  // + point cursor
+  L.off_count = off;  off += smos_align_up((L.cells + 4) * 4, 256);  // + point cursor, multi-cell counter
   L.off_start = off;  off += smos_align_up(L.cells * 4, 256);
   L.off_sorted = off; off += smos_align_up(bn * 8, 256);
+  // cells whose segment crosses a multiple of 32 (>= 2 pieces): at most one per 32 sorted points
+  L.off_multi = off;  off += smos_align_up((bn / 32 + 2) * 8, 256);
   L.bytes = off;
   return L;
 }
@@ -90,7 +92,7 @@ pool_cell_index_kernel(const float* __restrict__ ind, int64_t total, int32_t N,
 // global cursor replaces a device-wide prefix scan.
 __global__ void __launch_bounds__(kPlanThreads)
 pool_cell_alloc_kernel(const int32_t* __restrict__ count, int32_t* __restrict__ start, int32_t cells,
-                       int32_t* __restrict__ cursor) {
+                       int32_t* __restrict__ cursor, int2* __restrict__ multi) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t c = i < cells ? count[i] : 0;
   const int lane = threadIdx.x & 31;
@@ -104,12 +106,23 @@ pool_cell_alloc_kernel(const int32_t* __restrict__ count, int32_t* __restrict__ 
   int32_t base = 0;
   if (lane == 31 && warp_total > 0) base = atomicAdd(cursor, warp_total);
   base = __shfl_sync(0xffffffffu, base, 31);
-  if (i < cells) start[i] = base + x - c;
+  const int32_t s = base + x - c;
+  if (i < cells) start[i] = s;
+  // a segment [s, s+c) that crosses a multiple of 32 is reduced as several pieces by phase A; list it
+  // so the combine kernel can fold them into row s (cursor[1] counts the list)
+  const bool is_multi = c > 0 && ((s & 31) + c > 32);
+  const unsigned mm = __ballot_sync(0xffffffffu, is_multi);
+  if (mm) {
+    int32_t mbase = 0;
+    if (lane == 0) mbase = atomicAdd(cursor + 1, __popc(mm));
+    mbase = __shfl_sync(0xffffffffu, mbase, 0);
+    if (is_multi) multi[mbase + __popc(mm & smos_lanemask_lt())] = make_int2(s, c);
+  }
 }
 
 // ---- plan 3: place every valid point in its cell's segment -----------------------------------
 __global__ void __launch_bounds__(kPlanThreads)
-pool_cell_scatter_kernel(const int32_t* __restrict__ cell_in, const int32_t* __restrict__ rank_in,
+pool_cell_scatter_kernel(const int32_t* __restrict__ cell_in, int32_t* __restrict__ rank_io,
                          const int32_t* __restrict__ start, int64_t total, int32_t N, int32_t hw,
                          int2* __restrict__ sorted) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -119,23 +132,74 @@ pool_cell_scatter_kernel(const int32_t* __restrict__ cell_in, const int32_t* __r
   const int32_t b = static_cast<int32_t>(i / N);
   const int32_t n = static_cast<int32_t>(i - static_cast<int64_t>(b) * N);
   const int32_t gcell = b * hw + cell;
-  sorted[__ldg(start + gcell) + rank_in[i]] = make_int2(n, gcell);
+  const int32_t pos = __ldg(start + gcell) + rank_io[i];
+  rank_io[i] = pos;  // from here on the array holds each point's sorted position (-1 if invalid)
+  sorted[pos] = make_int2(n, gcell);
+}
+
+// ---- phase A0 (channel-major input only): permute into sorted point-major rows -----------------
+// A (B,C,N,1)-contiguous tensor (the PointNet output) keeps a point's channels N*4 bytes apart, so
+// gathering it in sorted order costs one 32-byte sector per 4 useful bytes. Instead read it in its own
+// order (fully coalesced), transpose 64 points x C channels through shared memory and write each
+// point's C-float row to its sorted position: every sector moved is fully used, and the reduction
+// below then streams rows in position order.
+constexpr int kPermPts = 64;
+constexpr int kPermThreads = 256;
+
+__global__ void __launch_bounds__(kPermThreads)
+pool_permute_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64_t f_sb, int64_t f_sc, int64_t f_sn,
+                    const int32_t* __restrict__ pos, float* __restrict__ rows) {
+  extern __shared__ float tile[];  // [kPermPts][C + 1]
+  __shared__ int32_t s_pos[kPermPts];
+  const int32_t b = blockIdx.y;
+  const int32_t n0 = blockIdx.x * kPermPts;
+  const int32_t np = min(kPermPts, N - n0);
+  const int32_t ld = C + 1;
+  if (threadIdx.x < kPermPts) s_pos[threadIdx.x] = threadIdx.x < np ? pos[static_cast<int64_t>(b) * N + n0 + threadIdx.x] : -1;
+  const float* fb = feat + b * f_sb + static_cast<int64_t>(n0) * f_sn;
+  // loads: consecutive threads -> consecutive points of one channel (coalesced when f_sn == 1)
+  for (int32_t i = threadIdx.x; i < C * kPermPts; i += kPermThreads) {
+    const int32_t c = i / kPermPts, p = i - c * kPermPts;
+    if (p < np) tile[p * ld + c] = __ldg(fb + static_cast<int64_t>(c) * f_sc + static_cast<int64_t>(p) * f_sn);
+  }
+  __syncthreads();
+  // stores: one warp per point row, lanes over channels (C*4 contiguous bytes per row)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int32_t p = wid; p < np; p += kPermThreads / 32) {
+    const int32_t q = s_pos[p];
+    if (q < 0) continue;  // invalid point: no row
+    float* dst = rows + static_cast<int64_t>(q) * C;
+    for (int32_t c = lane; c < C; c += 32) dst[c] = tile[p * ld + c];
+  }
 }
 
 // ---- phase A: piece maxima ------------------------------------------------------------------
 // Warp w owns sorted positions [32w, 32w+32). A piece = maximal run of equal cells inside that
 // range; its C maxima go to rows[first position of the piece][0..C).
-// POINT_MAJOR (f_sc == 1): a point's features are one contiguous row -> lanes run over channels
-//   and the row loads are issued four at a time.
-// otherwise (channel-major, e.g. the (B,C,N,1)-contiguous PointNet output): lanes run over the 32
-//   points for the (coherent) gather, 32 channels at a time are transposed through a per-warp
-//   shared-memory slab, then the same lanes-over-channels sweep runs from shared memory.
-template <bool POINT_MAJOR>
+// Lanes run over channels (VEC consecutive channels per lane, 32*VEC per pass); the 32 point rows of
+// the warp are loaded kBatch at a time so that enough independent loads are in flight to cover the
+// HBM latency (one wave of warps covers the whole input).
+// SORTED_ROWS: the point rows already sit at their sorted positions inside `rows` (after the permute
+//   kernel) and are reduced in place; otherwise they are read from `feat` (point-major, f_sc == 1)
+//   through the sorted list.
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int VEC> __device__ __forceinline__ typename VecT<VEC>::type vmax(typename VecT<VEC>::type a, typename VecT<VEC>::type b);
+template <> __device__ __forceinline__ float vmax<1>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ float2 vmax<2>(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+template <> __device__ __forceinline__ float4 vmax<4>(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
+template <int VEC, bool SORTED_ROWS>
 __global__ void __launch_bounds__(kReduceWarps * 32)
-pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int64_t f_sc, int64_t f_sn,
-                   int32_t hw, const int2* __restrict__ sorted, const int32_t* __restrict__ cursor,
-                   float* __restrict__ rows) {
-  __shared__ float slab[POINT_MAJOR ? 1 : kReduceWarps][POINT_MAJOR ? 1 : 32][33];
+pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int64_t f_sn, int32_t hw,
+                   const int2* __restrict__ sorted, const int32_t* __restrict__ cursor, float* rows) {
+  using V = typename VecT<VEC>::type;
+  constexpr int kBatch = VEC == 4 ? 8 : 16;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int32_t total = *cursor;
   const int32_t p0 = (blockIdx.x * kReduceWarps + wib) * 32;
@@ -144,105 +208,106 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
   int2 e = make_int2(0, -1 - lane);  // distinct negative cells for lanes past the end
   if (lane < cnt) e = sorted[p0 + lane];
   const int32_t prev = __shfl_up_sync(0xffffffffu, e.y, 1);
-  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || e.y != prev) & (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
-  const int32_t b_lane = e.y >= 0 ? e.y / hw : 0;
-  const int64_t base_lane = b_lane * f_sb + static_cast<int64_t>(e.x) * f_sn;  // offset of (b, c=0, n)
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || e.y != prev) &
+                         (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+  // element offset of my point's row (c = 0)
+  int64_t base_lane;
+  if (SORTED_ROWS) base_lane = static_cast<int64_t>(p0 + lane) * C;
+  else base_lane = (e.y >= 0 ? e.y / hw : 0) * f_sb + static_cast<int64_t>(e.x) * f_sn;
+  const float* src = SORTED_ROWS ? rows : feat;
 
-  for (int32_t c0 = 0; c0 < C; c0 += 32) {
-    const int32_t c = c0 + lane;
-    const bool c_ok = c < C;
-    if (!POINT_MAJOR) {
-      // gather 32 channels of my point (lanes over points), transpose through the slab
-      const int32_t nc = min(32, C - c0);
-      const float* fp = feat + base_lane + static_cast<int64_t>(c0) * f_sc;
-      if (lane < cnt) {
-#pragma unroll 8
-        for (int32_t k = 0; k < nc; ++k) slab[wib][lane][k] = __ldg(fp + static_cast<int64_t>(k) * f_sc);
-      }
-      __syncwarp();
-    }
-    float acc = 0.f;
+  for (int32_t c0 = 0; c0 < C; c0 += 32 * VEC) {
+    const int32_t c = c0 + lane * VEC;
+    const bool c_ok = c < C;  // C % VEC == 0 is guaranteed by the dispatcher
+    V acc;
     int32_t piece_pos = p0;
-    for (int32_t i0 = 0; i0 < cnt; i0 += 4) {
-      float v[4];
+    for (int32_t i0 = 0; i0 < cnt; i0 += kBatch) {
+      V v[kBatch];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kBatch; ++u) {
         const int32_t i = i0 + u;
-        v[u] = 0.f;
         // the shuffle is executed by the whole warp (i and cnt are warp-uniform); only the load is
         // predicated per lane
-        const int64_t off = POINT_MAJOR ? __shfl_sync(0xffffffffu, base_lane, i & 31) : 0;
-        if (i < cnt && c_ok) v[u] = POINT_MAJOR ? __ldg(feat + off + c) : slab[wib][i][lane];
+        const int64_t off = __shfl_sync(0xffffffffu, base_lane, i & 31);
+        if (i < cnt && c_ok) v[u] = __ldg(reinterpret_cast<const V*>(src + off + c));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kBatch; ++u) {
         const int32_t i = i0 + u;
-        if (i < cnt) {
+        if (i < cnt && c_ok) {
           if ((heads >> i) & 1u) {
-            if (i > 0 && c_ok) rows[static_cast<int64_t>(piece_pos) * C + c] = acc;
+            if (i > 0) *reinterpret_cast<V*>(rows + static_cast<int64_t>(piece_pos) * C + c) = acc;
             piece_pos = p0 + i;
             acc = v[u];
           } else {
-            acc = fmaxf(acc, v[u]);
+            acc = vmax<VEC>(acc, v[u]);
           }
         }
       }
     }
-    if (c_ok) rows[static_cast<int64_t>(piece_pos) * C + c] = acc;
-    if (!POINT_MAJOR) __syncwarp();
+    if (c_ok) *reinterpret_cast<V*>(rows + static_cast<int64_t>(piece_pos) * C + c) = acc;
+  }
+}
+
+// ---- phase A2: fold the pieces of multi-piece cells into their first row ------------------------
+// One warp per listed cell, lanes over channels, piece rows loaded kBatch at a time. After this every
+// occupied cell's maxima sit in rows[start[cell]].
+template <int VEC>
+__global__ void __launch_bounds__(kReduceWarps * 32)
+pool_combine_kernel(int32_t C, const int2* __restrict__ multi, const int32_t* __restrict__ cursor, float* rows) {
+  using V = typename VecT<VEC>::type;
+  constexpr int kBatch = VEC == 4 ? 8 : 16;
+  const int lane = threadIdx.x & 31;
+  const int32_t w = blockIdx.x * kReduceWarps + (threadIdx.x >> 5);
+  if (w >= cursor[1]) return;
+  const int2 sk = multi[w];
+  const int32_t s = sk.x, end = sk.x + sk.y;
+  const int32_t first_aligned = (s & ~31) + 32;
+  const int32_t npieces = 1 + (end - first_aligned + 31) / 32;  // end > first_aligned by construction
+  for (int32_t c0 = 0; c0 < C; c0 += 32 * VEC) {
+    const int32_t c = c0 + lane * VEC;
+    if (c >= C) continue;
+    V acc = *reinterpret_cast<const V*>(rows + static_cast<int64_t>(s) * C + c);
+    for (int32_t p0 = 1; p0 < npieces; p0 += kBatch) {
+      V v[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int32_t pi = p0 + u;
+        if (pi < npieces) v[u] = *reinterpret_cast<const V*>(rows + static_cast<int64_t>(first_aligned + (pi - 1) * 32) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+        if (p0 + u < npieces) acc = vmax<VEC>(acc, v[u]);
+    }
+    *reinterpret_cast<V*>(rows + static_cast<int64_t>(s) * C + c) = acc;
   }
 }
 
 // ---- phase B: dense writer --------------------------------------------------------------------
-// thread = 4 adjacent cells (along W) x kCG channels. Occupied cell with segment [s, s+k): its piece
-// rows start at s and at every multiple of 32 inside (s, s+k).
-__device__ __forceinline__ void cell_max(const float* __restrict__ rows, int32_t C, int32_t c0, int32_t nch,
-                                         int32_t s, int32_t k, bool vec, float* v) {
-  int32_t r = s;
-  bool first = true;
-  const int32_t end = s + k;
-  while (r < end) {
-    const float* rp = rows + static_cast<int64_t>(r) * C + c0;
-    float t[kCG];
-    if (vec) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(rp));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(rp) + 1);
-      t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b.x; t[5] = b.y; t[6] = b.z; t[7] = b.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < kCG; ++j) t[j] = j < nch ? __ldg(rp + j) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < kCG; ++j) v[j] = first ? t[j] : fmaxf(v[j], t[j]);
-    first = false;
-    r = (r & ~31) + 32;
-  }
-}
-
+// thread = 4 adjacent cells (along W); it walks the channel groups (kCG channels each) of its CTA's
+// channel range, so one read of count/start feeds up to C output stores. An occupied cell reads its
+// one row (rows[start]); all row loads of a channel group are issued together. Empty cells store zeros.
+// Every output element is written exactly once with 128-bit stores.
 template <bool VEC4>
 __global__ void __launch_bounds__(kWriteThreads)
-pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, const int32_t* __restrict__ count,
-                  const int32_t* __restrict__ start, float* __restrict__ out, int stream_out) {
+pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t groups_per_cta,
+                  const int32_t* __restrict__ count, const int32_t* __restrict__ start,
+                  float* __restrict__ out, int stream_out) {
   const int32_t b = blockIdx.z;
-  const int32_t c0 = blockIdx.y * kCG;
-  const int32_t nch = min(kCG, C - c0);
   const bool vec_rows = ((C & 7) == 0);
   constexpr int CPT = VEC4 ? 4 : 1;  // cells per thread
   const int32_t cell0 = (blockIdx.x * kWriteThreads + threadIdx.x) * CPT;
   if (cell0 >= hw) return;
   const int32_t g0 = b * hw + cell0;
   int32_t k[CPT], s[CPT];
+#pragma unroll
+  for (int q = 0; q < CPT; ++q) { k[q] = 0; s[q] = 0; }
   if (VEC4) {
     const int4 kk = __ldg(reinterpret_cast<const int4*>(count + g0));
     k[0] = kk.x; k[1 % CPT] = kk.y; k[2 % CPT] = kk.z; k[3 % CPT] = kk.w;
   } else {
     k[0] = __ldg(count + g0);
   }
-  float v[CPT][kCG];
-#pragma unroll
-  for (int q = 0; q < CPT; ++q)
-#pragma unroll
-    for (int j = 0; j < kCG; ++j) v[q][j] = 0.f;
   bool any = false;
 #pragma unroll
   for (int q = 0; q < CPT; ++q) any |= k[q] > 0;
@@ -253,21 +318,48 @@ pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, const i
     } else {
       s[0] = __ldg(start + g0);
     }
+  }
+  const int32_t ngroups = (C + kCG - 1) / kCG;
+  const int32_t cg_begin = blockIdx.y * groups_per_cta;
+  const int32_t cg_end = min(ngroups, cg_begin + groups_per_cta);
+  for (int32_t cg = cg_begin; cg < cg_end; ++cg) {
+    const int32_t c0 = cg * kCG;
+    const int32_t nch = min(kCG, C - c0);
+    float v[CPT][kCG];
 #pragma unroll
     for (int q = 0; q < CPT; ++q)
-      if (k[q] > 0) cell_max(rows, C, c0, nch, s[q], k[q], vec_rows, v[q]);
-  }
-  float* ob = out + (static_cast<int64_t>(b) * C + c0) * hw + cell0;
 #pragma unroll
-  for (int j = 0; j < kCG; ++j) {
-    if (j < nch) {
-      if (VEC4) {
-        const float4 o = make_float4(v[0][j], v[1 % CPT][j], v[2 % CPT][j], v[3 % CPT][j]);
-        float* dst = ob + static_cast<int64_t>(j) * hw;
-        if (stream_out) smos_st_cs_f4(dst, o);
-        else *reinterpret_cast<float4*>(dst) = o;
-      } else {
-        ob[static_cast<int64_t>(j) * hw] = v[0][j];
+      for (int j = 0; j < kCG; ++j) v[q][j] = 0.f;
+    if (any) {
+#pragma unroll
+      for (int q = 0; q < CPT; ++q) {
+        if (k[q] > 0) {
+          const float* rp = rows + static_cast<int64_t>(s[q]) * C + c0;
+          if (vec_rows) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(rp));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(rp) + 1);
+            v[q][0] = a.x; v[q][1] = a.y; v[q][2] = a.z; v[q][3] = a.w;
+            v[q][4] = bb.x; v[q][5] = bb.y; v[q][6] = bb.z; v[q][7] = bb.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < kCG; ++j)
+              if (j < nch) v[q][j] = __ldg(rp + j);
+          }
+        }
+      }
+    }
+    float* ob = out + (static_cast<int64_t>(b) * C + c0) * hw + cell0;
+#pragma unroll
+    for (int j = 0; j < kCG; ++j) {
+      if (j < nch) {
+        if (VEC4) {
+          const float4 o = make_float4(v[0][j], v[1 % CPT][j], v[2 % CPT][j], v[3 % CPT][j]);
+          float* dst = ob + static_cast<int64_t>(j) * hw;
+          if (stream_out) smos_st_cs_f4(dst, o);
+          else *reinterpret_cast<float4*>(dst) = o;
+        } else {
+          ob[static_cast<int64_t>(j) * hw] = v[0][j];
+        }
       }
     }
   }
@@ -337,7 +429,7 @@ int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N, int64_t in
         static_cast<int32_t>(L.hw), voxel_max_idx, idx_batch_stride, cell, rank, count);
   }
   pool_cell_alloc_kernel<<<smos_ceil_div(L.cells, kPlanThreads), kPlanThreads, 0, st>>>(
-      count, start, static_cast<int32_t>(L.cells), cursor);
+      count, start, static_cast<int32_t>(L.cells), cursor, reinterpret_cast<int2*>(base + L.off_multi));
   if (total > 0) {
     pool_cell_scatter_kernel<<<smos_ceil_div(total, kPlanThreads), kPlanThreads, 0, st>>>(
         cell, rank, start, total, static_cast<int32_t>(N), static_cast<int32_t>(L.hw), sorted);
@@ -358,31 +450,62 @@ int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int
   const int2* sorted = reinterpret_cast<const int2*>(base + L.off_sorted);
   const int32_t* cursor = count + L.cells;
   float* rows = static_cast<float*>(workspace);
+  const int32_t* pos = reinterpret_cast<const int32_t*>(base + L.off_rank);
   cudaStream_t st = smos_stream(stream);
   const int32_t hw = static_cast<int32_t>(L.hw);
+  const int32_t Ci = static_cast<int32_t>(C);
   const int64_t total = B * N;
   if (total > 0) {
     const int grid = smos_ceil_div(total, kReduceWarps * 32);
-    if (f_sc == 1 && C > 1)
-      pool_reduce_kernel<true><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, static_cast<int32_t>(C), f_sb, f_sc,
-                                                                   f_sn, hw, sorted, cursor, rows);
-    else
-      pool_reduce_kernel<false><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, static_cast<int32_t>(C), f_sb, f_sc,
-                                                                    f_sn, hw, sorted, cursor, rows);
+    const bool aligned = (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 && (f_sb & 3) == 0 && (f_sn & 3) == 0;
+    const bool point_major = (f_sc == 1 && C > 1);
+    if (!point_major) {
+      // channel-major: permute into sorted rows, then reduce those rows in place
+      static bool smem_opt_in[64] = {};
+      int device = 0;
+      cudaGetDevice(&device);
+      const size_t smem = static_cast<size_t>(kPermPts) * (C + 1) * 4;
+      if (smem > 200 * 1024) return SMOS_EUNSUPPORTED;
+      if (device >= 0 && device < 64 && !smem_opt_in[device]) {
+        cudaError_t e = cudaFuncSetAttribute(pool_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        smem_opt_in[device] = true;
+      }
+      dim3 pg(smos_ceil_div(N, kPermPts), static_cast<unsigned>(B));
+      pool_permute_kernel<<<pg, kPermThreads, smem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, f_sn, pos, rows);
+      if ((C & 127) == 0) pool_reduce_kernel<4, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
+      else if ((C & 63) == 0) pool_reduce_kernel<2, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
+      else pool_reduce_kernel<1, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
+    } else {
+      if ((C & 127) == 0 && aligned) pool_reduce_kernel<4, false><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
+      else if ((C & 63) == 0 && aligned) pool_reduce_kernel<2, false><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
+      else pool_reduce_kernel<1, false><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
+    }
+  }
+  if (total >= 32) {
+    // fold multi-piece cells (<= total/32 of them; the exact number is only known on the device)
+    const int2* multi = reinterpret_cast<const int2*>(base + L.off_multi);
+    const int cgrid = smos_ceil_div(total / 32 + 1, kReduceWarps);
+    if ((C & 127) == 0) pool_combine_kernel<4><<<cgrid, kReduceWarps * 32, 0, st>>>(Ci, multi, cursor, rows);
+    else if ((C & 63) == 0) pool_combine_kernel<2><<<cgrid, kReduceWarps * 32, 0, st>>>(Ci, multi, cursor, rows);
+    else pool_combine_kernel<1><<<cgrid, kReduceWarps * 32, 0, st>>>(Ci, multi, cursor, rows);
   }
   // outputs beyond L2 capacity are written with evict-first stores
   const int stream_out = (B * C * L.hw * 4 > (int64_t(96) << 20)) ? 1 : 0;
   const bool vec4 = ((hw & 3) == 0) && ((reinterpret_cast<uintptr_t>(voxel_out) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(count) & 15) == 0);
   const int cpt = vec4 ? 4 : 1;
-  dim3 grid(smos_ceil_div(smos_ceil_div(hw, cpt), kWriteThreads), smos_ceil_div(C, kCG), static_cast<unsigned>(B));
-  if (grid.y > 65535) return SMOS_EUNSUPPORTED;
+  const int gx = smos_ceil_div(smos_ceil_div(hw, cpt), kWriteThreads);
+  // split the channel groups over blockIdx.y only as far as needed to cover the SMs ~3x
+  const int32_t ngroups = (Ci + kCG - 1) / kCG;
+  int32_t groups_per_cta = ngroups;
+  while (groups_per_cta > 1 && static_cast<int64_t>(gx) * B * ((ngroups + groups_per_cta - 1) / groups_per_cta) < 3 * SMOS_SM_COUNT)
+    groups_per_cta = (groups_per_cta + 1) / 2;
+  dim3 grid(gx, (ngroups + groups_per_cta - 1) / groups_per_cta, static_cast<unsigned>(B));
   if (vec4)
-    pool_write_kernel<true><<<grid, kWriteThreads, 0, st>>>(rows, static_cast<int32_t>(C), hw, count, start,
-                                                           voxel_out, stream_out);
+    pool_write_kernel<true><<<grid, kWriteThreads, 0, st>>>(rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
   else
-    pool_write_kernel<false><<<grid, kWriteThreads, 0, st>>>(rows, static_cast<int32_t>(C), hw, count, start,
-                                                            voxel_out, stream_out);
+    pool_write_kernel<false><<<grid, kWriteThreads, 0, st>>>(rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
   return smos_launch_status();
 }
 

@@ -114,7 +114,7 @@ def voxel_maxpool_forward(pcds_feat, plan, out=None):
         rc = lib.smos_voxel_maxpool_forward(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2), plan.H, plan.W,
                                             _ptr(plan.buf), _ptr(ws), _ptr(out), _stream())
     _lib.check(rc, "smos_voxel_maxpool_forward")
-    _count(2)  # piece reduction + dense writer
+    _count(3 if f.stride(1) == 1 and C > 1 else 4)  # [permute +] piece reduction + combine + dense writer
     return out
 
 
