@@ -70,22 +70,32 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
   const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
   const int32_t c0 = blockIdx.y * kCPT;
   const int32_t nch = min(kCPT, C - c0);
-  const float* g = grid + b * gr_sb + static_cast<int64_t>(c0) * gr_sc + static_cast<int64_t>(t.y0) * gr_sh +
-                   static_cast<int64_t>(t.x0) * gr_sw;
+  // All 4*kCPT loads are UNCONDITIONAL (out-of-image taps and channels past C read a clamped, valid
+  // address and are zeroed by a select afterwards): predicated loads get serialised through one
+  // temporary register by ptxas, which made this kernel latency bound.
+  const int32_t xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
+  const int32_t ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
+  const float* g = grid + b * gr_sb;
+  const int64_t o_nw = static_cast<int64_t>(ya) * gr_sh + static_cast<int64_t>(xa) * gr_sw;
+  const int64_t o_ne = static_cast<int64_t>(ya) * gr_sh + static_cast<int64_t>(xb) * gr_sw;
+  const int64_t o_sw = static_cast<int64_t>(yb) * gr_sh + static_cast<int64_t>(xa) * gr_sw;
+  const int64_t o_se = static_cast<int64_t>(yb) * gr_sh + static_cast<int64_t>(xb) * gr_sw;
   float v[kCPT][4];
 #pragma unroll
   for (int k = 0; k < kCPT; ++k) {
-    const float* gc = g + static_cast<int64_t>(k) * gr_sc;
-    const bool ok = k < nch;
-    v[k][0] = (ok && t.in_nw) ? __ldg(gc) : 0.f;
-    v[k][1] = (ok && t.in_ne) ? __ldg(gc + gr_sw) : 0.f;
-    v[k][2] = (ok && t.in_sw) ? __ldg(gc + gr_sh) : 0.f;
-    v[k][3] = (ok && t.in_se) ? __ldg(gc + gr_sh + gr_sw) : 0.f;
+    const float* gc = g + static_cast<int64_t>(min(c0 + k, C - 1)) * gr_sc;
+    v[k][0] = __ldg(gc + o_nw);
+    v[k][1] = __ldg(gc + o_ne);
+    v[k][2] = __ldg(gc + o_sw);
+    v[k][3] = __ldg(gc + o_se);
   }
   float acc[kCPT];
 #pragma unroll
-  for (int k = 0; k < kCPT; ++k)
-    acc[k] = fmaf(v[k][3], t.w_se, fmaf(v[k][2], t.w_sw, fmaf(v[k][1], t.w_ne, fmaf(v[k][0], t.w_nw, 0.f))));
+  for (int k = 0; k < kCPT; ++k) {
+    const float a = t.in_nw ? v[k][0] : 0.f, bq = t.in_ne ? v[k][1] : 0.f;
+    const float c = t.in_sw ? v[k][2] : 0.f, d = t.in_se ? v[k][3] : 0.f;
+    acc[k] = fmaf(d, t.w_se, fmaf(c, t.w_sw, fmaf(bq, t.w_ne, fmaf(a, t.w_nw, 0.f))));
+  }
   float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(c0) * o_sc;
   const bool vec_out = (o_sc == 1) && (nch == kCPT) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
                        ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -115,13 +125,16 @@ gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H,
   if (n >= N) return;
   const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
   const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
-  const float* g = grid + b * gr_sb + static_cast<int64_t>(t.y0) * gr_sh +
-                   static_cast<int64_t>(t.x0) * gr_sw + (cq << 2);
+  const int32_t xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
+  const int32_t ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
+  const float* g = grid + b * gr_sb + (cq << 2);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 v_nw = t.in_nw ? __ldg(reinterpret_cast<const float4*>(g)) : z;
-  const float4 v_ne = t.in_ne ? __ldg(reinterpret_cast<const float4*>(g + gr_sw)) : z;
-  const float4 v_sw = t.in_sw ? __ldg(reinterpret_cast<const float4*>(g + gr_sh)) : z;
-  const float4 v_se = t.in_se ? __ldg(reinterpret_cast<const float4*>(g + gr_sh + gr_sw)) : z;
+  // unconditional loads from clamped pixels, selected afterwards (see the planar kernel)
+  const float4 l_nw = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(ya) * gr_sh + static_cast<int64_t>(xa) * gr_sw));
+  const float4 l_ne = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(ya) * gr_sh + static_cast<int64_t>(xb) * gr_sw));
+  const float4 l_sw = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(yb) * gr_sh + static_cast<int64_t>(xa) * gr_sw));
+  const float4 l_se = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(yb) * gr_sh + static_cast<int64_t>(xb) * gr_sw));
+  const float4 v_nw = t.in_nw ? l_nw : z, v_ne = t.in_ne ? l_ne : z, v_sw = t.in_sw ? l_sw : z, v_se = t.in_se ? l_se : z;
   float4 a;
   a.x = fmaf(v_se.x, t.w_se, fmaf(v_sw.x, t.w_sw, fmaf(v_ne.x, t.w_ne, fmaf(v_nw.x, t.w_nw, 0.f))));
   a.y = fmaf(v_se.y, t.w_se, fmaf(v_sw.y, t.w_sw, fmaf(v_ne.y, t.w_ne, fmaf(v_nw.y, t.w_nw, 0.f))));

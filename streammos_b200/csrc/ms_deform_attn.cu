@@ -75,24 +75,29 @@ msda_forward_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         if (h_im > -1 && w_im > -1 && h_im < H && w_im < W) {
           const Bilinear<T> s = make_bilinear<T>(h_im, w_im, H, W);
           const T w1 = s.hh * s.hw, w2 = s.hh * s.lw, w3 = s.lh * s.hw, w4 = s.lh * s.lw;
-          const T* v1 = vl + (static_cast<int64_t>(s.h_low) * W + s.w_low) * row;
+          // taps outside the map read a clamped (valid) pixel and get weight 0 via a select: unconditional
+          // loads stay independent, predicated ones are serialised through one register by ptxas
+          const int hl = max(s.h_low, 0), hh = min(s.h_low + 1, H - 1);
+          const int wl = max(s.w_low, 0), wh = min(s.w_low + 1, W - 1);
+          const T* p1 = vl + (static_cast<int64_t>(hl) * W + wl) * row;
+          const T* p2 = vl + (static_cast<int64_t>(hl) * W + wh) * row;
+          const T* p3 = vl + (static_cast<int64_t>(hh) * W + wl) * row;
+          const T* p4 = vl + (static_cast<int64_t>(hh) * W + wh) * row;
+          const T u1 = s.in1 ? w1 : T(0), u2 = s.in2 ? w2 : T(0), u3 = s.in3 ? w3 : T(0), u4 = s.in4 ? w4 : T(0);
           if constexpr (VEC == 4) {
             using V = typename Vec4<T>::type;
             V z; z.x = z.y = z.z = z.w = 0;
-            const V a1 = s.in1 ? *reinterpret_cast<const V*>(v1) : z;
-            const V a2 = s.in2 ? *reinterpret_cast<const V*>(v1 + row) : z;
-            const V a3 = s.in3 ? *reinterpret_cast<const V*>(v1 + static_cast<int64_t>(W) * row) : z;
-            const V a4 = s.in4 ? *reinterpret_cast<const V*>(v1 + static_cast<int64_t>(W) * row + row) : z;
-            acc[0] += (w1 * a1.x + w2 * a2.x + w3 * a3.x + w4 * a4.x) * wgt;
-            acc[1] += (w1 * a1.y + w2 * a2.y + w3 * a3.y + w4 * a4.y) * wgt;
-            acc[2] += (w1 * a1.z + w2 * a2.z + w3 * a3.z + w4 * a4.z) * wgt;
-            acc[3] += (w1 * a1.w + w2 * a2.w + w3 * a3.w + w4 * a4.w) * wgt;
+            const V l1 = *reinterpret_cast<const V*>(p1), l2 = *reinterpret_cast<const V*>(p2);
+            const V l3 = *reinterpret_cast<const V*>(p3), l4 = *reinterpret_cast<const V*>(p4);
+            const V a1 = s.in1 ? l1 : z, a2 = s.in2 ? l2 : z, a3 = s.in3 ? l3 : z, a4 = s.in4 ? l4 : z;
+            acc[0] += (u1 * a1.x + u2 * a2.x + u3 * a3.x + u4 * a4.x) * wgt;
+            acc[1] += (u1 * a1.y + u2 * a2.y + u3 * a3.y + u4 * a4.y) * wgt;
+            acc[2] += (u1 * a1.z + u2 * a2.z + u3 * a3.z + u4 * a4.z) * wgt;
+            acc[3] += (u1 * a1.w + u2 * a2.w + u3 * a3.w + u4 * a4.w) * wgt;
           } else {
-            const T a1 = s.in1 ? v1[0] : T(0);
-            const T a2 = s.in2 ? v1[row] : T(0);
-            const T a3 = s.in3 ? v1[static_cast<int64_t>(W) * row] : T(0);
-            const T a4 = s.in4 ? v1[static_cast<int64_t>(W) * row + row] : T(0);
-            acc[0] += (w1 * a1 + w2 * a2 + w3 * a3 + w4 * a4) * wgt;
+            const T l1 = p1[0], l2 = p2[0], l3 = p3[0], l4 = p4[0];
+            const T a1 = s.in1 ? l1 : T(0), a2 = s.in2 ? l2 : T(0), a3 = s.in3 ? l3 : T(0), a4 = s.in4 ? l4 : T(0);
+            acc[0] += (u1 * a1 + u2 * a2 + u3 * a3 + u4 * a4) * wgt;
           }
         }
       }

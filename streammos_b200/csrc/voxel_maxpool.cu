@@ -219,17 +219,18 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
   for (int32_t c0 = 0; c0 < C; c0 += 32 * VEC) {
     const int32_t c = c0 + lane * VEC;
     const bool c_ok = c < C;  // C % VEC == 0 is guaranteed by the dispatcher
+    const int32_t c_ld = c_ok ? c : 0;  // lanes past C load a valid address and discard the value
     V acc;
     int32_t piece_pos = p0;
     for (int32_t i0 = 0; i0 < cnt; i0 += kBatch) {
       V v[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const int32_t i = i0 + u;
-        // the shuffle is executed by the whole warp (i and cnt are warp-uniform); only the load is
-        // predicated per lane
-        const int64_t off = __shfl_sync(0xffffffffu, base_lane, i & 31);
-        if (i < cnt && c_ok) v[u] = __ldg(reinterpret_cast<const V*>(src + off + c));
+        // UNCONDITIONAL loads (rows past the end re-read the last valid row): a predicated load makes
+        // ptxas funnel every value through one temporary register, which serialises the batch
+        const int32_t i = min(i0 + u, cnt - 1);
+        const int64_t off = __shfl_sync(0xffffffffu, base_lane, i);
+        v[u] = __ldg(reinterpret_cast<const V*>(src + off + c_ld));
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
@@ -272,8 +273,8 @@ pool_combine_kernel(int32_t C, const int2* __restrict__ multi, const int32_t* __
       V v[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const int32_t pi = p0 + u;
-        if (pi < npieces) v[u] = *reinterpret_cast<const V*>(rows + static_cast<int64_t>(first_aligned + (pi - 1) * 32) * C + c);
+        const int32_t pi = min(p0 + u, npieces - 1);  // unconditional loads, see pool_reduce_kernel
+        v[u] = *reinterpret_cast<const V*>(rows + static_cast<int64_t>(first_aligned + (pi - 1) * 32) * C + c);
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u)
@@ -331,21 +332,31 @@ pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t
 #pragma unroll
       for (int j = 0; j < kCG; ++j) v[q][j] = 0.f;
     if (any) {
+      // all row loads of the thread are unconditional (empty cells re-read row s = 0, which is valid
+      // whenever any cell is occupied) and selected afterwards, so they are in flight together
+      if (vec_rows) {
+        float4 a[CPT], bb[CPT];
 #pragma unroll
-      for (int q = 0; q < CPT; ++q) {
-        if (k[q] > 0) {
-          const float* rp = rows + static_cast<int64_t>(s[q]) * C + c0;
-          if (vec_rows) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(rp));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(rp) + 1);
-            v[q][0] = a.x; v[q][1] = a.y; v[q][2] = a.z; v[q][3] = a.w;
-            v[q][4] = bb.x; v[q][5] = bb.y; v[q][6] = bb.z; v[q][7] = bb.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < kCG; ++j)
-              if (j < nch) v[q][j] = __ldg(rp + j);
-          }
+        for (int q = 0; q < CPT; ++q) {
+          const float4* rp = reinterpret_cast<const float4*>(rows + static_cast<int64_t>(s[q]) * C + c0);
+          a[q] = __ldg(rp);
+          bb[q] = __ldg(rp + 1);
         }
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) {
+          const bool occ = k[q] > 0;
+          v[q][0] = occ ? a[q].x : 0.f; v[q][1] = occ ? a[q].y : 0.f; v[q][2] = occ ? a[q].z : 0.f;
+          v[q][3] = occ ? a[q].w : 0.f; v[q][4] = occ ? bb[q].x : 0.f; v[q][5] = occ ? bb[q].y : 0.f;
+          v[q][6] = occ ? bb[q].z : 0.f; v[q][7] = occ ? bb[q].w : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < CPT; ++q)
+#pragma unroll
+          for (int j = 0; j < kCG; ++j) {
+            const float t = __ldg(rows + static_cast<int64_t>(s[q]) * C + c0 + (j < nch ? j : 0));
+            v[q][j] = (k[q] > 0 && j < nch) ? t : 0.f;
+          }
       }
     }
     float* ob = out + (static_cast<int64_t>(b) * C + c0) * hw + cell0;
