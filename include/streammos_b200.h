@@ -71,6 +71,22 @@ int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N,
                          int64_t* voxel_max_idx, int64_t idx_batch_stride,
                          void* plan, void* stream);
 
+/* Several plans in one go (three kernel launches for all of them instead of three each): a scan
+ * needs five — BEV at scales 1, 1/2, 1/4 and range view at 1/2, 1/4. Same semantics per entry as
+ * smos_pool_plan_build. n <= 8. If the plan buffers are carved out of one allocation they are
+ * cleared with a single memset. */
+typedef struct smos_pool_plan_desc {
+  const float* pcds_ind;
+  int64_t B, N, ind_sb, ind_sn, ind_sd;
+  int32_t H, W;
+  float scale_h, scale_w;
+  int64_t* voxel_max_idx; /* may be NULL */
+  int64_t idx_batch_stride;
+  void* plan;
+} smos_pool_plan_desc;
+
+int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n, void* stream);
+
 /* Forward: voxel_out[b,c,h,w] = max over points of the cell, 0 for empty cells
  * (true max even if negative: point_deep_cuda_kernel.cu:56-99).
  *   pcds_feat : (B, C, N) float32, element strides f_sb / f_sc / f_sn

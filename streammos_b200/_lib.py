@@ -11,6 +11,13 @@ LIB_PATH = os.path.join(_HERE, "lib", "libstreammos_b200.so")
 
 _i32, _i64, _f32, _vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
+class PoolPlanDesc(ctypes.Structure):
+    """struct smos_pool_plan_desc (include/streammos_b200.h)."""
+    _fields_ = [("pcds_ind", _vp), ("B", _i64), ("N", _i64), ("ind_sb", _i64), ("ind_sn", _i64), ("ind_sd", _i64),
+                ("H", _i32), ("W", _i32), ("scale_h", _f32), ("scale_w", _f32), ("voxel_max_idx", _vp),
+                ("idx_batch_stride", _i64), ("plan", _vp)]
+
+
 # name -> (restype, argtypes); mirrors include/streammos_b200.h one to one
 SIGNATURES = {
     "smos_abi_version": (ctypes.c_int, []),
@@ -19,6 +26,7 @@ SIGNATURES = {
     "smos_pool_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "smos_pool_plan_build": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _f32, _f32, _vp, _i64,
                                             _vp, _vp]),
+    "smos_pool_plan_build_multi": (ctypes.c_int, [ctypes.POINTER(PoolPlanDesc), _i32, _vp]),
     "smos_voxel_maxpool_forward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp,
                                                   _vp, _vp]),
     "smos_voxel_maxpool_backward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp,

@@ -50,101 +50,140 @@ __device__ __forceinline__ Taps make_taps(float cy, float cx, float sh, float sw
 }
 
 constexpr int kGatherThreads = 128;
-constexpr int kCPT = 8;  // channels per thread in the planar kernel
+constexpr int kGatherPts = 32;  // points per CTA
+constexpr int kCPT = 8;         // channels per thread-step in the planar kernel
 
-// Planar (NCHW-like: arbitrary channel stride) grid. thread = (point, group of kCPT channels); lanes run
-// over consecutive points, so in scan order the taps of a warp fall into a handful of sectors per
-// channel plane. All 4*kCPT tap loads of a thread are issued before the first use (the kernel is
-// latency bound otherwise), and for point-major outputs the kCPT results leave as one full 32-byte
-// sector per thread.
+// Per-point sampling state shared by all threads of a CTA: the replayed pixel arithmetic costs ~150
+// instructions (two IEEE divisions) and every channel of a point needs the same result, so it is
+// computed ONCE per point by the first 32 threads and broadcast through shared memory. (Recomputing
+// it per channel group made the kernel instruction bound.)
+struct TapsS {
+  int32_t o_nw, o_ne, o_sw, o_se;  // clamped (always valid) pixel offsets  y * W + x
+  float w_nw, w_ne, w_sw, w_se;    // bilinear weights, already zeroed for out-of-image taps? no: see in_*
+  uint32_t in_mask;                // bit0 nw, bit1 ne, bit2 sw, bit3 se
+};
+
+__device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict__ coord, int32_t b, int32_t n0,
+                                         int32_t N, int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
+                                         int32_t H, int32_t W) {
+  if (threadIdx.x < kGatherPts) {
+    const int32_t n = min(n0 + static_cast<int32_t>(threadIdx.x), N - 1);
+    const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
+    const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
+    const int32_t xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
+    const int32_t ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
+    TapsS r;
+    r.o_nw = ya * W + xa; r.o_ne = ya * W + xb; r.o_sw = yb * W + xa; r.o_se = yb * W + xb;
+    r.w_nw = t.w_nw; r.w_ne = t.w_ne; r.w_sw = t.w_sw; r.w_se = t.w_se;
+    r.in_mask = (t.in_nw ? 1u : 0u) | (t.in_ne ? 2u : 0u) | (t.in_sw ? 4u : 0u) | (t.in_se ? 8u : 0u);
+    s_taps[threadIdx.x] = r;
+  }
+  __syncthreads();
+}
+
+// Planar (NCHW-like: arbitrary channel stride, contiguous H x W planes up to gr_sh / gr_sw) grid.
+// CTA = 32 consecutive points x all channels; lanes run over the points (in scan order the taps of a
+// warp fall into a handful of sectors per channel plane), the 4 warps split the channel groups. All
+// 4*kCPT tap loads of a step are UNCONDITIONAL (out-of-image taps read a clamped, valid pixel and are
+// zeroed by a select afterwards): predicated loads get serialised through one temporary register by
+// ptxas. For point-major outputs the kCPT results leave as one full 32-byte sector per thread.
 __global__ void __launch_bounds__(kGatherThreads)
 gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                              int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
                              const float* __restrict__ coord, int32_t N,
                              int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
                              float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn) {
-  const int32_t n = blockIdx.x * kGatherThreads + threadIdx.x;
+  __shared__ TapsS s_taps[kGatherPts];
   const int32_t b = blockIdx.z;
-  if (n >= N) return;
-  const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
-  const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
-  const int32_t c0 = blockIdx.y * kCPT;
-  const int32_t nch = min(kCPT, C - c0);
-  // All 4*kCPT loads are UNCONDITIONAL (out-of-image taps and channels past C read a clamped, valid
-  // address and are zeroed by a select afterwards): predicated loads get serialised through one
-  // temporary register by ptxas, which made this kernel latency bound.
-  const int32_t xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-  const int32_t ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
+  const int32_t n0 = blockIdx.x * kGatherPts;
+  cta_taps(s_taps, coord, b, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int32_t n = n0 + lane;
+  const TapsS t = s_taps[lane];
+  // offsets in elements for general (gr_sh, gr_sw): y * gr_sh + x * gr_sw
+  const int64_t q_nw = static_cast<int64_t>(t.o_nw / W) * gr_sh + static_cast<int64_t>(t.o_nw % W) * gr_sw;
+  const int64_t q_ne = static_cast<int64_t>(t.o_ne / W) * gr_sh + static_cast<int64_t>(t.o_ne % W) * gr_sw;
+  const int64_t q_sw = static_cast<int64_t>(t.o_sw / W) * gr_sh + static_cast<int64_t>(t.o_sw % W) * gr_sw;
+  const int64_t q_se = static_cast<int64_t>(t.o_se / W) * gr_sh + static_cast<int64_t>(t.o_se % W) * gr_sw;
+  const bool i_nw = t.in_mask & 1u, i_ne = t.in_mask & 2u, i_sw = t.in_mask & 4u, i_se = t.in_mask & 8u;
   const float* g = grid + b * gr_sb;
-  const int64_t o_nw = static_cast<int64_t>(ya) * gr_sh + static_cast<int64_t>(xa) * gr_sw;
-  const int64_t o_ne = static_cast<int64_t>(ya) * gr_sh + static_cast<int64_t>(xb) * gr_sw;
-  const int64_t o_sw = static_cast<int64_t>(yb) * gr_sh + static_cast<int64_t>(xa) * gr_sw;
-  const int64_t o_se = static_cast<int64_t>(yb) * gr_sh + static_cast<int64_t>(xb) * gr_sw;
-  float v[kCPT][4];
+  const bool vec_ok = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int32_t ngroups = (C + kCPT - 1) / kCPT;
+  for (int32_t cg = wid; cg < ngroups; cg += kGatherThreads / 32) {
+    const int32_t c0 = cg * kCPT;
+    const int32_t nch = min(kCPT, C - c0);
+    float v[kCPT][4];
 #pragma unroll
-  for (int k = 0; k < kCPT; ++k) {
-    const float* gc = g + static_cast<int64_t>(min(c0 + k, C - 1)) * gr_sc;
-    v[k][0] = __ldg(gc + o_nw);
-    v[k][1] = __ldg(gc + o_ne);
-    v[k][2] = __ldg(gc + o_sw);
-    v[k][3] = __ldg(gc + o_se);
-  }
-  float acc[kCPT];
+    for (int k = 0; k < kCPT; ++k) {
+      const float* gc = g + static_cast<int64_t>(min(c0 + k, C - 1)) * gr_sc;
+      v[k][0] = __ldg(gc + q_nw);
+      v[k][1] = __ldg(gc + q_ne);
+      v[k][2] = __ldg(gc + q_sw);
+      v[k][3] = __ldg(gc + q_se);
+    }
+    float acc[kCPT];
 #pragma unroll
-  for (int k = 0; k < kCPT; ++k) {
-    const float a = t.in_nw ? v[k][0] : 0.f, bq = t.in_ne ? v[k][1] : 0.f;
-    const float c = t.in_sw ? v[k][2] : 0.f, d = t.in_se ? v[k][3] : 0.f;
-    acc[k] = fmaf(d, t.w_se, fmaf(c, t.w_sw, fmaf(bq, t.w_ne, fmaf(a, t.w_nw, 0.f))));
-  }
-  float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(c0) * o_sc;
-  const bool vec_out = (o_sc == 1) && (nch == kCPT) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (vec_out) {
-    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-  } else {
+    for (int k = 0; k < kCPT; ++k) {
+      const float a = i_nw ? v[k][0] : 0.f, bq = i_ne ? v[k][1] : 0.f;
+      const float c = i_sw ? v[k][2] : 0.f, d = i_se ? v[k][3] : 0.f;
+      acc[k] = fmaf(d, t.w_se, fmaf(c, t.w_sw, fmaf(bq, t.w_ne, fmaf(a, t.w_nw, 0.f))));
+    }
+    if (n < N) {
+      float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(c0) * o_sc;
+      if (vec_ok && nch == kCPT) {
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      } else {
 #pragma unroll
-    for (int k = 0; k < kCPT; ++k)
-      if (k < nch) o[static_cast<int64_t>(k) * o_sc] = acc[k];
+        for (int k = 0; k < kCPT; ++k)
+          if (k < nch) o[static_cast<int64_t>(k) * o_sc] = acc[k];
+      }
+    }
   }
 }
 
 // Channels-last grid (gr_sc == 1, C % 4 == 0): lanes run over channel quads, every tap is a
-// contiguous 16-byte load and a point's taps are four contiguous C*4-byte rows.
+// contiguous 16-byte load and a point's taps are four contiguous C*4-byte rows. CTA = 32 points.
 __global__ void __launch_bounds__(kGatherThreads)
 gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                            int64_t gr_sb, int64_t gr_sh, int64_t gr_sw,
                            const float* __restrict__ coord, int32_t N,
                            int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
                            float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn) {
-  const int32_t q = C >> 2;  // channel quads per point
-  const int64_t gid = static_cast<int64_t>(blockIdx.x) * kGatherThreads + threadIdx.x;
-  const int32_t n = static_cast<int32_t>(gid / q);
-  const int32_t cq = static_cast<int32_t>(gid - static_cast<int64_t>(n) * q);
+  __shared__ TapsS s_taps[kGatherPts];
   const int32_t b = blockIdx.z;
-  if (n >= N) return;
-  const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
-  const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
-  const int32_t xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-  const int32_t ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
-  const float* g = grid + b * gr_sb + (cq << 2);
+  const int32_t n0 = blockIdx.x * kGatherPts;
+  cta_taps(s_taps, coord, b, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W);
+  const int32_t q = C >> 2;  // channel quads per point
+  const float* g = grid + b * gr_sb;
+  const bool vec_ok = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  // unconditional loads from clamped pixels, selected afterwards (see the planar kernel)
-  const float4 l_nw = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(ya) * gr_sh + static_cast<int64_t>(xa) * gr_sw));
-  const float4 l_ne = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(ya) * gr_sh + static_cast<int64_t>(xb) * gr_sw));
-  const float4 l_sw = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(yb) * gr_sh + static_cast<int64_t>(xa) * gr_sw));
-  const float4 l_se = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(yb) * gr_sh + static_cast<int64_t>(xb) * gr_sw));
-  const float4 v_nw = t.in_nw ? l_nw : z, v_ne = t.in_ne ? l_ne : z, v_sw = t.in_sw ? l_sw : z, v_se = t.in_se ? l_se : z;
-  float4 a;
-  a.x = fmaf(v_se.x, t.w_se, fmaf(v_sw.x, t.w_sw, fmaf(v_ne.x, t.w_ne, fmaf(v_nw.x, t.w_nw, 0.f))));
-  a.y = fmaf(v_se.y, t.w_se, fmaf(v_sw.y, t.w_sw, fmaf(v_ne.y, t.w_ne, fmaf(v_nw.y, t.w_nw, 0.f))));
-  a.z = fmaf(v_se.z, t.w_se, fmaf(v_sw.z, t.w_sw, fmaf(v_ne.z, t.w_ne, fmaf(v_nw.z, t.w_nw, 0.f))));
-  a.w = fmaf(v_se.w, t.w_se, fmaf(v_sw.w, t.w_sw, fmaf(v_ne.w, t.w_ne, fmaf(v_nw.w, t.w_nw, 0.f))));
-  float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(cq << 2) * o_sc;
-  if (o_sc == 1 && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-    *reinterpret_cast<float4*>(o) = a;
-  } else {
-    o[0] = a.x; o[o_sc] = a.y; o[2 * o_sc] = a.z; o[3 * o_sc] = a.w;
+  for (int32_t i = threadIdx.x; i < kGatherPts * q; i += kGatherThreads) {
+    const int32_t p = i / q, cq = i - p * q;
+    const int32_t n = n0 + p;
+    if (n >= N) break;
+    const TapsS t = s_taps[p];
+    const float* gq = g + (cq << 2);
+    // unconditional loads from clamped pixels, selected afterwards (see the planar kernel)
+    const float4 l_nw = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_nw / W) * gr_sh + static_cast<int64_t>(t.o_nw % W) * gr_sw));
+    const float4 l_ne = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_ne / W) * gr_sh + static_cast<int64_t>(t.o_ne % W) * gr_sw));
+    const float4 l_sw = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_sw / W) * gr_sh + static_cast<int64_t>(t.o_sw % W) * gr_sw));
+    const float4 l_se = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_se / W) * gr_sh + static_cast<int64_t>(t.o_se % W) * gr_sw));
+    const float4 v_nw = (t.in_mask & 1u) ? l_nw : z, v_ne = (t.in_mask & 2u) ? l_ne : z;
+    const float4 v_sw = (t.in_mask & 4u) ? l_sw : z, v_se = (t.in_mask & 8u) ? l_se : z;
+    float4 a;
+    a.x = fmaf(v_se.x, t.w_se, fmaf(v_sw.x, t.w_sw, fmaf(v_ne.x, t.w_ne, fmaf(v_nw.x, t.w_nw, 0.f))));
+    a.y = fmaf(v_se.y, t.w_se, fmaf(v_sw.y, t.w_sw, fmaf(v_ne.y, t.w_ne, fmaf(v_nw.y, t.w_nw, 0.f))));
+    a.z = fmaf(v_se.z, t.w_se, fmaf(v_sw.z, t.w_sw, fmaf(v_ne.z, t.w_ne, fmaf(v_nw.z, t.w_nw, 0.f))));
+    a.w = fmaf(v_se.w, t.w_se, fmaf(v_sw.w, t.w_sw, fmaf(v_ne.w, t.w_ne, fmaf(v_nw.w, t.w_nw, 0.f))));
+    float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(cq << 2) * o_sc;
+    if (vec_ok) {
+      *reinterpret_cast<float4*>(o) = a;
+    } else {
+      o[0] = a.x; o[o_sc] = a.y; o[2 * o_sc] = a.z; o[3 * o_sc] = a.w;
+    }
   }
 }
 
@@ -187,15 +226,12 @@ int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_
   cudaStream_t st = smos_stream(stream);
   const bool nhwc = (gr_sc == 1) && ((C & 3) == 0) && ((gr_sw & 3) == 0) && ((gr_sh & 3) == 0) &&
                     ((gr_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+  dim3 g(smos_ceil_div(N, kGatherPts), 1, static_cast<unsigned>(B));
   if (nhwc) {
-    const int64_t threads = N * (C >> 2);
-    dim3 g(smos_ceil_div(threads, kGatherThreads), 1, static_cast<unsigned>(B));
     gather_forward_nhwc_kernel<<<g, kGatherThreads, 0, st>>>(
         grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb, co_sn,
         co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn);
   } else {
-    if (C > 65535 * kCPT) return SMOS_EUNSUPPORTED;
-    dim3 g(smos_ceil_div(N, kGatherThreads), smos_ceil_div(C, kCPT), static_cast<unsigned>(B));
     gather_forward_planar_kernel<<<g, kGatherThreads, 0, st>>>(
         grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb,
         co_sn, co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn);

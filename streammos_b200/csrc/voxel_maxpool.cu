@@ -48,93 +48,152 @@ PoolLayout pool_layout(int64_t B, int64_t N, int32_t H, int32_t W) {
   return L;
 }
 
+// ---- plan kernels ------------------------------------------------------------------------------
+// Up to kMaxPlans plans are built by ONE launch of each of the three kernels (a scan needs five: BEV at
+// three scales, range view at two), so the per-scan plan cost is 3 launches instead of 15.
+constexpr int kMaxPlans = 8;
+
+struct PlanDev {
+  const float* ind;
+  int64_t ind_sb, ind_sn, ind_sd;
+  int64_t* vmi;
+  int64_t vmi_stride;
+  int32_t* cell;
+  int32_t* rank;
+  int32_t* count;   // [cells] + cursor[0] (points) + cursor[1] (multi-piece cells)
+  int32_t* start;
+  int2* sorted;
+  int2* multi;
+  int64_t pt_begin;    // first global point index of this plan
+  int64_t quad_begin;  // first global cell-quad index (warp aligned)
+  int32_t N, H, W, hw, cells;
+  float sh, sw;
+};
+
+struct PlanBatch {
+  PlanDev p[kMaxPlans];
+  int64_t pt_total, quad_total;
+  int32_t n;
+};
+
 // ---- plan 1: cell index + warp-aggregated per-cell histogram -------------------------------
 __global__ void __launch_bounds__(kPlanThreads)
-pool_cell_index_kernel(const float* __restrict__ ind, int64_t total, int32_t N,
-                       int64_t ind_sb, int64_t ind_sn, int64_t ind_sd,
-                       int32_t H, int32_t W, float scale_h, float scale_w, int32_t hw,
-                       int64_t* __restrict__ voxel_max_idx, int64_t idx_batch_stride,
-                       int32_t* __restrict__ cell_out, int32_t* __restrict__ rank_out,
-                       int32_t* __restrict__ count) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  int32_t gcell = -1;
-  if (i < total) {
-    const int32_t b = static_cast<int32_t>(i / N);
-    const int32_t n = static_cast<int32_t>(i - static_cast<int64_t>(b) * N);
-    const float* p = ind + b * ind_sb + n * ind_sn;
+pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
+  const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int32_t* target = nullptr;  // &count[gcell] of my plan, or null if invalid
+  int32_t* rank_out = nullptr;
+  if (gi < pb.pt_total) {
+    int j = 0;
+    while (j + 1 < pb.n && gi >= pb.p[j + 1].pt_begin) ++j;
+    const PlanDev& P = pb.p[j];
+    const int64_t i = gi - P.pt_begin;
+    const int32_t b = static_cast<int32_t>(i / P.N);
+    const int32_t n = static_cast<int32_t>(i - static_cast<int64_t>(b) * P.N);
+    const float* q = P.ind + b * P.ind_sb + n * P.ind_sn;
     // fp32 multiply then C-cast truncation toward zero (reference .cu:40)
-    const float fh = __fmul_rn(p[0], scale_h);
-    const float fw = __fmul_rn(p[ind_sd], scale_w);
+    const float fh = __fmul_rn(q[0], P.sh);
+    const float fw = __fmul_rn(q[P.ind_sd], P.sw);
     const long long ih = static_cast<long long>(fh);
     const long long iw = static_cast<long long>(fw);
     int32_t cell = -1;
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-      cell = static_cast<int32_t>(ih) * W + static_cast<int32_t>(iw);
-      gcell = b * hw + cell;
+    if (ih >= 0 && ih < P.H && iw >= 0 && iw < P.W) {
+      cell = static_cast<int32_t>(ih) * P.W + static_cast<int32_t>(iw);
+      target = P.count + (b * P.hw + cell);
     }
-    cell_out[i] = cell;
-    if (voxel_max_idx != nullptr)
-      voxel_max_idx[i] = cell >= 0 ? static_cast<int64_t>(b) * idx_batch_stride + cell : -1;
+    P.cell[i] = cell;
+    rank_out = P.rank + i;
+    if (P.vmi != nullptr) P.vmi[i] = cell >= 0 ? static_cast<int64_t>(b) * P.vmi_stride + cell : -1;
   }
   // one atomic per (warp, cell): in scan order neighbouring points share cells, so lanes that hit
   // the same cell elect a leader which claims ranks for all of them
-  const unsigned peers = __match_any_sync(0xffffffffu, gcell);
+  const unsigned long long key = reinterpret_cast<unsigned long long>(target);
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
   const int leader = __ffs(peers) - 1;
   const int lane = threadIdx.x & 31;
   int32_t base = 0;
-  if (lane == leader && gcell >= 0) base = atomicAdd(&count[gcell], __popc(peers));
+  if (lane == leader && target != nullptr) base = atomicAdd(target, __popc(peers));
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (i < total) rank_out[i] = gcell >= 0 ? base + __popc(peers & smos_lanemask_lt()) : -1;
+  if (rank_out != nullptr) *rank_out = target != nullptr ? base + __popc(peers & smos_lanemask_lt()) : -1;
 }
 
 // ---- plan 2: give every occupied cell a segment of the sorted list ---------------------------
 // Order between warps is irrelevant (max is order independent), so a warp scan plus one atomic on a
-// global cursor replaces a device-wide prefix scan.
+// global cursor replaces a device-wide prefix scan. thread = 4 cells; a warp never straddles two plans.
 __global__ void __launch_bounds__(kPlanThreads)
-pool_cell_alloc_kernel(const int32_t* __restrict__ count, int32_t* __restrict__ start, int32_t cells,
-                       int32_t* __restrict__ cursor, int2* __restrict__ multi) {
-  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t c = i < cells ? count[i] : 0;
+pool_cell_alloc_kernel(const __grid_constant__ PlanBatch pb) {
+  const int64_t gq = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gq >= pb.quad_total) return;  // whole warps only (quad ranges are warp aligned)
+  int j = 0;
+  while (j + 1 < pb.n && gq >= pb.p[j + 1].quad_begin) ++j;
+  const PlanDev& P = pb.p[j];
+  const int32_t c0 = static_cast<int32_t>(gq - P.quad_begin) * 4;
   const int lane = threadIdx.x & 31;
-  int32_t x = c;
+  int32_t c[4] = {0, 0, 0, 0};
+  const bool vec = (c0 + 3 < P.cells) && ((reinterpret_cast<uintptr_t>(P.count) & 15) == 0);
+  if (vec) {
+    const int4 v = *reinterpret_cast<const int4*>(P.count + c0);
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (c0 + q < P.cells) c[q] = P.count[c0 + q];
+  }
+  const int32_t mine = c[0] + c[1] + c[2] + c[3];
+  int32_t x = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
     if (lane >= o) x += y;
   }
   const int32_t warp_total = __shfl_sync(0xffffffffu, x, 31);
+  int32_t* cursor = P.count + P.cells;
   int32_t base = 0;
   if (lane == 31 && warp_total > 0) base = atomicAdd(cursor, warp_total);
   base = __shfl_sync(0xffffffffu, base, 31);
-  const int32_t s = base + x - c;
-  if (i < cells) start[i] = s;
+  int32_t s[4];
+  s[0] = base + x - mine;
+  s[1] = s[0] + c[0];
+  s[2] = s[1] + c[1];
+  s[3] = s[2] + c[2];
+  if (vec && ((reinterpret_cast<uintptr_t>(P.start) & 15) == 0)) {
+    *reinterpret_cast<int4*>(P.start + c0) = make_int4(s[0], s[1], s[2], s[3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (c0 + q < P.cells) P.start[c0 + q] = s[q];
+  }
   // a segment [s, s+c) that crosses a multiple of 32 is reduced as several pieces by phase A; list it
   // so the combine kernel can fold them into row s (cursor[1] counts the list)
-  const bool is_multi = c > 0 && ((s & 31) + c > 32);
-  const unsigned mm = __ballot_sync(0xffffffffu, is_multi);
-  if (mm) {
-    int32_t mbase = 0;
-    if (lane == 0) mbase = atomicAdd(cursor + 1, __popc(mm));
-    mbase = __shfl_sync(0xffffffffu, mbase, 0);
-    if (is_multi) multi[mbase + __popc(mm & smos_lanemask_lt())] = make_int2(s, c);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bool is_multi = c[q] > 0 && ((s[q] & 31) + c[q] > 32);
+    const unsigned mm = __ballot_sync(0xffffffffu, is_multi);
+    if (mm) {
+      int32_t mbase = 0;
+      if (lane == 0) mbase = atomicAdd(cursor + 1, __popc(mm));
+      mbase = __shfl_sync(0xffffffffu, mbase, 0);
+      if (is_multi) P.multi[mbase + __popc(mm & smos_lanemask_lt())] = make_int2(s[q], c[q]);
+    }
   }
 }
 
 // ---- plan 3: place every valid point in its cell's segment -----------------------------------
 __global__ void __launch_bounds__(kPlanThreads)
-pool_cell_scatter_kernel(const int32_t* __restrict__ cell_in, int32_t* __restrict__ rank_io,
-                         const int32_t* __restrict__ start, int64_t total, int32_t N, int32_t hw,
-                         int2* __restrict__ sorted) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int32_t cell = cell_in[i];
+pool_cell_scatter_kernel(const __grid_constant__ PlanBatch pb) {
+  const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gi >= pb.pt_total) return;
+  int j = 0;
+  while (j + 1 < pb.n && gi >= pb.p[j + 1].pt_begin) ++j;
+  const PlanDev& P = pb.p[j];
+  const int64_t i = gi - P.pt_begin;
+  const int32_t cell = P.cell[i];
   if (cell < 0) return;
-  const int32_t b = static_cast<int32_t>(i / N);
-  const int32_t n = static_cast<int32_t>(i - static_cast<int64_t>(b) * N);
-  const int32_t gcell = b * hw + cell;
-  const int32_t pos = __ldg(start + gcell) + rank_io[i];
-  rank_io[i] = pos;  // from here on the array holds each point's sorted position (-1 if invalid)
-  sorted[pos] = make_int2(n, gcell);
+  const int32_t b = static_cast<int32_t>(i / P.N);
+  const int32_t n = static_cast<int32_t>(i - static_cast<int64_t>(b) * P.N);
+  const int32_t gcell = b * P.hw + cell;
+  const int32_t pos = __ldg(P.start + gcell) + P.rank[i];
+  P.rank[i] = pos;  // from here on the array holds each point's sorted position (-1 if invalid)
+  P.sorted[pos] = make_int2(n, gcell);
 }
 
 // ---- phase A0 (channel-major input only): permute into sorted point-major rows -----------------
@@ -158,9 +217,24 @@ pool_permute_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64_
   if (threadIdx.x < kPermPts) s_pos[threadIdx.x] = threadIdx.x < np ? pos[static_cast<int64_t>(b) * N + n0 + threadIdx.x] : -1;
   const float* fb = feat + b * f_sb + static_cast<int64_t>(n0) * f_sn;
   // loads: consecutive threads -> consecutive points of one channel (coalesced when f_sn == 1)
-  for (int32_t i = threadIdx.x; i < C * kPermPts; i += kPermThreads) {
-    const int32_t c = i / kPermPts, p = i - c * kPermPts;
-    if (p < np) tile[p * ld + c] = __ldg(fb + static_cast<int64_t>(c) * f_sc + static_cast<int64_t>(p) * f_sn);
+  // (eight unconditional loads per thread in flight; out-of-range slots re-read a clamped address)
+  const int32_t total = C * kPermPts;
+  for (int32_t i0 = threadIdx.x; i0 < total; i0 += kPermThreads * 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int32_t i = min(i0 + u * kPermThreads, total - 1);
+      const int32_t c = i / kPermPts, p = min(i - c * kPermPts, np - 1);
+      v[u] = __ldg(fb + static_cast<int64_t>(c) * f_sc + static_cast<int64_t>(p) * f_sn);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int32_t i = i0 + u * kPermThreads;
+      if (i < total) {
+        const int32_t c = i / kPermPts, p = i - c * kPermPts;
+        tile[p * ld + c] = v[u];
+      }
+    }
   }
   __syncthreads();
   // stores: one warp per point row, lanes over channels (C*4 contiguous bytes per row)
@@ -170,6 +244,70 @@ pool_permute_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64_
     if (q < 0) continue;  // invalid point: no row
     float* dst = rows + static_cast<int64_t>(q) * C;
     for (int32_t c = lane; c < C; c += 32) dst[c] = tile[p * ld + c];
+  }
+}
+
+// TMA variant of the permute (used when the channel rows are contiguous and 16-byte aligned, i.e.
+// the (B,C,N,1)-contiguous tensor the reference produces, N % 4 == 0). Persistent CTAs walk the
+// 64-point tiles; warp 0 streams the C channel rows of the NEXT tile into the other shared-memory
+// buffer with cp.async.bulk (one 256-byte bulk copy per channel, completion counted on an mbarrier)
+// while all warps write the rows of the current tile: no register staging, loads of tile t+1 overlap
+// stores of tile t.
+constexpr int kPermPitch = kPermPts + 4;  // floats; keeps every row 16-byte aligned, 4-way bank conflicts on read
+
+__global__ void __launch_bounds__(kPermThreads)
+pool_permute_tma_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int32_t B, int64_t f_sb, int64_t f_sc,
+                        const int32_t* __restrict__ pos, float* __restrict__ rows) {
+  extern __shared__ __align__(128) float ptile[];  // [2][C][kPermPitch]
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int32_t s_pos[2][kPermPts];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int32_t tiles_per_b = (N + kPermPts - 1) / kPermPts;
+  const int32_t ntiles = tiles_per_b * B;
+  const int32_t buf_floats = C * kPermPitch;
+  if (threadIdx.x == 0) {
+    smos_mbar_init(&bar[0], 1);
+    smos_mbar_init(&bar[1], 1);
+    smos_fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int32_t t, int buf) {
+    const int32_t b = t / tiles_per_b;
+    const int32_t n0 = (t - b * tiles_per_b) * kPermPts;
+    const int32_t np = min(kPermPts, N - n0);
+    if (wid == 0) {
+      if (lane == 0) smos_mbar_expect_tx(&bar[buf], static_cast<uint32_t>(C) * np * 4u);
+      __syncwarp();
+      const float* src = feat + b * f_sb + n0;
+      float* dst = ptile + buf * buf_floats;
+      for (int32_t c = lane; c < C; c += 32)
+        smos_bulk_g2s(dst + c * kPermPitch, src + static_cast<int64_t>(c) * f_sc, static_cast<uint32_t>(np) * 4u, &bar[buf]);
+    } else if (wid == 1 || wid == 2) {
+      const int32_t p = (wid - 1) * 32 + lane;
+      s_pos[buf][p] = p < np ? __ldg(pos + static_cast<int64_t>(b) * N + n0 + p) : -1;
+    }
+  };
+
+  int32_t t = blockIdx.x;
+  if (t < ntiles) issue(t, 0);
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;
+  for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+    const int32_t tn = t + gridDim.x;
+    if (tn < ntiles) issue(tn, buf ^ 1);  // the other buffer was released by the barrier below
+    smos_mbar_wait(&bar[buf], phase[buf]);
+    phase[buf] ^= 1u;
+    __syncthreads();  // s_pos[buf] (written one iteration ago) is visible; tile bytes have landed
+    const float* tile = ptile + buf * buf_floats;
+    for (int32_t p = wid; p < kPermPts; p += kPermThreads / 32) {
+      const int32_t q = s_pos[buf][p];
+      if (q < 0) continue;  // invalid point or past the end: no row
+      float* dst = rows + static_cast<int64_t>(q) * C;
+      for (int32_t c = lane; c < C; c += 32) dst[c] = tile[c * kPermPitch + p];
+    }
+    smos_fence_proxy_async();  // order my generic-proxy reads before the async-proxy refill
+    __syncthreads();           // everyone is done with `buf`: it may be refilled next iteration
   }
 }
 
@@ -416,36 +554,69 @@ int64_t smos_pool_workspace_bytes(int64_t B, int64_t C, int64_t N) {
   return smos_align_up(B * N * C * 4 + 256, 256);
 }
 
+int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n, void* stream) {
+  if (descs_host == nullptr || n <= 0 || n > kMaxPlans) return SMOS_EINVAL;
+  PlanBatch pb;
+  pb.n = n;
+  int64_t pt = 0, quad = 0;
+  uintptr_t lo = ~uintptr_t(0), hi = 0;
+  for (int32_t j = 0; j < n; ++j) {
+    const smos_pool_plan_desc& d = descs_host[j];
+    if (d.B <= 0 || d.N < 0 || d.H <= 0 || d.W <= 0 || d.plan == nullptr) return SMOS_EINVAL;
+    if (d.B * d.N >= (int64_t(1) << 31) || d.B * static_cast<int64_t>(d.H) * d.W >= (int64_t(1) << 31))
+      return SMOS_EUNSUPPORTED;
+    if (d.N > 0 && d.pcds_ind == nullptr) return SMOS_EINVAL;
+    const PoolLayout L = pool_layout(d.B, d.N, d.H, d.W);
+    char* base = static_cast<char*>(d.plan);
+    PlanDev& P = pb.p[j];
+    P.ind = d.pcds_ind; P.ind_sb = d.ind_sb; P.ind_sn = d.ind_sn; P.ind_sd = d.ind_sd;
+    P.vmi = d.voxel_max_idx; P.vmi_stride = d.idx_batch_stride;
+    P.cell = reinterpret_cast<int32_t*>(base + L.off_cell);
+    P.rank = reinterpret_cast<int32_t*>(base + L.off_rank);
+    P.count = reinterpret_cast<int32_t*>(base + L.off_count);
+    P.start = reinterpret_cast<int32_t*>(base + L.off_start);
+    P.sorted = reinterpret_cast<int2*>(base + L.off_sorted);
+    P.multi = reinterpret_cast<int2*>(base + L.off_multi);
+    P.N = static_cast<int32_t>(d.N); P.H = d.H; P.W = d.W;
+    P.hw = static_cast<int32_t>(L.hw); P.cells = static_cast<int32_t>(L.cells);
+    P.sh = d.scale_h; P.sw = d.scale_w;
+    P.pt_begin = pt; P.quad_begin = quad;
+    pt += d.B * d.N;
+    quad += smos_align_up((L.cells + 3) / 4, 32);
+    lo = lo < reinterpret_cast<uintptr_t>(base) ? lo : reinterpret_cast<uintptr_t>(base);
+    const uintptr_t end = reinterpret_cast<uintptr_t>(base) + static_cast<uintptr_t>(L.bytes);
+    hi = hi > end ? hi : end;
+  }
+  pb.pt_total = pt;
+  pb.quad_total = quad;
+  cudaStream_t st = smos_stream(stream);
+  // zero the per-cell counters (+ cursors). Plans carved out of one buffer are cleared with a single
+  // memset over the whole span (a few MB) instead of one memset node per plan.
+  int64_t sum_bytes = 0;
+  for (int32_t j = 0; j < n; ++j) sum_bytes += pool_layout(descs_host[j].B, descs_host[j].N, descs_host[j].H, descs_host[j].W).bytes;
+  if (n > 1 && static_cast<int64_t>(hi - lo) <= sum_bytes + 4096 * n) {
+    cudaError_t e = cudaMemsetAsync(reinterpret_cast<void*>(lo), 0, hi - lo, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  } else {
+    for (int32_t j = 0; j < n; ++j) {
+      cudaError_t e = cudaMemsetAsync(pb.p[j].count, 0, static_cast<size_t>(pb.p[j].cells + 4) * 4, st);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+  }
+  if (pt > 0) pool_cell_index_kernel<<<smos_ceil_div(pt, kPlanThreads), kPlanThreads, 0, st>>>(pb);
+  pool_cell_alloc_kernel<<<smos_ceil_div(quad, kPlanThreads), kPlanThreads, 0, st>>>(pb);
+  if (pt > 0) pool_cell_scatter_kernel<<<smos_ceil_div(pt, kPlanThreads), kPlanThreads, 0, st>>>(pb);
+  return smos_launch_status();
+}
+
 int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N, int64_t ind_sb, int64_t ind_sn,
                          int64_t ind_sd, int32_t H, int32_t W, float scale_h, float scale_w,
                          int64_t* voxel_max_idx, int64_t idx_batch_stride, void* plan, void* stream) {
-  if (B <= 0 || N < 0 || H <= 0 || W <= 0 || plan == nullptr) return SMOS_EINVAL;
-  if (B * N >= (int64_t(1) << 31) || B * static_cast<int64_t>(H) * W >= (int64_t(1) << 31)) return SMOS_EUNSUPPORTED;
-  if (N > 0 && pcds_ind == nullptr) return SMOS_EINVAL;
-  const PoolLayout L = pool_layout(B, N, H, W);
-  char* base = static_cast<char*>(plan);
-  int32_t* cell = reinterpret_cast<int32_t*>(base + L.off_cell);
-  int32_t* rank = reinterpret_cast<int32_t*>(base + L.off_rank);
-  int32_t* count = reinterpret_cast<int32_t*>(base + L.off_count);
-  int32_t* start = reinterpret_cast<int32_t*>(base + L.off_start);
-  int2* sorted = reinterpret_cast<int2*>(base + L.off_sorted);
-  int32_t* cursor = count + L.cells;
-  cudaStream_t st = smos_stream(stream);
-  const int64_t total = B * N;
-  cudaError_t e = cudaMemsetAsync(count, 0, static_cast<size_t>(L.cells + 4) * 4, st);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  if (total > 0) {
-    pool_cell_index_kernel<<<smos_ceil_div(total, kPlanThreads), kPlanThreads, 0, st>>>(
-        pcds_ind, total, static_cast<int32_t>(N), ind_sb, ind_sn, ind_sd, H, W, scale_h, scale_w,
-        static_cast<int32_t>(L.hw), voxel_max_idx, idx_batch_stride, cell, rank, count);
-  }
-  pool_cell_alloc_kernel<<<smos_ceil_div(L.cells, kPlanThreads), kPlanThreads, 0, st>>>(
-      count, start, static_cast<int32_t>(L.cells), cursor, reinterpret_cast<int2*>(base + L.off_multi));
-  if (total > 0) {
-    pool_cell_scatter_kernel<<<smos_ceil_div(total, kPlanThreads), kPlanThreads, 0, st>>>(
-        cell, rank, start, total, static_cast<int32_t>(N), static_cast<int32_t>(L.hw), sorted);
-  }
-  return smos_launch_status();
+  smos_pool_plan_desc d;
+  d.pcds_ind = pcds_ind; d.B = B; d.N = N; d.ind_sb = ind_sb; d.ind_sn = ind_sn; d.ind_sd = ind_sd;
+  d.H = H; d.W = W; d.scale_h = scale_h; d.scale_w = scale_w;
+  d.voxel_max_idx = voxel_max_idx; d.idx_batch_stride = idx_batch_stride; d.plan = plan;
+  return smos_pool_plan_build_multi(&d, 1, stream);
 }
 
 int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int64_t N, int64_t f_sb,
@@ -482,8 +653,28 @@ int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int
         if (e != cudaSuccess) return static_cast<int>(e);
         smem_opt_in[device] = true;
       }
-      dim3 pg(smos_ceil_div(N, kPermPts), static_cast<unsigned>(B));
-      pool_permute_kernel<<<pg, kPermThreads, smem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, f_sn, pos, rows);
+      const size_t smem_tma = static_cast<size_t>(2) * C * kPermPitch * 4;
+      const bool tma_ok = f_sn == 1 && (N & 3) == 0 && (f_sb & 3) == 0 && (f_sc & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 && smem_tma <= 96 * 1024;
+      if (tma_ok) {
+        static bool tma_opt_in[64] = {};
+        if (device >= 0 && device < 64 && !tma_opt_in[device]) {
+          cudaError_t e = cudaFuncSetAttribute(pool_permute_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+          if (e != cudaSuccess) return static_cast<int>(e);
+          tma_opt_in[device] = true;
+        }
+        const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kPermPts)) * B;
+        int ctas_per_sm = static_cast<int>((200 * 1024) / (smem_tma + 1024));
+        if (ctas_per_sm > 6) ctas_per_sm = 6;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        int64_t pgrid = static_cast<int64_t>(SMOS_SM_COUNT) * ctas_per_sm;
+        if (pgrid > ntiles) pgrid = ntiles;
+        pool_permute_tma_kernel<<<static_cast<unsigned>(pgrid), kPermThreads, smem_tma, st>>>(
+            pcds_feat, Ci, static_cast<int32_t>(N), static_cast<int32_t>(B), f_sb, f_sc, pos, rows);
+      } else {
+        dim3 pg(smos_ceil_div(N, kPermPts), static_cast<unsigned>(B));
+        pool_permute_kernel<<<pg, kPermThreads, smem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, f_sn, pos, rows);
+      }
       if ((C & 127) == 0) pool_reduce_kernel<4, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
       else if ((C & 63) == 0) pool_reduce_kernel<2, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
       else pool_reduce_kernel<1, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);

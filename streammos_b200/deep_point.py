@@ -17,7 +17,7 @@ from . import ops
 
 class VoxelMaxPoolFunction(Function):
     @staticmethod
-    def forward(ctx, pcds_feat, pcds_ind, output_size, scale_rate):
+    def forward(ctx, pcds_feat, pcds_ind, output_size, scale_rate, plan=None):
         assert pcds_feat.dtype == pcds_ind.dtype
         assert pcds_feat.dim() == 4
         assert pcds_ind.dim() == 4
@@ -27,7 +27,11 @@ class VoxelMaxPoolFunction(Function):
         if not pcds_feat.is_cuda:
             raise RuntimeError("deep_point.VoxelMaxPool: CPU tensors are not supported by the B200 build "
                                "(no CPU fallback); the CPU restatement lives in oracle/ for tests only")
-        plan = ops.pool_plan(pcds_ind, output_size, scale_rate)
+        if plan is None:
+            plan = ops.pool_plan(pcds_ind, output_size, scale_rate)
+        else:
+            assert (plan.B, plan.N, plan.H, plan.W) == (pcds_ind.size(0), pcds_ind.size(1), output_size[0],
+                                                        output_size[1]), "plan does not match this call"
         voxel_out = ops.voxel_maxpool_forward(pcds_feat, plan)
         ctx.plan = plan
         ctx.input_shape = pcds_feat.shape
@@ -39,9 +43,11 @@ class VoxelMaxPoolFunction(Function):
         pcds_feat, voxel_out = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
             grad_pcds_feat = ops.voxel_maxpool_backward(pcds_feat, ctx.plan, voxel_out, grad_voxel_out.contiguous())
-            return grad_pcds_feat, None, None, None
-        return None, None, None, None
+            return grad_pcds_feat, None, None, None, None
+        return None, None, None, None, None
 
 
-def VoxelMaxPool(pcds_feat, pcds_ind, output_size, scale_rate):
-    return VoxelMaxPoolFunction.apply(pcds_feat, pcds_ind, output_size, scale_rate)
+def VoxelMaxPool(pcds_feat, pcds_ind, output_size, scale_rate, plan=None):
+    """Reference signature plus an optional `plan` (ops.pool_plan / ops.pool_plan_multi) so that a caller
+    who knows all pooling calls of a scan up front can build their plans in one batch."""
+    return VoxelMaxPoolFunction.apply(pcds_feat, pcds_ind, output_size, scale_rate, plan)

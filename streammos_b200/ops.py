@@ -56,9 +56,7 @@ class PoolPlan:
         self.buf, self.B, self.N, self.H, self.W, self.voxel_max_idx = buf, B, N, H, W, voxel_max_idx
 
 
-def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=0):
-    """pcds_ind (B, N, 2[, 1]) float32 -> PoolPlan. `idx_out` (B, N) int64 receives the reference's
-    voxel_max_idx side product if given (deep_point/__init__.py:27)."""
+def _plan_inputs(pcds_ind, output_size, scale_rate):
     _need_cuda(pcds_ind, "pcds_ind")
     _need_f32(pcds_ind, "pcds_ind")
     if pcds_ind.dim() == 4:
@@ -69,8 +67,44 @@ def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=
         ind = pcds_ind
     if ind.dim() != 3 or ind.size(2) != 2 or len(output_size) != 2 or len(scale_rate) != 2:
         raise NotImplementedError("only 2-D grids (D == 2) are implemented — the shapes StreamMOS uses")
-    B, N = int(ind.size(0)), int(ind.size(1))
-    H, W = int(output_size[0]), int(output_size[1])
+    return ind, int(ind.size(0)), int(ind.size(1)), int(output_size[0]), int(output_size[1])
+
+
+def pool_plan_multi(specs):
+    """Build several plans with three kernel launches in total. `specs`: list of (pcds_ind, output_size,
+    scale_rate) — e.g. the five pooling calls of one scan. Returns a list of PoolPlan (views of one buffer)."""
+    lib = _lib.load()
+    items, offsets, total = [], [], 0
+    for pcds_ind, output_size, scale_rate in specs:
+        ind, B, N, H, W = _plan_inputs(pcds_ind, output_size, scale_rate)
+        nbytes = lib.smos_pool_plan_bytes(B, N, H, W)
+        if nbytes < 0:
+            _lib.check(int(nbytes), "smos_pool_plan_bytes")
+        items.append((ind, B, N, H, W, scale_rate, int(nbytes)))
+        offsets.append(total)
+        total += (int(nbytes) + 255) // 256 * 256
+    device = items[0][0].device
+    big = torch.empty(total, dtype=torch.uint8, device=device)
+    descs = (_lib.PoolPlanDesc * len(items))()
+    plans = []
+    for d, (ind, B, N, H, W, scale_rate, nbytes), off in zip(descs, items, offsets):
+        buf = big[off:off + nbytes]
+        d.pcds_ind, d.B, d.N = ind.data_ptr(), B, N
+        d.ind_sb, d.ind_sn, d.ind_sd = ind.stride(0), ind.stride(1), ind.stride(2)
+        d.H, d.W, d.scale_h, d.scale_w = H, W, float(scale_rate[0]), float(scale_rate[1])
+        d.voxel_max_idx, d.idx_batch_stride, d.plan = None, 0, buf.data_ptr()
+        plans.append(PoolPlan(buf, B, N, H, W, None))
+    with torch.cuda.device(device):
+        rc = lib.smos_pool_plan_build_multi(descs, len(items), _stream())
+    _lib.check(rc, "smos_pool_plan_build_multi")
+    _count(3)
+    return plans
+
+
+def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=0):
+    """pcds_ind (B, N, 2[, 1]) float32 -> PoolPlan. `idx_out` (B, N) int64 receives the reference's
+    voxel_max_idx side product if given (deep_point/__init__.py:27)."""
+    ind, B, N, H, W = _plan_inputs(pcds_ind, output_size, scale_rate)
     lib = _lib.load()
     nbytes = lib.smos_pool_plan_bytes(B, N, H, W)
     if nbytes < 0:

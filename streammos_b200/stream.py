@@ -80,8 +80,10 @@ class HotPath:
     """One scan stream. `step(batch)` runs the whole hot path for one scan on the current CUDA stream and
     returns the per-point labels after long-term voting plus the instance votes."""
 
-    def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference"):
+    def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
+                 batch_plans=True, grids_channels_last=False):
         self.device = torch.device(device)
+        self.batch_plans = batch_plans
         self.n_points = n_points
         self.point_major = point_major
         self.vote_api = vote_api
@@ -94,6 +96,10 @@ class HotPath:
         self.x0 = rnd(1, 32, 256, 256)
         self.x1 = rnd(1, 64, 128, 128)
         self.dec = rnd(1, 64, 256, 256)
+        if grids_channels_last:  # what a channels_last model hands to the gathers
+            self.x0 = self.x0.contiguous(memory_format=torch.channels_last)
+            self.x1 = self.x1.contiguous(memory_format=torch.channels_last)
+            self.dec = self.dec.contiguous(memory_format=torch.channels_last)
         # short-term memory: previous scan's attended BEV feature, (1, 4096, 128) (mve.py:433-439)
         self.memory = torch.randn(1, MEM_HW * MEM_HW, N_HEADS * HEAD_DIM, generator=g).to(self.device)
         self.shapes = torch.tensor([[MEM_HW, MEM_HW]], dtype=torch.int64, device=self.device)
@@ -122,15 +128,22 @@ class HotPath:
     def projection(self, b):
         """Cascade projection: 5 x VoxelMaxPool + 5 x BilinearSample."""
         cur_bev, cur_rv = b.coord_bev[:1], b.coord_rv
-        bev_in = deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0))          # StreamMOS.py:102
+        # all five pooling plans of the scan depend on the coordinates only: three launches build them all
+        if self.batch_plans:
+            pl = ops.pool_plan_multi([(b.coord_bev, (512, 512), (1.0, 1.0)), (cur_rv, (32, 1024), (0.5, 0.5)),
+                                      (cur_bev, (256, 256), (0.5, 0.5)), (cur_rv, (16, 512), (0.25, 0.25)),
+                                      (cur_bev, (128, 128), (0.25, 0.25))])
+        else:
+            pl = [None] * 5
+        bev_in = deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0), pl[0])    # StreamMOS.py:102
         x0_pt = self.g_half(self.x0, cur_bev)                                                   # mve.py:395
-        x0_rv = deep_point.VoxelMaxPool(x0_pt, cur_rv, (32, 1024), (0.5, 0.5))                  # :396
+        x0_rv = deep_point.VoxelMaxPool(x0_pt, cur_rv, (32, 1024), (0.5, 0.5), pl[1])           # :396
         x0_pt = self.g_half(x0_rv, cur_rv)                                                      # :400
-        x0_bev = deep_point.VoxelMaxPool(x0_pt, cur_bev, (256, 256), (0.5, 0.5))                # :402
+        x0_bev = deep_point.VoxelMaxPool(x0_pt, cur_bev, (256, 256), (0.5, 0.5), pl[2])         # :402
         x1_pt = self.g_quarter(self.x1, cur_bev)                                                # :410
-        x1_rv = deep_point.VoxelMaxPool(x1_pt, cur_rv, (16, 512), (0.25, 0.25))                 # :411
+        x1_rv = deep_point.VoxelMaxPool(x1_pt, cur_rv, (16, 512), (0.25, 0.25), pl[3])          # :411
         x1_pt = self.g_quarter(x1_rv, cur_rv)                                                   # :415
-        x1_bev = deep_point.VoxelMaxPool(x1_pt, cur_bev, (128, 128), (0.25, 0.25))              # :417
+        x1_bev = deep_point.VoxelMaxPool(x1_pt, cur_bev, (128, 128), (0.25, 0.25), pl[4])       # :417
         pt_bev = self.g_half(self.dec, cur_bev)                                                 # StreamMOS.py:105
         return bev_in, x0_bev, x1_bev, x1_pt, pt_bev
 

@@ -156,6 +156,25 @@ def test_pool_permutation_invariant():
     assert torch.equal(a, b)
 
 
+def test_pool_batched_plans_match_single_plans():
+    """ops.pool_plan_multi (three launches for all five pooling calls of a scan) gives the same grids."""
+    from streammos_b200 import deep_point, ops
+    rng = np.random.default_rng(3)
+    N = 50000
+    specs, feats = [], []
+    for (B, C, size, scale) in POOL_CONFIG:
+        ind = t(synth_scan(rng, B, N, size[0], size[1], scale, n_valid=47000))
+        specs.append((ind, size, scale))
+        feats.append(t(rng.standard_normal((B, C, N, 1)).astype(np.float32)))
+    plans = ops.pool_plan_multi(specs)
+    for (ind, size, scale), f, plan in zip(specs, feats, plans):
+        a = deep_point.VoxelMaxPool(f, ind, size, scale, plan)
+        b = deep_point.VoxelMaxPool(f, ind, size, scale)
+        assert torch.equal(a, b)
+        ref = O.voxel_maxpool_forward(f.cpu().numpy(), ind.cpu().numpy(), size, scale)
+        assert np.array_equal(a.cpu().numpy(), ref)
+
+
 def test_pool_rejects_cpu_tensors():
     from streammos_b200 import deep_point
     with pytest.raises(RuntimeError):

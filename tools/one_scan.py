@@ -14,9 +14,11 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--points", type=int, default=120000)
 ap.add_argument("--channel-major", action="store_true")
 ap.add_argument("--vote-api", default="reference")
+ap.add_argument("--grids-channels-last", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-hot = stream.HotPath(dev, a.points, seed=0, point_major=not a.channel_major, vote_api=a.vote_api)
+hot = stream.HotPath(dev, a.points, seed=0, point_major=not a.channel_major, vote_api=a.vote_api,
+                     grids_channels_last=a.grids_channels_last)
 scans = [stream.make_host_scan(i, a.points).to(dev) for i in range(2)]
 torch.cuda.synchronize()
 with torch.no_grad():
