@@ -87,6 +87,7 @@ __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict_
 // 4*kCPT tap loads of a step are UNCONDITIONAL (out-of-image taps read a clamped, valid pixel and are
 // zeroed by a select afterwards): predicated loads get serialised through one temporary register by
 // ptxas. For point-major outputs the kCPT results leave as one full 32-byte sector per thread.
+template <bool DENSE, bool ROWS_OUT>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                              int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
@@ -94,17 +95,22 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
                              int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
                              float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn) {
   __shared__ TapsS s_taps[kGatherPts];
+  extern __shared__ float s_out[];  // ROWS_OUT: [kGatherPts][C + 1]
   const int32_t b = blockIdx.z;
   const int32_t n0 = blockIdx.x * kGatherPts;
   cta_taps(s_taps, coord, b, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int32_t n = n0 + lane;
   const TapsS t = s_taps[lane];
-  // offsets in elements for general (gr_sh, gr_sw): y * gr_sh + x * gr_sw
-  const int64_t q_nw = static_cast<int64_t>(t.o_nw / W) * gr_sh + static_cast<int64_t>(t.o_nw % W) * gr_sw;
-  const int64_t q_ne = static_cast<int64_t>(t.o_ne / W) * gr_sh + static_cast<int64_t>(t.o_ne % W) * gr_sw;
-  const int64_t q_sw = static_cast<int64_t>(t.o_sw / W) * gr_sh + static_cast<int64_t>(t.o_sw % W) * gr_sw;
-  const int64_t q_se = static_cast<int64_t>(t.o_se / W) * gr_sh + static_cast<int64_t>(t.o_se % W) * gr_sw;
+  // DENSE: planes are contiguous H x W images (gr_sh == W, gr_sw == 1): the shared offsets y*W+x are
+  // used as they are (32-bit); otherwise they are re-expressed in the tensor's strides
+  int64_t q_nw = t.o_nw, q_ne = t.o_ne, q_sw = t.o_sw, q_se = t.o_se;
+  if (!DENSE) {
+    q_nw = static_cast<int64_t>(t.o_nw / W) * gr_sh + static_cast<int64_t>(t.o_nw % W) * gr_sw;
+    q_ne = static_cast<int64_t>(t.o_ne / W) * gr_sh + static_cast<int64_t>(t.o_ne % W) * gr_sw;
+    q_sw = static_cast<int64_t>(t.o_sw / W) * gr_sh + static_cast<int64_t>(t.o_sw % W) * gr_sw;
+    q_se = static_cast<int64_t>(t.o_se / W) * gr_sh + static_cast<int64_t>(t.o_se % W) * gr_sw;
+  }
   const bool i_nw = t.in_mask & 1u, i_ne = t.in_mask & 2u, i_sw = t.in_mask & 4u, i_se = t.in_mask & 8u;
   const float* g = grid + b * gr_sb;
   const bool vec_ok = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
@@ -114,9 +120,11 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
     const int32_t c0 = cg * kCPT;
     const int32_t nch = min(kCPT, C - c0);
     float v[kCPT][4];
+    const float* gc0 = g + static_cast<int64_t>(c0) * gr_sc;
+    const int64_t cstep = (nch == kCPT) ? gr_sc : 0;  // a partial last group re-reads its first channel
 #pragma unroll
     for (int k = 0; k < kCPT; ++k) {
-      const float* gc = g + static_cast<int64_t>(min(c0 + k, C - 1)) * gr_sc;
+      const float* gc = (nch == kCPT) ? gc0 + k * cstep : g + static_cast<int64_t>(min(c0 + k, C - 1)) * gr_sc;
       v[k][0] = __ldg(gc + q_nw);
       v[k][1] = __ldg(gc + q_ne);
       v[k][2] = __ldg(gc + q_sw);
@@ -129,7 +137,13 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
       const float c = i_sw ? v[k][2] : 0.f, d = i_se ? v[k][3] : 0.f;
       acc[k] = fmaf(d, t.w_se, fmaf(c, t.w_sw, fmaf(bq, t.w_ne, fmaf(a, t.w_nw, 0.f))));
     }
-    if (n < N) {
+    if (ROWS_OUT) {
+      // point-major output: park the results in shared memory ([point][channel], odd pitch) so that the
+      // rows can leave as contiguous C*4-byte segments instead of 32 scattered sectors per instruction
+#pragma unroll
+      for (int k = 0; k < kCPT; ++k)
+        if (k < nch) s_out[lane * (C + 1) + c0 + k] = acc[k];
+    } else if (n < N) {
       float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(c0) * o_sc;
       if (vec_ok && nch == kCPT) {
         *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -139,6 +153,14 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
         for (int k = 0; k < kCPT; ++k)
           if (k < nch) o[static_cast<int64_t>(k) * o_sc] = acc[k];
       }
+    }
+  }
+  if (ROWS_OUT) {
+    __syncthreads();
+    const int32_t np = min(kGatherPts, N - n0);
+    for (int32_t p = wid; p < np; p += kGatherThreads / 32) {
+      float* o = out + b * o_sb + static_cast<int64_t>(n0 + p) * o_sn;
+      for (int32_t c = lane; c < C; c += 32) o[c] = s_out[p * (C + 1) + c];
     }
   }
 }
@@ -232,9 +254,23 @@ int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_
         grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb, co_sn,
         co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn);
   } else {
-    gather_forward_planar_kernel<<<g, kGatherThreads, 0, st>>>(
-        grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb,
-        co_sn, co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn);
+    // point-major output rows are assembled in shared memory (needs (C+1)*32 floats <= 48 KB)
+    // (measured: assembling point-major rows in shared memory is SLOWER than letting every thread store its
+    //  own full 32-byte sector — the extra shared-memory wavefronts cost more than the scattered stores —
+    //  so the row path stays off; kept for outputs whose rows are not sector aligned)
+    const bool rows_out = (o_sc == 1) && C > 1 && ((o_sn & 7) != 0) &&
+                          (static_cast<size_t>(C + 1) * kGatherPts * 4 <= 40 * 1024);
+    const size_t smem = rows_out ? static_cast<size_t>(C + 1) * kGatherPts * 4 : 0;
+    const bool dense = (gr_sw == 1 && gr_sh == W);
+#define SMOS_LAUNCH_PLANAR(D, R)                                                                              \
+    gather_forward_planar_kernel<D, R><<<g, kGatherThreads, smem, st>>>(                                        \
+        grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb, \
+        co_sn, co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn)
+    if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true);
+    else if (dense) SMOS_LAUNCH_PLANAR(true, false);
+    else if (rows_out) SMOS_LAUNCH_PLANAR(false, true);
+    else SMOS_LAUNCH_PLANAR(false, false);
+#undef SMOS_LAUNCH_PLANAR
   }
   return smos_launch_status();
 }

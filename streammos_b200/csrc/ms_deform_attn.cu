@@ -41,23 +41,25 @@ __device__ __forceinline__ Bilinear<T> make_bilinear(T h, T w, int H, int W) {
 
 // ------------------------------- forward -----------------------------------------------
 // VEC channels per lane (4 when D % 4 == 0, else 1); LPG lanes per (b,q,m) group (power of 2).
-template <typename T, int VEC>
+template <typename T, int VEC, typename I>
 __global__ void __launch_bounds__(kMsdaThreads)
 msda_forward_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const T* __restrict__ loc,
                     const T* __restrict__ attn, int32_t S, int32_t M, int32_t D, int32_t L,
                     int32_t Q, int32_t P, int64_t n_groups, int32_t lpg, T* __restrict__ out) {
-  const int64_t tid = static_cast<int64_t>(blockIdx.x) * kMsdaThreads + threadIdx.x;
-  const int64_t grp = tid / lpg;  // (b*Q + q)*M + m
+  // I = int32_t when every tensor has < 2^31 elements (always true for StreamMOS): halves the integer
+  // instruction count of the address arithmetic, which dominated this latency-bound kernel
+  const I tid = static_cast<I>(blockIdx.x) * kMsdaThreads + threadIdx.x;
+  const I grp = tid / lpg;  // (b*Q + q)*M + m
   const int32_t gl = static_cast<int32_t>(tid - grp * lpg);
-  if (grp >= n_groups) return;
+  if (grp >= static_cast<I>(n_groups)) return;
   const int32_t m = static_cast<int32_t>(grp % M);
-  const int64_t bq = grp / M;
+  const I bq = grp / M;
   const int32_t b = static_cast<int32_t>(bq / Q);
-  const int64_t row = static_cast<int64_t>(M) * D;  // elements per spatial position
-  const T* vb = value + static_cast<int64_t>(b) * S * row + static_cast<int64_t>(m) * D;
-  const T* lp = loc + grp * L * P * 2;
-  const T* ap = attn + grp * L * P;
+  const I row = static_cast<I>(M) * D;  // elements per spatial position
+  const T* vb = value + static_cast<I>(b) * S * row + static_cast<I>(m) * D;
+  const T* lp = loc + grp * (L * P * 2);
+  const T* ap = attn + grp * (L * P);
   const int32_t dvec = D / VEC;
   for (int32_t dv = gl; dv < dvec; dv += lpg) {
     const int32_t d0 = dv * VEC;
@@ -66,7 +68,7 @@ msda_forward_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     for (int k = 0; k < VEC; ++k) acc[k] = 0;
     for (int32_t l = 0; l < L; ++l) {
       const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
-      const T* vl = vb + lsi[l] * row + d0;
+      const T* vl = vb + static_cast<I>(lsi[l]) * row + d0;
       for (int32_t p = 0; p < P; ++p) {
         const T loc_w = lp[(l * P + p) * 2], loc_h = lp[(l * P + p) * 2 + 1];
         const T wgt = ap[l * P + p];
@@ -79,10 +81,10 @@ msda_forward_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           // loads stay independent, predicated ones are serialised through one register by ptxas
           const int hl = max(s.h_low, 0), hh = min(s.h_low + 1, H - 1);
           const int wl = max(s.w_low, 0), wh = min(s.w_low + 1, W - 1);
-          const T* p1 = vl + (static_cast<int64_t>(hl) * W + wl) * row;
-          const T* p2 = vl + (static_cast<int64_t>(hl) * W + wh) * row;
-          const T* p3 = vl + (static_cast<int64_t>(hh) * W + wl) * row;
-          const T* p4 = vl + (static_cast<int64_t>(hh) * W + wh) * row;
+          const T* p1 = vl + static_cast<I>(hl * W + wl) * row;
+          const T* p2 = vl + static_cast<I>(hl * W + wh) * row;
+          const T* p3 = vl + static_cast<I>(hh * W + wl) * row;
+          const T* p4 = vl + static_cast<I>(hh * W + wh) * row;
           const T u1 = s.in1 ? w1 : T(0), u2 = s.in2 ? w2 : T(0), u3 = s.in3 ? w3 : T(0), u4 = s.in4 ? w4 : T(0);
           if constexpr (VEC == 4) {
             using V = typename Vec4<T>::type;
@@ -196,14 +198,17 @@ int forward_impl(const void* value, const int64_t* shapes, const int64_t* lsi, c
   const int32_t lpg = pick_lpg(vec ? D / 4 : D);
   const int64_t threads = n_groups * lpg;
   const int grid = smos_ceil_div(threads, kMsdaThreads);
-  if (vec)
-    msda_forward_kernel<T, 4><<<grid, kMsdaThreads, 0, st>>>(
-        static_cast<const T*>(value), shapes, lsi, static_cast<const T*>(loc), static_cast<const T*>(attn), S, M, D,
-        L, Q, P, n_groups, lpg, static_cast<T*>(out));
-  else
-    msda_forward_kernel<T, 1><<<grid, kMsdaThreads, 0, st>>>(
-        static_cast<const T*>(value), shapes, lsi, static_cast<const T*>(loc), static_cast<const T*>(attn), S, M, D,
-        L, Q, P, n_groups, lpg, static_cast<T*>(out));
+  const bool idx32 = static_cast<int64_t>(B) * S * M * D < (int64_t(1) << 31) &&
+                     threads + kMsdaThreads < (int64_t(1) << 31) && n_groups * L * P * 2 < (int64_t(1) << 31);
+#define SMOS_MSDA_FWD(V, I)                                                                                         \
+  msda_forward_kernel<T, V, I><<<grid, kMsdaThreads, 0, st>>>(                                                       \
+      static_cast<const T*>(value), shapes, lsi, static_cast<const T*>(loc), static_cast<const T*>(attn), S, M, D, L, \
+      Q, P, n_groups, lpg, static_cast<T*>(out))
+  if (vec && idx32) SMOS_MSDA_FWD(4, int32_t);
+  else if (vec) SMOS_MSDA_FWD(4, int64_t);
+  else if (idx32) SMOS_MSDA_FWD(1, int32_t);
+  else SMOS_MSDA_FWD(1, int64_t);
+#undef SMOS_MSDA_FWD
   return smos_launch_status();
 }
 

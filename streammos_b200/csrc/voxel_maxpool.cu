@@ -104,16 +104,21 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
     rank_out = P.rank + i;
     if (P.vmi != nullptr) P.vmi[i] = cell >= 0 ? static_cast<int64_t>(b) * P.vmi_stride + cell : -1;
   }
-  // one atomic per (warp, cell): in scan order neighbouring points share cells, so lanes that hit
-  // the same cell elect a leader which claims ranks for all of them
+  // one atomic per RUN of equal cells among adjacent lanes (in scan order neighbouring points share
+  // cells): a shuffle + ballot finds the runs, the first lane of a run claims ranks for all of it.
+  // (Equal cells in non-adjacent lanes simply form separate runs; __match_any_sync would merge them
+  // but costs far more issue slots than it saves atomics.)
   const unsigned long long key = reinterpret_cast<unsigned long long>(target);
-  const unsigned peers = __match_any_sync(0xffffffffu, key);
-  const int leader = __ffs(peers) - 1;
   const int lane = threadIdx.x & 31;
+  const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+  const int leader = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));       // last head at or before me
+  const unsigned after = lane == 31 ? 0u : (heads & (0xfffffffeu << lane));  // heads strictly after me
+  const int run_end = after ? __ffs(after) - 1 : 32;                        // first lane of the next run
   int32_t base = 0;
-  if (lane == leader && target != nullptr) base = atomicAdd(target, __popc(peers));
+  if (lane == leader && target != nullptr) base = atomicAdd(target, run_end - leader);
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (rank_out != nullptr) *rank_out = target != nullptr ? base + __popc(peers & smos_lanemask_lt()) : -1;
+  if (rank_out != nullptr) *rank_out = target != nullptr ? base + (lane - leader) : -1;
 }
 
 // ---- plan 2: give every occupied cell a segment of the sorted list ---------------------------
