@@ -29,15 +29,15 @@ N_SCANS = 8  # distinct synthetic scans cycled through (inputs >> L2: ~100 MB ea
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=120000)
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--channel-major", action="store_true",
                     help="keep gathered point features (B,C,N,1)-contiguous instead of point-major")
     ap.add_argument("--vote-api", default="reference", choices=["reference", "fused"])
-    ap.add_argument("--cpu-scans", type=int, default=6, help="scans timed for the cpu_baseline leg")
+    ap.add_argument("--cpu-scans", type=int, default=20, help="scans timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-operator table to stderr")
     return ap.parse_args()
@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -135,21 +135,26 @@ def cpu_state(hot):
             "box_lo": hot.box_lo.cpu(), "box_hi": hot.box_hi.cpu(), "scan_index": 0}
 
 
-def time_cpu_path(state, scans, n_scans, warmup=1):
-    """The reference's CPU path (oracle/cpu_path.py) on the host cores: scans/s over a bounded sample."""
+def time_cpu_path(state, scans, n_scans, warmup=1, budget_s=120.0):
+    """The reference's CPU path (oracle/cpu_path.py) on the host cores: scans/s over a bounded sample
+    (at most `n_scans` scans and at most `budget_s` seconds)."""
     import torch
     from oracle.cpu_path import CpuHotPath
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     path = CpuHotPath(state)
+    done = 0
     with torch.no_grad():
         for i in range(warmup):
             path.step(scans[i % len(scans)])
         t0 = time.perf_counter()
-        for i in range(n_scans):
-            path.step(scans[(warmup + i) % len(scans)])
+        while done < n_scans:
+            path.step(scans[(warmup + done) % len(scans)])
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
         dt = time.perf_counter() - t0
-    return n_scans / dt, dt / n_scans * 1e3, cores
+    return done / dt, dt / done * 1e3, cores, done
 
 
 def run_reference(args, world, rank):
@@ -160,8 +165,9 @@ def run_reference(args, world, rank):
     from streammos_b200 import stream
     hot = stream.HotPath("cpu", n_points=args.points, seed=0)
     scans = [stream.make_host_scan(i, args.points, pin=False) for i in range(min(N_SCANS, 4))]
-    sps, ms, cores = time_cpu_path(cpu_state(hot), scans, args.steps, warmup=max(1, min(args.warmup, 3)))
-    sample = "%d scans (1 scan per step), torch %s CPU ops on %d threads" % (args.steps, torch.__version__, cores)
+    sps, ms, cores, done = time_cpu_path(cpu_state(hot), scans, args.steps, warmup=max(1, min(args.warmup, 2)))
+    sample = ("%d scans timed (1 scan per step; capped at 120 s of the %d requested), oracle/cpu_path.py: torch %s CPU "
+              "ops on %d threads" % (done, args.steps, torch.__version__, cores))
     line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "scans/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -245,7 +251,6 @@ def run_b200(args, world, rank, local):
         e1.record(compute)
         torch.cuda.synchronize()
         barrier(world)
-        clocks = sampler.stop() if rank == 0 else None
         ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
         ms_step = ms_total / args.steps
         value = world * 1000.0 / ms_step
@@ -281,27 +286,42 @@ def run_b200(args, world, rank, local):
         f1.record(compute)
         torch.cuda.synchronize()
         barrier(world)
+        clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions
         e2e_ms = max_over_ranks(f0.elapsed_time(f1), world, dev) / args.steps
         e2e = {"value": world * 1000.0 / e2e_ms, "unit": "scans/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": host[0].nbytes(),
                "d2h_bytes_per_step": h_labels[0].numel() * 8 + h_sums[0].numel() * 8,
                "note": "pinned host -> HBM copy of scan i+1 overlaps the kernels of scan i (two streams)"}
 
-        # ---- dominant kernel: VoxelMaxPool #1 forward (3 x 64 x N -> 3 x 64 x 512 x 512) -----------------
+        # ---- dominant kernel: the dense writer of VoxelMaxPool #1 (3 x 64 x 512 x 512 fp32 out) --------------
+        # every stage of the call runs once, then the WRITE stage alone is re-launched and timed with CUDA
+        # events on its stream; the 201 MB output per launch (> 126 MB L2) is its own cache flush
         ab = stream.algorithmic_bytes(args.points)
-        plans = [ops.pool_plan(devb[j].coord_bev, (512, 512), (1.0, 1.0)) for j in range(N_SCANS)]
+        ksteps = min(args.steps, 200)
+        plan1 = ops.pool_plan(devb[0].coord_bev, (512, 512), (1.0, 1.0))
+        ws1 = ops.pool_workspace(3, 64, args.points, dev)
         out1 = torch.empty(3, 64, 512, 512, device=dev)
-        k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ops.voxel_maxpool_forward(devb[0].feat, plan1, out=out1, workspace=ws1)
         for i in range(3):
-            ops.voxel_maxpool_forward(devb[i].feat, plans[i], out=out1)
-        for i in range(args.steps):
-            j = i % N_SCANS
+            ops.voxel_maxpool_forward(devb[0].feat, plan1, out=out1, stages=ops.POOL_STAGE_WRITE, workspace=ws1)
+        k0 = [torch.cuda.Event(enable_timing=True) for _ in range(ksteps)]
+        k1 = [torch.cuda.Event(enable_timing=True) for _ in range(ksteps)]
+        for i in range(ksteps):
             k0[i].record(compute)
-            ops.voxel_maxpool_forward(devb[j].feat, plans[j], out=out1)
+            ops.voxel_maxpool_forward(devb[0].feat, plan1, out=out1, stages=ops.POOL_STAGE_WRITE, workspace=ws1)
             k1[i].record(compute)
         torch.cuda.synchronize()
-        kern_ms = sum(a.elapsed_time(b) for a, b in zip(k0, k1)) / args.steps
+        kern_ms = sum(a.elapsed_time(b) for a, b in zip(k0, k1)) / ksteps
+        # whole VoxelMaxPool #1 (plan + permute + reduce + combine + write) for the op-level figure
+        for i in range(3):
+            deep_point_pool1(devb[i])
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(compute)
+        for i in range(ksteps):
+            deep_point_pool1(devb[i % N_SCANS])
+        p1.record(compute)
+        torch.cuda.synchronize()
+        pool1_ms = p0.elapsed_time(p1) / ksteps
         breakdown = op_breakdown(hot, devb, compute, min(args.steps, 50)) if (rank == 0) else None
 
     peaks = {}
@@ -311,10 +331,22 @@ def run_b200(args, world, rank, local):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    achieved = ab["pool"][0] / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "pool_forward_kernel (VoxelMaxPool #1, 3x64xN -> 3x64x512x512)",
+    # algorithmic bytes of the writer per launch: the dense output (4*B'*C*H*W) + count/start per cell (8*B'*H*W);
+    # the rows of occupied cells are < 10 % more and are not counted
+    k_bytes = 4 * 3 * 64 * 512 * 512 + 8 * 3 * 512 * 512
+    achieved = k_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))["bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "pool_write_kernel (dense writer of VoxelMaxPool #1: 3x64x512x512 fp32)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab["pool"][0], "kernel_ms": kern_ms, "traffic": None,
+                "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": kern_ms, "traffic": traffic,
+                "voxelmaxpool1_op": {"algorithmic_bytes": ab["pool"][0], "ms": pool1_ms,
+                                     "achieved": ab["pool"][0] / (pool1_ms * 1e-3) / 1e9,
+                                     "frac": ab["pool"][0] / (pool1_ms * 1e-3) / 1e9 / peak,
+                                     "note": "eager launches: plan (3 kernels) + permute + reduce + combine + write"},
                 "whole_path": {"algorithmic_bytes_per_scan": ab["total"],
                                "achieved": ab["total"] / (ms_step * 1e-3) / 1e9,
                                "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak}}
@@ -328,15 +360,20 @@ def run_b200(args, world, rank, local):
             "clocks": clocks, "breakdown_ms": breakdown}
     if cpu_hot_state is not None:
         scans = [h for h in host[:4]]
-        sps, ms, cores = time_cpu_path(cpu_hot_state, scans, args.cpu_scans)
+        sps, ms, cores, done = time_cpu_path(cpu_hot_state, scans, args.cpu_scans, budget_s=30.0)
         line["cpu_baseline"] = {"value": sps, "unit": "scans/s", "cores": cores, "kind": "port", "ms_per_scan": ms,
-                                "sample": "%d scans of the same workload, oracle/cpu_path.py (torch CPU ops)" % args.cpu_scans}
+                                "sample": "%d scans of the same workload, oracle/cpu_path.py (torch CPU ops)" % done}
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
     if args.breakdown and breakdown:
         for k, v in breakdown.items():
             sys.stderr.write("%-28s %8.4f ms\n" % (k, v))
+
+
+def deep_point_pool1(b):
+    from streammos_b200 import deep_point
+    return deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0))
 
 
 def op_breakdown(hot, devb, stream_, iters):

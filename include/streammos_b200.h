@@ -101,6 +101,18 @@ int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int
                                int32_t H, int32_t W, const void* plan, void* workspace,
                                float* voxel_out, void* stream);
 
+/* Same call restricted to some of its stages (profiling / benchmarking of a single kernel; the
+ * stages must have run once in order before a later stage is launched alone):
+ *   REDUCE  [permute +] piece reduction   COMBINE  fold multi-piece cells   WRITE  dense output */
+#define SMOS_POOL_STAGE_REDUCE 1
+#define SMOS_POOL_STAGE_COMBINE 2
+#define SMOS_POOL_STAGE_WRITE 4
+#define SMOS_POOL_STAGE_ALL 7
+int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t C, int64_t N,
+                                      int64_t f_sb, int64_t f_sc, int64_t f_sn,
+                                      int32_t H, int32_t W, const void* plan, void* workspace,
+                                      float* voxel_out, int32_t stages, void* stream);
+
 /* Backward: grad_feat[b,c,n] = grad_out[b,c,cell] if voxel_out[b,c,cell] == feat[b,c,n]
  * else 0 — every tied point receives the gradient (point_deep_cuda_kernel.cu:109-132).
  *   grad_feat : (B, C, N) float32 with strides g_sb / g_sc / g_sn; every element written.

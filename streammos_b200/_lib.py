@@ -29,6 +29,8 @@ SIGNATURES = {
     "smos_pool_plan_build_multi": (ctypes.c_int, [ctypes.POINTER(PoolPlanDesc), _i32, _vp]),
     "smos_voxel_maxpool_forward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp,
                                                   _vp, _vp]),
+    "smos_voxel_maxpool_forward_stages": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp,
+                                                         _vp, _vp, _i32, _vp]),
     "smos_voxel_maxpool_backward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp,
                                                    _vp, _vp, _i64, _i64, _i64, _vp]),
     "smos_bilinear_gather_forward": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _i64,

@@ -627,6 +627,13 @@ int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N, int64_t in
 int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int64_t N, int64_t f_sb,
                                int64_t f_sc, int64_t f_sn, int32_t H, int32_t W, const void* plan,
                                void* workspace, float* voxel_out, void* stream) {
+  return smos_voxel_maxpool_forward_stages(pcds_feat, B, C, N, f_sb, f_sc, f_sn, H, W, plan, workspace, voxel_out,
+                                           SMOS_POOL_STAGE_ALL, stream);
+}
+
+int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t C, int64_t N, int64_t f_sb,
+                                      int64_t f_sc, int64_t f_sn, int32_t H, int32_t W, const void* plan,
+                                      void* workspace, float* voxel_out, int32_t stages, void* stream) {
   if (B <= 0 || C <= 0 || N < 0 || H <= 0 || W <= 0 || plan == nullptr || voxel_out == nullptr) return SMOS_EINVAL;
   if (N > 0 && (pcds_feat == nullptr || workspace == nullptr)) return SMOS_EINVAL;
   if (B * N >= (int64_t(1) << 31) || C >= (1 << 20) || B > 65535) return SMOS_EUNSUPPORTED;
@@ -642,7 +649,7 @@ int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int
   const int32_t hw = static_cast<int32_t>(L.hw);
   const int32_t Ci = static_cast<int32_t>(C);
   const int64_t total = B * N;
-  if (total > 0) {
+  if (total > 0 && (stages & SMOS_POOL_STAGE_REDUCE)) {
     const int grid = smos_ceil_div(total, kReduceWarps * 32);
     const bool aligned = (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 && (f_sb & 3) == 0 && (f_sn & 3) == 0;
     const bool point_major = (f_sc == 1 && C > 1);
@@ -689,7 +696,7 @@ int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int
       else pool_reduce_kernel<1, false><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
     }
   }
-  if (total >= 32) {
+  if (total >= 32 && (stages & SMOS_POOL_STAGE_COMBINE)) {
     // fold multi-piece cells (<= total/32 of them; the exact number is only known on the device)
     const int2* multi = reinterpret_cast<const int2*>(base + L.off_multi);
     const int cgrid = smos_ceil_div(total / 32 + 1, kReduceWarps);
@@ -709,10 +716,12 @@ int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int
   while (groups_per_cta > 1 && static_cast<int64_t>(gx) * B * ((ngroups + groups_per_cta - 1) / groups_per_cta) < 3 * SMOS_SM_COUNT)
     groups_per_cta = (groups_per_cta + 1) / 2;
   dim3 grid(gx, (ngroups + groups_per_cta - 1) / groups_per_cta, static_cast<unsigned>(B));
-  if (vec4)
-    pool_write_kernel<true><<<grid, kWriteThreads, 0, st>>>(rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
-  else
-    pool_write_kernel<false><<<grid, kWriteThreads, 0, st>>>(rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
+  if (stages & SMOS_POOL_STAGE_WRITE) {
+    if (vec4)
+      pool_write_kernel<true><<<grid, kWriteThreads, 0, st>>>(rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
+    else
+      pool_write_kernel<false><<<grid, kWriteThreads, 0, st>>>(rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
+  }
   return smos_launch_status();
 }
 

@@ -130,8 +130,12 @@ def _feat3(pcds_feat):
     return pcds_feat
 
 
-def voxel_maxpool_forward(pcds_feat, plan, out=None):
-    """pcds_feat (B, C, N[, 1]) float32, any strides -> (B, C, H, W) NCHW-contiguous."""
+POOL_STAGE_REDUCE, POOL_STAGE_COMBINE, POOL_STAGE_WRITE, POOL_STAGE_ALL = 1, 2, 4, 7
+
+
+def voxel_maxpool_forward(pcds_feat, plan, out=None, stages=POOL_STAGE_ALL, workspace=None):
+    """pcds_feat (B, C, N[, 1]) float32, any strides -> (B, C, H, W) NCHW-contiguous.
+    `stages` / `workspace` let a benchmark re-launch a single stage of a call that already ran once."""
     _need_cuda(pcds_feat, "pcds_feat")
     _need_f32(pcds_feat, "pcds_feat")
     f = _feat3(pcds_feat)
@@ -143,13 +147,20 @@ def voxel_maxpool_forward(pcds_feat, plan, out=None):
     else:
         assert out.is_contiguous() and out.shape == (B, C, plan.H, plan.W) and out.dtype == torch.float32
     lib = _lib.load()
-    ws = torch.empty(int(lib.smos_pool_workspace_bytes(B, C, N)), dtype=torch.uint8, device=f.device)
+    ws = workspace
+    if ws is None:
+        ws = torch.empty(int(lib.smos_pool_workspace_bytes(B, C, N)), dtype=torch.uint8, device=f.device)
+    point_major = f.stride(1) == 1 and C > 1
     with torch.cuda.device(f.device):
-        rc = lib.smos_voxel_maxpool_forward(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2), plan.H, plan.W,
-                                            _ptr(plan.buf), _ptr(ws), _ptr(out), _stream())
+        rc = lib.smos_voxel_maxpool_forward_stages(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2), plan.H,
+                                                   plan.W, _ptr(plan.buf), _ptr(ws), _ptr(out), int(stages), _stream())
     _lib.check(rc, "smos_voxel_maxpool_forward")
-    _count(3 if f.stride(1) == 1 and C > 1 else 4)  # [permute +] piece reduction + combine + dense writer
+    _count((1 if point_major else 2) * bool(stages & 1) + bool(stages & 2) + bool(stages & 4))
     return out
+
+
+def pool_workspace(B, C, N, device):
+    return torch.empty(int(_lib.load().smos_pool_workspace_bytes(B, C, N)), dtype=torch.uint8, device=device)
 
 
 def voxel_maxpool_backward(pcds_feat, plan, voxel_out, grad_voxel_out, grad_feat=None):

@@ -421,3 +421,32 @@ def test_instance_vote_many_boxes_vs_oracle():
     lo, hi = (c - half).astype(np.float32), (c + half).astype(np.float32)
     sums = ops.instance_vote(t(pts), t(pred), t(lo), t(hi))
     assert np.array_equal(sums.cpu().numpy(), O.instance_vote(pts, pred, lo, hi))
+
+
+# ------------------------------------------------------------------------------------------------
+# Whole hot path: streaming harness on the GPU vs the CPU restatement of the same sequence
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("point_major", [True, False])
+def test_whole_path_stream_matches_cpu_path(point_major):
+    """config #2/#3/#1 chained as one scan step (5 pools, 5 gathers, 2 deformable-attention layers, voxel +
+    instance voting) for three consecutive scans with carried short- and long-term memory."""
+    from oracle.cpu_path import CpuHotPath
+    from streammos_b200 import stream
+    n = 30000
+    hot = stream.HotPath(dev(), n_points=n, seed=5, point_major=point_major)
+    cpu = stream.HotPath("cpu", n_points=n, seed=5)
+    state = {"x0": cpu.x0, "x1": cpu.x1, "dec": cpu.dec, "memory": cpu.memory.clone(),
+             "local_pts": cpu.local_pts.clone(), "local_pred": cpu.local_pred.clone(), "box_lo": cpu.box_lo,
+             "box_hi": cpu.box_hi, "scan_index": 0}
+    ref = CpuHotPath(state)
+    with torch.no_grad():
+        for i in range(3):
+            scan = stream.make_host_scan(100 + i, n, pin=False)
+            labels, sums, proj = hot.step(scan.to(dev()))
+            r_labels, r_sums, r_proj = ref.step(scan)
+            assert torch.equal(labels.cpu(), r_labels)                       # voted point labels: bit-exact
+            assert np.array_equal(sums.cpu().numpy(), r_sums)                # instance votes: bit-exact
+            assert torch.equal(proj[0].cpu(), r_proj[0])                     # pool #1 (pure scatter-max): bit-exact
+            for a, b in zip(proj[1:], r_proj[1:]):                           # chains through bilinear gathers
+                torch.testing.assert_close(a.cpu(), b, rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(hot.memory.cpu(), state["memory"], rtol=1e-4, atol=1e-5)
