@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--vote-api", default="reference", choices=["reference", "fused"])
     ap.add_argument("--cpu-scans", type=int, default=20, help="scans timed for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grids-channels-last", action="store_true",
+                    help="CNN stand-in feature maps in channels_last (what a channels_last model hands to the gathers)")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-operator table to stderr")
     return ap.parse_args()
 
@@ -185,13 +187,16 @@ def workload_config(args, graph, world):
             "memory": [64, 64, 128], "streams": world, "parallelism": "1 independent scan stream per GPU, no collectives",
             "launch": "cuda-graph replay" if graph else "eager", "vote_api": args.vote_api,
             "point_feature_layout": "channel-major" if args.channel_major else "point-major (channels_last strides)",
+            "cnn_grid_layout": "channels_last" if args.grids_channels_last else "NCHW (reference default)",
+            "pipeline": "3 graphs per scan (projection / temporal fusion / voting) on 3 CUDA streams, two scans in "
+                        "flight; cross-scan dependencies (short-term memory, voting ring) enforced with events",
             "l2": "no explicit flush: %d distinct scans cycled, ~100 MB inputs and ~700 MB touched per step (>126 MB L2)" % N_SCANS}
 
 
 # ------------------------------------------------------------------------------------------------------------
 def run_b200(args, world, rank, local):
     import torch
-    from streammos_b200 import _lib, ops, stream
+    from streammos_b200 import _lib, ops, pipeline, stream
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device — the b200 arm has no CPU fallback (use --impl reference)")
     _lib.load()
@@ -199,7 +204,8 @@ def run_b200(args, world, rank, local):
     torch.cuda.set_device(dev)
     use_graph = not args.no_graph
     hot = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
-                         vote_api=args.vote_api)
+                         vote_api=args.vote_api, overlap_voting=False,
+                         grids_channels_last=args.grids_channels_last)
     host = [stream.make_host_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
     devb = [h.to(dev) for h in host]
     torch.cuda.synchronize()
@@ -207,37 +213,19 @@ def run_b200(args, world, rank, local):
 
     compute = torch.cuda.Stream(dev)
     copy = torch.cuda.Stream(dev)
-    outs = [None] * N_SCANS
-    graphs = [None] * N_SCANS
     launches_per_step = 0
     with torch.cuda.stream(compute), torch.no_grad():
-        for i in range(N_SCANS):  # eager warm-up: every scan / ring slot once
-            ops.reset_launch_count()
-            outs[i] = hot.step(devb[i])[:2]
-            launches_per_step = ops.launch_count()
+        ops.reset_launch_count()
+        hot.step(devb[0])
+        launches_per_step = ops.launch_count()
         torch.cuda.synchronize()
-        if use_graph:
-            pool = torch.cuda.graph_pool_handle()
-            for i in range(N_SCANS):
-                hot.scan_index = i
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, stream=compute):
-                    outs[i] = hot.step(devb[i])[:2]
-                graphs[i] = g
-            torch.cuda.synchronize()
-
-        def do_step(i):
-            j = i % N_SCANS
-            if use_graph:
-                graphs[j].replay()
-            else:
-                hot.scan_index = i
-                outs[j] = hot.step(devb[j])[:2]
-            return j
+        hot.scan_index = 0
+        pipe = pipeline.ScanPipeline(hot, devb, use_graphs=use_graph)
+        outs = pipe.out
 
         # ---- device-resident throughput ("value") -------------------------------------------------------
         for i in range(args.warmup):
-            do_step(i)
+            pipe.submit()
         torch.cuda.synchronize()
         barrier(world)
         sampler = ClockSampler(local)
@@ -246,8 +234,11 @@ def run_b200(args, world, rank, local):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(compute)
+        for st in pipe.streams():
+            st.wait_event(e0)
         for i in range(args.steps):
-            do_step(i)
+            pipe.submit()
+        pipe.join(compute)
         e1.record(compute)
         torch.cuda.synchronize()
         barrier(world)
@@ -258,31 +249,40 @@ def run_b200(args, world, rank, local):
         # ---- end to end: host buffers in, labels out, copies inside the timed region --------------------
         h_labels = [torch.empty(args.points, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
         h_sums = [torch.empty(stream.N_BOXES, 2, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
-        done = [torch.cuda.Event() for _ in range(N_SCANS)]
         ready = [torch.cuda.Event() for _ in range(N_SCANS)]
+        d2h = [torch.cuda.Event() for _ in range(N_SCANS)]
+        sC = pipe.streams()[2]
 
         def e2e_loop(n):
             for i in range(n):
-                j = i % N_SCANS
+                j = pipe.submitted % N_SCANS
                 with torch.cuda.stream(copy):
-                    copy.wait_event(done[j])            # buffer j is free once its previous step finished
+                    # buffer j is free once the previous scan that used it has been voted on and read back
+                    copy.wait_event(pipe.m_done[j])
+                    copy.wait_event(pipe.v_done[j])
+                    copy.wait_event(d2h[j])
                     devb[j].copy_from(host[j])          # H2D of this scan's inputs (pinned -> HBM)
                     ready[j].record(copy)
-                compute.wait_event(ready[j])
-                do_step(i)
-                h_labels[j].copy_(outs[j][0], non_blocking=True)   # D2H of the step's result
-                h_sums[j].copy_(outs[j][1], non_blocking=True)
-                done[j].record(compute)
+                pipe.submit(ready[j])
+                with torch.cuda.stream(sC):             # D2H of the step's result, behind the voting graph
+                    h_labels[j].copy_(outs[j][0], non_blocking=True)
+                    h_sums[j].copy_(outs[j][1], non_blocking=True)
+                    d2h[j].record(sC)
 
         for j in range(N_SCANS):
-            done[j].record(compute)
-        e2e_loop(max(3, min(args.warmup, N_SCANS)))
+            d2h[j].record(sC)
+        e2e_loop(max(4, min(args.warmup, 2 * N_SCANS)))
         torch.cuda.synchronize()
         barrier(world)
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(compute)
         copy.wait_event(f0)
+        for st in pipe.streams():
+            st.wait_event(f0)
         e2e_loop(args.steps)
+        pipe.join(compute)
+        for j in range(N_SCANS):
+            compute.wait_event(d2h[j])
         f1.record(compute)
         torch.cuda.synchronize()
         barrier(world)
@@ -291,7 +291,8 @@ def run_b200(args, world, rank, local):
         e2e = {"value": world * 1000.0 / e2e_ms, "unit": "scans/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": host[0].nbytes(),
                "d2h_bytes_per_step": h_labels[0].numel() * 8 + h_sums[0].numel() * 8,
-               "note": "pinned host -> HBM copy of scan i+1 overlaps the kernels of scan i (two streams)"}
+               "note": "pinned host -> HBM copy of the next scans overlaps the kernels of the current ones (copy stream "
+                       "+ scan pipeline)"}
 
         # ---- dominant kernel: the dense writer of VoxelMaxPool #1 (3 x 64 x 512 x 512 fp32 out) --------------
         # every stage of the call runs once, then the WRITE stage alone is re-launched and timed with CUDA
@@ -425,11 +426,12 @@ def op_breakdown(hot, devb, stream_, iters):
 
 def main():
     args = parse_args()
+    if args.impl == "reference":  # CPU only: rank 0 runs it, the other ranks exit without work (no process group)
+        run_reference(args, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")))
+        return
     world, rank, local = dist_setup()
     try:
-        if args.impl == "reference":
-            run_reference(args, world, rank)
-        else:
+        if True:
             run_b200(args, world, rank, local)
     finally:
         if world > 1:

@@ -81,8 +81,10 @@ class HotPath:
     returns the per-point labels after long-term voting plus the instance votes."""
 
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
-                 batch_plans=True, grids_channels_last=False):
+                 batch_plans=True, grids_channels_last=False, overlap_voting=False):
         self.device = torch.device(device)
+        self.overlap_voting = overlap_voting
+        self._side = None
         self.batch_plans = batch_plans
         self.n_points = n_points
         self.point_major = point_major
@@ -179,10 +181,26 @@ class HotPath:
         return point_labels, sums
 
     def step(self, b):
-        proj = self.projection(b)
-        fused = self.temporal_fusion(b)
-        self.memory.copy_(fused)  # becomes the next scan's query_embed_store (mve.py:456)
-        point_labels, sums = self.long_term_voting(b)
+        """One scan. With `overlap_voting` the long-term voting runs on a second stream next to the
+        projection + temporal fusion: voting post-processes PREDICTIONS (an input here, the network's argmax
+        in the reference), so in a stream it is the voting of scan t-1 that overlaps the network of scan t —
+        the two branches share no data. Under CUDA-graph capture the fork/join becomes two graph branches."""
+        if self.overlap_voting and self.device.type == "cuda":
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                point_labels, sums = self.long_term_voting(b)
+            proj = self.projection(b)
+            fused = self.temporal_fusion(b)
+            self.memory.copy_(fused)
+            main.wait_stream(self._side)
+        else:
+            proj = self.projection(b)
+            fused = self.temporal_fusion(b)
+            self.memory.copy_(fused)  # becomes the next scan's query_embed_store (mve.py:456)
+            point_labels, sums = self.long_term_voting(b)
         self.scan_index += 1
         return point_labels, sums, proj
 

@@ -450,3 +450,36 @@ def test_whole_path_stream_matches_cpu_path(point_major):
             for a, b in zip(proj[1:], r_proj[1:]):                           # chains through bilinear gathers
                 torch.testing.assert_close(a.cpu(), b, rtol=1e-4, atol=1e-5)
             torch.testing.assert_close(hot.memory.cpu(), state["memory"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("use_graphs", [True, False])
+def test_pipeline_matches_serial_step(use_graphs):
+    """ScanPipeline (3 graphs per scan on 3 streams, two scans in flight) == the serial step, scan by scan."""
+    from streammos_b200 import pipeline, stream
+    n, n_buf, n_scans = 20000, 8, 12  # graph replays bake the voting ring slot: buffers = a multiple of 8
+    host = [stream.make_host_scan(300 + j, n, pin=False) for j in range(n_buf)]
+    serial = stream.HotPath(dev(), n_points=n, seed=9)
+    want = []
+    with torch.no_grad():
+        for i in range(n_scans):
+            labels, sums, _ = serial.step(host[i % n_buf].to(dev()))
+            want.append((labels.clone(), sums.clone()))
+    torch.cuda.synchronize()
+    hot = stream.HotPath(dev(), n_points=n, seed=9)
+    state0 = (hot.memory.clone(), hot.local_pts.clone(), hot.local_pred.clone())
+    devb = [h.to(dev()) for h in host]
+    pipe = pipeline.ScanPipeline(hot, devb, use_graphs=use_graphs)
+    # the constructor's warm-up advanced the memories: restore the initial state before the real run
+    hot.memory.copy_(state0[0]); hot.local_pts.copy_(state0[1]); hot.local_pred.copy_(state0[2])
+    hot.scan_index = 0
+    torch.cuda.synchronize()
+    got = []
+    for i in range(n_scans):
+        j = pipe.submit()
+        pipe.join(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        got.append((pipe.out[j][0].clone(), pipe.out[j][1].clone()))
+    for i, ((wl, ws), (gl, gs)) in enumerate(zip(want, got)):
+        assert torch.equal(wl, gl), "labels differ at scan %d" % i
+        assert torch.equal(ws, gs), "instance votes differ at scan %d" % i
+    torch.testing.assert_close(hot.memory, serial.memory, rtol=0, atol=0)
