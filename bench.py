@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grids-channels-last", action="store_true",
                     help="CNN stand-in feature maps in channels_last (what a channels_last model hands to the gathers)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra layout/API variant measurement")
+    ap.add_argument("--in-flight", type=int, default=2, help="scans in flight per stream (projection streams)")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-operator table to stderr")
     return ap.parse_args()
 
@@ -188,8 +190,9 @@ def workload_config(args, graph, world):
             "launch": "cuda-graph replay" if graph else "eager", "vote_api": args.vote_api,
             "point_feature_layout": "channel-major" if args.channel_major else "point-major (channels_last strides)",
             "cnn_grid_layout": "channels_last" if args.grids_channels_last else "NCHW (reference default)",
-            "pipeline": "3 graphs per scan (projection / temporal fusion / voting) on 3 CUDA streams, two scans in "
-                        "flight; cross-scan dependencies (short-term memory, voting ring) enforced with events",
+            "pipeline": "3 graphs per scan (projection / temporal fusion / voting), %d scans in flight on %d CUDA streams; "
+                        "cross-scan dependencies (short-term memory, voting ring) enforced with events"
+                        % (args.in_flight, args.in_flight + 1),
             "l2": "no explicit flush: %d distinct scans cycled, ~100 MB inputs and ~700 MB touched per step (>126 MB L2)" % N_SCANS}
 
 
@@ -220,7 +223,7 @@ def run_b200(args, world, rank, local):
         launches_per_step = ops.launch_count()
         torch.cuda.synchronize()
         hot.scan_index = 0
-        pipe = pipeline.ScanPipeline(hot, devb, use_graphs=use_graph)
+        pipe = pipeline.ScanPipeline(hot, devb, use_graphs=use_graph, scans_in_flight=args.in_flight)
         outs = pipe.out
 
         # ---- device-resident throughput ("value") -------------------------------------------------------
@@ -251,7 +254,7 @@ def run_b200(args, world, rank, local):
         h_sums = [torch.empty(stream.N_BOXES, 2, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
         ready = [torch.cuda.Event() for _ in range(N_SCANS)]
         d2h = [torch.cuda.Event() for _ in range(N_SCANS)]
-        sC = pipe.streams()[2]
+        sC = pipe.streams()[-1]
 
         def e2e_loop(n):
             for i in range(n):
@@ -325,6 +328,35 @@ def run_b200(args, world, rank, local):
         pool1_ms = p0.elapsed_time(p1) / ksteps
         breakdown = op_breakdown(hot, devb, compute, min(args.steps, 50)) if (rank == 0) else None
 
+        # ---- variant (reported beside the headline, not instead of it): what a channels_last model and the fused
+        # streaming voting API buy on the same workload ------------------------------------------
+        variants = None
+        if rank == 0 and world == 1 and not args.no_variants and use_graph and \
+                not (args.grids_channels_last and args.vote_api == "fused"):
+            del pipe
+            hot2 = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
+                                  vote_api="fused", grids_channels_last=True)
+            pipe2 = pipeline.ScanPipeline(hot2, devb, use_graphs=True, scans_in_flight=args.in_flight)
+            vsteps = min(args.steps, 500)
+            for i in range(20):
+                pipe2.submit()
+            torch.cuda.synchronize()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record(compute)
+            for st in pipe2.streams():
+                st.wait_event(v0)
+            for i in range(vsteps):
+                pipe2.submit()
+            pipe2.join(compute)
+            v1.record(compute)
+            torch.cuda.synchronize()
+            vms = v0.elapsed_time(v1) / vsteps
+            variants = {"channels_last_cnn_grids+fused_voting_api": {
+                "value": 1000.0 / vms, "unit": "scans/s", "ms_per_step": vms,
+                "note": "same kernels; gathers read channels_last feature maps (model.to(memory_format=channels_last)) "
+                        "and voting takes float xyz + uint8 labels (smos_vote_fused) instead of the int64 staging of "
+                        "voxel_voting.py:234-243; results identical (tests)"}}
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -358,7 +390,7 @@ def run_b200(args, world, rank, local):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, use_graph, world), "roofline": roofline, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-            "clocks": clocks, "breakdown_ms": breakdown}
+            "clocks": clocks, "breakdown_ms": breakdown, "variants": variants}
     if cpu_hot_state is not None:
         scans = [h for h in host[:4]]
         sps, ms, cores, done = time_cpu_path(cpu_hot_state, scans, args.cpu_scans, budget_s=30.0)

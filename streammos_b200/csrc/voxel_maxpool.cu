@@ -25,6 +25,13 @@ constexpr int kPlanThreads = 256;
 constexpr int kReduceWarps = 8;   // warps per CTA in phase A
 constexpr int kWriteThreads = 256;
 constexpr int kCG = 8;            // channels per thread in phase B
+// A point that continues a run of equal cells begun by the lane before it (same 64-point tile, hence
+// consecutive sorted positions) is "merged": on the channel-major path only the run's first point gets a
+// row (the run maximum), which removes ~60 % of the permute's writes and of the reduction's reads in scan
+// order. Bit 30 of a plan position / bit 31 of sorted.x carry the mark.
+constexpr int32_t kMergedPos = 0x40000000;
+constexpr int32_t kPosMask = 0x3fffffff;
+constexpr uint32_t kMergedN = 0x80000000u;
 
 struct PoolLayout {
   int64_t hw, cells;   // H*W, B*H*W
@@ -82,6 +89,7 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
   const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   int32_t* target = nullptr;  // &count[gcell] of my plan, or null if invalid
   int32_t* rank_out = nullptr;
+  bool tile_head = false;
   if (gi < pb.pt_total) {
     int j = 0;
     while (j + 1 < pb.n && gi >= pb.p[j + 1].pt_begin) ++j;
@@ -102,6 +110,7 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
     }
     P.cell[i] = cell;
     rank_out = P.rank + i;
+    tile_head = (n & 63) == 0;  // runs never cross the 64-point tiles of the permute kernel
     if (P.vmi != nullptr) P.vmi[i] = cell >= 0 ? static_cast<int64_t>(b) * P.vmi_stride + cell : -1;
   }
   // one atomic per RUN of equal cells among adjacent lanes (in scan order neighbouring points share
@@ -111,14 +120,15 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
   const unsigned long long key = reinterpret_cast<unsigned long long>(target);
   const int lane = threadIdx.x & 31;
   const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
-  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev || tile_head);
   const int leader = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));       // last head at or before me
   const unsigned after = lane == 31 ? 0u : (heads & (0xfffffffeu << lane));  // heads strictly after me
   const int run_end = after ? __ffs(after) - 1 : 32;                        // first lane of the next run
   int32_t base = 0;
   if (lane == leader && target != nullptr) base = atomicAdd(target, run_end - leader);
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (rank_out != nullptr) *rank_out = target != nullptr ? base + (lane - leader) : -1;
+  if (rank_out != nullptr)
+    *rank_out = target != nullptr ? (base + (lane - leader)) | (lane != leader ? kMergedPos : 0) : -1;
 }
 
 // ---- plan 2: give every occupied cell a segment of the sorted list ---------------------------
@@ -196,9 +206,11 @@ pool_cell_scatter_kernel(const __grid_constant__ PlanBatch pb) {
   const int32_t b = static_cast<int32_t>(i / P.N);
   const int32_t n = static_cast<int32_t>(i - static_cast<int64_t>(b) * P.N);
   const int32_t gcell = b * P.hw + cell;
-  const int32_t pos = __ldg(P.start + gcell) + P.rank[i];
-  P.rank[i] = pos;  // from here on the array holds each point's sorted position (-1 if invalid)
-  P.sorted[pos] = make_int2(n, gcell);
+  const int32_t r = P.rank[i];
+  const int32_t merged = r & kMergedPos;
+  const int32_t pos = __ldg(P.start + gcell) + (r & kPosMask);
+  P.rank[i] = pos | merged;  // from here on: sorted position (| kMergedPos), -1 if invalid
+  P.sorted[pos] = make_int2(static_cast<int32_t>(static_cast<uint32_t>(n) | (merged ? kMergedN : 0u)), gcell);
 }
 
 // ---- phase A0 (channel-major input only): permute into sorted point-major rows -----------------
@@ -246,9 +258,15 @@ pool_permute_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64_
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int32_t p = wid; p < np; p += kPermThreads / 32) {
     const int32_t q = s_pos[p];
-    if (q < 0) continue;  // invalid point: no row
+    if (q < 0 || (q & kMergedPos)) continue;  // invalid point, or merged into the row of its run's first point
+    int32_t len = 1;
+    while (p + len < np && s_pos[p + len] >= 0 && (s_pos[p + len] & kMergedPos)) ++len;
     float* dst = rows + static_cast<int64_t>(q) * C;
-    for (int32_t c = lane; c < C; c += 32) dst[c] = tile[p * ld + c];
+    for (int32_t c = lane; c < C; c += 32) {
+      float v = tile[p * ld + c];
+      for (int32_t t = 1; t < len; ++t) v = fmaxf(v, tile[(p + t) * ld + c]);
+      dst[c] = v;
+    }
   }
 }
 
@@ -305,11 +323,27 @@ pool_permute_tma_kernel(const float* __restrict__ feat, int32_t C, int32_t N, in
     phase[buf] ^= 1u;
     __syncthreads();  // s_pos[buf] (written one iteration ago) is visible; tile bytes have landed
     const float* tile = ptile + buf * buf_floats;
-    for (int32_t p = wid; p < kPermPts; p += kPermThreads / 32) {
-      const int32_t q = s_pos[buf][p];
-      if (q < 0) continue;  // invalid point or past the end: no row
-      float* dst = rows + static_cast<int64_t>(q) * C;
-      for (int32_t c = lane; c < C; c += 32) dst[c] = tile[c * kPermPitch + p];
+    // thread = (channel, segment of the tile's points): it sweeps its points once, keeping a running max
+    // over a run (first point + merged followers) and storing one row element per run. A run that starts in
+    // my segment is followed to its end; leading merged points belong to the previous segment's sweep.
+    {
+      const int32_t nseg = max(1, kPermThreads / C);            // segments per tile (C <= 256 here)
+      const int32_t seg_len = (kPermPts + nseg - 1) / nseg;
+      for (int32_t item = threadIdx.x; item < C * nseg; item += kPermThreads) {
+        const int32_t seg = item / C, c = item - seg * C;
+        const float* tc = tile + c * kPermPitch;
+        int32_t p = seg * seg_len;
+        const int32_t seg_end = min(kPermPts, p + seg_len);
+        while (p < seg_end && s_pos[buf][p] >= 0 && (s_pos[buf][p] & kMergedPos)) ++p;  // someone else's run
+        while (p < seg_end) {
+          const int32_t q = s_pos[buf][p];
+          if (q < 0) { ++p; continue; }  // invalid point or past the end of the scan
+          float v = tc[p];
+          ++p;
+          while (p < kPermPts && s_pos[buf][p] >= 0 && (s_pos[buf][p] & kMergedPos)) { v = fmaxf(v, tc[p]); ++p; }
+          rows[static_cast<int64_t>(q) * C + c] = v;
+        }
+      }
     }
     smos_fence_proxy_async();  // order my generic-proxy reads before the async-proxy refill
     __syncthreads();           // everyone is done with `buf`: it may be refilled next iteration
@@ -337,6 +371,11 @@ template <> __device__ __forceinline__ float4 vmax<4>(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
+template <int VEC> __device__ __forceinline__ typename VecT<VEC>::type vneg_inf();
+template <> __device__ __forceinline__ float vneg_inf<1>() { return -INFINITY; }
+template <> __device__ __forceinline__ float2 vneg_inf<2>() { return make_float2(-INFINITY, -INFINITY); }
+template <> __device__ __forceinline__ float4 vneg_inf<4>() { return make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
+
 template <int VEC, bool SORTED_ROWS>
 __global__ void __launch_bounds__(kReduceWarps * 32)
 pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int64_t f_sn, int32_t hw,
@@ -355,8 +394,20 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
                          (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
   // element offset of my point's row (c = 0)
   int64_t base_lane;
-  if (SORTED_ROWS) base_lane = static_cast<int64_t>(p0 + lane) * C;
-  else base_lane = (e.y >= 0 ? e.y / hw : 0) * f_sb + static_cast<int64_t>(e.x) * f_sn;
+  bool absent = false;  // SORTED_ROWS: this position has no row of its own (merged into its run's first row)
+  if (SORTED_ROWS) {
+    absent = lane < cnt && (static_cast<uint32_t>(e.x) & kMergedN) != 0u;
+    // read a row that is needed anyway instead of the unwritten one: the nearest row-owning lane at or before
+    // me, else the first one after me (a 32-position window always contains one: runs are <= 32 long)
+    const unsigned owners = __ballot_sync(0xffffffffu, lane < cnt && !absent);
+    const unsigned before = owners & (0xffffffffu >> (31 - lane));
+    const int src_lane = before ? 31 - __clz(before) : (owners ? __ffs(owners) - 1 : lane);
+    base_lane = static_cast<int64_t>(p0 + src_lane) * C;
+  } else {
+    base_lane = (e.y >= 0 ? e.y / hw : 0) * f_sb +
+                static_cast<int64_t>(static_cast<uint32_t>(e.x) & ~kMergedN) * f_sn;
+  }
+  const unsigned absent_mask = __ballot_sync(0xffffffffu, absent);
   const float* src = SORTED_ROWS ? rows : feat;
 
   for (int32_t c0 = 0; c0 < C; c0 += 32 * VEC) {
@@ -379,6 +430,7 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
       for (int u = 0; u < kBatch; ++u) {
         const int32_t i = i0 + u;
         if (i < cnt && c_ok) {
+          if (SORTED_ROWS && ((absent_mask >> i) & 1u)) v[u] = vneg_inf<VEC>();  // no row of its own
           if ((heads >> i) & 1u) {
             if (i > 0) *reinterpret_cast<V*>(rows + static_cast<int64_t>(piece_pos) * C + c) = acc;
             piece_pos = p0 + i;

@@ -15,14 +15,15 @@ import torch
 
 
 class ScanPipeline:
-    def __init__(self, hot, dev_scans, use_graphs=True):
-        assert len(dev_scans) % 2 == 0, "an even number of resident scan buffers keeps stream parity fixed"
+    def __init__(self, hot, dev_scans, use_graphs=True, scans_in_flight=2):
+        assert len(dev_scans) % scans_in_flight == 0, "resident scan buffers must be a multiple of scans_in_flight"
         if use_graphs:  # a captured voting graph bakes its ring slot (scan index mod 8) in
             from .stream import HISTORY
             assert len(dev_scans) % HISTORY == 0, "graph mode needs a multiple of %d scan buffers" % HISTORY
         self.hot, self.scans, self.n = hot, dev_scans, len(dev_scans)
         dev = hot.device
-        self.sA, self.sB, self.sC = (torch.cuda.Stream(dev) for _ in range(3))
+        self.pm_streams = [torch.cuda.Stream(dev) for _ in range(scans_in_flight)]
+        self.sC = torch.cuda.Stream(dev)
         self.use_graphs = use_graphs
         self.gP, self.gM, self.gV = [None] * self.n, [None] * self.n, [None] * self.n
         self.proj, self.out = [None] * self.n, [None] * self.n
@@ -40,7 +41,7 @@ class ScanPipeline:
                     self.out[j] = hot.long_term_voting(dev_scans[j])
                 torch.cuda.synchronize(dev)
             if use_graphs:
-                pools = {id(self.sA): torch.cuda.graph_pool_handle(), id(self.sB): torch.cuda.graph_pool_handle()}
+                pools = {id(st): torch.cuda.graph_pool_handle() for st in self.pm_streams}
                 pool_c = torch.cuda.graph_pool_handle()
                 for j in range(self.n):
                     s = self._pm_stream(j)
@@ -58,10 +59,10 @@ class ScanPipeline:
         hot.scan_index = 0
 
     def _pm_stream(self, j):
-        return self.sA if j % 2 == 0 else self.sB
+        return self.pm_streams[j % len(self.pm_streams)]
 
     def streams(self):
-        return (self.sA, self.sB, self.sC)
+        return tuple(self.pm_streams) + (self.sC,)
 
     def submit(self, ready_event=None):
         """Enqueue the next scan (buffer index = scan number mod n). `ready_event`: its inputs are resident."""
