@@ -231,6 +231,30 @@ int smos_vote_fused(const float* points, int64_t P, int64_t row_stride,
                     void* workspace, uint8_t* voxel_labels_u8, int64_t* point_labels,
                     void* stream);
 
+/* Streaming long-term memory (replaces the per-frame loop body of voxel_voting.py:176-244):
+ * the last scans stay resident in HBM; one call per frame pose-aligns the history into the current frame
+ * (datasets/utils.py:116-126 Trans: float64 pose_diff x (x,y,z,1) -> float32), crops history and current to
+ * the open box crop_lo < p < crop_hi (utils/transforms.py:151-161; thresholds already include eps), quantises
+ * (voxel_voting.py:77-91), votes per voxel, and labels the current scan: a point inside the crop takes its
+ * voxel's majority label, a point outside keeps its own prediction (voxel_voting.py:243-244).
+ *   scans_host[j] : device points (n, row_stride>=3) f32, device labels (n,) u8, pose_diff = rows 0..2 of
+ *                   inv(pose_current) . pose_j (row major, float64), transform = 0 for the current scan
+ *   workspace     : smos_vote_workspace_bytes(sum n, X, Y, Z, num_classes) bytes
+ *   voxel_labels_u8 (X*Y*Z) and point_labels (n of scan `current`) are fully written. n_scans <= 16. */
+typedef struct smos_vote_stream_scan {
+  const float* points;
+  const uint8_t* labels;
+  int64_t n;
+  double pose_diff[12];
+  int32_t transform;
+} smos_vote_stream_scan;
+
+int smos_vote_stream(const smos_vote_stream_scan* scans_host, int32_t n_scans, int32_t current,
+                     int64_t row_stride, const float* crop_lo_host, const float* crop_hi_host,
+                     float min_x, float min_y, float min_z, float dx, float dy, float dz,
+                     int32_t X, int32_t Y, int32_t Z, int32_t num_classes,
+                     void* workspace, uint8_t* voxel_labels_u8, int64_t* point_labels, void* stream);
+
 /* Per-instance vote count (voxel_instance_voting.py:169-187, in_hull :62-76):
  * for each of K axis-aligned boxes count local-map points inside (inclusive
  * lo <= p <= hi) with prediction 1 (weight 1) and prediction 2 (weight 2).

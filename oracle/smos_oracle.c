@@ -310,3 +310,68 @@ API void oracle_instance_vote(const float* pts, int64_t P, int64_t row_stride, c
     sums[k * 2 + 1] = dy;
   }
 }
+
+/* ---------------------------------------------------------------------------------------- */
+/* Streaming long-term voting, one frame — the loop body of voxel_voting.py:176-244:          */
+/*   Trans (datasets/utils.py:116-126): float64 pose_diff . (x,y,z,1) -> float32 (numpy's dgemm */
+/*   accumulates the four products in k order with FMAs; restated as an fma chain);            */
+/*   Crop (utils/transforms.py:151-161): keep lo+eps < p < hi-eps, compared in float32;         */
+/*   Quantize + .to(int64) + determine_voxel_labels + get_point_labels_from_voxel_labels;       */
+/*   current_pred_result_orin[mask] = pred_result_new (voxel_voting.py:243-244).                */
+/* scans are concatenated: pts (sum n, rs), lab (sum n), begin[n_scans+1]; m[n_scans][12].     */
+/* ---------------------------------------------------------------------------------------- */
+static int stream_point(const float* p, const double* m, int transform, const float* lo, const float* hi,
+                        float* q) {
+  float x = p[0], y = p[1], z = p[2];
+  if (transform) {
+    const double dx = x, dy = y, dz = z;
+    x = (float)fma(m[3], 1.0, fma(m[2], dz, fma(m[1], dy, m[0] * dx)));
+    y = (float)fma(m[7], 1.0, fma(m[6], dz, fma(m[5], dy, m[4] * dx)));
+    z = (float)fma(m[11], 1.0, fma(m[10], dz, fma(m[9], dy, m[8] * dx)));
+  }
+  q[0] = x; q[1] = y; q[2] = z;
+  return x > lo[0] && x < hi[0] && y > lo[1] && y < hi[1] && z > lo[2] && z < hi[2];
+}
+
+static int quant_lin(const float* q, const float* mn, const float* d, int64_t X, int64_t Y, int64_t Z, int64_t* lin) {
+  volatile float fx = q[0] - mn[0], fy = q[1] - mn[1], fz = q[2] - mn[2];
+  volatile float gx = fx / d[0], gy = fy / d[1], gz = fz / d[2];
+  const int64_t x = (int64_t)gx, y = (int64_t)gy, z = (int64_t)gz;
+  if (x < 0 || x >= X || y < 0 || y >= Y || z < 0 || z >= Z) return 0;
+  *lin = x * Y * Z + y * Z + z;
+  return 1;
+}
+
+API int oracle_vote_stream(const float* pts, const uint8_t* lab, const int64_t* begin, const double* m,
+                           const int32_t* transform, int64_t n_scans, int64_t current, int64_t rs, const float* lo,
+                           const float* hi, const float* mn, const float* d, int64_t X, int64_t Y, int64_t Z,
+                           int64_t num_classes, uint8_t* voxel_labels, int64_t* point_labels, float* trans_out) {
+  const int64_t V = X * Y * Z;
+  int32_t* votes = (int32_t*)calloc((size_t)(V * num_classes), sizeof(int32_t));
+  if (!votes) return -1;
+  for (int64_t j = 0; j < n_scans; ++j)
+    for (int64_t i = begin[j]; i < begin[j + 1]; ++i) {
+      float q[3];
+      const int in = stream_point(pts + i * rs, m + j * 12, transform[j], lo, hi, q);
+      if (trans_out) { trans_out[i * 3] = q[0]; trans_out[i * 3 + 1] = q[1]; trans_out[i * 3 + 2] = q[2]; }
+      int64_t lin;
+      if (in && lab[i] < num_classes && quant_lin(q, mn, d, X, Y, Z, &lin)) votes[lin * num_classes + lab[i]] += 1;
+    }
+  for (int64_t v = 0; v < V; ++v) {
+    int64_t best = 0;
+    for (int64_t c = 1; c < num_classes; ++c)
+      if (votes[v * num_classes + c] > votes[v * num_classes + best]) best = c;
+    voxel_labels[v] = (uint8_t)best;
+  }
+  free(votes);
+  for (int64_t i = begin[current]; i < begin[current + 1]; ++i) {
+    float q[3];
+    int64_t r = lab[i];
+    if (stream_point(pts + i * rs, m + current * 12, transform[current], lo, hi, q)) {
+      int64_t lin;
+      r = quant_lin(q, mn, d, X, Y, Z, &lin) ? voxel_labels[lin] : 0;
+    }
+    point_labels[i - begin[current]] = r;
+  }
+  return 0;
+}

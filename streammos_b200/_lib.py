@@ -18,6 +18,12 @@ class PoolPlanDesc(ctypes.Structure):
                 ("idx_batch_stride", _i64), ("plan", _vp)]
 
 
+class VoteStreamScan(ctypes.Structure):
+    """struct smos_vote_stream_scan (include/streammos_b200.h)."""
+    _fields_ = [("points", _vp), ("labels", _vp), ("n", _i64), ("pose_diff", ctypes.c_double * 12),
+                ("transform", _i32)]
+
+
 # name -> (restype, argtypes); mirrors include/streammos_b200.h one to one
 SIGNATURES = {
     "smos_abi_version": (ctypes.c_int, []),
@@ -47,6 +53,9 @@ SIGNATURES = {
     "smos_vote_point_labels": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp]),
     "smos_vote_fused": (ctypes.c_int, [_vp, _i64, _i64, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _i32, _i32,
                                        _i32, _i32, _vp, _vp, _vp, _vp]),
+    "smos_vote_stream": (ctypes.c_int, [ctypes.POINTER(VoteStreamScan), _i32, _i32, _i64, ctypes.POINTER(_f32),
+                                        ctypes.POINTER(_f32), _f32, _f32, _f32, _f32, _f32, _f32, _i32, _i32, _i32, _i32,
+                                        _vp, _vp, _vp, _vp]),
     "smos_instance_vote": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
 }
 

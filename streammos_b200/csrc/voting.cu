@@ -213,6 +213,77 @@ instance_vote_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const
   }
 }
 
+// ---- streaming long-term memory -------------------------------------------------
+// One call per scan over a history that stays resident in HBM: pose alignment of the history scans
+// (datasets/utils.py:116-126 Trans: float64 4x4 x (x,y,z,1), stored as float32 — an FMA chain in k order
+// reproduces numpy's dgemm bit for bit), crop to the open box (utils/transforms.py:151-161), quantise
+// (voxel_voting.py:77-91), vote. Replaces the per-frame reload + numpy transform + crop + .cuda() round trip
+// of voxel_voting.py:176-230.
+constexpr int kMaxStreamScans = 16;
+
+struct StreamScans {
+  const float* pts[kMaxStreamScans];
+  const uint8_t* lab[kMaxStreamScans];
+  int64_t begin[kMaxStreamScans + 1];  // prefix of point counts
+  double m[kMaxStreamScans][12];       // rows 0..2 of pose_diff = inv(pose_cur) . pose_scan
+  int32_t transform[kMaxStreamScans];
+  int32_t n;
+};
+
+struct CropBox { float lo[3], hi[3]; };  // thresholds already include eps: keep iff lo < p < hi
+
+__device__ __forceinline__ bool stream_point(const StreamScans& S, int j, int64_t i, int64_t rs, const CropBox& box,
+                                             float* q) {
+  const float* p = S.pts[j] + i * rs;
+  float x = p[0], y = p[1], z = p[2];
+  if (S.transform[j]) {
+    const double dx = x, dy = y, dz = z;
+    const double* m = S.m[j];
+    x = static_cast<float>(fma(m[3], 1.0, fma(m[2], dz, fma(m[1], dy, m[0] * dx))));
+    y = static_cast<float>(fma(m[7], 1.0, fma(m[6], dz, fma(m[5], dy, m[4] * dx))));
+    z = static_cast<float>(fma(m[11], 1.0, fma(m[10], dz, fma(m[9], dy, m[8] * dx))));
+  }
+  q[0] = x; q[1] = y; q[2] = z;
+  return x > box.lo[0] && x < box.hi[0] && y > box.lo[1] && y < box.hi[1] && z > box.lo[2] && z < box.hi[2];
+}
+
+__global__ void __launch_bounds__(kVoteThreads)
+vote_stream_kernel(const __grid_constant__ StreamScans S, int64_t rs, const __grid_constant__ CropBox box, float mx,
+                   float my, float mz, float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z, int32_t C,
+                   int packed, void* __restrict__ ws) {
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (g >= S.begin[S.n]) return;
+  int j = 0;
+  while (j + 1 < S.n && g >= S.begin[j + 1]) ++j;
+  const int64_t i = g - S.begin[j];
+  float q[3];
+  if (!stream_point(S, j, i, rs, box, q)) return;
+  const int lab = S.lab[j][i];
+  int64_t lin;
+  if (lab >= C || !quant_voxel(q, mx, my, mz, dx, dy, dz, X, Y, Z, &lin)) return;
+  if (packed)
+    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << (kPackBits * lab));
+  else
+    atomicAdd(static_cast<unsigned int*>(ws) + lin * C + lab, 1u);
+}
+
+// current scan: points inside the crop take their voxel's label, the others keep their own prediction
+// (voxel_voting.py:243-244: current_pred_result_orin[mask] = pred_result_new)
+__global__ void __launch_bounds__(kVoteThreads)
+stream_point_labels_kernel(const __grid_constant__ StreamScans S, int cur, int64_t rs, const __grid_constant__ CropBox box,
+                           float mx, float my, float mz, float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z,
+                           const uint8_t* __restrict__ vlabels, int64_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= S.begin[cur + 1] - S.begin[cur]) return;
+  float q[3];
+  int64_t r = S.lab[cur][i];
+  if (stream_point(S, cur, i, rs, box, q)) {
+    int64_t lin;
+    r = quant_voxel(q, mx, my, mz, dx, dy, dz, X, Y, Z, &lin) ? vlabels[lin] : 0;
+  }
+  out[i] = r;
+}
+
 int64_t ws_bytes(int64_t P, int64_t V, int32_t C) {
   return use_packed(P, C) ? V * 8 : V * static_cast<int64_t>(C) * 4;
 }
@@ -287,6 +358,44 @@ int smos_vote_fused(const float* points, int64_t P, int64_t row_stride, const ui
     point_labels_fused_kernel<<<smos_ceil_div(Pc, kVoteThreads), kVoteThreads, 0, st>>>(
         points + (P - Pc) * row_stride, Pc, row_stride, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, voxel_labels_u8,
         point_labels);
+  return smos_launch_status();
+}
+
+int smos_vote_stream(const smos_vote_stream_scan* scans_host, int32_t n_scans, int32_t current, int64_t row_stride,
+                     const float* crop_lo_host, const float* crop_hi_host, float min_x, float min_y, float min_z,
+                     float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z, int32_t num_classes,
+                     void* workspace, uint8_t* voxel_labels_u8, int64_t* point_labels, void* stream) {
+  if (!scans_host || n_scans <= 0 || n_scans > kMaxStreamScans || current < 0 || current >= n_scans || row_stride < 3 ||
+      X <= 0 || Y <= 0 || Z <= 0 || num_classes <= 0 || num_classes > kMaxClasses || !crop_lo_host || !crop_hi_host)
+    return SMOS_EINVAL;
+  if (!workspace || !voxel_labels_u8 || !point_labels) return SMOS_EINVAL;
+  StreamScans S;
+  S.n = n_scans;
+  int64_t total = 0;
+  for (int32_t j = 0; j < n_scans; ++j) {
+    const smos_vote_stream_scan& d = scans_host[j];
+    if (d.n < 0 || (d.n > 0 && (!d.points || !d.labels))) return SMOS_EINVAL;
+    S.pts[j] = d.points; S.lab[j] = d.labels; S.begin[j] = total; S.transform[j] = d.transform;
+    for (int k = 0; k < 12; ++k) S.m[j][k] = d.pose_diff[k];
+    total += d.n;
+  }
+  S.begin[n_scans] = total;
+  CropBox box;
+  for (int k = 0; k < 3; ++k) { box.lo[k] = crop_lo_host[k]; box.hi[k] = crop_hi_host[k]; }
+  const int64_t V = static_cast<int64_t>(X) * Y * Z;
+  const int packed = use_packed(total, num_classes) ? 1 : 0;
+  cudaStream_t st = smos_stream(stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws_bytes(total, V, num_classes)), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (total > 0)
+    vote_stream_kernel<<<smos_ceil_div(total, kVoteThreads), kVoteThreads, 0, st>>>(
+        S, row_stride, box, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, num_classes, packed, workspace);
+  vote_argmax_kernel<uint8_t><<<smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st>>>(workspace, V, num_classes,
+                                                                                       packed, voxel_labels_u8);
+  const int64_t nc = scans_host[current].n;
+  if (nc > 0)
+    stream_point_labels_kernel<<<smos_ceil_div(nc, kVoteThreads), kVoteThreads, 0, st>>>(
+        S, current, row_stride, box, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, voxel_labels_u8, point_labels);
   return smos_launch_status();
 }
 

@@ -380,6 +380,48 @@ def vote_fused(points, labels_u8, num_current, mins, deltas, dims, num_classes=3
     return vl, pl
 
 
+def vote_stream(scans, current, crop_lo, crop_hi, mins, deltas, dims, num_classes=3):
+    """One frame of streaming long-term voting over scans resident in HBM (smos_vote_stream).
+    `scans`: list of (points (n, >=3) f32 CUDA, labels (n,) u8 CUDA, pose_diff 4x4 float64 array or None);
+    `current`: index of the current scan (not transformed). crop_lo/crop_hi: float32 thresholds incl. eps.
+    Returns (voxel_labels uint8 (X,Y,Z), point_labels int64 (n_current,))."""
+    import numpy as np
+    lib = _lib.load()
+    descs = (_lib.VoteStreamScan * len(scans))()
+    dev = scans[0][0].device
+    total, rs = 0, None
+    for d, (pts, lab, pose) in zip(descs, scans):
+        _need_cuda(pts, "points")
+        _need_f32(pts, "points")
+        assert lab.dtype == torch.uint8 and lab.is_contiguous() and lab.is_cuda
+        assert pts.dim() == 2 and pts.size(1) >= 3 and pts.stride(1) == 1
+        r = pts.stride(0) if pts.size(0) > 1 else pts.size(1)
+        rs = r if rs is None else rs
+        assert r == rs, "all scans must share a row stride"
+        d.points, d.labels, d.n = pts.data_ptr(), lab.data_ptr(), int(pts.size(0))
+        if pose is None:
+            d.transform = 0
+        else:
+            m = np.asarray(pose, dtype=np.float64).reshape(4, 4)
+            d.transform = 1
+            for k in range(12):
+                d.pose_diff[k] = float(m[k // 4, k % 4])
+        total += int(pts.size(0))
+    X, Y, Z = (int(v) for v in dims)
+    ws = _vote_ws(total, X, Y, Z, int(num_classes), dev)
+    vl = torch.empty((X, Y, Z), dtype=torch.uint8, device=dev)
+    pl = torch.empty((int(scans[current][0].size(0)),), dtype=torch.int64, device=dev)
+    lo = (ctypes.c_float * 3)(*[float(v) for v in crop_lo])
+    hi = (ctypes.c_float * 3)(*[float(v) for v in crop_hi])
+    with torch.cuda.device(dev):
+        rc = lib.smos_vote_stream(descs, len(scans), int(current), int(rs), lo, hi, float(mins[0]), float(mins[1]),
+                                  float(mins[2]), float(deltas[0]), float(deltas[1]), float(deltas[2]), X, Y, Z,
+                                  int(num_classes), _ptr(ws), _ptr(vl), _ptr(pl), _stream())
+    _lib.check(rc, "smos_vote_stream")
+    _count(3)
+    return vl, pl
+
+
 def instance_vote(points, pred, box_lo, box_hi):
     """points (P, >=3) f32, pred (P,) int64, box_lo/box_hi (K, 3) f32 -> sums (K, 2) int64
     [static_sum, dynamic_sum] with dynamic points weighted 2."""

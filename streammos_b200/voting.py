@@ -59,3 +59,46 @@ def instance_vote_counts(local_map_points, local_map_prediction, cluster_corners
     stat, dyn = sums[:, 0], sums[:, 1]
     label = torch.where(dyn > stat, torch.full_like(stat, 2), torch.full_like(stat, 1))
     return stat, dyn, label
+
+
+class StreamingVoter:
+    """GPU-resident long-term memory for one scan stream: the loop body of voxel_voting.py:176-244 without the
+    per-frame reload of 8 scans + predictions, the numpy pose transform, the crop and the .cuda() round trip.
+
+    push(points (n, 4) f32 CUDA, pred (n,) uint8 CUDA, pose 4x4 float64) appends a scan; vote() returns the
+    refined labels of the newest scan: history scans are pose-aligned into its frame (utils.Trans with
+    pose_diff = inv(pose_cur) . pose_hist), history and current are cropped to fov +/- eps (transforms.Crop),
+    quantised, voted per voxel, and points inside the crop take their voxel's label."""
+
+    def __init__(self, frames_num_max=8, fov=((-50, -50, -4), (50, 50, 2)), eps=1e-4, size=(512, 512, 30),
+                 num_classes=3):
+        import numpy as np
+        self.np = np
+        self.frames_num_max = frames_num_max
+        self.size = tuple(size)
+        self.num_classes = num_classes
+        # thresholds as the float32 tensor comparison of transforms.py:155-157 sees them
+        self.crop_lo = [float(np.float32(fov[0][i] + eps)) for i in range(3)]
+        self.crop_hi = [float(np.float32(fov[1][i] - eps)) for i in range(3)]
+        self.mins = [float(fov[0][i]) for i in range(3)]
+        self.deltas = [float(np.float32((fov[1][i] - fov[0][i]) / size[i])) for i in range(3)]
+        self.ring = []  # (points, labels, pose) of the last frames_num_max + 1 scans, newest last
+
+    def push(self, points, pred, pose):
+        self.ring.append((points, pred, self.np.asarray(pose, dtype=self.np.float64)))
+        if len(self.ring) > self.frames_num_max + 1:
+            self.ring.pop(0)
+
+    def vote(self, current=-1):
+        """Refined labels of ring entry `current` (default: the newest scan) voted against every other resident
+        scan. The steady-state branch of the reference (voxel_voting.py:177-194, id >= frames_num_max) is
+        push() + vote(); its warm-up branch (:195-214: the first frames_num_max scans vote against each other)
+        is frames_num_max push() calls followed by vote(current=i) for i in range(frames_num_max)."""
+        np = self.np
+        current = current % len(self.ring)
+        cur_pts, cur_pred, cur_pose = self.ring[current]
+        inv = np.linalg.inv(cur_pose)  # voxel_voting.py:179
+        scans = [(p, l, inv.dot(pose) if j != current else None)    # :187-188 pose_diff
+                 for j, (p, l, pose) in enumerate(self.ring)]
+        return ops.vote_stream(scans, current, self.crop_lo, self.crop_hi, self.mins, self.deltas, self.size,
+                               self.num_classes)

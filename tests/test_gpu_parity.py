@@ -424,6 +424,114 @@ def test_instance_vote_many_boxes_vs_oracle():
 
 
 # ------------------------------------------------------------------------------------------------
+# Streaming long-term memory: pose alignment + crop + quantise + vote on resident scans
+# ------------------------------------------------------------------------------------------------
+def _fov_thresholds(size):
+    fov, eps = ((-50, -50, -4), (50, 50, 2)), 1e-4
+    lo = [np.float32(fov[0][i] + eps) for i in range(3)]
+    hi = [np.float32(fov[1][i] - eps) for i in range(3)]
+    mins = [float(fov[0][i]) for i in range(3)]
+    deltas = [np.float32((fov[1][i] - fov[0][i]) / size[i]) for i in range(3)]
+    return lo, hi, mins, deltas
+
+
+def test_stream_vote_golden(golden):
+    """The reference's own loop body (Trans, Crop, Quantize, voting, write-back) on a 9-scan synthetic drive."""
+    from streammos_b200 import ops, voting
+    g = golden("stream_vote_a")
+    size = tuple(int(s) for s in g["size"])
+    lo, hi, mins, deltas = _fov_thresholds(size)
+    scans = [(t(g["scans"][j]), t(g["preds"][j]), g["pose_diffs"][j]) for j in range(8)]
+    scans.append((t(g["scans"][8]), t(g["preds"][8]), None))
+    vl, pl = ops.vote_stream(scans, 8, lo, hi, mins, deltas, size, 3)
+    assert np.array_equal(vl.cpu().numpy(), g["voxel_labels"])
+    assert np.array_equal(pl.cpu().numpy(), g["point_labels"])
+    # the same frame through the ring-buffer object, from absolute poses (inv(pose_cur) . pose_hist on the host)
+    sv = voting.StreamingVoter(frames_num_max=8, size=size)
+    for j in list(range(7, -1, -1)) + [8]:                 # oldest first; fixture stores history newest first
+        sv.push(t(g["scans"][j]), t(g["preds"][j]), g["poses"][j])
+    vl2, pl2 = sv.vote()
+    assert np.array_equal(vl2.cpu().numpy(), g["voxel_labels"])
+    assert np.array_equal(pl2.cpu().numpy(), g["point_labels"])
+
+
+def _drive(rng, n_scans, n):
+    """Synthetic drive: ring-shaped scans, a turning ego trajectory, random predictions."""
+    scans, preds, poses = [], [], []
+    for k in range(n_scans):
+        r = np.abs(rng.standard_normal(n)) * 20.0
+        th = rng.uniform(0, 2 * np.pi, n)
+        pts = np.stack([r * np.cos(th), r * np.sin(th), rng.normal(-1.5, 0.8, n), rng.uniform(0, 1, n)],
+                       -1).astype(np.float32)
+        yaw = 0.03 * k
+        c, s_ = np.cos(yaw), np.sin(yaw)
+        poses.append(np.array([[c, -s_, 0.001 * k, 1.1 * k], [s_, c, -0.002 * k, 0.02 * k * k],
+                               [-0.001 * k, 0.002 * k, 1.0, 0.03 * k], [0, 0, 0, 1]], np.float64))
+        scans.append(pts)
+        preds.append(rng.integers(0, 3, n).astype(np.uint8))
+    return scans, preds, poses
+
+
+def test_stream_vote_sequence_config_size_vs_oracle():
+    """A 12-scan stream at the config size (120k points, 512x512x30): the warm-up branch for the first 8 scans
+    (each votes against the other 7, voxel_voting.py:195-214) and the sliding window afterwards (:177-194)."""
+    from streammos_b200 import voting
+    rng = np.random.default_rng(2024)
+    n, size, hist = 120000, (512, 512, 30), 8
+    lo, hi, mins, deltas = _fov_thresholds(size)
+    scans, preds, poses = _drive(rng, 12, n)
+    sv = voting.StreamingVoter(frames_num_max=hist, size=size)
+
+    def oracle_frame(ids, cur):
+        inv = np.linalg.inv(poses[cur])
+        sc = [(scans[j], preds[j], inv.dot(poses[j]) if j != cur else None) for j in ids]
+        return O.vote_stream(sc, ids.index(cur), lo, hi, mins, deltas, size, 3)
+
+    for k in range(hist):
+        sv.push(t(scans[k]), t(preds[k]), poses[k])
+    changed = 0
+    for k in (0, 3, 7):                                       # warm-up branch
+        vl, pl = sv.vote(current=k)
+        vl_ref, pl_ref = oracle_frame(list(range(hist)), k)
+        assert np.array_equal(vl.cpu().numpy(), vl_ref) and np.array_equal(pl.cpu().numpy(), pl_ref)
+    for k in range(hist, 12):                                 # steady state
+        sv.push(t(scans[k]), t(preds[k]), poses[k])
+        vl, pl = sv.vote()
+        vl_ref, pl_ref = oracle_frame(list(range(k - hist, k + 1)), k)
+        assert np.array_equal(vl.cpu().numpy(), vl_ref) and np.array_equal(pl.cpu().numpy(), pl_ref)
+        changed += int((pl_ref != preds[k]).sum())
+        outside = ~((scans[k][:, :3] > np.array(lo)) & (scans[k][:, :3] < np.array(hi))).all(1)
+        assert outside.any() and np.array_equal(pl_ref[outside], preds[k][outside].astype(np.int64))
+    assert changed > 0 and len(sv.ring) == hist + 1
+
+
+def test_stream_vote_edge_cases():
+    from streammos_b200 import ops
+    size = (8, 8, 4)
+    lo, hi, mins, deltas = _fov_thresholds(size)
+    ident = np.eye(4)
+    shift = np.eye(4); shift[0, 3] = 200.0                    # history pushed out of the crop box entirely
+    cur = np.array([[0.5, 0.5, 0.0, 0], [49.99995, 0, 0, 0], [60, 0, 0, 0], [-49.9998, -49.9998, -3.9998, 0]], np.float32)
+    cur_l = np.array([1, 2, 2, 2], np.uint8)
+    h = np.array([[0.6, 0.6, 0.1, 0], [0.7, 0.4, 0.2, 0], [0.55, 0.45, 0.3, 0]], np.float32)
+    h_l = np.array([2, 2, 0], np.uint8)
+    empty = (torch.empty(0, 4, device=dev()), torch.empty(0, dtype=torch.uint8, device=dev()), ident)
+    for scans_np in ([(h, h_l, ident), (cur, cur_l, None)], [(h, h_l, shift), (cur, cur_l, None)]):
+        scans = [(t(a), t(b), m) for a, b, m in scans_np]
+        for with_empty in (False, True):
+            sc = ([empty] + scans) if with_empty else scans
+            ci = len(sc) - 1
+            vl, pl = ops.vote_stream(sc, ci, lo, hi, mins, deltas, size, 3)
+            vl_ref, pl_ref = O.vote_stream(scans_np, 1, lo, hi, mins, deltas, size, 3)
+            assert np.array_equal(vl.cpu().numpy(), vl_ref) and np.array_equal(pl.cpu().numpy(), pl_ref)
+    # first case: voxel of point 0 holds labels {1, 2, 2, 0} -> 2; points on/outside the open box keep their label
+    _, pl = ops.vote_stream([(t(h), t(h_l), ident), (t(cur), t(cur_l), None)], 1, lo, hi, mins, deltas, size, 3)
+    assert pl.tolist()[0] == 2 and pl.tolist()[2] == 2
+    with pytest.raises(Exception):
+        ops.vote_stream([(t(cur).cpu(), t(cur_l), None)], 0, lo, hi, mins, deltas, size, 3)
+
+
+# ------------------------------------------------------------------------------------------------
 # Whole hot path: streaming harness on the GPU vs the CPU restatement of the same sequence
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("point_major", [True, False])

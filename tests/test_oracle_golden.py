@@ -94,3 +94,31 @@ def test_instance_vote_bit_exact(golden):
     label = np.where(sums[:, 1] > sums[:, 0], 2, 1)
     assert np.array_equal(label, g["label"])
     assert set(label.tolist()) == {1, 2}  # the fixture exercises both outcomes
+
+
+def _stream_vote_setup(g):
+    """(scans, crop_lo, crop_hi, mins, deltas, size) of the fixture, thresholds as StreamingVoter derives them."""
+    size = tuple(int(s) for s in g["size"])
+    fov, eps = ((-50, -50, -4), (50, 50, 2)), 1e-4
+    lo = [np.float32(fov[0][i] + eps) for i in range(3)]
+    hi = [np.float32(fov[1][i] - eps) for i in range(3)]
+    mins = [float(fov[0][i]) for i in range(3)]
+    deltas = [np.float32((fov[1][i] - fov[0][i]) / size[i]) for i in range(3)]
+    n_hist = len(g["pose_diffs"])
+    scans = [(g["scans"][j], g["preds"][j], g["pose_diffs"][j]) for j in range(n_hist)]
+    scans.append((g["scans"][n_hist], g["preds"][n_hist], None))
+    return scans, lo, hi, mins, deltas, size
+
+
+def test_stream_vote_bit_exact(golden):
+    """One frame of the voxel_voting.py loop (Trans + Crop + Quantize + vote + write-back), reference outputs."""
+    g = golden("stream_vote_a")
+    scans, lo, hi, mins, deltas, size = _stream_vote_setup(g)
+    vl, pl, tout = O.vote_stream(scans, len(scans) - 1, lo, hi, mins, deltas, size, 3, want_transformed=True)
+    n = g["scans"].shape[1]
+    # float64 pose matmul stored as float32 (datasets/utils.py:116-126): bit-exact with numpy's dgemm
+    assert np.array_equal(tout[: 8 * n].reshape(8, n, 3), g["transformed"][..., :3])
+    assert np.array_equal(vl, g["voxel_labels"])
+    assert np.array_equal(pl, g["point_labels"])
+    assert 0 < int(g["n_cropped"]) < n                      # some current points lie outside the crop ...
+    assert (pl != g["preds"][-1]).any()                     # ... and voting changes some labels inside it

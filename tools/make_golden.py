@@ -252,6 +252,77 @@ def gen_instance(ref, rng):
     return ["instance_a"]
 
 
+def gen_stream_vote(ref, rng):
+    """One frame of the voxel_voting.py loop body (lines 176-244, `id >= frames_num_max` branch) with the
+    reference's own Trans, Crop, Quantize, determine_voxel_labels and get_point_labels_from_voxel_labels."""
+    g = {"torch": torch, "np": np}
+    extract_functions(os.path.join(ref, "voxel_voting.py"),
+                      ["get_point_labels_from_voxel_labels", "determine_voxel_labels", "Quantize"], g)
+    gu = {"np": np}
+    extract_functions(os.path.join(ref, "datasets", "utils.py"), ["Trans"], gu)
+    tr = load_by_path("ref_transforms", os.path.join(ref, "utils", "transforms.py"))
+    fov_xyz = [[-50, -50, -4], [50, 50, 2]]                       # voxel_voting.py:138
+    crop_to_fov = tr.Crop(dims=(0, 1, 2), fov=fov_xyz)            # :139
+    frames_num_max = 8                                            # :140
+    size = (64, 64, 12)
+    n = 6000
+    # synthetic sequence: the ego vehicle drives and turns; points straddle the crop box and voxel borders
+    poses, scans, preds = [], [], []
+    for t in range(frames_num_max + 1):
+        yaw = 0.02 * t
+        c, s_ = np.cos(yaw), np.sin(yaw)
+        pose = np.array([[c, -s_, 0.0005 * t, 0.9 * t], [s_, c, -0.0003 * t, 0.05 * t * t],
+                         [-0.0005 * t, 0.0003 * t, 1.0, 0.01 * t], [0, 0, 0, 1]], dtype=np.float64)
+        poses.append(pose)
+        pts = np.stack([rng.uniform(-58, 58, n), rng.uniform(-58, 58, n), rng.uniform(-5, 3, n),
+                        rng.uniform(0, 1, n)], -1).astype(np.float32)
+        pts[: n // 2, :3] *= np.array([0.25, 0.25, 0.6], np.float32)   # dense near the sensor: shared voxels
+        pts[:20, 0] = np.float32(50 - 1e-4)                            # on the open crop boundary
+        pts[20:40, 1] = np.float32(-50 + 1e-4)
+        scans.append(pts)
+        preds.append(rng.integers(0, 3, n).astype(np.uint32))
+    idx = frames_num_max
+    current_points, current_pred_result = scans[idx], preds[idx]
+    current_pose_inv = np.linalg.inv(poses[idx])                       # :179
+    history_points_list, history_pred_result_list, pose_diffs, transformed = [], [], [], []
+    for history_id in np.arange(idx - 1, idx - frames_num_max - 1, -1):   # :182
+        pose_diff = current_pose_inv.dot(poses[history_id])            # :187
+        hp = gu["Trans"](scans[history_id], pose_diff)                  # :188
+        pose_diffs.append(pose_diff)
+        transformed.append(hp)
+        history_points_list.append(hp)
+        history_pred_result_list.append(preds[history_id])
+    history_points = np.concatenate(history_points_list, axis=0)       # :193
+    history_pred_result = np.concatenate(history_pred_result_list, axis=0)
+    current_pred_result_orin = current_pred_result.copy()              # :216
+    history_points_t = torch.tensor(history_points)                     # :218 (CPU here)
+    history_pred_t = torch.tensor(history_pred_result.astype("uint8"))
+    current_points_t = torch.tensor(current_points)
+    current_pred_t = torch.tensor(current_pred_result.astype("uint8"))
+    history_points_t, history_pred_t, _ = crop_to_fov(history_points_t, history_pred_t)    # :225
+    current_points_t, current_pred_t, mask = crop_to_fov(current_points_t, current_pred_t)  # :226
+    history_points_num = len(history_points_t)
+    local_map_points = torch.cat((history_points_t, current_points_t), dim=0)              # :229
+    local_map_prediction = torch.cat((history_pred_t, current_pred_t), dim=0)
+    pcds_coord_voxel = g["Quantize"](local_map_points, range_x=(-50.0, 50.0), range_y=(-50.0, 50.0),
+                                     range_z=(-4.0, 2.0), size=size)                        # :234
+    pcds_coord_cur = pcds_coord_voxel[history_points_num:]
+    voxel_label = g["determine_voxel_labels"](pcds_coord_voxel.to(torch.int64), local_map_prediction.to(torch.int64),
+                                              size)                                          # :240
+    pred_result_new = g["get_point_labels_from_voxel_labels"](pcds_coord_cur.to(torch.int64), voxel_label, size)
+    current_pred_result_orin[mask.numpy()] = pred_result_new.numpy()                        # :244
+    # history order in the fixture: oldest-independent — stored in the order the script visits them
+    hist_ids = list(np.arange(idx - 1, idx - frames_num_max - 1, -1))
+    np.savez_compressed(os.path.join(GOLD, "stream_vote_a.npz"),
+                        scans=np.stack([scans[i] for i in hist_ids] + [scans[idx]]),
+                        preds=np.stack([preds[i] for i in hist_ids] + [preds[idx]]).astype(np.uint8),
+                        pose_diffs=np.stack(pose_diffs), transformed=np.stack(transformed),
+                        poses=np.stack([poses[i] for i in hist_ids] + [poses[idx]]),
+                        size=np.array(size), voxel_labels=voxel_label.numpy().astype(np.uint8),
+                        point_labels=current_pred_result_orin.astype(np.int64), n_cropped=int(mask.sum()))
+    return ["stream_vote_a"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -266,6 +337,7 @@ def main():
     made += gen_msda(a.ref, rng)
     made += gen_voting(a.ref, rng)
     made += gen_instance(a.ref, rng)
+    made += gen_stream_vote(a.ref, np.random.default_rng(77))
     for m in made:
         p = os.path.join(GOLD, m + ".npz")
         print("%-28s %8.1f KB" % (m, os.path.getsize(p) / 1024))
