@@ -44,6 +44,11 @@ def parse_args():
     ap.add_argument("--no-variants", action="store_true", help="skip the extra layout/API variant measurement")
     ap.add_argument("--in-flight", type=int, default=2, help="scans in flight per stream (projection streams)")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-operator table to stderr")
+    ap.add_argument("--no-branches", action="store_true",
+                    help="capture each graph as one chain instead of parallel branches for independent operators")
+    ap.add_argument("--no-ordered-gathers", action="store_true",
+                    help="BEV gathers visit the points in scan order instead of the pooling plan's cell order")
+    ap.add_argument("--ordered-rv", action="store_true", help="range-view gathers in cell order too")
     return ap.parse_args()
 
 
@@ -191,8 +196,12 @@ def workload_config(args, graph, world):
             "point_feature_layout": "channel-major" if args.channel_major else "point-major (channels_last strides)",
             "cnn_grid_layout": "channels_last" if args.grids_channels_last else "NCHW (reference default)",
             "pipeline": "3 graphs per scan (projection / temporal fusion / voting), %d scans in flight on %d CUDA streams; "
-                        "cross-scan dependencies (short-term memory, voting ring) enforced with events"
-                        % (args.in_flight, args.in_flight + 1),
+                        "cross-scan dependencies (short-term memory, voting ring) enforced with events; %s"
+                        % (args.in_flight, args.in_flight + 1,
+                           "chains only" if args.no_branches else "independent operators of a scan are parallel graph "
+                           "branches (pool #1 | half-scale chain | quarter-scale chain | gather #5; voxel | instance votes)"),
+            "gather_order": "scan order" if args.no_ordered_gathers else
+                            ("cell order of the shared pooling plan (BEV%s)" % (" + RV" if args.ordered_rv else "")),
             "l2": "no explicit flush: %d distinct scans cycled, ~100 MB inputs and ~700 MB touched per step (>126 MB L2)" % N_SCANS}
 
 
@@ -208,7 +217,8 @@ def run_b200(args, world, rank, local):
     use_graph = not args.no_graph
     hot = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
                          vote_api=args.vote_api, overlap_voting=False,
-                         grids_channels_last=args.grids_channels_last)
+                         grids_channels_last=args.grids_channels_last, branches=not args.no_branches,
+                         ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv)
     host = [stream.make_host_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
     devb = [h.to(dev) for h in host]
     torch.cuda.synchronize()
@@ -335,7 +345,8 @@ def run_b200(args, world, rank, local):
                 not (args.grids_channels_last and args.vote_api == "fused"):
             del pipe
             hot2 = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
-                                  vote_api="fused", grids_channels_last=True)
+                                  vote_api="fused", grids_channels_last=True, branches=not args.no_branches,
+                                  ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv)
             pipe2 = pipeline.ScanPipeline(hot2, devb, use_graphs=True, scans_in_flight=args.in_flight)
             vsteps = min(args.steps, 500)
             for i in range(20):

@@ -108,6 +108,7 @@ int smos_voxel_maxpool_forward(const float* pcds_feat, int64_t B, int64_t C, int
 #define SMOS_POOL_STAGE_COMBINE 2
 #define SMOS_POOL_STAGE_WRITE 4
 #define SMOS_POOL_STAGE_ALL 7
+#define SMOS_POOL_STAGE_NO_REDUCE 8 /* with REDUCE on a channel-major input: run the permute only (profiling) */
 int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t C, int64_t N,
                                       int64_t f_sb, int64_t f_sc, int64_t f_sn,
                                       int32_t H, int32_t W, const void* plan, void* workspace,
@@ -143,6 +144,20 @@ int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_
                                  float scale_h, float scale_w,
                                  float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
                                  void* stream);
+
+/* Same result, points visited in the cell order of a pooling plan built from the SAME coordinate array
+ * (B, N as here; any grid plan_H x plan_W and scale): `plan` lists the points grouped by cell, out-of-grid
+ * points at the tail, so a warp's taps share one or two cache lines per channel plane instead of one line
+ * per point (a BEV arc in scan order crosses image rows at every point). Used when `out` is point-major
+ * (o_sc == 1); otherwise identical to smos_bilinear_gather_forward. The reference model pools and gathers
+ * with the same coordinates (networks/multi_view_encoder.py:395-417), so the plan exists anyway. */
+int smos_bilinear_gather_forward_ordered(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W,
+                                         int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
+                                         const float* coord, int64_t N,
+                                         int64_t co_sb, int64_t co_sn, int64_t co_sd,
+                                         float scale_h, float scale_w,
+                                         float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
+                                         const void* plan, int32_t plan_H, int32_t plan_W, void* stream);
 
 /* grad_grid (B, C, H, W) NCHW-contiguous must be ZERO-FILLED by the caller;
  * contributions are accumulated with fp32 atomics (grid_sampler backward). */
@@ -254,6 +269,12 @@ int smos_vote_stream(const smos_vote_stream_scan* scans_host, int32_t n_scans, i
                      float min_x, float min_y, float min_z, float dx, float dy, float dz,
                      int32_t X, int32_t Y, int32_t Z, int32_t num_classes,
                      void* workspace, uint8_t* voxel_labels_u8, int64_t* point_labels, void* stream);
+
+/* Long-term memory ring insert (the bookkeeping around voxel_voting.py:176-194 once the scans stay in HBM):
+ * the scan held in the "current" slot moves to its history slot (skipped when hist_* are NULL) and the new scan
+ * takes the current slot. points (n, row_floats) f32, pred (n,) u8; slots have the same shapes. One kernel. */
+int smos_memory_push(const float* points, const uint8_t* pred, int64_t n, int64_t row_floats,
+                     float* cur_points, uint8_t* cur_pred, float* hist_points, uint8_t* hist_pred, void* stream);
 
 /* Per-instance vote count (voxel_instance_voting.py:169-187, in_hull :62-76):
  * for each of K axis-aligned boxes count local-map points inside (inclusive

@@ -41,6 +41,8 @@ SIGNATURES = {
                                                    _vp, _vp, _i64, _i64, _i64, _vp]),
     "smos_bilinear_gather_forward": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _i64,
                                                     _i64, _i64, _i64, _f32, _f32, _vp, _i64, _i64, _i64, _vp]),
+    "smos_bilinear_gather_forward_ordered": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _i64,
+                                                    _i64, _i64, _i64, _f32, _f32, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp]),
     "smos_bilinear_gather_backward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                                      _f32, _f32, _i32, _i32, _vp, _vp]),
     "smos_ms_deform_attn_forward": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
@@ -56,6 +58,7 @@ SIGNATURES = {
     "smos_vote_stream": (ctypes.c_int, [ctypes.POINTER(VoteStreamScan), _i32, _i32, _i64, ctypes.POINTER(_f32),
                                         ctypes.POINTER(_f32), _f32, _f32, _f32, _f32, _f32, _f32, _i32, _i32, _i32, _i32,
                                         _vp, _vp, _vp, _vp]),
+    "smos_memory_push": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "smos_instance_vote": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
 }
 

@@ -9,11 +9,11 @@ from . import ops
 
 class _BilinearSampleFunction(Function):
     @staticmethod
-    def forward(ctx, grid_feat, grid_coord, scale_rate, point_major_out):
+    def forward(ctx, grid_feat, grid_coord, scale_rate, point_major_out, order=None):
         ctx.scale_rate = scale_rate
         ctx.hw = (grid_feat.shape[2], grid_feat.shape[3])
         ctx.save_for_backward(grid_coord)
-        return ops.bilinear_gather_forward(grid_feat, grid_coord, scale_rate, point_major_out)
+        return ops.bilinear_gather_forward(grid_feat, grid_coord, scale_rate, point_major_out, order)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -21,7 +21,7 @@ class _BilinearSampleFunction(Function):
         grad_grid = None
         if ctx.needs_input_grad[0]:
             grad_grid = ops.bilinear_gather_backward(grad_out, grid_coord, ctx.scale_rate, ctx.hw[0], ctx.hw[1])
-        return grad_grid, None, None, None
+        return grad_grid, None, None, None, None
 
 
 class BilinearSample(nn.Module):
@@ -36,6 +36,8 @@ class BilinearSample(nn.Module):
         super(BilinearSample, self).__init__()
         self.scale_rate = scale_rate
 
-    def forward(self, grid_feat, grid_coord):
+    def forward(self, grid_feat, grid_coord, order=None):
+        """Reference signature plus an optional `order` (an ops.PoolPlan of the same coordinates, e.g. the one the
+        neighbouring VoxelMaxPool uses): the points are then visited in cell order — same values, faster."""
         return _BilinearSampleFunction.apply(grid_feat.float(), grid_coord, tuple(self.scale_rate),
-                                             bool(self.point_major_out))
+                                             bool(self.point_major_out), order)

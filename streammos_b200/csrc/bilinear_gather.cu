@@ -61,13 +61,28 @@ struct TapsS {
   int32_t o_nw, o_ne, o_sw, o_se;  // clamped (always valid) pixel offsets  y * W + x
   float w_nw, w_ne, w_sw, w_se;    // bilinear weights, already zeroed for out-of-image taps? no: see in_*
   uint32_t in_mask;                // bit0 nw, bit1 ne, bit2 sw, bit3 se
+  int32_t n, b;                    // the point this slot samples for (n < 0: no point)
 };
 
+// ORDERED: slot i of the CTA serves entry p0 + i of a pooling plan's `sorted` list (points grouped by grid cell,
+// out-of-grid points at the tail) instead of point n0 + i. Consecutive slots then sample the same or adjacent
+// cells: in scan order a BEV arc crosses a different image row at almost every point (one 128-byte line per
+// lane and tap), in cell order a warp's taps share one or two lines per channel plane.
+template <bool ORDERED>
 __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict__ coord, int32_t b, int32_t n0,
                                          int32_t N, int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
-                                         int32_t H, int32_t W) {
+                                         int32_t H, int32_t W, const int2* __restrict__ order, int32_t order_hw,
+                                         int64_t order_len) {
   if (threadIdx.x < kGatherPts) {
-    const int32_t n = min(n0 + static_cast<int32_t>(threadIdx.x), N - 1);
+    int32_t n = min(n0 + static_cast<int32_t>(threadIdx.x), N - 1);
+    bool live = n0 + static_cast<int32_t>(threadIdx.x) < N;
+    if (ORDERED) {
+      const int64_t p = static_cast<int64_t>(blockIdx.x) * kGatherPts + threadIdx.x;
+      live = p < order_len;
+      const int2 e = __ldg(order + (live ? p : order_len - 1));
+      n = static_cast<int32_t>(static_cast<uint32_t>(e.x) & 0x7fffffffu);  // bit 31: the plan's run-merge mark
+      b = e.y >= 0 ? e.y / order_hw : -1 - e.y;                            // out-of-grid entries carry -1 - b
+    }
     const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
     const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
     const int32_t xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
@@ -76,6 +91,8 @@ __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict_
     r.o_nw = ya * W + xa; r.o_ne = ya * W + xb; r.o_sw = yb * W + xa; r.o_se = yb * W + xb;
     r.w_nw = t.w_nw; r.w_ne = t.w_ne; r.w_sw = t.w_sw; r.w_se = t.w_se;
     r.in_mask = (t.in_nw ? 1u : 0u) | (t.in_ne ? 2u : 0u) | (t.in_sw ? 4u : 0u) | (t.in_se ? 8u : 0u);
+    r.n = live ? n : -1;
+    r.b = b;
     s_taps[threadIdx.x] = r;
   }
   __syncthreads();
@@ -87,21 +104,22 @@ __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict_
 // 4*kCPT tap loads of a step are UNCONDITIONAL (out-of-image taps read a clamped, valid pixel and are
 // zeroed by a select afterwards): predicated loads get serialised through one temporary register by
 // ptxas. For point-major outputs the kCPT results leave as one full 32-byte sector per thread.
-template <bool DENSE, bool ROWS_OUT>
+template <bool DENSE, bool ROWS_OUT, bool ORDERED>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                              int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
                              const float* __restrict__ coord, int32_t N,
                              int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
-                             float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn) {
+                             float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
+                             const int2* __restrict__ order, int32_t order_hw, int64_t order_len) {
   __shared__ TapsS s_taps[kGatherPts];
   extern __shared__ float s_out[];  // ROWS_OUT: [kGatherPts][C + 1]
-  const int32_t b = blockIdx.z;
   const int32_t n0 = blockIdx.x * kGatherPts;
-  cta_taps(s_taps, coord, b, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W);
+  cta_taps<ORDERED>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int32_t n = n0 + lane;
   const TapsS t = s_taps[lane];
+  const int32_t b = t.b;
+  const int32_t n = t.n;  // < 0: slot without a point
   // DENSE: planes are contiguous H x W images (gr_sh == W, gr_sw == 1): the shared offsets y*W+x are
   // used as they are (32-bit); otherwise they are re-expressed in the tensor's strides
   int64_t q_nw = t.o_nw, q_ne = t.o_ne, q_sw = t.o_sw, q_se = t.o_se;
@@ -143,7 +161,7 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
 #pragma unroll
       for (int k = 0; k < kCPT; ++k)
         if (k < nch) s_out[lane * (C + 1) + c0 + k] = acc[k];
-    } else if (n < N) {
+    } else if (n >= 0) {
       float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(c0) * o_sc;
       if (vec_ok && nch == kCPT) {
         *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -157,9 +175,10 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
   }
   if (ROWS_OUT) {
     __syncthreads();
-    const int32_t np = min(kGatherPts, N - n0);
-    for (int32_t p = wid; p < np; p += kGatherThreads / 32) {
-      float* o = out + b * o_sb + static_cast<int64_t>(n0 + p) * o_sn;
+    for (int32_t p = wid; p < kGatherPts; p += kGatherThreads / 32) {
+      const int32_t pn = s_taps[p].n;
+      if (pn < 0) continue;
+      float* o = out + s_taps[p].b * o_sb + static_cast<int64_t>(pn) * o_sn;
       for (int32_t c = lane; c < C; c += 32) o[c] = s_out[p * (C + 1) + c];
     }
   }
@@ -167,27 +186,27 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
 
 // Channels-last grid (gr_sc == 1, C % 4 == 0): lanes run over channel quads, every tap is a
 // contiguous 16-byte load and a point's taps are four contiguous C*4-byte rows. CTA = 32 points.
+template <bool ORDERED>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                            int64_t gr_sb, int64_t gr_sh, int64_t gr_sw,
                            const float* __restrict__ coord, int32_t N,
                            int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
-                           float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn) {
+                           float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
+                           const int2* __restrict__ order, int32_t order_hw, int64_t order_len) {
   __shared__ TapsS s_taps[kGatherPts];
-  const int32_t b = blockIdx.z;
   const int32_t n0 = blockIdx.x * kGatherPts;
-  cta_taps(s_taps, coord, b, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W);
+  cta_taps<ORDERED>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len);
   const int32_t q = C >> 2;  // channel quads per point
-  const float* g = grid + b * gr_sb;
   const bool vec_ok = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int32_t i = threadIdx.x; i < kGatherPts * q; i += kGatherThreads) {
     const int32_t p = i / q, cq = i - p * q;
-    const int32_t n = n0 + p;
-    if (n >= N) break;
     const TapsS t = s_taps[p];
-    const float* gq = g + (cq << 2);
+    const int32_t n = t.n, b = t.b;
+    if (n < 0) break;  // slots without a point are the last ones of the last CTA
+    const float* gq = grid + b * gr_sb + (cq << 2);
     // unconditional loads from clamped pixels, selected afterwards (see the planar kernel)
     const float4 l_nw = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_nw / W) * gr_sh + static_cast<int64_t>(t.o_nw % W) * gr_sw));
     const float4 l_ne = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_ne / W) * gr_sh + static_cast<int64_t>(t.o_ne % W) * gr_sw));
@@ -237,22 +256,32 @@ gather_backward_kernel(const float* __restrict__ gout, int32_t C, int32_t N, int
 
 extern "C" {
 
-int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W, int64_t gr_sb,
+static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W, int64_t gr_sb,
                                  int64_t gr_sc, int64_t gr_sh, int64_t gr_sw, const float* coord, int64_t N,
                                  int64_t co_sb, int64_t co_sn, int64_t co_sd, float scale_h, float scale_w,
-                                 float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, void* stream) {
+                                 float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, const int2* order,
+                                 int32_t order_hw, void* stream) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || N < 0) return SMOS_EINVAL;
   if (N == 0) return SMOS_OK;
   if (!grid || !coord || !out) return SMOS_EINVAL;
-  if (B > 65535 || N >= (int64_t(1) << 31) || C >= (1 << 24)) return SMOS_EUNSUPPORTED;
+  if (B > 65535 || N >= (int64_t(1) << 31) || C >= (1 << 24) || B * N >= (int64_t(1) << 31)) return SMOS_EUNSUPPORTED;
   cudaStream_t st = smos_stream(stream);
   const bool nhwc = (gr_sc == 1) && ((C & 3) == 0) && ((gr_sw & 3) == 0) && ((gr_sh & 3) == 0) &&
                     ((gr_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
-  dim3 g(smos_ceil_div(N, kGatherPts), 1, static_cast<unsigned>(B));
+  // cell order only pays when a point's channels leave as whole sectors (point-major output rows)
+  const bool ordered = order != nullptr && o_sc == 1 && C > 1;
+  const int64_t order_len = B * N;
+  dim3 g(smos_ceil_div(ordered ? order_len : N, kGatherPts), 1, ordered ? 1u : static_cast<unsigned>(B));
+  const int32_t Ni = static_cast<int32_t>(N), Ci = static_cast<int32_t>(C);
   if (nhwc) {
-    gather_forward_nhwc_kernel<<<g, kGatherThreads, 0, st>>>(
-        grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb, co_sn,
-        co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn);
+    if (ordered)
+      gather_forward_nhwc_kernel<true><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
+                                                                      co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb,
+                                                                      o_sc, o_sn, order, order_hw, order_len);
+    else
+      gather_forward_nhwc_kernel<false><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
+                                                                       co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb,
+                                                                       o_sc, o_sn, nullptr, 1, 0);
   } else {
     // point-major output rows are assembled in shared memory (needs (C+1)*32 floats <= 48 KB)
     // (measured: assembling point-major rows in shared memory is SLOWER than letting every thread store its
@@ -262,17 +291,44 @@ int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_
                           (static_cast<size_t>(C + 1) * kGatherPts * 4 <= 40 * 1024);
     const size_t smem = rows_out ? static_cast<size_t>(C + 1) * kGatherPts * 4 : 0;
     const bool dense = (gr_sw == 1 && gr_sh == W);
-#define SMOS_LAUNCH_PLANAR(D, R)                                                                              \
-    gather_forward_planar_kernel<D, R><<<g, kGatherThreads, smem, st>>>(                                        \
-        grid, static_cast<int32_t>(C), H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, static_cast<int32_t>(N), co_sb, \
-        co_sn, co_sd, scale_h, scale_w, out, o_sb, o_sc, o_sn)
-    if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true);
-    else if (dense) SMOS_LAUNCH_PLANAR(true, false);
-    else if (rows_out) SMOS_LAUNCH_PLANAR(false, true);
-    else SMOS_LAUNCH_PLANAR(false, false);
+#define SMOS_LAUNCH_PLANAR(D, R, O)                                                                          \
+    gather_forward_planar_kernel<D, R, O><<<g, kGatherThreads, smem, st>>>(                                    \
+        grid, Ci, H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, Ni, co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb, \
+        o_sc, o_sn, order, order_hw, order_len)
+    if (ordered) {
+      if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true, true);
+      else if (dense) SMOS_LAUNCH_PLANAR(true, false, true);
+      else if (rows_out) SMOS_LAUNCH_PLANAR(false, true, true);
+      else SMOS_LAUNCH_PLANAR(false, false, true);
+    } else {
+      if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true, false);
+      else if (dense) SMOS_LAUNCH_PLANAR(true, false, false);
+      else if (rows_out) SMOS_LAUNCH_PLANAR(false, true, false);
+      else SMOS_LAUNCH_PLANAR(false, false, false);
+    }
 #undef SMOS_LAUNCH_PLANAR
   }
   return smos_launch_status();
+}
+
+int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W, int64_t gr_sb,
+                                 int64_t gr_sc, int64_t gr_sh, int64_t gr_sw, const float* coord, int64_t N,
+                                 int64_t co_sb, int64_t co_sn, int64_t co_sd, float scale_h, float scale_w,
+                                 float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, void* stream) {
+  return gather_forward_launch(grid, B, C, H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, N, co_sb, co_sn, co_sd, scale_h,
+                               scale_w, out, o_sb, o_sc, o_sn, nullptr, 1, stream);
+}
+
+int smos_bilinear_gather_forward_ordered(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W, int64_t gr_sb,
+                                         int64_t gr_sc, int64_t gr_sh, int64_t gr_sw, const float* coord, int64_t N,
+                                         int64_t co_sb, int64_t co_sn, int64_t co_sd, float scale_h, float scale_w,
+                                         float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, const void* plan,
+                                         int32_t plan_H, int32_t plan_W, void* stream) {
+  if (!plan || plan_H <= 0 || plan_W <= 0 || B <= 0 || N < 0) return SMOS_EINVAL;
+  const PoolLayout L = smos_pool_layout(B, N, plan_H, plan_W);
+  const int2* sorted = reinterpret_cast<const int2*>(static_cast<const char*>(plan) + L.off_sorted);
+  return gather_forward_launch(grid, B, C, H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, N, co_sb, co_sn, co_sd, scale_h,
+                               scale_w, out, o_sb, o_sc, o_sn, sorted, static_cast<int32_t>(L.hw), stream);
 }
 
 int smos_bilinear_gather_backward(const float* grad_out, int64_t B, int64_t C, int64_t N, int64_t go_sb,

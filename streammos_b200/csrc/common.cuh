@@ -57,11 +57,58 @@ __device__ __forceinline__ void smos_bulk_g2s(void* dst_smem, const void* src_gm
 }
 __device__ __forceinline__ void smos_mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
+  uint32_t polls = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(smos_smem_u32(bar)), "r"(parity)
         : "memory");
+    if (!done && ++polls > (1u << 26)) __trap();  // a copy that never lands must fail the launch, not hang the GPU
   } while (!done);
+}
+
+// ---- pooling plan layout (built by voxel_maxpool.cu, also walked by the ordered gather) ------------
+struct PoolLayout {
+  int64_t hw, cells;   // H*W, B*H*W
+  int64_t off_cell, off_rank, off_count, off_start, off_sorted, off_multi, bytes;
+};
+
+static inline PoolLayout smos_pool_layout(int64_t B, int64_t N, int32_t H, int32_t W) {
+  PoolLayout L;
+  L.hw = static_cast<int64_t>(H) * W;
+  L.cells = B * L.hw;
+  const int64_t bn = B * N;
+  int64_t off = 0;
+  L.off_cell = off;   off += smos_align_up(bn * 4, 256);
+  L.off_rank = off;   off += smos_align_up(bn * 4, 256);
+  L.off_count = off;  off += smos_align_up((L.cells + 4) * 4, 256);  // + cursors: points, multi-piece cells, out-of-grid
+  L.off_start = off;  off += smos_align_up(L.cells * 4, 256);
+  L.off_sorted = off; off += smos_align_up(bn * 8, 256);
+  // cells whose segment crosses a multiple of 32 (>= 2 pieces): at most one per 32 sorted points
+  L.off_multi = off;  off += smos_align_up((bn / 32 + 2) * 8, 256);
+  L.bytes = off;
+  return L;
+}
+
+// ---- zero fill ---------------------------------------------------------------------------------------
+// Our own fill kernel instead of cudaMemsetAsync: measured on B200, a 63 MB memset node costs ~80 us inside
+// the voting call (it is not a kernel ncu lists); 128-bit stores from a grid sized to the SM count run at the
+// HBM write rate.
+static __global__ void __launch_bounds__(256) smos_zero_kernel(uint4* __restrict__ p, int64_t n16) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n16;
+       i += static_cast<int64_t>(gridDim.x) * 256)
+    p[i] = z;
+}
+
+static inline cudaError_t smos_zero_async(void* p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0 || (bytes & 15) != 0) return cudaMemsetAsync(p, 0, bytes, st);
+  const int64_t n16 = static_cast<int64_t>(bytes >> 4);
+  int64_t blocks = (n16 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(SMOS_SM_COUNT) * 16;
+  if (blocks > cap) blocks = cap;
+  smos_zero_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<uint4*>(p), n16);
+  return cudaGetLastError();
 }

@@ -93,6 +93,39 @@ vote_argmax_kernel(const void* __restrict__ ws, int64_t V, int32_t C, int packed
   out[i] = static_cast<OutT>(best);
 }
 
+// In-place variant for the int64 label grid of the reference API: the 8-byte label slots themselves are the packed
+// counters (zero-filled, voted into with RED), and this pass turns every non-empty slot into its label. Empty
+// voxels already hold label 0 and are not written again: 63 MB read + a few MB written instead of a separate
+// 63 MB counter array (memset + read) plus a 63 MB label write.
+__device__ __forceinline__ unsigned long long packed_argmax(unsigned long long w) {
+  const unsigned c0 = static_cast<unsigned>(w & kPackMask);
+  const unsigned c1 = static_cast<unsigned>((w >> kPackBits) & kPackMask);
+  const unsigned c2 = static_cast<unsigned>((w >> (2 * kPackBits)) & kPackMask);
+  unsigned long long best = 0ull;
+  unsigned bv = c0;
+  if (c1 > bv) { bv = c1; best = 1ull; }
+  if (c2 > bv) { bv = c2; best = 2ull; }
+  return best;
+}
+
+__global__ void __launch_bounds__(kVoteThreads)
+vote_argmax_inplace_kernel(unsigned long long* __restrict__ slots, int64_t V) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x) * 2;
+  if (i >= V) return;
+  if (i + 1 < V && (reinterpret_cast<uintptr_t>(slots) & 15) == 0) {
+    ulonglong2 w = *reinterpret_cast<const ulonglong2*>(slots + i);
+    if ((w.x | w.y) == 0ull) return;
+    w.x = packed_argmax(w.x);
+    w.y = packed_argmax(w.y);
+    *reinterpret_cast<ulonglong2*>(slots + i) = w;
+  } else {
+    for (int64_t k = i; k < V && k < i + 2; ++k) {
+      const unsigned long long w = slots[k];
+      if (w != 0ull) slots[k] = packed_argmax(w);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kVoteThreads)
 point_labels_i64_kernel(const int64_t* __restrict__ coords, int64_t Pc, const int64_t* __restrict__ vlabels,
                         int32_t X, int32_t Y, int32_t Z, int64_t* __restrict__ out) {
@@ -284,6 +317,37 @@ stream_point_labels_kernel(const __grid_constant__ StreamScans S, int cur, int64
   out[i] = r;
 }
 
+// ---- long-term memory ring: insert the new scan -----------------------------------
+// One kernel per scan instead of four memcpy nodes: the scan that was current until now moves from the "current"
+// slot into its history slot and the new scan (points + predicted labels) takes the current slot.
+__global__ void __launch_bounds__(kVoteThreads)
+memory_push_kernel(const float* __restrict__ pts_in, const uint8_t* __restrict__ pred_in, int64_t nfloat, int64_t n,
+                   float* __restrict__ cur_pts, uint8_t* __restrict__ cur_pred, float* __restrict__ hist_pts,
+                   uint8_t* __restrict__ hist_pred, int vec) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * kVoteThreads;
+  if (vec) {  // every pointer 16-byte aligned, nfloat % 4 == 0, n % 16 == 0
+    const int64_t n4 = nfloat >> 2, n16 = n >> 4;
+    for (int64_t i = tid; i < n4; i += nthreads) {
+      if (hist_pts) reinterpret_cast<float4*>(hist_pts)[i] = reinterpret_cast<const float4*>(cur_pts)[i];
+      reinterpret_cast<float4*>(cur_pts)[i] = __ldg(reinterpret_cast<const float4*>(pts_in) + i);
+    }
+    for (int64_t i = tid; i < n16; i += nthreads) {
+      if (hist_pred) reinterpret_cast<uint4*>(hist_pred)[i] = reinterpret_cast<const uint4*>(cur_pred)[i];
+      reinterpret_cast<uint4*>(cur_pred)[i] = __ldg(reinterpret_cast<const uint4*>(pred_in) + i);
+    }
+  } else {
+    for (int64_t i = tid; i < nfloat; i += nthreads) {
+      if (hist_pts) hist_pts[i] = cur_pts[i];
+      cur_pts[i] = pts_in[i];
+    }
+    for (int64_t i = tid; i < n; i += nthreads) {
+      if (hist_pred) hist_pred[i] = cur_pred[i];
+      cur_pred[i] = pred_in[i];
+    }
+  }
+}
+
 int64_t ws_bytes(int64_t P, int64_t V, int32_t C) {
   return use_packed(P, C) ? V * 8 : V * static_cast<int64_t>(C) * 4;
 }
@@ -315,13 +379,24 @@ int smos_vote_voxel_labels(const int64_t* voxel_coords, const int64_t* semantic_
   const int64_t V = static_cast<int64_t>(X) * Y * Z;
   const int packed = use_packed(P, num_classes) ? 1 : 0;
   cudaStream_t st = smos_stream(stream);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws_bytes(P, V, num_classes)), st);
+  if (packed) {  // the label slots double as the packed counters (workspace untouched)
+    cudaError_t e = smos_zero_async(voxel_labels, static_cast<size_t>(V) * 8, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (P > 0) {
+      vote_i64_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st>>>(voxel_coords, semantic_labels, P, X, Y,
+                                                                               Z, num_classes, 1, voxel_labels);
+      vote_argmax_inplace_kernel<<<smos_ceil_div((V + 1) / 2, kVoteThreads), kVoteThreads, 0, st>>>(
+          reinterpret_cast<unsigned long long*>(voxel_labels), V);
+    }
+    return smos_launch_status();
+  }
+  cudaError_t e = smos_zero_async(workspace, static_cast<size_t>(ws_bytes(P, V, num_classes)), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (P > 0)
     vote_i64_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st>>>(voxel_coords, semantic_labels, P, X, Y,
-                                                                             Z, num_classes, packed, workspace);
+                                                                             Z, num_classes, 0, workspace);
   vote_argmax_kernel<int64_t><<<smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st>>>(workspace, V, num_classes,
-                                                                                       packed, voxel_labels);
+                                                                                       0, voxel_labels);
   return smos_launch_status();
 }
 
@@ -347,7 +422,7 @@ int smos_vote_fused(const float* points, int64_t P, int64_t row_stride, const ui
   const int64_t V = static_cast<int64_t>(X) * Y * Z;
   const int packed = use_packed(P, num_classes) ? 1 : 0;
   cudaStream_t st = smos_stream(stream);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws_bytes(P, V, num_classes)), st);
+  cudaError_t e = smos_zero_async(workspace, static_cast<size_t>(ws_bytes(P, V, num_classes)), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (P > 0)
     vote_fused_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st>>>(
@@ -385,7 +460,7 @@ int smos_vote_stream(const smos_vote_stream_scan* scans_host, int32_t n_scans, i
   const int64_t V = static_cast<int64_t>(X) * Y * Z;
   const int packed = use_packed(total, num_classes) ? 1 : 0;
   cudaStream_t st = smos_stream(stream);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(ws_bytes(total, V, num_classes)), st);
+  cudaError_t e = smos_zero_async(workspace, static_cast<size_t>(ws_bytes(total, V, num_classes)), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (total > 0)
     vote_stream_kernel<<<smos_ceil_div(total, kVoteThreads), kVoteThreads, 0, st>>>(
@@ -396,6 +471,22 @@ int smos_vote_stream(const smos_vote_stream_scan* scans_host, int32_t n_scans, i
   if (nc > 0)
     stream_point_labels_kernel<<<smos_ceil_div(nc, kVoteThreads), kVoteThreads, 0, st>>>(
         S, current, row_stride, box, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, voxel_labels_u8, point_labels);
+  return smos_launch_status();
+}
+
+int smos_memory_push(const float* points, const uint8_t* pred, int64_t n, int64_t row_floats, float* cur_points,
+                     uint8_t* cur_pred, float* hist_points, uint8_t* hist_pred, void* stream) {
+  if (n < 0 || row_floats < 3) return SMOS_EINVAL;
+  if (n == 0) return SMOS_OK;
+  if (!points || !pred || !cur_points || !cur_pred || ((hist_points == nullptr) != (hist_pred == nullptr))) return SMOS_EINVAL;
+  const int64_t nfloat = n * row_floats;
+  auto a16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int vec = (a16(points) && a16(pred) && a16(cur_points) && a16(cur_pred) && a16(hist_points) && a16(hist_pred) &&
+                   (nfloat & 3) == 0 && (n & 15) == 0) ? 1 : 0;
+  int64_t blocks = smos_ceil_div(vec ? (nfloat >> 2) : nfloat, kVoteThreads);
+  if (blocks > SMOS_SM_COUNT * 8) blocks = SMOS_SM_COUNT * 8;
+  memory_push_kernel<<<static_cast<unsigned>(blocks), kVoteThreads, 0, smos_stream(stream)>>>(
+      points, pred, nfloat, n, cur_points, cur_pred, hist_points, hist_pred, vec);
   return smos_launch_status();
 }
 

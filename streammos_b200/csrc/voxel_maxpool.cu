@@ -17,6 +17,10 @@
 //         zeros, occupied cells combine their <= 1 + count/32 piece rows. Every output element
 //         is written exactly once with 128-bit stores: the 201 MB zero-fill of the reference
 //         is fused away and HBM traffic stays at the algorithmic minimum.
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -25,35 +29,13 @@ constexpr int kPlanThreads = 256;
 constexpr int kReduceWarps = 8;   // warps per CTA in phase A
 constexpr int kWriteThreads = 256;
 constexpr int kCG = 8;            // channels per thread in phase B
-// A point that continues a run of equal cells begun by the lane before it (same 64-point tile, hence
+// A point that continues a run of equal cells begun by the lane before it (same 16-point segment, hence
 // consecutive sorted positions) is "merged": on the channel-major path only the run's first point gets a
 // row (the run maximum), which removes ~60 % of the permute's writes and of the reduction's reads in scan
 // order. Bit 30 of a plan position / bit 31 of sorted.x carry the mark.
 constexpr int32_t kMergedPos = 0x40000000;
 constexpr int32_t kPosMask = 0x3fffffff;
 constexpr uint32_t kMergedN = 0x80000000u;
-
-struct PoolLayout {
-  int64_t hw, cells;   // H*W, B*H*W
-  int64_t off_cell, off_rank, off_count, off_start, off_sorted, off_multi, bytes;
-};
-
-PoolLayout pool_layout(int64_t B, int64_t N, int32_t H, int32_t W) {
-  PoolLayout L;
-  L.hw = static_cast<int64_t>(H) * W;
-  L.cells = B * L.hw;
-  const int64_t bn = B * N;
-  int64_t off = 0;
-  L.off_cell = off;   off += smos_align_up(bn * 4, 256);
-  L.off_rank = off;   off += smos_align_up(bn * 4, 256);
-  L.off_count = off;  off += smos_align_up((L.cells + 4) * 4, 256);  // + point cursor, multi-cell counter
-  L.off_start = off;  off += smos_align_up(L.cells * 4, 256);
-  L.off_sorted = off; off += smos_align_up(bn * 8, 256);
-  // cells whose segment crosses a multiple of 32 (>= 2 pieces): at most one per 32 sorted points
-  L.off_multi = off;  off += smos_align_up((bn / 32 + 2) * 8, 256);
-  L.bytes = off;
-  return L;
-}
 
 // ---- plan kernels ------------------------------------------------------------------------------
 // Up to kMaxPlans plans are built by ONE launch of each of the three kernels (a scan needs five: BEV at
@@ -73,7 +55,7 @@ struct PlanDev {
   int2* multi;
   int64_t pt_begin;    // first global point index of this plan
   int64_t quad_begin;  // first global cell-quad index (warp aligned)
-  int32_t N, H, W, hw, cells;
+  int32_t N, H, W, hw, cells, bn;
   float sh, sw;
 };
 
@@ -83,13 +65,35 @@ struct PlanBatch {
   int32_t n;
 };
 
+// ---- plan 0: clear count[cells] and the four cursors of every plan (thread = 4 cells) -----------
+__global__ void __launch_bounds__(kPlanThreads)
+pool_zero_counts_kernel(const __grid_constant__ PlanBatch pb) {
+  const int64_t gq = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gq >= pb.quad_total) return;
+  int j = 0;
+  while (j + 1 < pb.n && gq >= pb.p[j + 1].quad_begin) ++j;
+  const PlanDev& P = pb.p[j];
+  const int32_t c0 = static_cast<int32_t>(gq - P.quad_begin) * 4;
+  if (c0 == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) P.count[P.cells + q] = 0;
+  }
+  if (c0 + 3 < P.cells && (reinterpret_cast<uintptr_t>(P.count) & 15) == 0) {
+    *reinterpret_cast<int4*>(P.count + c0) = make_int4(0, 0, 0, 0);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (c0 + q < P.cells) P.count[c0 + q] = 0;
+  }
+}
+
 // ---- plan 1: cell index + warp-aggregated per-cell histogram -------------------------------
 __global__ void __launch_bounds__(kPlanThreads)
 pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
   const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  int32_t* target = nullptr;  // &count[gcell] of my plan, or null if invalid
+  int32_t* target = nullptr;  // &count[gcell] of my plan; the out-of-grid cursor for invalid points; null past the end
   int32_t* rank_out = nullptr;
-  bool tile_head = false;
+  bool tile_head = false, valid = false;
   if (gi < pb.pt_total) {
     int j = 0;
     while (j + 1 < pb.n && gi >= pb.p[j + 1].pt_begin) ++j;
@@ -104,13 +108,15 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
     const long long ih = static_cast<long long>(fh);
     const long long iw = static_cast<long long>(fw);
     int32_t cell = -1;
+    target = P.count + P.cells + 2;  // cursor[2]: out-of-grid points, listed at the tail of `sorted`
     if (ih >= 0 && ih < P.H && iw >= 0 && iw < P.W) {
       cell = static_cast<int32_t>(ih) * P.W + static_cast<int32_t>(iw);
       target = P.count + (b * P.hw + cell);
+      valid = true;
     }
     P.cell[i] = cell;
     rank_out = P.rank + i;
-    tile_head = (n & 63) == 0;  // runs never cross the 64-point tiles of the permute kernel
+    tile_head = (n & 15) == 0;  // runs never cross the 16-point segments the permute kernels sweep
     if (P.vmi != nullptr) P.vmi[i] = cell >= 0 ? static_cast<int64_t>(b) * P.vmi_stride + cell : -1;
   }
   // one atomic per RUN of equal cells among adjacent lanes (in scan order neighbouring points share
@@ -127,8 +133,9 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
   int32_t base = 0;
   if (lane == leader && target != nullptr) base = atomicAdd(target, run_end - leader);
   base = __shfl_sync(0xffffffffu, base, leader);
+  // valid: rank inside the cell (| kMergedPos for run followers); invalid: -2 - rank among the out-of-grid points
   if (rank_out != nullptr)
-    *rank_out = target != nullptr ? (base + (lane - leader)) | (lane != leader ? kMergedPos : 0) : -1;
+    *rank_out = valid ? (base + (lane - leader)) | (lane != leader ? kMergedPos : 0) : -2 - (base + (lane - leader));
 }
 
 // ---- plan 2: give every occupied cell a segment of the sorted list ---------------------------
@@ -202,14 +209,19 @@ pool_cell_scatter_kernel(const __grid_constant__ PlanBatch pb) {
   const PlanDev& P = pb.p[j];
   const int64_t i = gi - P.pt_begin;
   const int32_t cell = P.cell[i];
-  if (cell < 0) return;
   const int32_t b = static_cast<int32_t>(i / P.N);
   const int32_t n = static_cast<int32_t>(i - static_cast<int64_t>(b) * P.N);
-  const int32_t gcell = b * P.hw + cell;
   const int32_t r = P.rank[i];
+  if (cell < 0) {
+    // out-of-grid points fill `sorted` from the end (their .y = -1 - b); pooling never reads them (it stops at
+    // cursor[0]) but a gather that walks the list in cell order must still produce their (zero-padded) samples
+    P.sorted[P.bn - 1 - (-2 - r)] = make_int2(n, -1 - b);
+    return;
+  }
+  const int32_t gcell = b * P.hw + cell;
   const int32_t merged = r & kMergedPos;
   const int32_t pos = __ldg(P.start + gcell) + (r & kPosMask);
-  P.rank[i] = pos | merged;  // from here on: sorted position (| kMergedPos), -1 if invalid
+  P.rank[i] = pos | merged;  // from here on: sorted position (| kMergedPos), negative if invalid
   P.sorted[pos] = make_int2(static_cast<int32_t>(static_cast<uint32_t>(n) | (merged ? kMergedN : 0u)), gcell);
 }
 
@@ -270,84 +282,309 @@ pool_permute_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64_
   }
 }
 
-// TMA variant of the permute (used when the channel rows are contiguous and 16-byte aligned, i.e.
-// the (B,C,N,1)-contiguous tensor the reference produces, N % 4 == 0). Persistent CTAs walk the
-// 64-point tiles; warp 0 streams the C channel rows of the NEXT tile into the other shared-memory
-// buffer with cp.async.bulk (one 256-byte bulk copy per channel, completion counted on an mbarrier)
-// while all warps write the rows of the current tile: no register staging, loads of tile t+1 overlap
-// stores of tile t.
-constexpr int kPermPitch = kPermPts + 4;  // floats; keeps every row 16-byte aligned, 4-way bank conflicts on read
+// Sweep of one 16-point segment of a staged tile for CPL channels per lane (lane, lane + 32, ...): runs never
+// cross a multiple of 16 points (pool_cell_index_kernel breaks them there), so the segment is self-contained and
+// its run structure (hm: heads, mm: merged followers, 16 bits each) is the same for every channel: the code below
+// is fully unrolled with warp-uniform predicates. ld(j, k) returns the four values of points 4k..4k+3 of the
+// lane's j-th channel; q_of(p) the sorted position of point p of the segment.
+template <int CPL, typename Ld, typename Qof>
+__device__ __forceinline__ void perm_sweep16(unsigned hm, unsigned mm, int32_t C, int32_t c0, bool (&ok)[CPL], Ld ld,
+                                             Qof q_of, float* __restrict__ rows) {
+  float v[CPL][16];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 t = ld(j, k);
+      v[j][4 * k] = t.x; v[j][4 * k + 1] = t.y; v[j][4 * k + 2] = t.z; v[j][4 * k + 3] = t.w;
+    }
+  float acc[CPL];
+  int32_t q = -1;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    if ((mm >> p) & 1u) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc[j] = fmaxf(acc[j], v[j][p]);
+    } else {
+      if (q >= 0) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+          if (ok[j]) rows[static_cast<int64_t>(q) * C + c0 + 32 * j] = acc[j];
+      }
+      q = -1;
+      if ((hm >> p) & 1u) {
+        q = q_of(p);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) acc[j] = v[j][p];
+      }
+    }
+  }
+  if (q >= 0) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+      if (ok[j]) rows[static_cast<int64_t>(q) * C + c0 + 32 * j] = acc[j];
+  }
+}
 
+// LDG variant of the permute for the same layouts as the TMA kernel: one 64-point x C tile per CTA, every thread
+// issues all of its 128-bit loads (4 points of one channel each) back to back, parks them in shared memory
+// ([channel][68]: conflict-free 128-bit column reads) and sweeps 16-point segments. Many small CTAs per SM instead
+// of a software pipeline: the LSU path keeps far more requests in flight per SM than the TMA unit.
+template <int CPL>
 __global__ void __launch_bounds__(kPermThreads)
-pool_permute_tma_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int32_t B, int64_t f_sb, int64_t f_sc,
+pool_permute_ldg_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64_t f_sb, int64_t f_sc,
                         const int32_t* __restrict__ pos, float* __restrict__ rows) {
-  extern __shared__ __align__(128) float ptile[];  // [2][C][kPermPitch]
-  __shared__ __align__(8) uint64_t bar[2];
-  __shared__ int32_t s_pos[2][kPermPts];
+  constexpr int PTS = kPermPts;
+  constexpr int kPitch = PTS + 4;
+  extern __shared__ __align__(16) float ltile[];  // [C][kPitch]
+  __shared__ int32_t s_pos[PTS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int32_t tiles_per_b = (N + kPermPts - 1) / kPermPts;
-  const int32_t ntiles = tiles_per_b * B;
-  const int32_t buf_floats = C * kPermPitch;
+  const int32_t b = blockIdx.y;
+  const int32_t n0 = blockIdx.x * PTS;
+  const int32_t np = min(PTS, N - n0);  // multiple of 4
+  if (threadIdx.x < PTS) s_pos[threadIdx.x] = threadIdx.x < np ? __ldg(pos + static_cast<int64_t>(b) * N + n0 + threadIdx.x) : -1;
+  const float* fb = feat + b * f_sb + n0;
+  const int32_t nvec = C * (PTS / 4);
+  for (int32_t i0 = threadIdx.x; i0 < nvec; i0 += kPermThreads * 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int32_t i = min(i0 + u * kPermThreads, nvec - 1);
+      const int32_t c = i >> 4, p4 = min((i & 15) << 2, np - 4);  // unconditional loads on clamped addresses
+      v[u] = __ldg(reinterpret_cast<const float4*>(fb + static_cast<int64_t>(c) * f_sc + p4));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int32_t i = i0 + u * kPermThreads;
+      if (i < nvec) *reinterpret_cast<float4*>(ltile + (i >> 4) * kPitch + ((i & 15) << 2)) = v[u];
+    }
+  }
+  __syncthreads();
+  const int32_t q0 = s_pos[lane], q1 = s_pos[32 + lane];
+  const unsigned long long hmask =
+      static_cast<unsigned long long>(__ballot_sync(0xffffffffu, q0 >= 0 && !(q0 & kMergedPos))) |
+      (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, q1 >= 0 && !(q1 & kMergedPos))) << 32);
+  const unsigned long long mmask =
+      static_cast<unsigned long long>(__ballot_sync(0xffffffffu, q0 >= 0 && (q0 & kMergedPos))) |
+      (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, q1 >= 0 && (q1 & kMergedPos))) << 32);
+  const int32_t ncg = (C + 32 * CPL - 1) / (32 * CPL);  // channel groups of 32 * CPL
+  constexpr int32_t nseg = PTS / 16;
+  for (int32_t item = wid; item < ncg * nseg; item += kPermThreads / 32) {
+    const int32_t cg = item / nseg, seg = item - cg * nseg;
+    const int32_t c0 = cg * 32 * CPL + lane;
+    bool ok[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) ok[j] = c0 + 32 * j < C;
+    const unsigned hm = static_cast<unsigned>(hmask >> (seg * 16)) & 0xffffu;
+    const unsigned mm = static_cast<unsigned>(mmask >> (seg * 16)) & 0xffffu;
+    if (hm == 0u) continue;  // no row owner in this segment
+    perm_sweep16<CPL>(
+        hm, mm, C, c0, ok,
+        [&](int j, int k) { return *reinterpret_cast<const float4*>(ltile + (ok[j] ? c0 + 32 * j : 0) * kPitch + seg * 16 + 4 * k); },
+        [&](int p) { return s_pos[seg * 16 + p]; }, rows);
+  }
+}
+
+// TMA variant of the permute (used when the channel rows are contiguous and 16-byte aligned, i.e. the
+// (B,C,N,1)-contiguous tensor the reference produces, N % 4 == 0, C % 32 == 0). Persistent CTAs walk tiles of
+// 32 channels x 128 points. A tile arrives with four tiled-TMA operations (cp.async.bulk.tensor over a rank-3
+// tensor map {N, C, B}, box {32 points, 32 channels, 1}, 128-byte swizzle, SASS UTMALDG) plus one linear bulk
+// copy for its sorted positions; STAGES tiles are in flight per CTA and one __syncthreads per tile releases a
+// stage. (Earlier versions: one 256-byte cp.async.bulk per channel row of a 64-point x C tile, a proxy fence
+// (MEMBAR.ALL.CTA) and two barriers per tile — 43 us; the sweep below waited on every one of those latencies.)
+constexpr int kTmBox = 32;  // points per TMA box: 32 floats = one 128-byte swizzle span
+
+__device__ __forceinline__ void smos_tma_load_3d(void* dst_smem, const CUtensorMap* tm, int32_t x, int32_t y, int32_t z,
+                                                 uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smos_smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(z), "r"(smos_smem_u32(bar))
+      : "memory");
+}
+
+constexpr int kTmCh = 32;    // channels per tile (one lane per channel)
+constexpr int kTmPts = 128;  // points per tile: 512 contiguous bytes per channel row and DRAM page visit
+
+template <int STAGES>
+__global__ void __launch_bounds__(kPermThreads)
+pool_permute_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ feat, int32_t C, int32_t N,
+                        int32_t B, int64_t f_sb, int64_t f_sc, const int32_t* __restrict__ pos,
+                        float* __restrict__ rows) {
+  constexpr int PTS = kTmPts;
+  constexpr int kBoxes = PTS / kTmBox;            // TMA boxes per tile (32 points x 32 channels, 4 KB each)
+  constexpr int kBoxFloats = kTmCh * kTmBox;      // 1024 floats: boxes stay 1024-byte aligned
+  constexpr int kSeg = PTS / (kPermThreads / 32); // points per warp segment (16)
+  static_assert(kSeg % 4 == 0 && PTS == 128, "masks are kept as two 64-bit words");
+  extern __shared__ float ptile_raw[];  // [STAGES][kBoxes][32 channels][32 points], 128-byte swizzle
+  __shared__ __align__(8) uint64_t bar[STAGES];
+  __shared__ __align__(16) int32_t s_pos[STAGES][PTS];
+  float* ptile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ptile_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int32_t tiles_per_row = (N + PTS - 1) / PTS;
+  const int32_t ncg = C / kTmCh;                       // channel groups (C % 32 == 0 on this path)
+  const int32_t ntiles = tiles_per_row * ncg * B;      // tile id = (b * ncg + cg) * tiles_per_row + point tile
   if (threadIdx.x == 0) {
-    smos_mbar_init(&bar[0], 1);
-    smos_mbar_init(&bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) smos_mbar_init(&bar[i], 1);
     smos_fence_mbar_init();
   }
   __syncthreads();
 
+  // one thread arms the stage's mbarrier and issues every copy of a tile: the tile's sorted positions (one linear
+  // bulk copy) and, for whole tiles, its features (four tiled-TMA boxes). Partial tiles at the end of a scan do
+  // not rely on out-of-bounds fill: their features are read straight from global memory by the sweep.
   auto issue = [&](int32_t t, int buf) {
-    const int32_t b = t / tiles_per_b;
-    const int32_t n0 = (t - b * tiles_per_b) * kPermPts;
-    const int32_t np = min(kPermPts, N - n0);
-    if (wid == 0) {
-      if (lane == 0) smos_mbar_expect_tx(&bar[buf], static_cast<uint32_t>(C) * np * 4u);
-      __syncwarp();
-      const float* src = feat + b * f_sb + n0;
-      float* dst = ptile + buf * buf_floats;
-      for (int32_t c = lane; c < C; c += 32)
-        smos_bulk_g2s(dst + c * kPermPitch, src + static_cast<int64_t>(c) * f_sc, static_cast<uint32_t>(np) * 4u, &bar[buf]);
-    } else if (wid == 1 || wid == 2) {
-      const int32_t p = (wid - 1) * 32 + lane;
-      s_pos[buf][p] = p < np ? __ldg(pos + static_cast<int64_t>(b) * N + n0 + p) : -1;
+    const int32_t bc = t / tiles_per_row;
+    const int32_t b = bc / ncg, cg = bc - b * ncg;
+    const int32_t n0 = (t - bc * tiles_per_row) * PTS;
+    const int32_t np = min(PTS, N - n0);  // multiple of 4
+    const bool whole = np == PTS;
+    smos_mbar_expect_tx(&bar[buf], static_cast<uint32_t>(np) * 4u + (whole ? static_cast<uint32_t>(PTS) * kTmCh * 4u : 0u));
+    smos_bulk_g2s(&s_pos[buf][0], pos + static_cast<int64_t>(b) * N + n0, static_cast<uint32_t>(np) * 4u, &bar[buf]);
+    if (whole) {
+#pragma unroll
+      for (int k = 0; k < kBoxes; ++k)
+        smos_tma_load_3d(ptile + (buf * kBoxes + k) * kBoxFloats, &tmap, n0 + k * kTmBox, cg * kTmCh, b, &bar[buf]);
     }
   };
 
+  const int32_t stride = gridDim.x;
   int32_t t = blockIdx.x;
-  if (t < ntiles) issue(t, 0);
-  uint32_t phase[2] = {0u, 0u};
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i)
+      if (t + i * stride < ntiles) issue(t + i * stride, i);
+  }
+  uint32_t phases = 0u;  // bit i: parity to wait for on bar[i]
   int buf = 0;
-  for (; t < ntiles; t += gridDim.x, buf ^= 1) {
-    const int32_t tn = t + gridDim.x;
-    if (tn < ntiles) issue(tn, buf ^ 1);  // the other buffer was released by the barrier below
-    smos_mbar_wait(&bar[buf], phase[buf]);
-    phase[buf] ^= 1u;
-    __syncthreads();  // s_pos[buf] (written one iteration ago) is visible; tile bytes have landed
-    const float* tile = ptile + buf * buf_floats;
-    // thread = (channel, segment of the tile's points): it sweeps its points once, keeping a running max
-    // over a run (first point + merged followers) and storing one row element per run. A run that starts in
-    // my segment is followed to its end; leading merged points belong to the previous segment's sweep.
+  for (; t < ntiles; t += stride) {
+    const int32_t bc = t / tiles_per_row;
+    const int32_t b = bc / ncg, cg = bc - b * ncg;
+    const int32_t n0 = (t - bc * tiles_per_row) * PTS;
+    const int32_t np = min(PTS, N - n0);
+    const bool whole = np == PTS;
+    smos_mbar_wait(&bar[buf], (phases >> buf) & 1u);  // every thread observes the completion: the bytes are visible
+    phases ^= 1u << buf;
+    const float* tile = ptile + buf * kBoxes * kBoxFloats;
+    // run structure of the tile, the same for every channel: heads (points that own a row) and merged followers
+    unsigned long long hmask[2], mmask[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int32_t pa = h * 64 + lane, pb = pa + 32;
+      const int32_t qa = pa < np ? s_pos[buf][pa] : -1, qb = pb < np ? s_pos[buf][pb] : -1;
+      hmask[h] = static_cast<unsigned long long>(__ballot_sync(0xffffffffu, qa >= 0 && !(qa & kMergedPos))) |
+                 (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, qb >= 0 && !(qb & kMergedPos))) << 32);
+      mmask[h] = static_cast<unsigned long long>(__ballot_sync(0xffffffffu, qa >= 0 && (qa & kMergedPos))) |
+                 (static_cast<unsigned long long>(__ballot_sync(0xffffffffu, qb >= 0 && (qb & kMergedPos))) << 32);
+    }
+    // warp = 16-point segment of the tile, lane = channel; all control flow below is warp uniform. A run that starts
+    // in my segment is followed to its end (runs never cross a multiple of 64 points); leading merged points belong
+    // to the previous segment's sweep. Four points per 128-bit shared-memory load: with the 128-byte swizzle the
+    // 16-byte chunk j of channel row c sits at chunk j ^ (c & 7) — eight consecutive lanes, eight bank groups.
     {
-      const int32_t nseg = max(1, kPermThreads / C);            // segments per tile (C <= 256 here)
-      const int32_t seg_len = (kPermPts + nseg - 1) / nseg;
-      for (int32_t item = threadIdx.x; item < C * nseg; item += kPermThreads) {
-        const int32_t seg = item / C, c = item - seg * C;
-        const float* tc = tile + c * kPermPitch;
-        int32_t p = seg * seg_len;
-        const int32_t seg_end = min(kPermPts, p + seg_len);
-        while (p < seg_end && s_pos[buf][p] >= 0 && (s_pos[buf][p] & kMergedPos)) ++p;  // someone else's run
-        while (p < seg_end) {
-          const int32_t q = s_pos[buf][p];
-          if (q < 0) { ++p; continue; }  // invalid point or past the end of the scan
-          float v = tc[p];
-          ++p;
-          while (p < kPermPts && s_pos[buf][p] >= 0 && (s_pos[buf][p] & kMergedPos)) { v = fmaxf(v, tc[p]); ++p; }
-          rows[static_cast<int64_t>(q) * C + c] = v;
+      const int32_t c = cg * kTmCh + lane;
+      const float* gsrc = feat + b * f_sb + static_cast<int64_t>(c) * f_sc + n0;  // partial tiles only
+      const int32_t p_end = (wid + 1) * kSeg;
+      float acc = 0.f;
+      int32_t q = -1;  // sorted position of the open run's row, -1: none
+      bool done = false;
+      for (int32_t g = wid * kSeg; g < PTS && !done; g += 4) {
+        const unsigned hm = static_cast<unsigned>((g & 64 ? hmask[1] : hmask[0]) >> (g & 63)) & 0xfu;
+        const unsigned mm = static_cast<unsigned>((g & 64 ? mmask[1] : mmask[0]) >> (g & 63)) & 0xfu;
+        if (g >= p_end && !(q >= 0 && (mm & 1u))) break;  // beyond my segment and no run of mine continues
+        float4 v4;
+        if (whole) {
+          v4 = *reinterpret_cast<const float4*>(tile + (g >> 5) * kBoxFloats + lane * kTmBox + ((((g & 31) >> 2) ^ (lane & 7)) << 2));
+        } else {  // N % 4 == 0: a group of four points is inside the scan or entirely past its end
+          v4 = g < np ? __ldg(reinterpret_cast<const float4*>(gsrc + g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if ((mm >> k) & 1u) {
+            if (q >= 0) acc = fmaxf(acc, v[k]);
+          } else {  // a head or an invalid point closes the open run
+            if (q >= 0) rows[static_cast<int64_t>(q) * C + c] = acc;
+            q = -1;
+            if (g + k >= p_end) { done = true; break; }
+            if ((hm >> k) & 1u) { q = s_pos[buf][g + k]; acc = v[k]; }
+          }
         }
       }
+      if (q >= 0) rows[static_cast<int64_t>(q) * C + c] = acc;
     }
-    smos_fence_proxy_async();  // order my generic-proxy reads before the async-proxy refill
-    __syncthreads();           // everyone is done with `buf`: it may be refilled next iteration
+    // everyone is done reading `buf` (generic-proxy reads ordered by the barrier); refill it right away with the
+    // tile STAGES strides ahead, so that STAGES - 1 tiles are in flight during the next sweep
+    __syncthreads();
+    if (threadIdx.x == 0 && t + STAGES * stride < ntiles) issue(t + STAGES * stride, buf);
+    buf = buf + 1 == STAGES ? 0 : buf + 1;
   }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time dependency on libcuda)
+typedef CUresult (*smos_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static smos_encode_tiled_fn encode_tiled() {
+  static smos_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<smos_encode_tiled_fn>(p);
+  }
+  return fn;
+}
+
+template <int STAGES>
+static int launch_permute_tma(const float* feat, int32_t C, int64_t N, int64_t B, int64_t f_sb, int64_t f_sc,
+                              const int32_t* pos, float* rows, int device, cudaStream_t st) {
+  smos_encode_tiled_fn enc = encode_tiled();
+  if (enc == nullptr) return SMOS_EUNSUPPORTED;
+  CUtensorMap tm;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(B)};
+  const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(f_sc) * 4u, static_cast<cuuint64_t>(f_sb) * 4u};
+  const cuuint32_t box[3] = {kTmBox, kTmCh, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(feat), gdim, gstr, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return SMOS_EUNSUPPORTED;
+  const size_t smem = static_cast<size_t>(STAGES) * kTmPts * kTmCh * 4 + 1024;
+  static bool opt_in[64] = {};
+  if (device >= 0 && device < 64 && !opt_in[device]) {
+    cudaError_t e = cudaFuncSetAttribute(pool_permute_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    opt_in[device] = true;
+  }
+  const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kTmPts)) * (C / kTmCh) * B;
+  int ctas_per_sm = static_cast<int>((224 * 1024) / (smem + 2048));
+  if (ctas_per_sm > 6) ctas_per_sm = 6;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int want = env_int("SMOS_PERM_CTAS", 0);
+  if (want >= 1 && want < ctas_per_sm) ctas_per_sm = want;
+  int64_t pgrid = static_cast<int64_t>(SMOS_SM_COUNT) * ctas_per_sm;
+  if (pgrid > ntiles) pgrid = ntiles;
+  pool_permute_tma_kernel<STAGES><<<static_cast<unsigned>(pgrid), kPermThreads, smem, st>>>(
+      tm, feat, C, static_cast<int32_t>(N), static_cast<int32_t>(B), f_sb, f_sc, pos, rows);
+  return SMOS_OK;
+}
+
+// pipeline depth of the TMA permute; SMOS_PERM_STAGES (2 / 3 / 4) overrides the default for experiments
+static int perm_stages() {
+  static int v = 0;
+  if (v == 0) { const int x = env_int("SMOS_PERM_STAGES", 0); v = (x >= 2 && x <= 4) ? x : 3; }
+  return v;
 }
 
 // ---- phase A: piece maxima ------------------------------------------------------------------
@@ -603,7 +840,7 @@ extern "C" {
 
 int64_t smos_pool_plan_bytes(int64_t B, int64_t N, int32_t H, int32_t W) {
   if (B <= 0 || N < 0 || H <= 0 || W <= 0) return SMOS_EINVAL;
-  return pool_layout(B, N, H, W).bytes;
+  return smos_pool_layout(B, N, H, W).bytes;
 }
 
 int64_t smos_pool_workspace_bytes(int64_t B, int64_t C, int64_t N) {
@@ -616,14 +853,13 @@ int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n,
   PlanBatch pb;
   pb.n = n;
   int64_t pt = 0, quad = 0;
-  uintptr_t lo = ~uintptr_t(0), hi = 0;
   for (int32_t j = 0; j < n; ++j) {
     const smos_pool_plan_desc& d = descs_host[j];
     if (d.B <= 0 || d.N < 0 || d.H <= 0 || d.W <= 0 || d.plan == nullptr) return SMOS_EINVAL;
     if (d.B * d.N >= (int64_t(1) << 31) || d.B * static_cast<int64_t>(d.H) * d.W >= (int64_t(1) << 31))
       return SMOS_EUNSUPPORTED;
     if (d.N > 0 && d.pcds_ind == nullptr) return SMOS_EINVAL;
-    const PoolLayout L = pool_layout(d.B, d.N, d.H, d.W);
+    const PoolLayout L = smos_pool_layout(d.B, d.N, d.H, d.W);
     char* base = static_cast<char*>(d.plan);
     PlanDev& P = pb.p[j];
     P.ind = d.pcds_ind; P.ind_sb = d.ind_sb; P.ind_sn = d.ind_sn; P.ind_sd = d.ind_sd;
@@ -636,30 +872,18 @@ int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n,
     P.multi = reinterpret_cast<int2*>(base + L.off_multi);
     P.N = static_cast<int32_t>(d.N); P.H = d.H; P.W = d.W;
     P.hw = static_cast<int32_t>(L.hw); P.cells = static_cast<int32_t>(L.cells);
+    P.bn = static_cast<int32_t>(d.B * d.N);
     P.sh = d.scale_h; P.sw = d.scale_w;
     P.pt_begin = pt; P.quad_begin = quad;
     pt += d.B * d.N;
     quad += smos_align_up((L.cells + 3) / 4, 32);
-    lo = lo < reinterpret_cast<uintptr_t>(base) ? lo : reinterpret_cast<uintptr_t>(base);
-    const uintptr_t end = reinterpret_cast<uintptr_t>(base) + static_cast<uintptr_t>(L.bytes);
-    hi = hi > end ? hi : end;
   }
   pb.pt_total = pt;
   pb.quad_total = quad;
   cudaStream_t st = smos_stream(stream);
-  // zero the per-cell counters (+ cursors). Plans carved out of one buffer are cleared with a single
-  // memset over the whole span (a few MB) instead of one memset node per plan.
-  int64_t sum_bytes = 0;
-  for (int32_t j = 0; j < n; ++j) sum_bytes += pool_layout(descs_host[j].B, descs_host[j].N, descs_host[j].H, descs_host[j].W).bytes;
-  if (n > 1 && static_cast<int64_t>(hi - lo) <= sum_bytes + 4096 * n) {
-    cudaError_t e = cudaMemsetAsync(reinterpret_cast<void*>(lo), 0, hi - lo, st);
-    if (e != cudaSuccess) return static_cast<int>(e);
-  } else {
-    for (int32_t j = 0; j < n; ++j) {
-      cudaError_t e = cudaMemsetAsync(pb.p[j].count, 0, static_cast<size_t>(pb.p[j].cells + 4) * 4, st);
-      if (e != cudaSuccess) return static_cast<int>(e);
-    }
-  }
+  // zero the per-cell counters and the cursors of every plan: one launch (a cudaMemsetAsync node per plan, or one
+  // over the whole span of the plans, cost more than the three plan kernels together)
+  pool_zero_counts_kernel<<<smos_ceil_div(quad, kPlanThreads), kPlanThreads, 0, st>>>(pb);
   if (pt > 0) pool_cell_index_kernel<<<smos_ceil_div(pt, kPlanThreads), kPlanThreads, 0, st>>>(pb);
   pool_cell_alloc_kernel<<<smos_ceil_div(quad, kPlanThreads), kPlanThreads, 0, st>>>(pb);
   if (pt > 0) pool_cell_scatter_kernel<<<smos_ceil_div(pt, kPlanThreads), kPlanThreads, 0, st>>>(pb);
@@ -689,7 +913,7 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
   if (B <= 0 || C <= 0 || N < 0 || H <= 0 || W <= 0 || plan == nullptr || voxel_out == nullptr) return SMOS_EINVAL;
   if (N > 0 && (pcds_feat == nullptr || workspace == nullptr)) return SMOS_EINVAL;
   if (B * N >= (int64_t(1) << 31) || C >= (1 << 20) || B > 65535) return SMOS_EUNSUPPORTED;
-  const PoolLayout L = pool_layout(B, N, H, W);
+  const PoolLayout L = smos_pool_layout(B, N, H, W);
   const char* base = static_cast<const char*>(plan);
   const int32_t* count = reinterpret_cast<const int32_t*>(base + L.off_count);
   const int32_t* start = reinterpret_cast<const int32_t*>(base + L.off_start);
@@ -717,29 +941,39 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
         if (e != cudaSuccess) return static_cast<int>(e);
         smem_opt_in[device] = true;
       }
-      const size_t smem_tma = static_cast<size_t>(2) * C * kPermPitch * 4;
-      const bool tma_ok = f_sn == 1 && (N & 3) == 0 && (f_sb & 3) == 0 && (f_sc & 3) == 0 &&
-                          (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 && smem_tma <= 96 * 1024;
-      if (tma_ok) {
-        static bool tma_opt_in[64] = {};
-        if (device >= 0 && device < 64 && !tma_opt_in[device]) {
-          cudaError_t e = cudaFuncSetAttribute(pool_permute_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      const int depth = perm_stages();
+      const bool tma_ok = f_sn == 1 && (N & 3) == 0 && (f_sb & 3) == 0 && (f_sc & 3) == 0 && (C % kTmCh) == 0 &&
+                          (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 && N >= kTmPts && encode_tiled() != nullptr;
+      const bool vec_ok = f_sn == 1 && (N & 3) == 0 && (f_sb & 3) == 0 && (f_sc & 3) == 0 && N >= 4 &&
+                          (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 &&
+                          static_cast<size_t>(C) * (kPermPts + 4) * 4 <= 200 * 1024;
+      if (vec_ok && env_int("SMOS_PERM_LDG", 1)) {  // default; SMOS_PERM_LDG=0 selects the TMA pipeline below
+        static bool ldg_opt_in[64] = {};
+        if (device >= 0 && device < 64 && !ldg_opt_in[device]) {
+          cudaError_t e = cudaFuncSetAttribute(pool_permute_ldg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
           if (e != cudaSuccess) return static_cast<int>(e);
-          tma_opt_in[device] = true;
+          e = cudaFuncSetAttribute(pool_permute_ldg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          if (e != cudaSuccess) return static_cast<int>(e);
+          ldg_opt_in[device] = true;
         }
-        const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kPermPts)) * B;
-        int ctas_per_sm = static_cast<int>((200 * 1024) / (smem_tma + 1024));
-        if (ctas_per_sm > 6) ctas_per_sm = 6;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-        int64_t pgrid = static_cast<int64_t>(SMOS_SM_COUNT) * ctas_per_sm;
-        if (pgrid > ntiles) pgrid = ntiles;
-        pool_permute_tma_kernel<<<static_cast<unsigned>(pgrid), kPermThreads, smem_tma, st>>>(
-            pcds_feat, Ci, static_cast<int32_t>(N), static_cast<int32_t>(B), f_sb, f_sc, pos, rows);
+        dim3 pg(smos_ceil_div(N, kPermPts), static_cast<unsigned>(B));
+        const size_t lsmem = static_cast<size_t>(C) * (kPermPts + 4) * 4;
+        if (C > 32)
+          pool_permute_ldg_kernel<2><<<pg, kPermThreads, lsmem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, pos, rows);
+        else
+          pool_permute_ldg_kernel<1><<<pg, kPermThreads, lsmem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, pos, rows);
+      } else if (tma_ok) {
+        int rc;
+        if (depth == 2) rc = launch_permute_tma<2>(pcds_feat, Ci, N, B, f_sb, f_sc, pos, rows, device, st);
+        else if (depth == 4) rc = launch_permute_tma<4>(pcds_feat, Ci, N, B, f_sb, f_sc, pos, rows, device, st);
+        else rc = launch_permute_tma<3>(pcds_feat, Ci, N, B, f_sb, f_sc, pos, rows, device, st);
+        if (rc != SMOS_OK) return rc;
       } else {
         dim3 pg(smos_ceil_div(N, kPermPts), static_cast<unsigned>(B));
         pool_permute_kernel<<<pg, kPermThreads, smem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, f_sn, pos, rows);
       }
-      if ((C & 127) == 0) pool_reduce_kernel<4, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
+      if (stages & SMOS_POOL_STAGE_NO_REDUCE) {}
+      else if ((C & 127) == 0) pool_reduce_kernel<4, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
       else if ((C & 63) == 0) pool_reduce_kernel<2, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
       else pool_reduce_kernel<1, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
     } else {
@@ -784,7 +1018,7 @@ int smos_voxel_maxpool_backward(const float* pcds_feat, int64_t B, int64_t C, in
   if (B <= 0 || C <= 0 || N < 0 || H <= 0 || W <= 0 || plan == nullptr) return SMOS_EINVAL;
   if (N == 0) return SMOS_OK;
   if (!pcds_feat || !voxel_out || !grad_voxel_out || !grad_feat) return SMOS_EINVAL;
-  const PoolLayout L = pool_layout(B, N, H, W);
+  const PoolLayout L = smos_pool_layout(B, N, H, W);
   const int32_t* cell = reinterpret_cast<const int32_t*>(static_cast<const char*>(plan) + L.off_cell);
   const int64_t total = B * C * N;
   const int fast_n = (f_sc == 1 && C > 1) ? 0 : 1;

@@ -97,7 +97,7 @@ def pool_plan_multi(specs):
     with torch.cuda.device(device):
         rc = lib.smos_pool_plan_build_multi(descs, len(items), _stream())
     _lib.check(rc, "smos_pool_plan_build_multi")
-    _count(3)
+    _count(4)  # zero counts + cell index + cell allocation + scatter
     return plans
 
 
@@ -118,7 +118,7 @@ def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=
                                       float(scale_rate[0]), float(scale_rate[1]), _ptr(idx_out),
                                       int(idx_batch_stride), _ptr(buf), _stream())
     _lib.check(rc, "smos_pool_plan_build")
-    _count(3)  # cell index + cell allocation + scatter
+    _count(4)  # zero counts + cell index + cell allocation + scatter
     return PoolPlan(buf, B, N, H, W, idx_out)
 
 
@@ -186,10 +186,12 @@ def voxel_maxpool_backward(pcds_feat, plan, voxel_out, grad_voxel_out, grad_feat
 # ----------------------------------------------------------------------------------------------
 # BilinearSample
 # ----------------------------------------------------------------------------------------------
-def bilinear_gather_forward(grid_feat, grid_coord, scale_rate, point_major_out=False):
+def bilinear_gather_forward(grid_feat, grid_coord, scale_rate, point_major_out=False, order=None):
     """grid_feat (B, C, H, W) float32 (NCHW or channels_last), grid_coord (B, N, 2, S) float32
     -> (B, C, N, S). With point_major_out the result is channels_last-strided (each point's C
-    features contiguous), the layout the pooling kernel reads fastest."""
+    features contiguous), the layout the pooling kernel reads fastest.
+    `order`: a PoolPlan built from the same `grid_coord` (any grid/scale): points are visited in its cell
+    order (same values, far fewer cache lines per warp load for BEV coordinates); S == 1, point-major only."""
     _need_cuda(grid_feat, "grid_feat")
     _need_cuda(grid_coord, "grid_coord")
     _need_f32(grid_feat, "grid_feat")
@@ -209,11 +211,18 @@ def bilinear_gather_forward(grid_feat, grid_coord, scale_rate, point_major_out=F
         out = torch.empty((B, C, N, S), dtype=torch.float32, device=grid_feat.device)
     o_sb, o_sc = out.stride(0), out.stride(1)
     o_sn = out.stride(3)  # flattened (n, s) index advances by the stride of s
+    if order is not None and not (S == 1 and point_major_out):
+        order = None
+    if order is not None and (order.B, order.N) != (B, N):
+        raise RuntimeError("order plan (B=%d, N=%d) does not match grid_coord (B=%d, N=%d)" % (order.B, order.N, B, N))
     with torch.cuda.device(grid_feat.device):
-        rc = _lib.load().smos_bilinear_gather_forward(
-            _ptr(grid_feat), B, C, H, W, grid_feat.stride(0), grid_feat.stride(1), grid_feat.stride(2),
-            grid_feat.stride(3), _ptr(co), NP, co.stride(0), co.stride(1), co.stride(2), float(scale_rate[0]),
-            float(scale_rate[1]), _ptr(out), o_sb, o_sc, o_sn, _stream())
+        args = (_ptr(grid_feat), B, C, H, W, grid_feat.stride(0), grid_feat.stride(1), grid_feat.stride(2),
+                grid_feat.stride(3), _ptr(co), NP, co.stride(0), co.stride(1), co.stride(2), float(scale_rate[0]),
+                float(scale_rate[1]), _ptr(out), o_sb, o_sc, o_sn)
+        if order is None:
+            rc = _lib.load().smos_bilinear_gather_forward(*args, _stream())
+        else:
+            rc = _lib.load().smos_bilinear_gather_forward_ordered(*args, _ptr(order.buf), order.H, order.W, _stream())
     _lib.check(rc, "smos_bilinear_gather_forward")
     _count(1)
     return out
@@ -335,7 +344,7 @@ def vote_voxel_labels(voxel_coords, semantic_labels, dims, num_classes):
         rc = _lib.load().smos_vote_voxel_labels(_ptr(voxel_coords), _ptr(semantic_labels), P, X, Y, Z,
                                                 int(num_classes), _ptr(ws), _ptr(out), _stream())
     _lib.check(rc, "smos_vote_voxel_labels")
-    _count(2)  # vote + argmax
+    _count(3)  # zero + vote + argmax
     return out
 
 
@@ -376,7 +385,7 @@ def vote_fused(points, labels_u8, num_current, mins, deltas, dims, num_classes=3
                                          float(mins[2]), float(deltas[0]), float(deltas[1]), float(deltas[2]), X, Y,
                                          Z, int(num_classes), _ptr(ws), _ptr(vl), _ptr(pl), _stream())
     _lib.check(rc, "smos_vote_fused")
-    _count(3)
+    _count(4)
     return vl, pl
 
 
@@ -418,8 +427,30 @@ def vote_stream(scans, current, crop_lo, crop_hi, mins, deltas, dims, num_classe
                                   float(mins[2]), float(deltas[0]), float(deltas[1]), float(deltas[2]), X, Y, Z,
                                   int(num_classes), _ptr(ws), _ptr(vl), _ptr(pl), _stream())
     _lib.check(rc, "smos_vote_stream")
-    _count(3)
+    _count(4)
     return vl, pl
+
+
+def memory_push(points, pred, cur_points, cur_pred, hist_points=None, hist_pred=None):
+    """Long-term memory ring insert: (cur_points, cur_pred) -> (hist_points, hist_pred) if given, then
+    (points (n, r) f32, pred (n,) u8) -> (cur_points, cur_pred). All CUDA, contiguous, same shapes. One kernel."""
+    _need_cuda(points, "points")
+    _need_f32(points, "points")
+    ts = [points, pred, cur_points, cur_pred] + ([hist_points, hist_pred] if hist_points is not None else [])
+    for t in ts:
+        if not (t.is_cuda and t.is_contiguous()):
+            raise RuntimeError("memory_push: tensors must be contiguous CUDA tensors")
+    assert pred.dtype == torch.uint8 and cur_pred.dtype == torch.uint8 and cur_points.dtype == torch.float32
+    assert cur_points.shape == points.shape and cur_pred.shape == pred.shape and points.dim() == 2
+    if hist_points is not None:
+        assert hist_points.shape == points.shape and hist_pred.shape == pred.shape
+        assert hist_points.dtype == torch.float32 and hist_pred.dtype == torch.uint8
+    with torch.cuda.device(points.device):
+        rc = _lib.load().smos_memory_push(_ptr(points), _ptr(pred), int(points.size(0)), int(points.size(1)),
+                                          _ptr(cur_points), _ptr(cur_pred), _ptr(hist_points), _ptr(hist_pred),
+                                          _stream())
+    _lib.check(rc, "smos_memory_push")
+    _count(1)
 
 
 def instance_vote(points, pred, box_lo, box_hi):

@@ -81,10 +81,14 @@ class HotPath:
     returns the per-point labels after long-term voting plus the instance votes."""
 
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
-                 batch_plans=True, grids_channels_last=False, overlap_voting=False):
+                 batch_plans=True, grids_channels_last=False, overlap_voting=False, branches=True,
+                 ordered_gathers=True, ordered_rv=False):
         self.device = torch.device(device)
         self.overlap_voting = overlap_voting
+        self.branches = branches and self.device.type == "cuda"
+        self.ordered_gathers, self.ordered_rv = ordered_gathers, ordered_rv
         self._side = None
+        self._branch_streams = []
         self.batch_plans = batch_plans
         self.n_points = n_points
         self.point_major = point_major
@@ -114,6 +118,9 @@ class HotPath:
             self.local_pts[h].copy_(torch.from_numpy(s["xyzi"][0]))
             r = np.random.default_rng(seed * 1000 + 200 + h).integers(0, 3, n_points).astype(np.uint8)
             self.local_pred[h].copy_(torch.from_numpy(r))
+        # the "current" slot starts as a copy of the newest history scan: the first push moves it onto itself
+        self.local_pts[HISTORY].copy_(self.local_pts[HISTORY - 1])
+        self.local_pred[HISTORY].copy_(self.local_pred[HISTORY - 1])
         lo, hi = synthetic.synthetic_boxes(np.random.default_rng(seed + 31), N_BOXES)
         self.box_lo, self.box_hi = torch.from_numpy(lo).to(self.device), torch.from_numpy(hi).to(self.device)
         self.g_half = BilinearSample(in_dim=32, scale_rate=(0.5, 0.5))
@@ -127,8 +134,24 @@ class HotPath:
                             zip((synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z), self.size))
 
     # --- the three pieces of the hot path ----------------------------------------------------------
+    def _fork(self, n):
+        """n side streams that start after everything enqueued so far on the current stream. Under CUDA-graph
+        capture they become parallel branches of the graph (independent operators of one scan overlap: the
+        latency-bound small kernels of one branch run under the HBM-bound kernels of another)."""
+        main = torch.cuda.current_stream(self.device)
+        while len(self._branch_streams) < n:
+            self._branch_streams.append(torch.cuda.Stream(self.device))
+        sides = self._branch_streams[:n]
+        for s in sides:
+            s.wait_stream(main)
+        return main, sides
+
     def projection(self, b):
-        """Cascade projection: 5 x VoxelMaxPool + 5 x BilinearSample."""
+        """Cascade projection: 5 x VoxelMaxPool + 5 x BilinearSample.
+
+        Data dependencies (models/StreamMOS.py:101-105, mve.py:393-417): pool #1 and gather #5 depend on the
+        coordinates only; gather1 -> pool2 -> gather2 -> pool3 and gather3 -> pool4 -> gather4 -> pool5 are two
+        chains. With `branches` the four run as parallel branches (results are identical)."""
         cur_bev, cur_rv = b.coord_bev[:1], b.coord_rv
         # all five pooling plans of the scan depend on the coordinates only: three launches build them all
         if self.batch_plans:
@@ -137,16 +160,41 @@ class HotPath:
                                       (cur_bev, (128, 128), (0.25, 0.25))])
         else:
             pl = [None] * 5
-        bev_in = deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0), pl[0])    # StreamMOS.py:102
-        x0_pt = self.g_half(self.x0, cur_bev)                                                   # mve.py:395
-        x0_rv = deep_point.VoxelMaxPool(x0_pt, cur_rv, (32, 1024), (0.5, 0.5), pl[1])           # :396
-        x0_pt = self.g_half(x0_rv, cur_rv)                                                      # :400
-        x0_bev = deep_point.VoxelMaxPool(x0_pt, cur_bev, (256, 256), (0.5, 0.5), pl[2])         # :402
-        x1_pt = self.g_quarter(self.x1, cur_bev)                                                # :410
-        x1_rv = deep_point.VoxelMaxPool(x1_pt, cur_rv, (16, 512), (0.25, 0.25), pl[3])          # :411
-        x1_pt = self.g_quarter(x1_rv, cur_rv)                                                   # :415
-        x1_bev = deep_point.VoxelMaxPool(x1_pt, cur_bev, (128, 128), (0.25, 0.25), pl[4])       # :417
-        pt_bev = self.g_half(self.dec, cur_bev)                                                 # StreamMOS.py:105
+        # gathers visit the points in the cell order of the plan that shares their coordinates (BEV only by default:
+        # range-view coordinates are already row-coherent in scan order)
+        od = [p if (self.ordered_gathers and self.point_major and (i in (2, 4) or self.ordered_rv)) else None
+              for i, p in enumerate(pl)]
+
+        def half_chain():
+            x0_pt = self.g_half(self.x0, cur_bev, od[2])                                                 # mve.py:395
+            x0_rv = deep_point.VoxelMaxPool(x0_pt, cur_rv, (32, 1024), (0.5, 0.5), pl[1])           # :396
+            x0_pt2 = self.g_half(x0_rv, cur_rv, od[1])                                              # :400
+            return deep_point.VoxelMaxPool(x0_pt2, cur_bev, (256, 256), (0.5, 0.5), pl[2]), (x0_pt, x0_rv, x0_pt2)
+
+        def quarter_chain():
+            x1_pt = self.g_quarter(self.x1, cur_bev, od[4])                                         # :410
+            x1_rv = deep_point.VoxelMaxPool(x1_pt, cur_rv, (16, 512), (0.25, 0.25), pl[3])          # :411
+            x1_pt2 = self.g_quarter(x1_rv, cur_rv, od[3])                                           # :415
+            return deep_point.VoxelMaxPool(x1_pt2, cur_bev, (128, 128), (0.25, 0.25), pl[4]), x1_pt2, (x1_pt, x1_rv)
+
+        if not self.branches:
+            bev_in = deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0), pl[0])    # StreamMOS.py:102
+            x0_bev, _ = half_chain()
+            x1_bev, x1_pt, _ = quarter_chain()
+            pt_bev = self.g_half(self.dec, cur_bev, od[2])                                          # StreamMOS.py:105
+            return bev_in, x0_bev, x1_bev, x1_pt, pt_bev
+        main, (s1, s2, s3) = self._fork(3)
+        with torch.cuda.stream(s1):
+            x0_bev, keep1 = half_chain()
+        with torch.cuda.stream(s2):
+            x1_bev, x1_pt, keep2 = quarter_chain()
+        with torch.cuda.stream(s3):
+            pt_bev = self.g_half(self.dec, cur_bev, od[2])
+        bev_in = deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0), pl[0])
+        for s in (s1, s2, s3):
+            main.wait_stream(s)
+        # intermediates stay referenced until the join so the caching allocator cannot hand their blocks out early
+        self._keep = (keep1, keep2, pl)
         return bev_in, x0_bev, x1_bev, x1_pt, pt_bev
 
     def temporal_fusion(self, b):
@@ -160,24 +208,37 @@ class HotPath:
     def long_term_voting(self, b):
         """Voxel voting over 8 history scans + the current one, then per-instance votes."""
         cur = HISTORY
-        self.local_pts[cur].copy_(b.xyzi)
-        self.local_pred[cur].copy_(b.pred)
+        if self.device.type == "cuda":
+            # the previous scan moves from the current slot into its ring slot and the new scan takes the current
+            # slot: one kernel (the window slides exactly as voxel_voting.py:182 walks it)
+            prev = (self.scan_index - 1) % HISTORY
+            ops.memory_push(b.xyzi, b.pred, self.local_pts[cur], self.local_pred[cur], self.local_pts[prev],
+                            self.local_pred[prev])
+        else:
+            self.local_pts[cur].copy_(b.xyzi)
+            self.local_pred[cur].copy_(b.pred)
         pts = self.local_pts.view(-1, 4)
         n = self.n_points
+        labels = self.local_pred.view(-1).to(torch.int64)              # voxel_voting.py:241
+        if self.branches:  # the instance votes do not depend on the voxel votes: a parallel branch
+            main, (side,) = self._fork(1)
+            with torch.cuda.stream(side):
+                sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi)
         if self.vote_api == "reference":
             q = voting.Quantize(pts, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, self.size)
             coords = q.to(torch.int64)                                 # voxel_voting.py:240
-            labels = self.local_pred.view(-1).to(torch.int64)
             vl = voting.determine_voxel_labels(coords, labels, self.size, num_classes=3)
             point_labels = voting.get_point_labels_from_voxel_labels(coords[cur * n:], vl, self.size)
         else:  # fused streaming variant (SURVEY §8f rank 1): float xyz + uint8 labels in, no int64 staging
             _, point_labels = ops.vote_fused(pts, self.local_pred.view(-1), n, self.mins, self.deltas, self.size, 3)
-            labels = self.local_pred.view(-1).to(torch.int64)
-        sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi)
-        # the current scan becomes history (ring slot), as the next frame's window slides
-        slot = self.scan_index % HISTORY
-        self.local_pts[slot].copy_(self.local_pts[cur])
-        self.local_pred[slot].copy_(self.local_pred[cur])
+        if self.branches:
+            main.wait_stream(side)
+        else:
+            sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi)
+        if self.device.type != "cuda":  # CPU harness state (tests): the current scan becomes history at the end
+            slot = self.scan_index % HISTORY
+            self.local_pts[slot].copy_(self.local_pts[cur])
+            self.local_pred[slot].copy_(self.local_pred[cur])
         return point_labels, sums
 
     def step(self, b):

@@ -227,6 +227,33 @@ def test_bilinear_config_sizes_vs_oracle(C, H, W, scale):
     assert float(out[:, :, 118000:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("C,H,W,scale", [(32, 256, 256, (0.5, 0.5)), (64, 16, 512, (0.25, 0.25)), (5, 31, 47, (1.0, 1.0))])
+def test_bilinear_cell_order_matches_scan_order(C, H, W, scale):
+    """Visiting the points in the cell order of a pooling plan (any grid / scale built from the same
+    coordinates) is a pure re-ordering: bit-identical to the scan-order kernel, out-of-grid pads included."""
+    from streammos_b200 import ops
+    rng = np.random.default_rng(C * H)
+    B, N = 2, 60001
+    coord = synth_scan(rng, B, N, H, W, scale, n_valid=57000)
+    coord[1, 100:300] = 1e9                                     # far outside (int32 overflow range) on one batch
+    grid = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    ref = O.bilinear_sample(grid, coord, scale)
+    plans = [ops.pool_plan(t(coord), (H, W), scale), ops.pool_plan(t(coord), (7, 9), (0.01, 0.02))]
+    plans += ops.pool_plan_multi([(t(coord), (H // 2 + 1, W // 2 + 1), (scale[0] / 2, scale[1] / 2))])
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        g = t(grid).contiguous(memory_format=fmt)
+        base = ops.bilinear_gather_forward(g, t(coord), scale, True)
+        for plan in plans:
+            out = ops.bilinear_gather_forward(g, t(coord), scale, True, order=plan)
+            assert out.stride(1) == 1 and torch.equal(out, base)
+        np.testing.assert_allclose(out[..., 0].cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    # channel-major outputs ignore the order (same kernel as without it)
+    out = ops.bilinear_gather_forward(t(grid), t(coord), scale, False, order=plans[0])
+    assert out.is_contiguous() and torch.equal(out, base.contiguous())
+    with pytest.raises(RuntimeError):
+        ops.bilinear_gather_forward(t(grid)[:1], t(coord)[:1], scale, True, order=plans[0])
+
+
 def test_bilinear_multi_sample_dim_and_linearity():
     from streammos_b200 import ops
     rng = np.random.default_rng(5)
