@@ -260,52 +260,76 @@ def run_b200(args, world, rank, local):
         value = world * 1000.0 / ms_step
 
         # ---- end to end: host buffers in, labels out, copies inside the timed region --------------------
-        h_labels = [torch.empty(args.points, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
-        h_sums = [torch.empty(stream.N_BOXES, 2, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
-        ready = [torch.cuda.Event() for _ in range(N_SCANS)]
-        d2h = [torch.cuda.Event() for _ in range(N_SCANS)]
-        sC = pipe.streams()[-1]
+        def measure_e2e(pipe_, host_, devb_):
+            outs_ = pipe_.out
+            h_labels = [torch.empty(args.points, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
+            h_sums = [torch.empty(stream.N_BOXES, 2, dtype=torch.int64).pin_memory() for _ in range(N_SCANS)]
+            ready = [torch.cuda.Event() for _ in range(N_SCANS)]
+            d2h = [torch.cuda.Event() for _ in range(N_SCANS)]
+            sC = pipe_.streams()[-1]
 
-        def e2e_loop(n):
-            for i in range(n):
-                j = pipe.submitted % N_SCANS
-                with torch.cuda.stream(copy):
-                    # buffer j is free once the previous scan that used it has been voted on and read back
-                    copy.wait_event(pipe.m_done[j])
-                    copy.wait_event(pipe.v_done[j])
-                    copy.wait_event(d2h[j])
-                    devb[j].copy_from(host[j])          # H2D of this scan's inputs (pinned -> HBM)
-                    ready[j].record(copy)
-                pipe.submit(ready[j])
-                with torch.cuda.stream(sC):             # D2H of the step's result, behind the voting graph
-                    h_labels[j].copy_(outs[j][0], non_blocking=True)
-                    h_sums[j].copy_(outs[j][1], non_blocking=True)
-                    d2h[j].record(sC)
+            def e2e_loop(n):
+                for i in range(n):
+                    j = pipe_.submitted % N_SCANS
+                    with torch.cuda.stream(copy):
+                        # buffer j is free once the previous scan that used it has been voted on and read back
+                        copy.wait_event(pipe_.m_done[j])
+                        copy.wait_event(pipe_.v_done[j])
+                        copy.wait_event(d2h[j])
+                        devb_[j].copy_from(host_[j])        # H2D of this scan's inputs (pinned -> HBM)
+                        ready[j].record(copy)
+                    pipe_.submit(ready[j])
+                    with torch.cuda.stream(sC):             # D2H of the step's result, behind the voting graph
+                        h_labels[j].copy_(outs_[j][0], non_blocking=True)
+                        h_sums[j].copy_(outs_[j][1], non_blocking=True)
+                        d2h[j].record(sC)
 
-        for j in range(N_SCANS):
-            d2h[j].record(sC)
-        e2e_loop(max(4, min(args.warmup, 2 * N_SCANS)))
+            for j in range(N_SCANS):
+                d2h[j].record(sC)
+            e2e_loop(max(4, min(args.warmup, 2 * N_SCANS)))
+            torch.cuda.synchronize()
+            barrier(world)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(compute)
+            copy.wait_event(f0)
+            for st in pipe_.streams():
+                st.wait_event(f0)
+            e2e_loop(args.steps)
+            pipe_.join(compute)
+            for j in range(N_SCANS):
+                compute.wait_event(d2h[j])
+            f1.record(compute)
+            torch.cuda.synchronize()
+            barrier(world)
+            ms = max_over_ranks(f0.elapsed_time(f1), world, dev) / args.steps
+            return {"value": world * 1000.0 / ms, "unit": "scans/s", "ms_per_step": ms,
+                    "h2d_bytes_per_step": host_[0].nbytes(),
+                    "d2h_bytes_per_step": h_labels[0].numel() * 8 + h_sums[0].numel() * 8}
+
+        # (1) hot-path inputs themselves in host memory: the 64-channel point features (92 MB per scan) cross PCIe —
+        #     something the reference never does (its PointNet stem produces them on the GPU)
+        e2e_feat = measure_e2e(pipe, host, devb)
+        e2e_feat["note"] = ("hot-path input tensors in pinned host memory (3x64xN point features = 92 MB of the H2D bytes): "
+                            "PCIe bound; kept for reference")
+        # (2) headline e2e: the LOADER's tensors in host memory, as in the reference (models/StreamMOS.py:86-103): 7-channel
+        #     point features + BEV / range-view coordinates per frame; the PointNet stem (torch, out of scope) runs on the
+        #     device inside the timed region and feeds VoxelMaxPool #1
+        hot_l = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
+                               vote_api=args.vote_api, grids_channels_last=args.grids_channels_last,
+                               branches=not args.no_branches, ordered_gathers=not args.no_ordered_gathers,
+                               ordered_rv=args.ordered_rv)
+        host_l = [stream.make_host_loader_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
+        devb_l = [h.to(dev) for h in host_l]
         torch.cuda.synchronize()
-        barrier(world)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(compute)
-        copy.wait_event(f0)
-        for st in pipe.streams():
-            st.wait_event(f0)
-        e2e_loop(args.steps)
-        pipe.join(compute)
-        for j in range(N_SCANS):
-            compute.wait_event(d2h[j])
-        f1.record(compute)
-        torch.cuda.synchronize()
-        barrier(world)
-        clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions
-        e2e_ms = max_over_ranks(f0.elapsed_time(f1), world, dev) / args.steps
-        e2e = {"value": world * 1000.0 / e2e_ms, "unit": "scans/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": host[0].nbytes(),
-               "d2h_bytes_per_step": h_labels[0].numel() * 8 + h_sums[0].numel() * 8,
-               "note": "pinned host -> HBM copy of the next scans overlaps the kernels of the current ones (copy stream "
-                       "+ scan pipeline)"}
+        pipe_l = pipeline.ScanPipeline(hot_l, devb_l, use_graphs=use_graph, scans_in_flight=args.in_flight)
+        e2e = measure_e2e(pipe_l, host_l, devb_l)
+        clocks = sampler.stop() if rank == 0 else None  # sampled across the timed regions
+        e2e["note"] = ("host buffers = what the reference's loader hands to the model (T x 7-channel point features, BEV and "
+                       "range-view coordinates, + predicted labels and attention samples as stand-ins for network "
+                       "intermediates); H2D copy, PointNet stem (torch conv1x1 x2, out of scope), the whole hot path and the "
+                       "D2H of the labels are inside the timed region; the copy of scan i+1 overlaps scan i")
+        e2e["hot_path_inputs_over_pcie"] = e2e_feat
+        del pipe_l, devb_l, hot_l
 
         # ---- dominant kernel: the dense writer of VoxelMaxPool #1 (3 x 64 x 512 x 512 fp32 out) --------------
         # every stage of the call runs once, then the WRITE stage alone is re-launched and timed with CUDA

@@ -206,6 +206,26 @@ int smos_ms_deform_attn_backward(int32_t dtype, const void* value,
                                  void* grad_attn_weight, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* (D, next: SURVEY 8f rank 4) PointNet stem in front of VoxelMaxPool #1.      */
+/* Replaces networks/backbone.py:199-250 PointNetStacker(Cin, 64, pre_bn=True, */
+/* stack_num=2) in eval mode (models/StreamMOS.py:77,101):                     */
+/*   h = relu(bn1(W1 . bn0(x))) ; y = relu(bn2(W2 . h))                         */
+/* with every eval BatchNorm given as the per-channel affine torch applies:     */
+/*   alpha = weight / sqrt(running_var + eps), beta = bias - running_mean*alpha */
+/* ------------------------------------------------------------------------- */
+
+/*   x  : (B, Cin, N) float32, strides x_sb / x_sc / x_sn ; Cin <= 16
+ *   w1 : (C1, Cin) row major ; w2 : (C2, C1) row major ; C1 == C2 == 64
+ *   bn0_alpha / bn0_beta may both be NULL (no pre-BN)
+ *   y  : (B, C2, N) float32, strides y_sb / y_sc, points contiguous; every element written. */
+int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, int64_t N,
+                            int64_t x_sb, int64_t x_sc, int64_t x_sn,
+                            const float* bn0_alpha, const float* bn0_beta, const float* w1,
+                            const float* bn1_alpha, const float* bn1_beta, const float* w2,
+                            const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
+                            float* y, int64_t y_sb, int64_t y_sc, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* (C) Long-term-memory voting.                                               */
 /* ------------------------------------------------------------------------- */
 

@@ -375,3 +375,39 @@ API int oracle_vote_stream(const float* pts, const uint8_t* lab, const int64_t* 
   }
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------- */
+/* PointNet stem — networks/backbone.py:199-250 PointNetStacker(cin, 64,   */
+/* pre_bn=True, stack_num=2) in eval mode as models/StreamMOS.py:77,101 runs it:              */
+/*   BatchNorm2d -> Conv2d 1x1 (no bias) -> BatchNorm2d -> ReLU -> Conv2d 1x1 -> BatchNorm2d   */
+/*   -> ReLU. Eval BatchNorm = per-channel affine y = x*alpha + beta (alpha = weight /         */
+/*   sqrt(running_var + eps), beta = bias - running_mean*alpha, as ATen's CPU kernel folds it).*/
+/* x (B, Cin, N), w1 (C1, Cin), w2 (C2, C1), y (B, C2, N); a0/b0 may be NULL.                  */
+/* ---------------------------------------------------------------------------------------- */
+API void oracle_point_stem(const float* x, int64_t B, int64_t Cin, int64_t N, const float* a0, const float* b0,
+                           const float* w1, const float* a1, const float* b1, int64_t C1, const float* w2,
+                           const float* a2, const float* b2, int64_t C2, float* y) {
+  float* xin = (float*)malloc(sizeof(float) * (size_t)Cin);
+  float* h = (float*)malloc(sizeof(float) * (size_t)C1);
+  for (int64_t b = 0; b < B; ++b)
+    for (int64_t n = 0; n < N; ++n) {
+      for (int64_t ci = 0; ci < Cin; ++ci) {
+        const float v = x[(b * Cin + ci) * N + n];
+        xin[ci] = a0 ? fmaf(v, a0[ci], b0[ci]) : v;
+      }
+      for (int64_t c = 0; c < C1; ++c) {
+        float acc = 0.f;
+        for (int64_t ci = 0; ci < Cin; ++ci) acc = fmaf(w1[c * Cin + ci], xin[ci], acc);
+        const float t = fmaf(acc, a1[c], b1[c]);
+        h[c] = t > 0.f ? t : 0.f;
+      }
+      for (int64_t c = 0; c < C2; ++c) {
+        float acc = 0.f;
+        for (int64_t k = 0; k < C1; ++k) acc = fmaf(w2[c * C1 + k], h[k], acc);
+        const float t = fmaf(acc, a2[c], b2[c]);
+        y[(b * C2 + c) * N + n] = t > 0.f ? t : 0.f;
+      }
+    }
+  free(xin);
+  free(h);
+}

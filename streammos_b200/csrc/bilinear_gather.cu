@@ -113,7 +113,7 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
                              float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
                              const int2* __restrict__ order, int32_t order_hw, int64_t order_len) {
   __shared__ TapsS s_taps[kGatherPts];
-  extern __shared__ float s_out[];  // ROWS_OUT: [kGatherPts][C + 1]
+  extern __shared__ __align__(16) float s_out[];  // ROWS_OUT: [kGatherPts][C + 4]
   const int32_t n0 = blockIdx.x * kGatherPts;
   cta_taps<ORDERED>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -156,11 +156,12 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
       acc[k] = fmaf(d, t.w_se, fmaf(c, t.w_sw, fmaf(bq, t.w_ne, fmaf(a, t.w_nw, 0.f))));
     }
     if (ROWS_OUT) {
-      // point-major output: park the results in shared memory ([point][channel], odd pitch) so that the
-      // rows can leave as contiguous C*4-byte segments instead of 32 scattered sectors per instruction
-#pragma unroll
-      for (int k = 0; k < kCPT; ++k)
-        if (k < nch) s_out[lane * (C + 1) + c0 + k] = acc[k];
+      // point-major output: park the results in shared memory ([point][C + 4]: the two 128-bit stores of a thread
+      // are conflict free) so that the rows leave as whole 128-byte lines, 4 lines per store instruction, instead of
+      // 32 different lines per instruction (one 16-byte piece per lane)
+      float* so = s_out + lane * (C + 4) + c0;
+      *reinterpret_cast<float4*>(so) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(so + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     } else if (n >= 0) {
       float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(c0) * o_sc;
       if (vec_ok && nch == kCPT) {
@@ -175,11 +176,14 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
   }
   if (ROWS_OUT) {
     __syncthreads();
-    for (int32_t p = wid; p < kGatherPts; p += kGatherThreads / 32) {
+    // C % 8 == 0 here: a row is C / 4 float4 pieces; thread t of the CTA moves piece t % q of row t / q
+    const int32_t q = C >> 2;
+    for (int32_t i = threadIdx.x; i < kGatherPts * q; i += kGatherThreads) {
+      const int32_t p = i / q, j = i - p * q;
       const int32_t pn = s_taps[p].n;
       if (pn < 0) continue;
-      float* o = out + s_taps[p].b * o_sb + static_cast<int64_t>(pn) * o_sn;
-      for (int32_t c = lane; c < C; c += 32) o[c] = s_out[p * (C + 1) + c];
+      const float4 r = *reinterpret_cast<const float4*>(s_out + p * (C + 4) + (j << 2));
+      *reinterpret_cast<float4*>(out + s_taps[p].b * o_sb + static_cast<int64_t>(pn) * o_sn + (j << 2)) = r;
     }
   }
 }
@@ -283,13 +287,11 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
                                                                        co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb,
                                                                        o_sc, o_sn, nullptr, 1, 0);
   } else {
-    // point-major output rows are assembled in shared memory (needs (C+1)*32 floats <= 48 KB)
-    // (measured: assembling point-major rows in shared memory is SLOWER than letting every thread store its
-    //  own full 32-byte sector — the extra shared-memory wavefronts cost more than the scattered stores —
-    //  so the row path stays off; kept for outputs whose rows are not sector aligned)
-    const bool rows_out = (o_sc == 1) && C > 1 && ((o_sn & 7) != 0) &&
-                          (static_cast<size_t>(C + 1) * kGatherPts * 4 <= 40 * 1024);
-    const size_t smem = rows_out ? static_cast<size_t>(C + 1) * kGatherPts * 4 : 0;
+    // point-major output rows (C % 8 == 0, 16-byte aligned) are assembled in shared memory and leave as whole lines
+    const bool rows_out = (o_sc == 1) && C > 1 && ((C & 7) == 0) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                          (static_cast<size_t>(C + 4) * kGatherPts * 4 <= 40 * 1024) && smos_env_int("SMOS_GATHER_ROWS", 1);
+    const size_t smem = rows_out ? static_cast<size_t>(C + 4) * kGatherPts * 4 : 0;
     const bool dense = (gr_sw == 1 && gr_sh == W);
 #define SMOS_LAUNCH_PLANAR(D, R, O)                                                                          \
     gather_forward_planar_kernel<D, R, O><<<g, kGatherThreads, smem, st>>>(                                    \

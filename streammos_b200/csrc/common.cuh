@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/streammos_b200.h"
 
@@ -14,6 +15,12 @@ static inline cudaStream_t smos_stream(void* s) { return reinterpret_cast<cudaSt
 static inline int smos_launch_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? SMOS_OK : static_cast<int>(e);
+}
+
+// experiment knobs (environment overrides, read per call: host-side only)
+static inline int smos_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 static inline int64_t smos_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

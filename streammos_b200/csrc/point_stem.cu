@@ -1,0 +1,155 @@
+// PointNet stem for sm_100a: the two stacked point-wise layers in front of VoxelMaxPool #1.
+//
+// Replaces networks/backbone.py:199-250 PointNetStacker(7, 64, pre_bn=True, stack_num=2) in eval mode as
+// models/StreamMOS.py:77,101 uses it: BatchNorm2d(Cin) -> Conv2d 1x1 (Cin -> C1, no bias) -> BatchNorm2d -> ReLU ->
+// Conv2d 1x1 (C1 -> C2) -> BatchNorm2d -> ReLU, i.e. 7 torch kernels and six passes over (B', 64, N) tensors. Here
+// one kernel reads the (B', Cin, N) input once and writes the (B', C2, N) output once (the channel-major tensor
+// VoxelMaxPool #1 consumes); the hidden activations live in shared memory. Every eval-mode BatchNorm is the
+// per-channel affine torch applies (y = x * alpha + beta, alpha = weight / sqrt(var + eps), beta = bias - mean *
+// alpha), kept separate from the convolutions so the arithmetic follows the reference's sequence. fp32 FMA on the
+// CUDA cores: TF32 tensor-core products would miss the 1e-5 parity bar.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kStemPts = 128;     // points per CTA
+constexpr int kStemThreads = 128;  // 4 warps: one thread per point in layer 1, 16 channels x 4 points per thread in layer 2
+constexpr int kStemC = 64;        // C1 == C2 == 64 (the only configuration StreamMOS builds)
+constexpr int kStemCinMax = 16;
+
+struct StemSmem {
+  float h[kStemC][kStemPts];      // hidden activations, [channel][point]
+  float w2t[kStemC][kStemC];      // W2 transposed: [k][c]
+  float w1[kStemC][kStemCinMax];
+  float2 ab1[kStemC];             // (alpha, beta) of the hidden BatchNorm, one 64-bit broadcast load per channel
+  float a2[kStemC], b2[kStemC];
+  float a0[kStemCinMax], b0[kStemCinMax];
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(kStemThreads)
+point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int64_t x_sb, int64_t x_sc, int64_t x_sn,
+                  const float* __restrict__ a0, const float* __restrict__ b0, const float* __restrict__ w1,
+                  const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ w2,
+                  const float* __restrict__ a2, const float* __restrict__ b2, float* __restrict__ y, int64_t y_sb,
+                  int64_t y_sc) {
+  extern __shared__ __align__(16) unsigned char stem_raw[];
+  StemSmem& S = *reinterpret_cast<StemSmem*>(stem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int32_t b = blockIdx.y;
+  const int32_t n0 = blockIdx.x * kStemPts;
+  // parameters -> shared memory. W2 is kept transposed ([k][c]: the 8 output channels of a warp are contiguous per
+  // k); lanes run over c so the transposing stores are conflict free (the 128-bit global reads are strided, 16 KB
+  // from L2 per CTA)
+  for (int i = tid; i < kStemC * (kStemC / 4); i += kStemThreads) {
+    const int c = i & (kStemC - 1), kq = i >> 6;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w2 + c * kStemC) + kq);
+    S.w2t[4 * kq][c] = v.x; S.w2t[4 * kq + 1][c] = v.y; S.w2t[4 * kq + 2][c] = v.z; S.w2t[4 * kq + 3][c] = v.w;
+  }
+  for (int i = tid; i < kStemC * kStemCinMax; i += kStemThreads) {
+    const int c = i / kStemCinMax, ci = i % kStemCinMax;
+    S.w1[c][ci] = ci < Cin ? __ldg(w1 + c * Cin + ci) : 0.f;  // zero padded rows: whole 128-bit reads below
+  }
+  if (tid < kStemC) { S.ab1[tid] = make_float2(__ldg(a1 + tid), __ldg(b1 + tid)); S.a2[tid] = __ldg(a2 + tid); S.b2[tid] = __ldg(b2 + tid); }
+  if (tid < Cin) { S.a0[tid] = a0 ? __ldg(a0 + tid) : 1.f; S.b0[tid] = b0 ? __ldg(b0 + tid) : 0.f; }
+  __syncthreads();
+  // layer 1: thread = point, all hidden channels (weights are warp-uniform broadcast loads)
+  {
+    constexpr int KI = CIN > 0 ? (CIN + 3) / 4 * 4 : kStemCinMax;  // inputs rounded up to whole float4 (zero weights)
+    const int p = tid;
+    const int32_t n = min(n0 + p, N - 1);
+    float xin[KI];
+#pragma unroll
+    for (int ci = 0; ci < KI; ++ci)
+      xin[ci] = ci < Cin ? fmaf(__ldg(x + b * x_sb + ci * x_sc + static_cast<int64_t>(n) * x_sn), S.a0[ci], S.b0[ci]) : 0.f;
+#pragma unroll 4
+    for (int c = 0; c < kStemC; ++c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < KI / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(&S.w1[c][4 * q]);
+        acc = fmaf(w.x, xin[4 * q], acc); acc = fmaf(w.y, xin[4 * q + 1], acc);
+        acc = fmaf(w.z, xin[4 * q + 2], acc); acc = fmaf(w.w, xin[4 * q + 3], acc);
+      }
+      const float2 ab = S.ab1[c];
+      S.h[c][p] = fmaxf(fmaf(acc, ab.x, ab.y), 0.f);
+    }
+  }
+  __syncthreads();
+  // layer 2: warp = 16 output channels, lane = 4 consecutive points: 64 FMAs per 5 shared-memory loads (8 wavefronts)
+  // — with 8 channels per warp the kernel sat at 79 % of the shared-memory pipe and 52 % of the FMA pipe
+  constexpr int CW = 16;
+  const int c0 = wid * CW;
+  float acc[CW][4];
+#pragma unroll
+  for (int j = 0; j < CW; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < kStemC; ++k) {
+    const float4 hv = *reinterpret_cast<const float4*>(&S.h[k][lane * 4]);
+    const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+    for (int jq = 0; jq < CW / 4; ++jq) {
+      const float4 wv = *reinterpret_cast<const float4*>(&S.w2t[k][c0 + 4 * jq]);
+      const float w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[4 * jq + j][i] = fmaf(w[j], hh[i], acc[4 * jq + j][i]);
+    }
+  }
+  const int32_t n = n0 + lane * 4;
+  const bool vec = (n + 3 < N) && ((y_sc & 3) == 0) && ((y_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+#pragma unroll
+  for (int j = 0; j < CW; ++j) {
+    const int c = c0 + j;
+    const float al = S.a2[c], be = S.b2[c];
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = fmaxf(fmaf(acc[j][i], al, be), 0.f);
+    float* dst = y + b * y_sb + c * y_sc + n;
+    if (vec) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n + i < N) dst[i] = o[i];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, int64_t N, int64_t x_sb, int64_t x_sc,
+                                       int64_t x_sn, const float* bn0_alpha, const float* bn0_beta, const float* w1,
+                                       const float* bn1_alpha, const float* bn1_beta, const float* w2,
+                                       const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2, float* y,
+                                       int64_t y_sb, int64_t y_sc, void* stream) {
+  if (B <= 0 || N < 0 || Cin <= 0) return SMOS_EINVAL;
+  if (N == 0) return SMOS_OK;
+  if (!x || !w1 || !bn1_alpha || !bn1_beta || !w2 || !bn2_alpha || !bn2_beta || !y) return SMOS_EINVAL;
+  if ((bn0_alpha == nullptr) != (bn0_beta == nullptr)) return SMOS_EINVAL;
+  if (C1 != kStemC || C2 != kStemC || Cin > kStemCinMax || B > 65535 || N >= (int64_t(1) << 31)) return SMOS_EUNSUPPORTED;
+  static bool opt_in[64] = {};
+  int device = 0;
+  cudaGetDevice(&device);
+  if (device >= 0 && device < 64 && !opt_in[device]) {
+    cudaError_t e = cudaFuncSetAttribute(point_stem_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaFuncSetAttribute(point_stem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    opt_in[device] = true;
+  }
+  dim3 grid(smos_ceil_div(N, kStemPts), static_cast<unsigned>(B));
+  if ((reinterpret_cast<uintptr_t>(w2) & 15) != 0) return SMOS_EINVAL;
+  if (Cin == 7)  // the StreamMOS stem: x, y, z, intensity, dist, diff_x, diff_y
+    point_stem_kernel<7><<<grid, kStemThreads, sizeof(StemSmem), smos_stream(stream)>>>(
+        x, Cin, static_cast<int32_t>(N), x_sb, x_sc, x_sn, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
+        bn2_beta, y, y_sb, y_sc);
+  else
+    point_stem_kernel<0><<<grid, kStemThreads, sizeof(StemSmem), smos_stream(stream)>>>(
+        x, Cin, static_cast<int32_t>(N), x_sb, x_sc, x_sn, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
+        bn2_beta, y, y_sb, y_sc);
+  return smos_launch_status();
+}

@@ -250,6 +250,45 @@ def bilinear_gather_backward(grad_out, grid_coord, scale_rate, H, W):
 
 
 # ----------------------------------------------------------------------------------------------
+# PointNet stem (next: SURVEY 8f rank 4)
+# ----------------------------------------------------------------------------------------------
+def point_stem_forward(x, bn0, w1, bn1, w2, bn2, out=None):
+    """Fused eval-mode PointNetStacker(Cin, 64, pre_bn=True, stack_num=2): x (B, Cin, N[, 1]) float32 ->
+    (B, 64, N, 1) contiguous. bn* = (alpha, beta) per-channel affines of the eval BatchNorms (bn0 may be None);
+    w1 (64, Cin[, 1, 1]), w2 (64, 64[, 1, 1])."""
+    _need_cuda(x, "x")
+    _need_f32(x, "x")
+    x3 = _feat3(x)
+    B, Cin, N = (int(v) for v in x3.shape)
+    for name, w in (("w1", w1), ("w2", w2)):
+        _need_cuda(w, name)
+        _need_f32(w, name)
+    w1 = w1.reshape(w1.shape[0], -1).contiguous()
+    w2 = w2.reshape(w2.shape[0], -1).contiguous()
+    C1, C2 = int(w1.shape[0]), int(w2.shape[0])
+    if w1.shape[1] != Cin or w2.shape[1] != C1:
+        raise RuntimeError("point_stem: weight shapes do not chain (Cin=%d, w1 %s, w2 %s)" % (Cin, tuple(w1.shape), tuple(w2.shape)))
+    vecs = [t for t in ((bn0 or (None, None)) + tuple(bn1) + tuple(bn2)) if t is not None]
+    for v in vecs:
+        _need_cuda(v, "BatchNorm affine")
+        _need_f32(v, "BatchNorm affine")
+    vecs = [v.contiguous() for v in vecs]
+    a0, b0 = (vecs[0], vecs[1]) if bn0 is not None else (None, None)
+    a1, b1, a2, b2 = vecs[-4:]
+    if out is None:
+        out = torch.empty((B, C2, N, 1), dtype=torch.float32, device=x.device)
+    else:
+        assert out.is_contiguous() and out.shape == (B, C2, N, 1) and out.dtype == torch.float32
+    with torch.cuda.device(x.device):
+        rc = _lib.load().smos_point_stem_forward(_ptr(x3), B, Cin, N, x3.stride(0), x3.stride(1), x3.stride(2), _ptr(a0),
+                                                 _ptr(b0), _ptr(w1), _ptr(a1), _ptr(b1), _ptr(w2), _ptr(a2), _ptr(b2),
+                                                 C1, C2, _ptr(out), out.stride(0), out.stride(1), _stream())
+    _lib.check(rc, "smos_point_stem_forward")
+    _count(1)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # MSDeformAttn
 # ----------------------------------------------------------------------------------------------
 _DT = {torch.float32: 0, torch.float64: 1}

@@ -76,6 +76,53 @@ def make_host_scan(seed, n_points=120000, t_frames=3, channels=64, pin=True):
     return out
 
 
+class LoaderBatch:
+    """What the reference's val loader hands to the model for one scan (datasets/data_StreamMOS.py:565-574,
+    models/StreamMOS.py:86-93): T pose-aligned frames of 7-channel point features, BEV and range-view quantised
+    coordinates — plus the stand-ins for network intermediates this harness cannot produce (predicted labels,
+    deformable-attention sampling locations / weights). The 64-channel point features are computed ON THE DEVICE
+    by the PointNet stem (HotPath.point_pre), as in the reference: they never cross PCIe."""
+
+    FIELDS = ("pcds_xyzi", "pcds_coord", "pcds_sphere_coord", "pred", "loc", "attn")
+
+    def __init__(self, **kw):
+        for f in self.FIELDS:
+            setattr(self, f, kw[f])
+
+    coord_bev = property(lambda self: self.pcds_coord[:, :, :2])          # StreamMOS.py:102 (view, no copy)
+    coord_rv = property(lambda self: self.pcds_sphere_coord[:1])          # :99
+
+    def nbytes(self):
+        return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
+
+    def to(self, device, non_blocking=True):
+        return LoaderBatch(**{f: getattr(self, f).to(device, non_blocking=non_blocking) for f in self.FIELDS})
+
+    def copy_from(self, other):
+        for f in self.FIELDS:
+            getattr(self, f).copy_(getattr(other, f), non_blocking=True)
+
+
+def make_host_loader_scan(seed, n_points=120000, t_frames=3, pin=True):
+    """Synthetic loader output of one scan (see LoaderBatch). Point features as make_point_feat builds them
+    (data_StreamMOS.py:25-50): x, y, z, intensity, dist, diff_x, diff_y."""
+    s = synthetic.make_scan(seed, n_points, t_frames)
+    rng = np.random.default_rng(seed + 7919)
+    xyzi = s["xyzi"]                                                           # (T, N, 4)
+    dist = np.sqrt((xyzi[..., :3].astype(np.float64) ** 2).sum(-1)) + 1e-12
+    c = s["pcds_coord"][..., 0]                                                # (T, N, 3)
+    feat7 = np.stack((xyzi[..., 0], xyzi[..., 1], xyzi[..., 2], xyzi[..., 3], dist.astype(np.float32),
+                      c[..., 0] - np.floor(c[..., 0]), c[..., 1] - np.floor(c[..., 1])), 1)  # (T, 7, N)
+    other = make_host_scan(seed, n_points, t_frames, channels=1, pin=False)   # same pred / loc / attn stand-ins
+    out = LoaderBatch(pcds_xyzi=torch.from_numpy(np.ascontiguousarray(feat7[..., None].astype(np.float32))),
+                      pcds_coord=torch.from_numpy(np.ascontiguousarray(s["pcds_coord"])),
+                      pcds_sphere_coord=torch.from_numpy(np.ascontiguousarray(s["pcds_sphere_coord"])),
+                      pred=other.pred, loc=other.loc, attn=other.attn)
+    if pin and torch.cuda.is_available():
+        out = LoaderBatch(**{f: getattr(out, f).pin_memory() for f in LoaderBatch.FIELDS})
+    return out
+
+
 class HotPath:
     """One scan stream. `step(batch)` runs the whole hot path for one scan on the current CUDA stream and
     returns the per-point labels after long-term voting plus the instance votes."""
@@ -106,6 +153,25 @@ class HotPath:
             self.x0 = self.x0.contiguous(memory_format=torch.channels_last)
             self.x1 = self.x1.contiguous(memory_format=torch.channels_last)
             self.dec = self.dec.contiguous(memory_format=torch.channels_last)
+        # PointNet stem (models/StreamMOS.py:77 PointNetStacker(7, 64, pre_bn=True, stack_num=2)), eval mode, random
+        # weights and BatchNorm statistics: only used when a step starts from loader tensors. On CUDA it runs as the
+        # fused smos_point_stem_forward kernel
+        from .backbone import PointNetStacker
+        self.stem = PointNetStacker(7, 64, pre_bn=True, stack_num=2)
+        with torch.no_grad():
+            for mod in self.stem.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    c = mod.num_features
+                    mod.weight.copy_(torch.rand(c, generator=g) + 0.5)
+                    mod.bias.copy_(torch.randn(c, generator=g) * 0.2)
+                    mod.running_mean.copy_(torch.randn(c, generator=g) * 0.3)
+                    mod.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+                elif isinstance(mod, torch.nn.Conv2d):
+                    mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) / mod.weight.shape[1] ** 0.5)
+            bn0 = self.stem.layer[0].layer[0]   # the input BatchNorm sees raw metres
+            bn0.running_mean.copy_(torch.tensor([0.5, -0.3, -1.2, 0.3, 18.0, 0.5, 0.5]))
+            bn0.running_var.copy_(torch.tensor([300.0, 280.0, 0.8, 0.05, 150.0, 0.08, 0.08]))
+        self.stem.eval().to(self.device)
         # short-term memory: previous scan's attended BEV feature, (1, 4096, 128) (mve.py:433-439)
         self.memory = torch.randn(1, MEM_HW * MEM_HW, N_HEADS * HEAD_DIM, generator=g).to(self.device)
         self.shapes = torch.tensor([[MEM_HW, MEM_HW]], dtype=torch.int64, device=self.device)
@@ -134,6 +200,11 @@ class HotPath:
                             zip((synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z), self.size))
 
     # --- the three pieces of the hot path ----------------------------------------------------------
+    def point_pre(self, pcds_xyzi):
+        """(T, 7, N, 1) -> (T, 64, N, 1) contiguous, post-ReLU: the tensor VoxelMaxPool #1 consumes."""
+        with torch.no_grad():
+            return self.stem(pcds_xyzi)
+
     def _fork(self, n):
         """n side streams that start after everything enqueued so far on the current stream. Under CUDA-graph
         capture they become parallel branches of the graph (independent operators of one scan overlap: the
@@ -152,10 +223,12 @@ class HotPath:
         Data dependencies (models/StreamMOS.py:101-105, mve.py:393-417): pool #1 and gather #5 depend on the
         coordinates only; gather1 -> pool2 -> gather2 -> pool3 and gather3 -> pool4 -> gather4 -> pool5 are two
         chains. With `branches` the four run as parallel branches (results are identical)."""
-        cur_bev, cur_rv = b.coord_bev[:1], b.coord_rv
-        # all five pooling plans of the scan depend on the coordinates only: three launches build them all
+        coord_bev = b.coord_bev
+        cur_bev, cur_rv = coord_bev[:1], b.coord_rv
+        feat = b.feat if hasattr(b, "feat") else self.point_pre(b.pcds_xyzi)
+        # all five pooling plans of the scan depend on the coordinates only: four launches build them all
         if self.batch_plans:
-            pl = ops.pool_plan_multi([(b.coord_bev, (512, 512), (1.0, 1.0)), (cur_rv, (32, 1024), (0.5, 0.5)),
+            pl = ops.pool_plan_multi([(coord_bev, (512, 512), (1.0, 1.0)), (cur_rv, (32, 1024), (0.5, 0.5)),
                                       (cur_bev, (256, 256), (0.5, 0.5)), (cur_rv, (16, 512), (0.25, 0.25)),
                                       (cur_bev, (128, 128), (0.25, 0.25))])
         else:
@@ -178,7 +251,7 @@ class HotPath:
             return deep_point.VoxelMaxPool(x1_pt2, cur_bev, (128, 128), (0.25, 0.25), pl[4]), x1_pt2, (x1_pt, x1_rv)
 
         if not self.branches:
-            bev_in = deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0), pl[0])    # StreamMOS.py:102
+            bev_in = deep_point.VoxelMaxPool(feat, coord_bev, (512, 512), (1.0, 1.0), pl[0])        # StreamMOS.py:102
             x0_bev, _ = half_chain()
             x1_bev, x1_pt, _ = quarter_chain()
             pt_bev = self.g_half(self.dec, cur_bev, od[2])                                          # StreamMOS.py:105
@@ -190,11 +263,11 @@ class HotPath:
             x1_bev, x1_pt, keep2 = quarter_chain()
         with torch.cuda.stream(s3):
             pt_bev = self.g_half(self.dec, cur_bev, od[2])
-        bev_in = deep_point.VoxelMaxPool(b.feat, b.coord_bev, (512, 512), (1.0, 1.0), pl[0])
+        bev_in = deep_point.VoxelMaxPool(feat, coord_bev, (512, 512), (1.0, 1.0), pl[0])
         for s in (s1, s2, s3):
             main.wait_stream(s)
         # intermediates stay referenced until the join so the caching allocator cannot hand their blocks out early
-        self._keep = (keep1, keep2, pl)
+        self._keep = (keep1, keep2, pl, feat)
         return bev_in, x0_bev, x1_bev, x1_pt, pt_bev
 
     def temporal_fusion(self, b):
@@ -208,14 +281,16 @@ class HotPath:
     def long_term_voting(self, b):
         """Voxel voting over 8 history scans + the current one, then per-instance votes."""
         cur = HISTORY
+        # raw points of the current frame: loader batches carry them as the first 4 channels of pcds_xyzi
+        xyzi = b.xyzi if hasattr(b, "xyzi") else b.pcds_xyzi[0, :4, :, 0].t().contiguous()
         if self.device.type == "cuda":
             # the previous scan moves from the current slot into its ring slot and the new scan takes the current
             # slot: one kernel (the window slides exactly as voxel_voting.py:182 walks it)
             prev = (self.scan_index - 1) % HISTORY
-            ops.memory_push(b.xyzi, b.pred, self.local_pts[cur], self.local_pred[cur], self.local_pts[prev],
+            ops.memory_push(xyzi, b.pred, self.local_pts[cur], self.local_pred[cur], self.local_pts[prev],
                             self.local_pred[prev])
         else:
-            self.local_pts[cur].copy_(b.xyzi)
+            self.local_pts[cur].copy_(xyzi)
             self.local_pred[cur].copy_(b.pred)
         pts = self.local_pts.view(-1, 4)
         n = self.n_points

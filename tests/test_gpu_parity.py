@@ -559,6 +559,73 @@ def test_stream_vote_edge_cases():
 
 
 # ------------------------------------------------------------------------------------------------
+# PointNet stem (next: SURVEY §8f rank 4)
+# ------------------------------------------------------------------------------------------------
+def _stem_params(g):
+    bn = [O.bn_affine(g["bn%d_weight" % i], g["bn%d_bias" % i], g["bn%d_mean" % i], g["bn%d_var" % i],
+                      float(g["bn%d_eps" % i])) for i in range(3)]
+    return bn[0], g["w1"], bn[1], g["w2"], bn[2]
+
+
+def test_point_stem_golden(golden):
+    from streammos_b200 import ops
+    from streammos_b200.backbone import PointNetStacker
+    g = golden("point_stem_a")
+    bn0, w1, bn1, w2, bn2 = _stem_params(g)
+    tt = lambda pair: (t(pair[0]), t(pair[1]))
+    y = ops.point_stem_forward(t(g["x"]), tt(bn0), t(w1), tt(bn1), t(w2), tt(bn2))
+    assert y.shape == g["out"].shape and y.is_contiguous()
+    # same FMA order as the oracle: bit-exact against it; against the reference within fp32 rounding
+    assert np.array_equal(y[..., 0].cpu().numpy(), O.point_stem(g["x"], bn0, w1, bn1, w2, bn2))
+    body, pads = slice(0, -50), slice(-50, None)
+    np.testing.assert_allclose(y[:, :, body, 0].cpu().numpy(), g["out"][:, :, body, 0], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(y[:, :, pads, 0].cpu().numpy(), g["out64"][:, :, pads, 0], rtol=1e-5, atol=1e-3)
+    # the drop-in module: the reference's state_dict loads, eval forward runs the fused kernel, train forward torch
+    m = PointNetStacker(7, 64, pre_bn=True, stack_num=2)
+    assert sorted(m.state_dict().keys()) == list(g["state_keys"])
+    sd = {"layer.0.layer.1.weight": g["w1"], "layer.1.layer.0.weight": g["w2"]}
+    for i, pre in enumerate(("layer.0.layer.0", "layer.0.layer.2", "layer.1.layer.1")):
+        sd.update({pre + ".weight": g["bn%d_weight" % i], pre + ".bias": g["bn%d_bias" % i],
+                   pre + ".running_mean": g["bn%d_mean" % i], pre + ".running_var": g["bn%d_var" % i],
+                   pre + ".num_batches_tracked": np.int64(0)})
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    m = m.to(dev()).eval()
+    from streammos_b200 import ops as _ops
+    _ops.reset_launch_count()
+    with torch.no_grad():
+        ym = m(t(g["x"]))
+    assert _ops.launch_count() == 1
+    np.testing.assert_allclose(ym[:, :, body, 0].cpu().numpy(), g["out"][:, :, body, 0], rtol=1e-5, atol=1e-5)
+    with torch.enable_grad():                                   # autograd / training go through the torch layers
+        yt = m(t(g["x"]).requires_grad_(True))
+    assert yt.requires_grad
+    # torch runs these convolutions in TF32 on the GPU (cudnn.allow_tf32): only a loose check that the path works
+    np.testing.assert_allclose(yt[:, :, body, 0].detach().cpu().numpy(), g["out"][:, :, body, 0], rtol=5e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize("B,Cin,N", [(3, 7, 120000), (1, 7, 1), (2, 5, 131), (1, 16, 4097)])
+def test_point_stem_sizes_vs_oracle(B, Cin, N):
+    from streammos_b200 import ops
+    rng = np.random.default_rng(B * 1000 + N)
+    x = rng.standard_normal((B, Cin, N, 1)).astype(np.float32) * 3
+    w1 = (rng.standard_normal((64, Cin)) / np.sqrt(Cin)).astype(np.float32)
+    w2 = rng.standard_normal((64, 64)).astype(np.float32) / 8
+    bn = [(rng.uniform(0.5, 1.5, c).astype(np.float32), rng.standard_normal(c).astype(np.float32) * 0.2) for c in (Cin, 64, 64)]
+    tt = lambda pair: (t(pair[0]), t(pair[1]))
+    for bn0 in (bn[0], None):
+        y = ops.point_stem_forward(t(x), tt(bn0) if bn0 else None, t(w1), tt(bn[1]), t(w2), tt(bn[2]))
+        assert np.array_equal(y[..., 0].cpu().numpy(), O.point_stem(x, bn0, w1, bn[1], w2, bn[2]))
+    # strided input view (channels 0..Cin-1 of a wider tensor)
+    wide = rng.standard_normal((B, Cin + 2, N, 1)).astype(np.float32)
+    y = ops.point_stem_forward(t(wide)[:, :Cin], tt(bn[0]), t(w1), tt(bn[1]), t(w2), tt(bn[2]))
+    assert np.array_equal(y[..., 0].cpu().numpy(), O.point_stem(wide[:, :Cin], bn[0], w1, bn[1], w2, bn[2]))
+    with pytest.raises(RuntimeError):
+        ops.point_stem_forward(t(x).cpu(), None, t(w1), tt(bn[1]), t(w2), tt(bn[2]))
+    with pytest.raises(NotImplementedError):                    # float64 weights are refused, not reinterpreted
+        ops.point_stem_forward(t(x), None, t(w1).double(), tt(bn[1]), t(w2), tt(bn[2]))
+
+
+# ------------------------------------------------------------------------------------------------
 # Whole hot path: streaming harness on the GPU vs the CPU restatement of the same sequence
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("point_major", [True, False])
@@ -585,6 +652,27 @@ def test_whole_path_stream_matches_cpu_path(point_major):
             for a, b in zip(proj[1:], r_proj[1:]):                           # chains through bilinear gathers
                 torch.testing.assert_close(a.cpu(), b, rtol=1e-4, atol=1e-5)
             torch.testing.assert_close(hot.memory.cpu(), state["memory"], rtol=1e-4, atol=1e-5)
+
+
+def test_step_from_loader_tensors_matches_explicit_inputs():
+    """A step that starts from the loader's tensors (7-channel point features, (T,N,3,1) coordinates used through a
+    strided [:, :, :2] view, raw points taken from pcds_xyzi) equals the step on explicitly materialised inputs."""
+    from streammos_b200 import stream
+    n = 20000
+    a = stream.HotPath(dev(), n_points=n, seed=3)
+    b = stream.HotPath(dev(), n_points=n, seed=3)
+    with torch.no_grad():
+        for i in range(2):
+            lb = stream.make_host_loader_scan(700 + i, n, pin=False).to(dev())
+            sb = stream.ScanBatch(feat=a.point_pre(lb.pcds_xyzi), coord_bev=lb.pcds_coord[:, :, :2].contiguous(),
+                                  coord_rv=lb.pcds_sphere_coord[:1].contiguous(),
+                                  xyzi=lb.pcds_xyzi[0, :4, :, 0].t().contiguous(), pred=lb.pred, loc=lb.loc, attn=lb.attn)
+            la, sa, pa = a.step(sb)
+            l2, s2, p2 = b.step(lb)
+            assert torch.equal(la, l2) and torch.equal(sa, s2)
+            for x, y in zip(pa, p2):
+                assert torch.equal(x, y)
+            assert not lb.coord_bev.is_contiguous() and float(pa[0].abs().sum()) > 0
 
 
 @pytest.mark.parametrize("use_graphs", [True, False])

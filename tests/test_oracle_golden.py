@@ -122,3 +122,25 @@ def test_stream_vote_bit_exact(golden):
     assert np.array_equal(pl, g["point_labels"])
     assert 0 < int(g["n_cropped"]) < n                      # some current points lie outside the crop ...
     assert (pl != g["preds"][-1]).any()                     # ... and voting changes some labels inside it
+
+
+def _stem_params(g):
+    bn = [O.bn_affine(g["bn%d_weight" % i], g["bn%d_bias" % i], g["bn%d_mean" % i], g["bn%d_var" % i],
+                      float(g["bn%d_eps" % i])) for i in range(3)]
+    return bn[0], g["w1"], bn[1], g["w2"], bn[2]
+
+
+def test_point_stem_matches_reference_module(golden):
+    """PointNetStacker(7, 64, pre_bn=True, stack_num=2).eval() of the reference (networks/backbone.py:199-250)."""
+    g = golden("point_stem_a")
+    y = O.point_stem(g["x"], *_stem_params(g))
+    ref, ref64 = g["out"][..., 0], g["out64"][..., 0]
+    body, pads = slice(0, -50), slice(-50, None)
+    # fp32, 1e-5 relative (+ 1e-5 absolute at the ReLU kink and for sums that cancel)
+    np.testing.assert_allclose(y[..., body], ref[..., body], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(y[..., body], ref64[..., body], rtol=1e-5, atol=1e-5)
+    # loader pads (x = y = -1000, z = -4000): terms of 1e3..1e4 cancel, fp32 itself is only good to ~4e-4 there
+    # (the reference's own fp32 forward differs from its fp64 forward by that much)
+    assert np.abs(ref[..., pads] - ref64[..., pads]).max() > 1e-4
+    np.testing.assert_allclose(y[..., pads], ref64[..., pads], rtol=1e-5, atol=1e-3)
+    assert 0.2 < (ref > 0).mean() < 0.8   # both sides of the ReLU are exercised

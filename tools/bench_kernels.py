@@ -112,4 +112,7 @@ with torch.no_grad():
     timeit("vote point labels", lambda i: voting.get_point_labels_from_voxel_labels(coords[8 * N:], vl, hot.size), 40 * N / 1e6)
     timeit("vote fused API", lambda i: ops.vote_fused(pts, hot.local_pred.view(-1), N, hot.mins, hot.deltas, hot.size, 3))
     timeit("instance votes (32 boxes)", lambda i: ops.instance_vote(pts, labels, hot.box_lo, hot.box_hi), 24 * P / 1e6)
+    lscans = [stream.make_host_loader_scan(i, N).to(dev) for i in range(4)]
+    timeit("point stem 3x7xN -> 3x64xN (fused)", lambda i: hot.point_pre(lscans[i % 4].pcds_xyzi), (4 * 3 * 7 * N + 4 * 3 * 64 * N) / 1e6)
+    timeit("point stem (torch layers)", lambda i: hot.stem.layer(lscans[i % 4].pcds_xyzi), (4 * 3 * 7 * N + 4 * 3 * 64 * N) / 1e6)
     timeit("whole step (eager, serial)", lambda i: hot.step(S(i)))

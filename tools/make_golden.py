@@ -8,6 +8,7 @@ What runs, unmodified:
   * deformattn/functions/ms_deform_attn_func.py:ms_deform_attn_core_pytorch (+ torch autograd for grads)
   * voxel_voting.py / voxel_instance_voting.py functions, extracted with `ast` because the scripts run
     argparse at import time (voxel_voting.py:128-136)
+  * networks/backbone.py:PointNetStacker(7, 64, pre_bn=True, stack_num=2).eval()   (the stem of models/StreamMOS.py:77)
 
     python tools/make_golden.py [--ref /root/reference]
 """
@@ -323,21 +324,68 @@ def gen_stream_vote(ref, rng):
     return ["stream_vote_a"]
 
 
+def gen_point_stem(ref, rng):
+    """networks/backbone.py PointNetStacker(7, 64, pre_bn=True, stack_num=2) exactly as models/StreamMOS.py:77 builds
+    it, in eval mode with non-trivial BatchNorm statistics, on loader-shaped 7-channel point features."""
+    bb = load_by_path("ref_backbone", os.path.join(ref, "networks", "backbone.py"))
+    g = torch.Generator().manual_seed(1234)
+    m = bb.PointNetStacker(7, 64, pre_bn=True, stack_num=2)
+    bns = [mod for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)]
+    convs = [mod for mod in m.modules() if isinstance(mod, torch.nn.Conv2d)]
+    assert len(bns) == 3 and len(convs) == 2
+    with torch.no_grad():
+        for bn in bns:
+            c = bn.num_features
+            bn.weight.copy_(torch.rand(c, generator=g) * 1.5 + 0.25)
+            bn.bias.copy_(torch.randn(c, generator=g) * 0.3)
+            bn.running_mean.copy_(torch.randn(c, generator=g) * 0.5)
+            bn.running_var.copy_(torch.rand(c, generator=g) * 2.0 + 0.1)
+        # the input BatchNorm sees raw metres: statistics of that scale
+        bns[0].running_mean.copy_(torch.tensor([0.5, -0.3, -1.2, 0.3, 18.0, 0.5, 0.5]))
+        bns[0].running_var.copy_(torch.tensor([300.0, 280.0, 0.8, 0.05, 150.0, 0.08, 0.08]))
+    m.eval()
+    T, N = 3, 4000
+    x = np.stack([rng.uniform(-50, 50, (T, N)), rng.uniform(-50, 50, (T, N)), rng.uniform(-4, 2, (T, N)),
+                  rng.uniform(0, 1, (T, N)), rng.uniform(1, 70, (T, N)), rng.uniform(0, 1, (T, N)),
+                  rng.uniform(0, 1, (T, N))], 1).astype(np.float32)[..., None]          # (T, 7, N, 1)
+    x[:, :3, -50:] = np.array([-1000.0, -1000.0, -4000.0], np.float32)[None, :, None, None]  # loader pads
+    with torch.no_grad():
+        out = m(torch.from_numpy(x)).numpy()
+        out64 = m.double()(torch.from_numpy(x).double()).numpy()
+        m.float()
+    p = {}
+    for i, bn in enumerate(bns):
+        p.update({"bn%d_weight" % i: bn.weight.detach().numpy(), "bn%d_bias" % i: bn.bias.detach().numpy(),
+                  "bn%d_mean" % i: bn.running_mean.numpy(), "bn%d_var" % i: bn.running_var.numpy(),
+                  "bn%d_eps" % i: np.float64(bn.eps)})
+    np.savez_compressed(os.path.join(GOLD, "point_stem_a.npz"), x=x, w1=convs[0].weight.detach().numpy(),
+                        w2=convs[1].weight.detach().numpy(), out=out, out64=out64,
+                        state_keys=np.array(sorted(m.state_dict().keys())), **p)
+    return ["point_stem_a"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", default="", help="generate one family only (e.g. point_stem) and leave the others")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(1)
     rng = np.random.default_rng(20261018)
     made = []
+    if a.only == "point_stem":
+        made += gen_point_stem(a.ref, np.random.default_rng(99))
+        for m in made:
+            print("%-28s %8.1f KB" % (m, os.path.getsize(os.path.join(GOLD, m + ".npz")) / 1024))
+        return
     made += gen_pool(a.ref, rng)
     made += gen_bilinear(a.ref, rng)
     made += gen_msda(a.ref, rng)
     made += gen_voting(a.ref, rng)
     made += gen_instance(a.ref, rng)
     made += gen_stream_vote(a.ref, np.random.default_rng(77))
+    made += gen_point_stem(a.ref, np.random.default_rng(99))
     for m in made:
         p = os.path.join(GOLD, m + ".npz")
         print("%-28s %8.1f KB" % (m, os.path.getsize(p) / 1024))

@@ -17,10 +17,11 @@ ap.add_argument("--steps", type=int, default=8)
 ap.add_argument("--points", type=int, default=120000)
 ap.add_argument("--what", default="step")
 ap.add_argument("--vote-api", default="reference")
+ap.add_argument("--loader", action="store_true", help="start every step from the loader tensors (PointNet stem on device)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 hot = stream.HotPath(dev, a.points, seed=0, branches=False, vote_api=a.vote_api)
-scans = [stream.make_host_scan(i, a.points).to(dev) for i in range(4)]
+scans = [(stream.make_host_loader_scan if a.loader else stream.make_host_scan)(i, a.points).to(dev) for i in range(4)]
 fn = {"step": hot.step, "vote": hot.long_term_voting, "proj": hot.projection}[a.what]
 with torch.no_grad():
     for i in range(3):
