@@ -30,4 +30,7 @@ def install(point_major_points=False):
             ref_backbone = None
     if ref_backbone is not None:
         ref_backbone.BilinearSample = b200_backbone.BilinearSample
+        # models/StreamMOS.py:77 builds `backbone.PointNetStacker(7, C, pre_bn=True, stack_num=2)`: same constructor and
+        # parameter names, eval forward fused into one kernel (training / autograd keep the torch layers)
+        ref_backbone.PointNetStacker = b200_backbone.PointNetStacker
     return True

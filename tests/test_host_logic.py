@@ -65,6 +65,36 @@ def test_dropin_registers_reference_module_names():
                 sys.modules[k] = v
 
 
+def test_dropin_replaces_backbone_classes_and_stem_keeps_reference_layout():
+    import types
+    from streammos_b200 import backbone as b200_backbone
+    from streammos_b200 import dropin
+    saved = {k: sys.modules.get(k) for k in ("deep_point", "point_deep", "point_deep.cuda_kernel", "point_deep.cpu_kernel",
+                                             "MultiScaleDeformableAttention", "networks.backbone", "networks")}
+    fake = types.ModuleType("networks.backbone")
+    fake.BilinearSample = fake.PointNetStacker = object
+    sys.modules["networks.backbone"] = fake
+    try:
+        dropin.install()
+        assert fake.BilinearSample is b200_backbone.BilinearSample
+        assert fake.PointNetStacker is b200_backbone.PointNetStacker
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    # parameter names of networks/backbone.py:199-250 (checkpoints load); CPU / training inputs run the torch layers,
+    # exactly the reference's own code path for this module
+    m = b200_backbone.PointNetStacker(7, 64, pre_bn=True, stack_num=2)
+    keys = set(m.state_dict().keys())
+    assert {"layer.0.layer.0.running_mean", "layer.0.layer.1.weight", "layer.0.layer.2.weight",
+            "layer.1.layer.0.weight", "layer.1.layer.1.running_var"} <= keys and len(keys) == 17
+    y = m.eval()(torch.randn(2, 7, 50, 1))
+    assert y.shape == (2, 64, 50, 1) and float(y.min()) >= 0.0
+    assert b200_backbone.PointNetStacker(7, 32, stack_num=1)(torch.randn(1, 7, 5, 1)).shape == (1, 32, 5, 1)
+
+
 def test_bilinear_sample_signature():
     from streammos_b200.backbone import BilinearSample
     m = BilinearSample(in_dim=4, scale_rate=(0.5, 0.5))

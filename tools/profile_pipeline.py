@@ -1,0 +1,58 @@
+"""Timeline of the pipelined graph replays (CUPTI through torch.profiler): how much of a scan's wall time has
+0 / 1 / 2+ kernels running, and which kernels the time goes to when they overlap.
+    python tools/profile_pipeline.py [--scans 32]"""
+import argparse
+import os
+import sys
+from collections import defaultdict
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from streammos_b200 import pipeline, stream  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scans", type=int, default=32)
+ap.add_argument("--points", type=int, default=120000)
+ap.add_argument("--in-flight", type=int, default=2)
+ap.add_argument("--no-branches", action="store_true")
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+hot = stream.HotPath(dev, a.points, seed=0, branches=not a.no_branches)
+scans = [stream.make_host_scan(i, a.points).to(dev) for i in range(8)]
+pipe = pipeline.ScanPipeline(hot, scans, use_graphs=True, scans_in_flight=a.in_flight)
+for _ in range(16):
+    pipe.submit()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(a.scans):
+        pipe.submit()
+    torch.cuda.synchronize()
+evs = [(e.time_range.start, e.time_range.end, e.name) for e in prof.events()
+       if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort()
+t0, t1 = evs[0][0], max(e[1] for e in evs)
+span = t1 - t0
+print("scans %d  span %.1f us  -> %.1f us/scan ; kernels/scan %.1f ; sum of kernel time %.1f us/scan"
+      % (a.scans, span, span / a.scans, len(evs) / a.scans, sum(e[1] - e[0] for e in evs) / a.scans))
+# sweep line: time with k kernels active
+pts = []
+for s, e, n in evs:
+    pts.append((s, 1))
+    pts.append((e, -1))
+pts.sort()
+hist = defaultdict(float)
+k, last = 0, pts[0][0]
+for t, d in pts:
+    hist[min(k, 4)] += t - last
+    last = t
+    k += d
+for kk in sorted(hist):
+    print("  %s kernels active: %6.1f us/scan (%4.1f %%)" % (("%d" % kk) if kk < 4 else "4+", hist[kk] / a.scans, 100 * hist[kk] / span))
+by = defaultdict(float)
+for s, e, n in evs:
+    by[n[:70]] += e - s
+print("in-pipeline kernel time per scan (durations stretch when kernels share the GPU):")
+for n, v in sorted(by.items(), key=lambda x: -x[1])[:16]:
+    print("  %-70s %7.1f us" % (n, v / a.scans))
