@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-ordered-gathers", action="store_true",
                     help="BEV gathers visit the points in scan order instead of the pooling plan's cell order")
     ap.add_argument("--ordered-rv", action="store_true", help="range-view gathers in cell order too")
+    ap.add_argument("--gather-taps", action="store_true",
+                    help="gathers read their sampling state from records the plan build emits (measured: no gain)")
     return ap.parse_args()
 
 
@@ -201,7 +203,9 @@ def workload_config(args, graph, world):
                            "chains only" if args.no_branches else "independent operators of a scan are parallel graph "
                            "branches (pool #1 | half-scale chain | quarter-scale chain | gather #5; voxel | instance votes)"),
             "gather_order": "scan order" if args.no_ordered_gathers else
-                            ("cell order of the shared pooling plan (BEV%s)" % (" + RV" if args.ordered_rv else "")),
+                            ("cell order of the shared pooling plan (BEV%s)%s" % (
+                                " + RV" if (args.ordered_rv or args.gather_taps) else "",
+                                "; sampling state emitted by the plan build" if args.gather_taps else "")),
             "l2": "no explicit flush: %d distinct scans cycled, ~100 MB inputs and ~700 MB touched per step (>126 MB L2)" % N_SCANS}
 
 
@@ -218,7 +222,8 @@ def run_b200(args, world, rank, local):
     hot = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
                          vote_api=args.vote_api, overlap_voting=False,
                          grids_channels_last=args.grids_channels_last, branches=not args.no_branches,
-                         ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv)
+                         ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv,
+                         gather_taps=args.gather_taps)
     host = [stream.make_host_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
     devb = [h.to(dev) for h in host]
     torch.cuda.synchronize()
@@ -312,12 +317,12 @@ def run_b200(args, world, rank, local):
         e2e_feat["note"] = ("hot-path input tensors in pinned host memory (3x64xN point features = 92 MB of the H2D bytes): "
                             "PCIe bound; kept for reference")
         # (2) headline e2e: the LOADER's tensors in host memory, as in the reference (models/StreamMOS.py:86-103): 7-channel
-        #     point features + BEV / range-view coordinates per frame; the PointNet stem (torch, out of scope) runs on the
+        #     point features + BEV / range-view coordinates per frame; the PointNet stem (our fused kernel) runs on the
         #     device inside the timed region and feeds VoxelMaxPool #1
         hot_l = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
                                vote_api=args.vote_api, grids_channels_last=args.grids_channels_last,
                                branches=not args.no_branches, ordered_gathers=not args.no_ordered_gathers,
-                               ordered_rv=args.ordered_rv)
+                               ordered_rv=args.ordered_rv, gather_taps=args.gather_taps)
         host_l = [stream.make_host_loader_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
         devb_l = [h.to(dev) for h in host_l]
         torch.cuda.synchronize()
@@ -326,8 +331,8 @@ def run_b200(args, world, rank, local):
         clocks = sampler.stop() if rank == 0 else None  # sampled across the timed regions
         e2e["note"] = ("host buffers = what the reference's loader hands to the model (T x 7-channel point features, BEV and "
                        "range-view coordinates, + predicted labels and attention samples as stand-ins for network "
-                       "intermediates); H2D copy, PointNet stem (torch conv1x1 x2, out of scope), the whole hot path and the "
-                       "D2H of the labels are inside the timed region; the copy of scan i+1 overlaps scan i")
+                       "intermediates); H2D copy, PointNet stem (fused smos_point_stem_forward kernel, SURVEY 8f rank 4), the whole "
+                       "hot path and the D2H of the labels are inside the timed region; the copy of scan i+1 overlaps scan i")
         e2e["hot_path_inputs_over_pcie"] = e2e_feat
         del pipe_l, devb_l, hot_l
 
@@ -370,7 +375,8 @@ def run_b200(args, world, rank, local):
             del pipe
             hot2 = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
                                   vote_api="fused", grids_channels_last=True, branches=not args.no_branches,
-                                  ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv)
+                                  ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv,
+                         gather_taps=args.gather_taps)
             pipe2 = pipeline.ScanPipeline(hot2, devb, use_graphs=True, scans_in_flight=args.in_flight)
             vsteps = min(args.steps, 500)
             for i in range(20):

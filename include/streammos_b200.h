@@ -83,6 +83,9 @@ typedef struct smos_pool_plan_desc {
   int64_t* voxel_max_idx; /* may be NULL */
   int64_t idx_batch_stride;
   void* plan;
+  void* gather_taps; /* may be NULL; else smos_gather_taps_bytes(B, N) bytes, 16-byte aligned: the BilinearSample
+                        sampling state of every point for THIS grid and scale (networks/backbone.py:458-475), one
+                        48-byte record per slot of the plan's cell order, for smos_bilinear_gather_forward_taps */
 } smos_pool_plan_desc;
 
 int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n, void* stream);
@@ -158,6 +161,16 @@ int smos_bilinear_gather_forward_ordered(const float* grid, int64_t B, int64_t C
                                          float scale_h, float scale_w,
                                          float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
                                          const void* plan, int32_t plan_H, int32_t plan_W, void* stream);
+
+/* Same result again from sampling records that a pooling plan build emitted as a by-product
+ * (smos_pool_plan_desc.gather_taps: same coordinates, H, W and scale as this gather): the kernel's prologue is one
+ * 48-byte load per point instead of order entry -> coordinates -> replayed pixel arithmetic. Points are visited in
+ * the plan's cell order; `out` must be point-major (o_sc == 1). N = points per batch entry of the plan. */
+int64_t smos_gather_taps_bytes(int64_t B, int64_t N);
+int smos_bilinear_gather_forward_taps(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W,
+                                      int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
+                                      const void* taps, int64_t N,
+                                      float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, void* stream);
 
 /* grad_grid (B, C, H, W) NCHW-contiguous must be ZERO-FILLED by the caller;
  * contributions are accumulated with fp32 atomics (grid_sampler backward). */

@@ -15,7 +15,7 @@ class PoolPlanDesc(ctypes.Structure):
     """struct smos_pool_plan_desc (include/streammos_b200.h)."""
     _fields_ = [("pcds_ind", _vp), ("B", _i64), ("N", _i64), ("ind_sb", _i64), ("ind_sn", _i64), ("ind_sd", _i64),
                 ("H", _i32), ("W", _i32), ("scale_h", _f32), ("scale_w", _f32), ("voxel_max_idx", _vp),
-                ("idx_batch_stride", _i64), ("plan", _vp)]
+                ("idx_batch_stride", _i64), ("plan", _vp), ("gather_taps", _vp)]
 
 
 class VoteStreamScan(ctypes.Structure):
@@ -43,6 +43,9 @@ SIGNATURES = {
                                                     _i64, _i64, _i64, _f32, _f32, _vp, _i64, _i64, _i64, _vp]),
     "smos_bilinear_gather_forward_ordered": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _i64,
                                                     _i64, _i64, _i64, _f32, _f32, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp]),
+    "smos_gather_taps_bytes": (ctypes.c_int64, [_i64, _i64]),
+    "smos_bilinear_gather_forward_taps": (ctypes.c_int, [_vp, _i64, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _i64,
+                                                         _vp, _i64, _i64, _i64, _vp]),
     "smos_bilinear_gather_backward": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                                      _f32, _f32, _i32, _i32, _vp, _vp]),
     "smos_ms_deform_attn_forward": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,

@@ -6,48 +6,9 @@
 // reference's float sequence (normalise then un-normalise) is replayed with explicitly
 // rounded fp32 operations so results stay within 1e-5 of grid_sample.
 #include "common.cuh"
+#include "gather_taps.cuh"
 
 namespace {
-
-struct Taps {
-  int32_t x0, y0;        // north-west integer pixel
-  float w_nw, w_ne, w_sw, w_se;
-  bool in_nw, in_ne, in_sw, in_se;
-};
-
-// pix = ((g + 1) / 2) * (size - 1), g = 2 * c * s / (size - 1) - 1   (backbone.py:469-470 + ATen
-// grid_sampler_unnormalize with align_corners=True). Every step individually rounded.
-__device__ __forceinline__ float replay_pixel(float c, float s, int32_t size) {
-  const float sm1 = static_cast<float>(size - 1);
-  float g = __fmul_rn(__fmul_rn(2.0f, c), s);
-  g = __fdiv_rn(g, sm1);
-  g = __fsub_rn(g, 1.0f);
-  float p = __fadd_rn(g, 1.0f);
-  p = __fmul_rn(p, 0.5f);
-  return __fmul_rn(p, sm1);
-}
-
-__device__ __forceinline__ Taps make_taps(float cy, float cx, float sh, float sw, int32_t H, int32_t W) {
-  Taps t;
-  const float ix = replay_pixel(cx, sw, W);
-  const float iy = replay_pixel(cy, sh, H);
-  const float fx = floorf(ix), fy = floorf(iy);
-  // weights as in ATen grid_sampler_2d: nw = (x_se - x)(y_se - y) ...
-  const float x1 = __fadd_rn(fx, 1.0f), y1 = __fadd_rn(fy, 1.0f);
-  t.w_nw = __fmul_rn(__fsub_rn(x1, ix), __fsub_rn(y1, iy));
-  t.w_ne = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(y1, iy));
-  t.w_sw = __fmul_rn(__fsub_rn(x1, ix), __fsub_rn(iy, fy));
-  t.w_se = __fmul_rn(__fsub_rn(ix, fx), __fsub_rn(iy, fy));
-  // clamp before the int cast so far-away pads (and NaN) become plain out-of-bounds
-  const float cxl = fminf(fmaxf(fx, -2.0f), static_cast<float>(W) + 1.0f);
-  const float cyl = fminf(fmaxf(fy, -2.0f), static_cast<float>(H) + 1.0f);
-  t.x0 = (fx == fx) ? static_cast<int32_t>(cxl) : -2;
-  t.y0 = (fy == fy) ? static_cast<int32_t>(cyl) : -2;
-  const bool xl = t.x0 >= 0 && t.x0 < W, xh = t.x0 + 1 >= 0 && t.x0 + 1 < W;
-  const bool yl = t.y0 >= 0 && t.y0 < H, yh = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-  t.in_nw = xl && yl; t.in_ne = xh && yl; t.in_sw = xl && yh; t.in_se = xh && yh;
-  return t;
-}
 
 constexpr int kGatherThreads = 128;
 constexpr int kGatherPts = 32;  // points per CTA
@@ -57,22 +18,31 @@ constexpr int kCPT = 8;         // channels per thread-step in the planar kernel
 // instructions (two IEEE divisions) and every channel of a point needs the same result, so it is
 // computed ONCE per point by the first 32 threads and broadcast through shared memory. (Recomputing
 // it per channel group made the kernel instruction bound.)
-struct TapsS {
-  int32_t o_nw, o_ne, o_sw, o_se;  // clamped (always valid) pixel offsets  y * W + x
-  float w_nw, w_ne, w_sw, w_se;    // bilinear weights, already zeroed for out-of-image taps? no: see in_*
-  uint32_t in_mask;                // bit0 nw, bit1 ne, bit2 sw, bit3 se
-  int32_t n, b;                    // the point this slot samples for (n < 0: no point)
-};
-
 // ORDERED: slot i of the CTA serves entry p0 + i of a pooling plan's `sorted` list (points grouped by grid cell,
 // out-of-grid points at the tail) instead of point n0 + i. Consecutive slots then sample the same or adjacent
 // cells: in scan order a BEV arc crosses a different image row at almost every point (one 128-byte line per
 // lane and tap), in cell order a warp's taps share one or two lines per channel plane.
-template <bool ORDERED>
+// TAPS: the records were written by the pooling plan builder (same coordinates, grid and scale), one per slot of its
+// cell order: the prologue is a single 48-byte load per slot instead of order entry -> coordinates -> arithmetic.
+template <bool ORDERED, bool TAPS>
 __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict__ coord, int32_t b, int32_t n0,
                                          int32_t N, int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
                                          int32_t H, int32_t W, const int2* __restrict__ order, int32_t order_hw,
-                                         int64_t order_len) {
+                                         int64_t order_len, const TapsS* __restrict__ taps) {
+  if (TAPS) {
+    // 32 records x three 128-bit words, one word per thread
+    const int64_t p0 = static_cast<int64_t>(blockIdx.x) * kGatherPts;
+    if (threadIdx.x < kGatherPts * 3) {
+      const int32_t slot = threadIdx.x / 3, w = threadIdx.x - slot * 3;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      const bool live = p0 + slot < order_len;
+      if (live) v = __ldg(reinterpret_cast<const uint4*>(taps + p0 + slot) + w);
+      if (!live && w == 2) v.y = 0xffffffffu;  // n = -1: slot without a point
+      reinterpret_cast<uint4*>(s_taps + slot)[w] = v;
+    }
+    __syncthreads();
+    return;
+  }
   if (threadIdx.x < kGatherPts) {
     int32_t n = min(n0 + static_cast<int32_t>(threadIdx.x), N - 1);
     bool live = n0 + static_cast<int32_t>(threadIdx.x) < N;
@@ -84,16 +54,7 @@ __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict_
       b = e.y >= 0 ? e.y / order_hw : -1 - e.y;                            // out-of-grid entries carry -1 - b
     }
     const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
-    const Taps t = make_taps(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W);
-    const int32_t xa = min(max(t.x0, 0), W - 1), xb = min(max(t.x0 + 1, 0), W - 1);
-    const int32_t ya = min(max(t.y0, 0), H - 1), yb = min(max(t.y0 + 1, 0), H - 1);
-    TapsS r;
-    r.o_nw = ya * W + xa; r.o_ne = ya * W + xb; r.o_sw = yb * W + xa; r.o_se = yb * W + xb;
-    r.w_nw = t.w_nw; r.w_ne = t.w_ne; r.w_sw = t.w_sw; r.w_se = t.w_se;
-    r.in_mask = (t.in_nw ? 1u : 0u) | (t.in_ne ? 2u : 0u) | (t.in_sw ? 4u : 0u) | (t.in_se ? 8u : 0u);
-    r.n = live ? n : -1;
-    r.b = b;
-    s_taps[threadIdx.x] = r;
+    s_taps[threadIdx.x] = make_taps_record(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W, live ? n : -1, b);
   }
   __syncthreads();
 }
@@ -104,18 +65,20 @@ __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict_
 // 4*kCPT tap loads of a step are UNCONDITIONAL (out-of-image taps read a clamped, valid pixel and are
 // zeroed by a select afterwards): predicated loads get serialised through one temporary register by
 // ptxas. For point-major outputs the kCPT results leave as one full 32-byte sector per thread.
-template <bool DENSE, bool ROWS_OUT, bool ORDERED>
+template <bool DENSE, bool ROWS_OUT, bool ORDERED, bool TAPS>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                              int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
                              const float* __restrict__ coord, int32_t N,
                              int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
                              float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
-                             const int2* __restrict__ order, int32_t order_hw, int64_t order_len) {
+                             const int2* __restrict__ order, int32_t order_hw, int64_t order_len,
+                             const TapsS* __restrict__ taps) {
   __shared__ TapsS s_taps[kGatherPts];
   extern __shared__ __align__(16) float s_out[];  // ROWS_OUT: [kGatherPts][C + 4]
   const int32_t n0 = blockIdx.x * kGatherPts;
-  cta_taps<ORDERED>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len);
+  cta_taps<ORDERED, TAPS>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len,
+                          taps);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const TapsS t = s_taps[lane];
   const int32_t b = t.b;
@@ -190,17 +153,19 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
 
 // Channels-last grid (gr_sc == 1, C % 4 == 0): lanes run over channel quads, every tap is a
 // contiguous 16-byte load and a point's taps are four contiguous C*4-byte rows. CTA = 32 points.
-template <bool ORDERED>
+template <bool ORDERED, bool TAPS>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                            int64_t gr_sb, int64_t gr_sh, int64_t gr_sw,
                            const float* __restrict__ coord, int32_t N,
                            int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
                            float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
-                           const int2* __restrict__ order, int32_t order_hw, int64_t order_len) {
+                           const int2* __restrict__ order, int32_t order_hw, int64_t order_len,
+                           const TapsS* __restrict__ taps) {
   __shared__ TapsS s_taps[kGatherPts];
   const int32_t n0 = blockIdx.x * kGatherPts;
-  cta_taps<ORDERED>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len);
+  cta_taps<ORDERED, TAPS>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len,
+                          taps);
   const int32_t q = C >> 2;  // channel quads per point
   const bool vec_ok = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -264,28 +229,33 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
                                  int64_t gr_sc, int64_t gr_sh, int64_t gr_sw, const float* coord, int64_t N,
                                  int64_t co_sb, int64_t co_sn, int64_t co_sd, float scale_h, float scale_w,
                                  float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, const int2* order,
-                                 int32_t order_hw, void* stream) {
+                                 int32_t order_hw, const TapsS* taps, void* stream) {
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || N < 0) return SMOS_EINVAL;
   if (N == 0) return SMOS_OK;
-  if (!grid || !coord || !out) return SMOS_EINVAL;
+  if (!grid || (!coord && !taps) || !out) return SMOS_EINVAL;
   if (B > 65535 || N >= (int64_t(1) << 31) || C >= (1 << 24) || B * N >= (int64_t(1) << 31)) return SMOS_EUNSUPPORTED;
   cudaStream_t st = smos_stream(stream);
   const bool nhwc = (gr_sc == 1) && ((C & 3) == 0) && ((gr_sw & 3) == 0) && ((gr_sh & 3) == 0) &&
                     ((gr_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
   // cell order only pays when a point's channels leave as whole sectors (point-major output rows)
-  const bool ordered = order != nullptr && o_sc == 1 && C > 1;
+  const bool with_taps = taps != nullptr;  // implies slot (cell) order; the caller checked the output layout
+  const bool ordered = (order != nullptr && o_sc == 1 && C > 1) || with_taps;
   const int64_t order_len = B * N;
   dim3 g(smos_ceil_div(ordered ? order_len : N, kGatherPts), 1, ordered ? 1u : static_cast<unsigned>(B));
   const int32_t Ni = static_cast<int32_t>(N), Ci = static_cast<int32_t>(C);
   if (nhwc) {
-    if (ordered)
-      gather_forward_nhwc_kernel<true><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
-                                                                      co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb,
-                                                                      o_sc, o_sn, order, order_hw, order_len);
+    if (with_taps)
+      gather_forward_nhwc_kernel<true, true><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
+                                                                            co_sb, co_sn, co_sd, scale_h, scale_w, out,
+                                                                            o_sb, o_sc, o_sn, order, order_hw, order_len, taps);
+    else if (ordered)
+      gather_forward_nhwc_kernel<true, false><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
+                                                                             co_sb, co_sn, co_sd, scale_h, scale_w, out,
+                                                                             o_sb, o_sc, o_sn, order, order_hw, order_len, nullptr);
     else
-      gather_forward_nhwc_kernel<false><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
-                                                                       co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb,
-                                                                       o_sc, o_sn, nullptr, 1, 0);
+      gather_forward_nhwc_kernel<false, false><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord,
+                                                                              Ni, co_sb, co_sn, co_sd, scale_h, scale_w, out,
+                                                                              o_sb, o_sc, o_sn, nullptr, 1, 0, nullptr);
   } else {
     // point-major output rows (C % 8 == 0, 16-byte aligned) are assembled in shared memory and leave as whole lines
     const bool rows_out = (o_sc == 1) && C > 1 && ((C & 7) == 0) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
@@ -293,20 +263,25 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
                           (static_cast<size_t>(C + 4) * kGatherPts * 4 <= 40 * 1024) && smos_env_int("SMOS_GATHER_ROWS", 1);
     const size_t smem = rows_out ? static_cast<size_t>(C + 4) * kGatherPts * 4 : 0;
     const bool dense = (gr_sw == 1 && gr_sh == W);
-#define SMOS_LAUNCH_PLANAR(D, R, O)                                                                          \
-    gather_forward_planar_kernel<D, R, O><<<g, kGatherThreads, smem, st>>>(                                    \
+#define SMOS_LAUNCH_PLANAR(D, R, O, T)                                                                       \
+    gather_forward_planar_kernel<D, R, O, T><<<g, kGatherThreads, smem, st>>>(                                 \
         grid, Ci, H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, Ni, co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb, \
-        o_sc, o_sn, order, order_hw, order_len)
-    if (ordered) {
-      if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true, true);
-      else if (dense) SMOS_LAUNCH_PLANAR(true, false, true);
-      else if (rows_out) SMOS_LAUNCH_PLANAR(false, true, true);
-      else SMOS_LAUNCH_PLANAR(false, false, true);
+        o_sc, o_sn, order, order_hw, order_len, taps)
+    if (with_taps) {
+      if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true, true, true);
+      else if (dense) SMOS_LAUNCH_PLANAR(true, false, true, true);
+      else if (rows_out) SMOS_LAUNCH_PLANAR(false, true, true, true);
+      else SMOS_LAUNCH_PLANAR(false, false, true, true);
+    } else if (ordered) {
+      if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true, true, false);
+      else if (dense) SMOS_LAUNCH_PLANAR(true, false, true, false);
+      else if (rows_out) SMOS_LAUNCH_PLANAR(false, true, true, false);
+      else SMOS_LAUNCH_PLANAR(false, false, true, false);
     } else {
-      if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true, false);
-      else if (dense) SMOS_LAUNCH_PLANAR(true, false, false);
-      else if (rows_out) SMOS_LAUNCH_PLANAR(false, true, false);
-      else SMOS_LAUNCH_PLANAR(false, false, false);
+      if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true, false, false);
+      else if (dense) SMOS_LAUNCH_PLANAR(true, false, false, false);
+      else if (rows_out) SMOS_LAUNCH_PLANAR(false, true, false, false);
+      else SMOS_LAUNCH_PLANAR(false, false, false, false);
     }
 #undef SMOS_LAUNCH_PLANAR
   }
@@ -318,7 +293,7 @@ int smos_bilinear_gather_forward(const float* grid, int64_t B, int64_t C, int32_
                                  int64_t co_sb, int64_t co_sn, int64_t co_sd, float scale_h, float scale_w,
                                  float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, void* stream) {
   return gather_forward_launch(grid, B, C, H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, N, co_sb, co_sn, co_sd, scale_h,
-                               scale_w, out, o_sb, o_sc, o_sn, nullptr, 1, stream);
+                               scale_w, out, o_sb, o_sc, o_sn, nullptr, 1, nullptr, stream);
 }
 
 int smos_bilinear_gather_forward_ordered(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W, int64_t gr_sb,
@@ -330,7 +305,20 @@ int smos_bilinear_gather_forward_ordered(const float* grid, int64_t B, int64_t C
   const PoolLayout L = smos_pool_layout(B, N, plan_H, plan_W);
   const int2* sorted = reinterpret_cast<const int2*>(static_cast<const char*>(plan) + L.off_sorted);
   return gather_forward_launch(grid, B, C, H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, N, co_sb, co_sn, co_sd, scale_h,
-                               scale_w, out, o_sb, o_sc, o_sn, sorted, static_cast<int32_t>(L.hw), stream);
+                               scale_w, out, o_sb, o_sc, o_sn, sorted, static_cast<int32_t>(L.hw), nullptr, stream);
+}
+
+int64_t smos_gather_taps_bytes(int64_t B, int64_t N) {
+  if (B <= 0 || N < 0) return SMOS_EINVAL;
+  return B * N * static_cast<int64_t>(sizeof(TapsS));
+}
+
+int smos_bilinear_gather_forward_taps(const float* grid, int64_t B, int64_t C, int32_t H, int32_t W, int64_t gr_sb,
+                                      int64_t gr_sc, int64_t gr_sh, int64_t gr_sw, const void* taps, int64_t N,
+                                      float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, void* stream) {
+  if (!taps || (reinterpret_cast<uintptr_t>(taps) & 15) != 0 || o_sc != 1) return SMOS_EINVAL;
+  return gather_forward_launch(grid, B, C, H, W, gr_sb, gr_sc, gr_sh, gr_sw, nullptr, N, 0, 0, 0, 0.f, 0.f, out, o_sb,
+                               o_sc, o_sn, nullptr, 1, static_cast<const TapsS*>(taps), stream);
 }
 
 int smos_bilinear_gather_backward(const float* grad_out, int64_t B, int64_t C, int64_t N, int64_t go_sb,

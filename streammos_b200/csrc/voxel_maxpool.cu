@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gather_taps.cuh"
 
 namespace {
 
@@ -53,6 +54,7 @@ struct PlanDev {
   int32_t* start;
   int2* sorted;
   int2* multi;
+  TapsS* taps;       // optional: BilinearSample sampling records, one per slot of `sorted`
   int64_t pt_begin;    // first global point index of this plan
   int64_t quad_begin;  // first global cell-quad index (warp aligned)
   int32_t N, H, W, hw, cells, bn;
@@ -215,7 +217,12 @@ pool_cell_scatter_kernel(const __grid_constant__ PlanBatch pb) {
   if (cell < 0) {
     // out-of-grid points fill `sorted` from the end (their .y = -1 - b); pooling never reads them (it stops at
     // cursor[0]) but a gather that walks the list in cell order must still produce their (zero-padded) samples
-    P.sorted[P.bn - 1 - (-2 - r)] = make_int2(n, -1 - b);
+    const int32_t slot = P.bn - 1 - (-2 - r);
+    P.sorted[slot] = make_int2(n, -1 - b);
+    if (P.taps != nullptr) {
+      const float* q = P.ind + b * P.ind_sb + n * P.ind_sn;
+      P.taps[slot] = make_taps_record(__ldg(q), __ldg(q + P.ind_sd), P.sh, P.sw, P.H, P.W, n, b);
+    }
     return;
   }
   const int32_t gcell = b * P.hw + cell;
@@ -223,6 +230,10 @@ pool_cell_scatter_kernel(const __grid_constant__ PlanBatch pb) {
   const int32_t pos = __ldg(P.start + gcell) + (r & kPosMask);
   P.rank[i] = pos | merged;  // from here on: sorted position (| kMergedPos), negative if invalid
   P.sorted[pos] = make_int2(static_cast<int32_t>(static_cast<uint32_t>(n) | (merged ? kMergedN : 0u)), gcell);
+  if (P.taps != nullptr) {
+    const float* q = P.ind + b * P.ind_sb + n * P.ind_sn;
+    P.taps[pos] = make_taps_record(__ldg(q), __ldg(q + P.ind_sd), P.sh, P.sw, P.H, P.W, n, b);
+  }
 }
 
 // ---- phase A0 (channel-major input only): permute into sorted point-major rows -----------------
@@ -870,6 +881,8 @@ int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n,
     P.start = reinterpret_cast<int32_t*>(base + L.off_start);
     P.sorted = reinterpret_cast<int2*>(base + L.off_sorted);
     P.multi = reinterpret_cast<int2*>(base + L.off_multi);
+    if (d.gather_taps != nullptr && (reinterpret_cast<uintptr_t>(d.gather_taps) & 15) != 0) return SMOS_EINVAL;
+    P.taps = static_cast<TapsS*>(d.gather_taps);
     P.N = static_cast<int32_t>(d.N); P.H = d.H; P.W = d.W;
     P.hw = static_cast<int32_t>(L.hw); P.cells = static_cast<int32_t>(L.cells);
     P.bn = static_cast<int32_t>(d.B * d.N);
@@ -897,6 +910,7 @@ int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N, int64_t in
   d.pcds_ind = pcds_ind; d.B = B; d.N = N; d.ind_sb = ind_sb; d.ind_sn = ind_sn; d.ind_sd = ind_sd;
   d.H = H; d.W = W; d.scale_h = scale_h; d.scale_w = scale_w;
   d.voxel_max_idx = voxel_max_idx; d.idx_batch_stride = idx_batch_stride; d.plan = plan;
+  d.gather_taps = nullptr;
   return smos_pool_plan_build_multi(&d, 1, stream);
 }
 

@@ -50,10 +50,12 @@ class PoolPlan:
 
     Re-usable across every pooling call that shares the coordinates (forward and backward)."""
 
-    __slots__ = ("buf", "B", "N", "H", "W", "voxel_max_idx")
+    __slots__ = ("buf", "B", "N", "H", "W", "voxel_max_idx", "scale", "taps")
 
-    def __init__(self, buf, B, N, H, W, voxel_max_idx):
+    def __init__(self, buf, B, N, H, W, voxel_max_idx, scale=None, taps=None):
         self.buf, self.B, self.N, self.H, self.W, self.voxel_max_idx = buf, B, N, H, W, voxel_max_idx
+        self.scale = None if scale is None else (float(scale[0]), float(scale[1]))
+        self.taps = taps  # BilinearSample sampling records for this grid / scale (48 bytes per point), or None
 
 
 def _plan_inputs(pcds_ind, output_size, scale_rate):
@@ -70,30 +72,37 @@ def _plan_inputs(pcds_ind, output_size, scale_rate):
     return ind, int(ind.size(0)), int(ind.size(1)), int(output_size[0]), int(output_size[1])
 
 
-def pool_plan_multi(specs):
-    """Build several plans with three kernel launches in total. `specs`: list of (pcds_ind, output_size,
-    scale_rate) — e.g. the five pooling calls of one scan. Returns a list of PoolPlan (views of one buffer)."""
+def pool_plan_multi(specs, gather_taps=None):
+    """Build several plans with four kernel launches in total. `specs`: list of (pcds_ind, output_size,
+    scale_rate) — e.g. the five pooling calls of one scan. Returns a list of PoolPlan (views of one buffer).
+    `gather_taps`: optional list of bools — plans that should also carry the BilinearSample sampling state of their
+    points for their own grid and scale (used by bilinear_gather_forward(..., order=plan) when the geometry matches)."""
     lib = _lib.load()
     items, offsets, total = [], [], 0
-    for pcds_ind, output_size, scale_rate in specs:
+    want = list(gather_taps) if gather_taps is not None else [False] * len(specs)
+    for (pcds_ind, output_size, scale_rate), wt in zip(specs, want):
         ind, B, N, H, W = _plan_inputs(pcds_ind, output_size, scale_rate)
         nbytes = lib.smos_pool_plan_bytes(B, N, H, W)
         if nbytes < 0:
             _lib.check(int(nbytes), "smos_pool_plan_bytes")
-        items.append((ind, B, N, H, W, scale_rate, int(nbytes)))
+        tbytes = int(lib.smos_gather_taps_bytes(B, N)) if wt else 0
+        items.append((ind, B, N, H, W, scale_rate, int(nbytes), tbytes))
         offsets.append(total)
-        total += (int(nbytes) + 255) // 256 * 256
+        total += (int(nbytes) + 255) // 256 * 256 + (tbytes + 255) // 256 * 256
     device = items[0][0].device
     big = torch.empty(total, dtype=torch.uint8, device=device)
     descs = (_lib.PoolPlanDesc * len(items))()
     plans = []
-    for d, (ind, B, N, H, W, scale_rate, nbytes), off in zip(descs, items, offsets):
+    for d, (ind, B, N, H, W, scale_rate, nbytes, tbytes), off in zip(descs, items, offsets):
         buf = big[off:off + nbytes]
+        toff = off + (nbytes + 255) // 256 * 256
+        taps = big[toff:toff + tbytes] if tbytes else None
         d.pcds_ind, d.B, d.N = ind.data_ptr(), B, N
         d.ind_sb, d.ind_sn, d.ind_sd = ind.stride(0), ind.stride(1), ind.stride(2)
         d.H, d.W, d.scale_h, d.scale_w = H, W, float(scale_rate[0]), float(scale_rate[1])
         d.voxel_max_idx, d.idx_batch_stride, d.plan = None, 0, buf.data_ptr()
-        plans.append(PoolPlan(buf, B, N, H, W, None))
+        d.gather_taps = taps.data_ptr() if taps is not None else None
+        plans.append(PoolPlan(buf, B, N, H, W, None, scale_rate, taps))
     with torch.cuda.device(device):
         rc = lib.smos_pool_plan_build_multi(descs, len(items), _stream())
     _lib.check(rc, "smos_pool_plan_build_multi")
@@ -119,7 +128,7 @@ def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=
                                       int(idx_batch_stride), _ptr(buf), _stream())
     _lib.check(rc, "smos_pool_plan_build")
     _count(4)  # zero counts + cell index + cell allocation + scatter
-    return PoolPlan(buf, B, N, H, W, idx_out)
+    return PoolPlan(buf, B, N, H, W, idx_out, scale_rate)
 
 
 def _feat3(pcds_feat):
@@ -215,11 +224,16 @@ def bilinear_gather_forward(grid_feat, grid_coord, scale_rate, point_major_out=F
         order = None
     if order is not None and (order.B, order.N) != (B, N):
         raise RuntimeError("order plan (B=%d, N=%d) does not match grid_coord (B=%d, N=%d)" % (order.B, order.N, B, N))
+    use_taps = (order is not None and order.taps is not None and (order.H, order.W) == (H, W) and
+                order.scale == (float(scale_rate[0]), float(scale_rate[1])))
     with torch.cuda.device(grid_feat.device):
         args = (_ptr(grid_feat), B, C, H, W, grid_feat.stride(0), grid_feat.stride(1), grid_feat.stride(2),
                 grid_feat.stride(3), _ptr(co), NP, co.stride(0), co.stride(1), co.stride(2), float(scale_rate[0]),
                 float(scale_rate[1]), _ptr(out), o_sb, o_sc, o_sn)
-        if order is None:
+        if use_taps:  # the plan carries the sampling state of exactly this gather: no coordinates needed
+            rc = _lib.load().smos_bilinear_gather_forward_taps(*args[:9], _ptr(order.taps), NP, _ptr(out), o_sb, o_sc,
+                                                               o_sn, _stream())
+        elif order is None:
             rc = _lib.load().smos_bilinear_gather_forward(*args, _stream())
         else:
             rc = _lib.load().smos_bilinear_gather_forward_ordered(*args, _ptr(order.buf), order.H, order.W, _stream())

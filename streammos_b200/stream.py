@@ -129,11 +129,12 @@ class HotPath:
 
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
                  batch_plans=True, grids_channels_last=False, overlap_voting=False, branches=True,
-                 ordered_gathers=True, ordered_rv=False):
+                 ordered_gathers=True, ordered_rv=False, gather_taps=False):
         self.device = torch.device(device)
         self.overlap_voting = overlap_voting
         self.branches = branches and self.device.type == "cuda"
         self.ordered_gathers, self.ordered_rv = ordered_gathers, ordered_rv
+        self.gather_taps = gather_taps and ordered_gathers and point_major and batch_plans
         self._side = None
         self._branch_streams = []
         self.batch_plans = batch_plans
@@ -230,13 +231,14 @@ class HotPath:
         if self.batch_plans:
             pl = ops.pool_plan_multi([(coord_bev, (512, 512), (1.0, 1.0)), (cur_rv, (32, 1024), (0.5, 0.5)),
                                       (cur_bev, (256, 256), (0.5, 0.5)), (cur_rv, (16, 512), (0.25, 0.25)),
-                                      (cur_bev, (128, 128), (0.25, 0.25))])
+                                      (cur_bev, (128, 128), (0.25, 0.25))],
+                                     gather_taps=[False] + [self.gather_taps] * 4)
         else:
             pl = [None] * 5
         # gathers visit the points in the cell order of the plan that shares their coordinates (BEV only by default:
         # range-view coordinates are already row-coherent in scan order)
-        od = [p if (self.ordered_gathers and self.point_major and (i in (2, 4) or self.ordered_rv)) else None
-              for i, p in enumerate(pl)]
+        od = [p if (self.ordered_gathers and self.point_major and (i in (2, 4) or self.ordered_rv or self.gather_taps))
+              else None for i, p in enumerate(pl)]
 
         def half_chain():
             x0_pt = self.g_half(self.x0, cur_bev, od[2])                                                 # mve.py:395

@@ -247,6 +247,16 @@ def test_bilinear_cell_order_matches_scan_order(C, H, W, scale):
             out = ops.bilinear_gather_forward(g, t(coord), scale, True, order=plan)
             assert out.stride(1) == 1 and torch.equal(out, base)
         np.testing.assert_allclose(out[..., 0].cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    # sampling records emitted by the plan build (same grid and scale): bit-identical again, no coordinates read
+    tp = ops.pool_plan_multi([(t(coord), (H, W), scale), (t(coord), (H + 3, W), scale)], gather_taps=[True, True])
+    assert tp[0].taps is not None and tp[0].taps.numel() == B * N * 48
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        g = t(grid).contiguous(memory_format=fmt)
+        base = ops.bilinear_gather_forward(g, t(coord), scale, True)
+        ops.reset_launch_count()
+        assert torch.equal(ops.bilinear_gather_forward(g, t(coord), scale, True, order=tp[0]), base)
+        # a plan of another geometry only lends its order, its records do not apply
+        assert torch.equal(ops.bilinear_gather_forward(g, t(coord), scale, True, order=tp[1]), base)
     # channel-major outputs ignore the order (same kernel as without it)
     out = ops.bilinear_gather_forward(t(grid), t(coord), scale, False, order=plans[0])
     assert out.is_contiguous() and torch.equal(out, base.contiguous())

@@ -53,7 +53,9 @@ with torch.no_grad():
                        (b.coord_bev[:1], (256, 256), (0.5, 0.5)), (b.coord_rv, (16, 512), (0.25, 0.25)),
                        (b.coord_bev[:1], (128, 128), (0.25, 0.25))]
     timeit("plan x5 (3 kernels)", lambda i: ops.pool_plan_multi(specs(S(i))))
+    timeit("plan x5 + gather taps x4", lambda i: ops.pool_plan_multi(specs(S(i)), gather_taps=[False, True, True, True, True]))
     plans = [ops.pool_plan_multi(specs(s)) for s in scans]
+    tplans = [ops.pool_plan_multi(specs(s), gather_taps=[False, True, True, True, True]) for s in scans]
     ws = ops.pool_workspace(3, 64, N, dev)
     out1 = torch.empty(3, 64, 512, 512, device=dev)
     for s, p in zip(scans, plans):
@@ -72,11 +74,13 @@ with torch.no_grad():
         mb = (4 * C * H * W + 8 * N + 4 * C * N) / 1e6
         timeit(name + " scan-order", lambda i: mod(grid, S(i).coord_bev[:1]), mb)
         timeit(name + " cell-order", lambda i: mod(grid, S(i).coord_bev[:1], plans[i % 4][pi]), mb)
+        timeit(name + " plan taps", lambda i: mod(grid, S(i).coord_bev[:1], tplans[i % 4][pi]), mb)
     x0_pt = [hot.g_half(hot.x0, s.coord_bev[:1]) for s in scans]
     x0_rv = deep_point.VoxelMaxPool(x0_pt[0], scans[0].coord_rv, (32, 1024), (0.5, 0.5), plans[0][1])
     mb = (4 * 32 * 32 * 1024 + 8 * N + 4 * 32 * N) / 1e6
     timeit("gather2 rv 32ch@32x1024 scan-order", lambda i: hot.g_half(x0_rv, S(i).coord_rv), mb)
     timeit("gather2 rv 32ch@32x1024 cell-order", lambda i: hot.g_half(x0_rv, S(i).coord_rv, plans[i % 4][1]), mb)
+    timeit("gather2 rv 32ch@32x1024 plan taps", lambda i: hot.g_half(x0_rv, S(i).coord_rv, tplans[i % 4][1]), mb)
     # small pools (point-major input): stages
     for name, C, pi, size in (("pool2 rv32x1024 c32", 32, 1, (32, 1024)), ("pool3 bev256 c32", 32, 2, (256, 256))):
         o = torch.empty(1, C, *size, device=dev)
