@@ -175,6 +175,26 @@ def test_pool_batched_plans_match_single_plans():
         assert np.array_equal(a.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("path", ["ldg", "tma"])
+def test_pool_channel_major_permute_paths_random_shapes(path, monkeypatch):
+    """Both permute kernels of the channel-major path (128-bit-load tiles and the tiled-TMA pipeline, selected with
+    SMOS_PERM_LDG) over ragged shapes: N not a multiple of the 64-/128-point tiles, partial tiles, B > 1, channel
+    counts around the 32-channel groups, dense duplicates (long runs) and all-invalid tails."""
+    from streammos_b200 import deep_point
+    monkeypatch.setenv("SMOS_PERM_LDG", "1" if path == "ldg" else "0")
+    rng = np.random.default_rng(11 if path == "ldg" else 12)
+    shapes = [(1, 64, 120000, (512, 512), (1.0, 1.0)), (3, 64, 4100, (64, 64), (1.0, 1.0)), (2, 32, 132, (8, 8), (0.5, 0.5)),
+              (1, 96, 8192, (16, 16), (0.25, 0.25)), (2, 128, 2052, (32, 8), (1.0, 0.5)), (1, 8, 64, (4, 4), (1.0, 1.0)),
+              (1, 64, 60, (4, 4), (1.0, 1.0)), (2, 160, 1028, (12, 20), (1.0, 1.0))]
+    for B, C, N, size, scale in shapes:
+        ind = synth_scan(rng, B, N, size[0], size[1], scale, n_valid=max(1, N - N // 7))
+        ind[:, : N // 3] = np.floor(ind[:, : N // 3] / 3) * 3          # many equal neighbours: long merged runs
+        feat = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+        out = deep_point.VoxelMaxPool(t(feat), t(ind), size, scale)
+        ref = O.voxel_maxpool_forward(feat, ind, size, scale)
+        assert np.array_equal(out.cpu().numpy(), ref), (path, B, C, N, size)
+
+
 def test_pool_rejects_cpu_tensors():
     from streammos_b200 import deep_point
     with pytest.raises(RuntimeError):
