@@ -324,7 +324,7 @@ def run_b200(args, world, rank, local):
                                branches=not args.no_branches, ordered_gathers=not args.no_ordered_gathers,
                                ordered_rv=args.ordered_rv, gather_taps=args.gather_taps)
         host_l = [stream.make_host_loader_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
-        devb_l = [h.to(dev) for h in host_l]
+        devb_l = [h.pack(device=dev) for h in host_l]   # one flat buffer per scan: one H2D copy per step
         torch.cuda.synchronize()
         pipe_l = pipeline.ScanPipeline(hot_l, devb_l, use_graphs=use_graph, scans_in_flight=args.in_flight)
         e2e = measure_e2e(pipe_l, host_l, devb_l)

@@ -8,6 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libstreammos_b200.so")
+LIB_PATH = os.environ.get("SMOS_LIB", LIB_PATH)  # experiments: A/B two builds in one GPU call
 
 _i32, _i64, _f32, _vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 

@@ -11,6 +11,9 @@
 namespace {
 
 constexpr int kGatherThreads = 128;
+#ifndef SMOS_GATHER_MIN_CTAS
+#define SMOS_GATHER_MIN_CTAS 10  // <= 42 registers: the kernel's speed follows the number of resident warps
+#endif
 constexpr int kGatherPts = 32;  // points per CTA
 constexpr int kCPT = 8;         // channels per thread-step in the planar kernel
 
@@ -66,7 +69,7 @@ __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict_
 // zeroed by a select afterwards): predicated loads get serialised through one temporary register by
 // ptxas. For point-major outputs the kCPT results leave as one full 32-byte sector per thread.
 template <bool DENSE, bool ROWS_OUT, bool ORDERED, bool TAPS>
-__global__ void __launch_bounds__(kGatherThreads)
+__global__ void __launch_bounds__(kGatherThreads, SMOS_GATHER_MIN_CTAS)
 gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                              int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
                              const float* __restrict__ coord, int32_t N,

@@ -28,19 +28,18 @@ struct StemSmem {
 
 template <int CIN>
 __global__ void __launch_bounds__(kStemThreads)
-point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int64_t x_sb, int64_t x_sc, int64_t x_sn,
+point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B, int64_t x_sb, int64_t x_sc, int64_t x_sn,
                   const float* __restrict__ a0, const float* __restrict__ b0, const float* __restrict__ w1,
                   const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ w2,
                   const float* __restrict__ a2, const float* __restrict__ b2, float* __restrict__ y, int64_t y_sb,
                   int64_t y_sc) {
   extern __shared__ __align__(16) unsigned char stem_raw[];
   StemSmem& S = *reinterpret_cast<StemSmem*>(stem_raw);
+  constexpr int KI = CIN > 0 ? (CIN + 3) / 4 * 4 : kStemCinMax;  // inputs rounded up to whole float4 (zero weights)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int32_t b = blockIdx.y;
-  const int32_t n0 = blockIdx.x * kStemPts;
-  // parameters -> shared memory. W2 is kept transposed ([k][c]: the 8 output channels of a warp are contiguous per
-  // k); lanes run over c so the transposing stores are conflict free (the 128-bit global reads are strided, 16 KB
-  // from L2 per CTA)
+  // parameters -> shared memory, ONCE per CTA (the CTAs are persistent and walk the 128-point tiles). W2 is kept
+  // transposed ([k][c]: the 16 output channels of a warp are contiguous per k); lanes run over c so the transposing
+  // stores are conflict free (the 128-bit global reads are strided, 16 KB from L2 per CTA)
   for (int i = tid; i < kStemC * (kStemC / 4); i += kStemThreads) {
     const int c = i & (kStemC - 1), kq = i >> 6;
     const float4 v = __ldg(reinterpret_cast<const float4*>(w2 + c * kStemC) + kq);
@@ -53,69 +52,85 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int64_t x
   if (tid < kStemC) { S.ab1[tid] = make_float2(__ldg(a1 + tid), __ldg(b1 + tid)); S.a2[tid] = __ldg(a2 + tid); S.b2[tid] = __ldg(b2 + tid); }
   if (tid < Cin) { S.a0[tid] = a0 ? __ldg(a0 + tid) : 1.f; S.b0[tid] = b0 ? __ldg(b0 + tid) : 0.f; }
   __syncthreads();
-  // layer 1: thread = point, all hidden channels (weights are warp-uniform broadcast loads)
-  {
-    constexpr int KI = CIN > 0 ? (CIN + 3) / 4 * 4 : kStemCinMax;  // inputs rounded up to whole float4 (zero weights)
-    const int p = tid;
-    const int32_t n = min(n0 + p, N - 1);
-    float xin[KI];
+
+  const int32_t tiles_per_b = (N + kStemPts - 1) / kStemPts;
+  const int32_t ntiles = tiles_per_b * B;
+  // raw inputs of my point in tile t (one point per thread), fetched one tile ahead of their use
+  auto fetch = [&](int32_t t, float (&xr)[KI]) {
+    const int32_t b = t / tiles_per_b;
+    const int32_t n = min((t - b * tiles_per_b) * kStemPts + tid, N - 1);
 #pragma unroll
     for (int ci = 0; ci < KI; ++ci)
-      xin[ci] = ci < Cin ? fmaf(__ldg(x + b * x_sb + ci * x_sc + static_cast<int64_t>(n) * x_sn), S.a0[ci], S.b0[ci]) : 0.f;
-#pragma unroll 4
-    for (int c = 0; c < kStemC; ++c) {
-      float acc = 0.f;
+      xr[ci] = ci < Cin ? __ldg(x + b * x_sb + ci * x_sc + static_cast<int64_t>(n) * x_sn) : 0.f;
+  };
+  float xr[KI];
+  int32_t t = blockIdx.x;
+  if (t < ntiles) fetch(t, xr);
+  for (; t < ntiles; t += gridDim.x) {
+    const int32_t b = t / tiles_per_b;
+    const int32_t n0 = (t - b * tiles_per_b) * kStemPts;
+    // layer 1: thread = point, all hidden channels (weights are warp-uniform broadcast loads)
+    {
+      float xin[KI];
 #pragma unroll
-      for (int q = 0; q < KI / 4; ++q) {
-        const float4 w = *reinterpret_cast<const float4*>(&S.w1[c][4 * q]);
-        acc = fmaf(w.x, xin[4 * q], acc); acc = fmaf(w.y, xin[4 * q + 1], acc);
-        acc = fmaf(w.z, xin[4 * q + 2], acc); acc = fmaf(w.w, xin[4 * q + 3], acc);
+      for (int ci = 0; ci < KI; ++ci) xin[ci] = ci < Cin ? fmaf(xr[ci], S.a0[ci], S.b0[ci]) : 0.f;
+#pragma unroll 4
+      for (int c = 0; c < kStemC; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < KI / 4; ++q) {
+          const float4 w = *reinterpret_cast<const float4*>(&S.w1[c][4 * q]);
+          acc = fmaf(w.x, xin[4 * q], acc); acc = fmaf(w.y, xin[4 * q + 1], acc);
+          acc = fmaf(w.z, xin[4 * q + 2], acc); acc = fmaf(w.w, xin[4 * q + 3], acc);
+        }
+        const float2 ab = S.ab1[c];
+        S.h[c][tid] = fmaxf(fmaf(acc, ab.x, ab.y), 0.f);
       }
-      const float2 ab = S.ab1[c];
-      S.h[c][p] = fmaxf(fmaf(acc, ab.x, ab.y), 0.f);
     }
-  }
-  __syncthreads();
-  // layer 2: warp = 16 output channels, lane = 4 consecutive points: 64 FMAs per 5 shared-memory loads (8 wavefronts)
-  // — with 8 channels per warp the kernel sat at 79 % of the shared-memory pipe and 52 % of the FMA pipe
-  constexpr int CW = 16;
-  const int c0 = wid * CW;
-  float acc[CW][4];
+    if (t + gridDim.x < ntiles) fetch(t + gridDim.x, xr);  // in flight during layer 2
+    __syncthreads();
+    // layer 2: warp = 16 output channels, lane = 4 consecutive points: 64 FMAs per 5 shared-memory loads (8
+    // wavefronts) — with 8 channels per warp the kernel sat at 79 % of the shared-memory pipe and 52 % of the FMA pipe
+    constexpr int CW = 16;
+    const int c0 = wid * CW;
+    float acc[CW][4];
 #pragma unroll
-  for (int j = 0; j < CW; ++j)
+    for (int j = 0; j < CW; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll 4
-  for (int k = 0; k < kStemC; ++k) {
-    const float4 hv = *reinterpret_cast<const float4*>(&S.h[k][lane * 4]);
-    const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+    for (int k = 0; k < kStemC; ++k) {
+      const float4 hv = *reinterpret_cast<const float4*>(&S.h[k][lane * 4]);
+      const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-    for (int jq = 0; jq < CW / 4; ++jq) {
-      const float4 wv = *reinterpret_cast<const float4*>(&S.w2t[k][c0 + 4 * jq]);
-      const float w[4] = {wv.x, wv.y, wv.z, wv.w};
+      for (int jq = 0; jq < CW / 4; ++jq) {
+        const float4 wv = *reinterpret_cast<const float4*>(&S.w2t[k][c0 + 4 * jq]);
+        const float w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[4 * jq + j][i] = fmaf(w[j], hh[i], acc[4 * jq + j][i]);
+          for (int i = 0; i < 4; ++i) acc[4 * jq + j][i] = fmaf(w[j], hh[i], acc[4 * jq + j][i]);
+      }
     }
-  }
-  const int32_t n = n0 + lane * 4;
-  const bool vec = (n + 3 < N) && ((y_sc & 3) == 0) && ((y_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    const int32_t n = n0 + lane * 4;
+    const bool vec = (n + 3 < N) && ((y_sc & 3) == 0) && ((y_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
 #pragma unroll
-  for (int j = 0; j < CW; ++j) {
-    const int c = c0 + j;
-    const float al = S.a2[c], be = S.b2[c];
-    float o[4];
+    for (int j = 0; j < CW; ++j) {
+      const int c = c0 + j;
+      const float al = S.a2[c], be = S.b2[c];
+      float o[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = fmaxf(fmaf(acc[j][i], al, be), 0.f);
-    float* dst = y + b * y_sb + c * y_sc + n;
-    if (vec) {
-      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-    } else {
+      for (int i = 0; i < 4; ++i) o[i] = fmaxf(fmaf(acc[j][i], al, be), 0.f);
+      float* dst = y + b * y_sb + c * y_sc + n;
+      if (vec) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (n + i < N) dst[i] = o[i];
+        for (int i = 0; i < 4; ++i)
+          if (n + i < N) dst[i] = o[i];
+      }
     }
+    __syncthreads();  // every warp is done reading h: the next tile's layer 1 may overwrite it
   }
 }
 
@@ -141,15 +156,18 @@ extern "C" int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, i
     if (e != cudaSuccess) return static_cast<int>(e);
     opt_in[device] = true;
   }
-  dim3 grid(smos_ceil_div(N, kStemPts), static_cast<unsigned>(B));
+  // persistent CTAs: 4 per SM (53 KB of shared memory each), each walks the 128-point tiles with a grid stride
+  const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kStemPts)) * B;
+  const int64_t want = static_cast<int64_t>(SMOS_SM_COUNT) * 4;
+  dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));
   if ((reinterpret_cast<uintptr_t>(w2) & 15) != 0) return SMOS_EINVAL;
   if (Cin == 7)  // the StreamMOS stem: x, y, z, intensity, dist, diff_x, diff_y
     point_stem_kernel<7><<<grid, kStemThreads, sizeof(StemSmem), smos_stream(stream)>>>(
-        x, Cin, static_cast<int32_t>(N), x_sb, x_sc, x_sn, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
+        x, Cin, static_cast<int32_t>(N), static_cast<int32_t>(B), x_sb, x_sc, x_sn, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
         bn2_beta, y, y_sb, y_sc);
   else
     point_stem_kernel<0><<<grid, kStemThreads, sizeof(StemSmem), smos_stream(stream)>>>(
-        x, Cin, static_cast<int32_t>(N), x_sb, x_sc, x_sn, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
+        x, Cin, static_cast<int32_t>(N), static_cast<int32_t>(B), x_sb, x_sc, x_sn, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
         bn2_beta, y, y_sb, y_sc);
   return smos_launch_status();
 }

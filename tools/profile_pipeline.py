@@ -50,6 +50,25 @@ for t, d in pts:
     k += d
 for kk in sorted(hist):
     print("  %s kernels active: %6.1f us/scan (%4.1f %%)" % (("%d" % kk) if kk < 4 else "4+", hist[kk] / a.scans, 100 * hist[kk] / span))
+# which kernels run ALONE (time with exactly one kernel active, attributed to that kernel)
+active, alone = {}, defaultdict(float)
+ev2 = []
+for idx, (s, e, n) in enumerate(evs):
+    ev2.append((s, 0, idx))
+    ev2.append((e, 1, idx))
+ev2.sort()
+last = ev2[0][0]
+for tt, kind, idx in ev2:
+    if len(active) == 1:
+        alone[evs[next(iter(active))][2][:70]] += tt - last
+    last = tt
+    if kind == 0:
+        active[idx] = True
+    else:
+        active.pop(idx, None)
+print("time with exactly ONE kernel active, by kernel (us/scan):")
+for n, v in sorted(alone.items(), key=lambda x: -x[1])[:14]:
+    print("  %-70s %7.1f us" % (n, v / a.scans))
 by = defaultdict(float)
 for s, e, n in evs:
     by[n[:70]] += e - s
