@@ -457,6 +457,37 @@ def test_voting_empty_and_out_of_range():
     assert int(vl[0, 0, 0]) == 1
 
 
+@pytest.mark.parametrize("size,P", [((3, 3, 3), 500), ((5, 7, 3), 4000), ((1, 1, 1), 10)])
+def test_voting_odd_grid_sizes_in_place_counters(size, P):
+    """The int64 label slots double as the packed vote counters: odd voxel counts exercise the scalar tail of the
+    in-place argmax pass, and the result must not depend on what the output buffer held before."""
+    from streammos_b200 import ops
+    rng = np.random.default_rng(P)
+    coords = np.stack([rng.integers(-1, s + 1, P) for s in size], -1).astype(np.int64)   # some out of range
+    labels = rng.integers(0, 3, P).astype(np.int64)
+    ref = O.determine_voxel_labels(coords, labels, size, 3)
+    for _ in range(2):
+        torch.full((64,), 7, dtype=torch.int64, device=dev())                          # dirty the allocator's cache
+        vl = ops.vote_voxel_labels(t(coords), t(labels), size, 3)
+        assert np.array_equal(vl.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("n", [1, 17, 4099, 120000])
+def test_memory_push_moves_current_into_history(n):
+    from streammos_b200 import ops
+    rng = np.random.default_rng(n)
+    new_p, new_l = rng.standard_normal((n, 4)).astype(np.float32), rng.integers(0, 3, n).astype(np.uint8)
+    cur_p, cur_l = rng.standard_normal((n, 4)).astype(np.float32), rng.integers(0, 3, n).astype(np.uint8)
+    ring_p, ring_l = torch.zeros(3, n, 4, device=dev()), torch.zeros(3, n, dtype=torch.uint8, device=dev())
+    ring_p[2].copy_(t(cur_p)); ring_l[2].copy_(t(cur_l))
+    ops.memory_push(t(new_p), t(new_l), ring_p[2], ring_l[2], ring_p[1], ring_l[1])
+    assert np.array_equal(ring_p[1].cpu().numpy(), cur_p) and np.array_equal(ring_l[1].cpu().numpy(), cur_l)
+    assert np.array_equal(ring_p[2].cpu().numpy(), new_p) and np.array_equal(ring_l[2].cpu().numpy(), new_l)
+    assert float(ring_p[0].abs().sum()) == 0.0
+    ops.memory_push(t(cur_p), t(cur_l), ring_p[2], ring_l[2])                            # no history slot: overwrite only
+    assert np.array_equal(ring_p[2].cpu().numpy(), cur_p) and np.array_equal(ring_p[1].cpu().numpy(), cur_p)
+
+
 def test_instance_vote_golden(golden):
     from streammos_b200 import voting
     g = golden("instance_a")
