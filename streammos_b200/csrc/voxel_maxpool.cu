@@ -145,19 +145,20 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
 // global cursor replaces a device-wide prefix scan. thread = 4 cells; a warp never straddles two plans.
 __global__ void __launch_bounds__(kPlanThreads)
 pool_cell_alloc_kernel(const __grid_constant__ PlanBatch pb) {
+  __shared__ int32_t s_tot[kPlanThreads / 32], s_plan[kPlanThreads / 32], s_base;
   const int64_t gq = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gq >= pb.quad_total) return;  // whole warps only (quad ranges are warp aligned)
+  const bool active = gq < pb.quad_total;  // whole warps only (quad ranges are warp aligned)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int j = 0;
   while (j + 1 < pb.n && gq >= pb.p[j + 1].quad_begin) ++j;
   const PlanDev& P = pb.p[j];
-  const int32_t c0 = static_cast<int32_t>(gq - P.quad_begin) * 4;
-  const int lane = threadIdx.x & 31;
+  const int32_t c0 = active ? static_cast<int32_t>(gq - P.quad_begin) * 4 : 0;
   int32_t c[4] = {0, 0, 0, 0};
-  const bool vec = (c0 + 3 < P.cells) && ((reinterpret_cast<uintptr_t>(P.count) & 15) == 0);
+  const bool vec = active && (c0 + 3 < P.cells) && ((reinterpret_cast<uintptr_t>(P.count) & 15) == 0);
   if (vec) {
     const int4 v = *reinterpret_cast<const int4*>(P.count + c0);
     c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
-  } else {
+  } else if (active) {
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       if (c0 + q < P.cells) c[q] = P.count[c0 + q];
@@ -171,9 +172,30 @@ pool_cell_alloc_kernel(const __grid_constant__ PlanBatch pb) {
   }
   const int32_t warp_total = __shfl_sync(0xffffffffu, x, 31);
   int32_t* cursor = P.count + P.cells;
+  // one atomic per CTA on the plan's cursor (thousands of same-address returning atomics, one per warp, were the
+  // kernel's critical path); a CTA whose warps belong to different plans falls back to one atomic per warp
+  if (lane == 31) { s_tot[wid] = warp_total; s_plan[wid] = active ? j : -1; }
+  __syncthreads();
+  bool uniform = true;
+  int32_t before = 0, cta_total = 0;
+#pragma unroll
+  for (int w = 0; w < kPlanThreads / 32; ++w) {
+    const int32_t pw = s_plan[w];
+    if (pw >= 0 && pw != s_plan[0]) uniform = false;
+    if (w < wid) before += s_tot[w];
+    cta_total += s_tot[w];
+  }
+  if (s_plan[0] < 0) uniform = false;
   int32_t base = 0;
-  if (lane == 31 && warp_total > 0) base = atomicAdd(cursor, warp_total);
-  base = __shfl_sync(0xffffffffu, base, 31);
+  if (uniform) {
+    if (threadIdx.x == 0) s_base = cta_total > 0 ? atomicAdd(cursor, cta_total) : 0;
+    __syncthreads();
+    base = s_base + before;
+  } else {
+    if (lane == 31 && warp_total > 0) base = atomicAdd(cursor, warp_total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+  }
+  if (!active) return;
   int32_t s[4];
   s[0] = base + x - mine;
   s[1] = s[0] + c[0];
