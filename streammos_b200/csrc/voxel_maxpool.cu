@@ -662,48 +662,53 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
   const int32_t prev = __shfl_up_sync(0xffffffffu, e.y, 1);
   const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || e.y != prev) &
                          (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
-  // element offset of my point's row (c = 0)
-  int64_t base_lane;
-  bool absent = false;  // SORTED_ROWS: this position has no row of its own (merged into its run's first row)
+  // Entries to reduce, compacted to the low lanes: lane j holds the row offset (c = 0) of entry j and the position
+  // of the piece it belongs to (the first position of its cell inside this window). Without SORTED_ROWS every
+  // position is an entry. With SORTED_ROWS only the row owners are: a merged follower has no row (its value is
+  // already in its run head's row), so ~55 % of the positions cost nothing here.
+  int32_t m = cnt;
+  int64_t ent_off;
+  int32_t ent_idx = lane;  // window index of my entry
   if (SORTED_ROWS) {
-    absent = lane < cnt && (static_cast<uint32_t>(e.x) & kMergedN) != 0u;
-    // read a row that is needed anyway instead of the unwritten one: the nearest row-owning lane at or before
-    // me, else the first one after me (a 32-position window always contains one: runs are <= 32 long)
+    const bool absent = lane < cnt && (static_cast<uint32_t>(e.x) & kMergedN) != 0u;
     const unsigned owners = __ballot_sync(0xffffffffu, lane < cnt && !absent);
-    const unsigned before = owners & (0xffffffffu >> (31 - lane));
-    const int src_lane = before ? 31 - __clz(before) : (owners ? __ffs(owners) - 1 : lane);
-    base_lane = static_cast<int64_t>(p0 + src_lane) * C;
+    m = __popc(owners);
+    ent_idx = lane < m ? static_cast<int32_t>(__fns(owners, 0, lane + 1)) : 0;
+    ent_off = static_cast<int64_t>(p0 + ent_idx) * C;
   } else {
-    base_lane = (e.y >= 0 ? e.y / hw : 0) * f_sb +
-                static_cast<int64_t>(static_cast<uint32_t>(e.x) & ~kMergedN) * f_sn;
+    ent_off = (e.y >= 0 ? e.y / hw : 0) * f_sb + static_cast<int64_t>(static_cast<uint32_t>(e.x) & ~kMergedN) * f_sn;
   }
-  const unsigned absent_mask = __ballot_sync(0xffffffffu, absent);
+  const int32_t ent_pp = p0 + (31 - __clz(heads & (0xffffffffu >> (31 - ent_idx))));  // head at or before my entry
+  // SORTED_ROWS: a window can begin with followers of a run whose head sits in the previous window; if their cell
+  // has no owner in this window the piece is empty, but the combine stage reads a row at its position: -inf
+  const bool lead_empty = SORTED_ROWS && (m == 0 || __shfl_sync(0xffffffffu, ent_pp, 0) != p0);
   const float* src = SORTED_ROWS ? rows : feat;
 
   for (int32_t c0 = 0; c0 < C; c0 += 32 * VEC) {
     const int32_t c = c0 + lane * VEC;
     const bool c_ok = c < C;  // C % VEC == 0 is guaranteed by the dispatcher
     const int32_t c_ld = c_ok ? c : 0;  // lanes past C load a valid address and discard the value
+    if (lead_empty && c_ok) *reinterpret_cast<V*>(rows + static_cast<int64_t>(p0) * C + c) = vneg_inf<VEC>();
     V acc;
-    int32_t piece_pos = p0;
-    for (int32_t i0 = 0; i0 < cnt; i0 += kBatch) {
+    int32_t piece_pos = -1;
+    for (int32_t j0 = 0; j0 < m; j0 += kBatch) {
       V v[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        // UNCONDITIONAL loads (rows past the end re-read the last valid row): a predicated load makes
-        // ptxas funnel every value through one temporary register, which serialises the batch
-        const int32_t i = min(i0 + u, cnt - 1);
-        const int64_t off = __shfl_sync(0xffffffffu, base_lane, i);
+        // UNCONDITIONAL loads (entries past the end re-read the last one): a predicated load makes ptxas funnel
+        // every value through one temporary register, which serialises the batch
+        const int32_t jj = min(j0 + u, m - 1);
+        const int64_t off = __shfl_sync(0xffffffffu, ent_off, jj);
         v[u] = __ldg(reinterpret_cast<const V*>(src + off + c_ld));
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const int32_t i = i0 + u;
-        if (i < cnt && c_ok) {
-          if (SORTED_ROWS && ((absent_mask >> i) & 1u)) v[u] = vneg_inf<VEC>();  // no row of its own
-          if ((heads >> i) & 1u) {
-            if (i > 0) *reinterpret_cast<V*>(rows + static_cast<int64_t>(piece_pos) * C + c) = acc;
-            piece_pos = p0 + i;
+        const int32_t jj = j0 + u;
+        const int32_t pp = __shfl_sync(0xffffffffu, ent_pp, min(jj, m - 1));
+        if (jj < m && c_ok) {
+          if (pp != piece_pos) {  // warp uniform
+            if (piece_pos >= 0) *reinterpret_cast<V*>(rows + static_cast<int64_t>(piece_pos) * C + c) = acc;
+            piece_pos = pp;
             acc = v[u];
           } else {
             acc = vmax<VEC>(acc, v[u]);
@@ -711,7 +716,7 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
         }
       }
     }
-    if (c_ok) *reinterpret_cast<V*>(rows + static_cast<int64_t>(piece_pos) * C + c) = acc;
+    if (c_ok && piece_pos >= 0) *reinterpret_cast<V*>(rows + static_cast<int64_t>(piece_pos) * C + c) = acc;
   }
 }
 
