@@ -118,7 +118,20 @@ def dist_setup():
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
-        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+        # NCCL prints its version banner (the image sets NCCL_DEBUG=VERSION) with printf to stdout when the first
+        # communicator comes up: send fd 1 to stderr while that happens, so stdout carries the ONE JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+            dist.barrier()
+            if backend == "nccl":
+                torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return world, rank, local
 
 
