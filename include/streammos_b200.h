@@ -239,6 +239,24 @@ int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, int64_t N,
                             float* y, int64_t y_sb, int64_t y_sc, void* stream);
 
 /* ------------------------------------------------------------------------- */
+/* (E, next: SURVEY 8f rank 2, exact part) model input tensors from raw scans. */
+/* Replaces utils.Quantize (datasets/utils.py:151-169) + make_point_feat        */
+/* (datasets/data_StreamMOS.py:25-50) inside the loader's form_batch (:471-493) */
+/* and the TTA flips of form_batch_tta (:495-513). SphereQuantize stays on the  */
+/* host (numpy's float32 arctan2 / arcsin cannot be matched bit for bit).       */
+/* ------------------------------------------------------------------------- */
+
+/*   points     : (T*N, row_stride>=4) float32 raw x, y, z, intensity of T frames (range filtered, padded)
+ *   x_sign/y_sign : TTA flip factors (+1 / -1)
+ *   min_*, d*  : Quantize origin and cell size, d = float32((range_hi - range_lo) / size)
+ *   pcds_xyzi  : (T, 7, N) float32 out: x, y, z, intensity, dist, diff_x, diff_y
+ *   pcds_coord : (T, N, 3) float32 out: x_quan, y_quan, z_quan
+ * Bit-exact with the reference's numpy float32 arithmetic. */
+int smos_form_batch(const float* points, int64_t T, int64_t N, int64_t row_stride, float x_sign, float y_sign,
+                    float min_x, float min_y, float min_z, float dx, float dy, float dz,
+                    float* pcds_xyzi, float* pcds_coord, void* stream);
+
+/* ------------------------------------------------------------------------- */
 /* (C) Long-term-memory voting.                                               */
 /* ------------------------------------------------------------------------- */
 

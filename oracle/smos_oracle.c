@@ -411,3 +411,33 @@ API void oracle_point_stem(const float* x, int64_t B, int64_t Cin, int64_t N, co
   free(xin);
   free(h);
 }
+
+/* ---------------------------------------------------------------------------------------- */
+/* Loader form_batch without SphereQuantize (exact part):                   */
+/*   utils.Quantize (datasets/utils.py:151-169): (v - min) / d in float32;                    */
+/*   make_point_feat (datasets/data_StreamMOS.py:25-50): x, y, z, intensity,                   */
+/*   dist = sqrt(x**2 + y**2 + z**2) + 1e-12, diff = coord - floor(coord), all float32;        */
+/*   TTA flips of form_batch_tta (:495-513) as sign factors.                                   */
+/* pts (T*N, rs), feat (T, 7, N), coord (T, N, 3).                                             */
+/* ---------------------------------------------------------------------------------------- */
+API void oracle_form_batch(const float* pts, int64_t T, int64_t N, int64_t rs, float sx, float sy, const float* mn,
+                           const float* d, float* feat, float* coord) {
+  for (int64_t t = 0; t < T; ++t)
+    for (int64_t n = 0; n < N; ++n) {
+      const float* p = pts + (t * N + n) * rs;
+      volatile float x = p[0] * sx, y = p[1] * sy, z = p[2];
+      volatile float ax = x - mn[0], ay = y - mn[1], az = z - mn[2];
+      volatile float qx = ax / d[0], qy = ay / d[1], qz = az / d[2];
+      volatile float xx = x * x, yy = y * y, zz = z * z;
+      volatile float s1 = xx + yy;
+      volatile float s2 = s1 + zz;
+      volatile float r = sqrtf(s2);
+      volatile float dist = r + 1e-12f;
+      float* f = feat + t * 7 * N + n;
+      f[0] = x; f[N] = y; f[2 * N] = z; f[3 * N] = p[3]; f[4 * N] = dist;
+      f[5 * N] = qx - floorf(qx);
+      f[6 * N] = qy - floorf(qy);
+      float* c = coord + (t * N + n) * 3;
+      c[0] = qx; c[1] = qy; c[2] = qz;
+    }
+}

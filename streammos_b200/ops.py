@@ -264,6 +264,30 @@ def bilinear_gather_backward(grad_out, grid_coord, scale_rate, H, W):
 
 
 # ----------------------------------------------------------------------------------------------
+# Model input tensors from raw scans (next: SURVEY 8f rank 2, the exact part)
+# ----------------------------------------------------------------------------------------------
+def form_batch(points, range_x, range_y, range_z, size, x_sign=1.0, y_sign=1.0):
+    """points (T, N, >=4) float32 CUDA raw x, y, z, intensity (range filtered and padded as the loader does) ->
+    (pcds_xyzi (T, 7, N, 1), pcds_coord (T, N, 3, 1)): Quantize + make_point_feat of the loader's form_batch,
+    bit-exact with its numpy float32 arithmetic."""
+    import numpy as np
+    _need_cuda(points, "points")
+    _need_f32(points, "points")
+    assert points.dim() == 3 and points.size(2) >= 4 and points.stride(2) == 1 and points.stride(0) == points.size(1) * points.stride(1)
+    T, N = int(points.size(0)), int(points.size(1))
+    d = [float(np.float32((r[1] - r[0]) / s)) for r, s in zip((range_x, range_y, range_z), size)]
+    feat = torch.empty((T, 7, N, 1), dtype=torch.float32, device=points.device)
+    coord = torch.empty((T, N, 3, 1), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = _lib.load().smos_form_batch(_ptr(points), T, N, points.stride(1) if N > 1 else points.size(2), float(x_sign),
+                                         float(y_sign), float(range_x[0]), float(range_y[0]), float(range_z[0]), d[0],
+                                         d[1], d[2], _ptr(feat), _ptr(coord), _stream())
+    _lib.check(rc, "smos_form_batch")
+    _count(1)
+    return feat, coord
+
+
+# ----------------------------------------------------------------------------------------------
 # PointNet stem (next: SURVEY 8f rank 4)
 # ----------------------------------------------------------------------------------------------
 def point_stem_forward(x, bn0, w1, bn1, w2, bn2, out=None):

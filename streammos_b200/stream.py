@@ -76,22 +76,16 @@ def make_host_scan(seed, n_points=120000, t_frames=3, channels=64, pin=True):
     return out
 
 
-class LoaderBatch:
-    """What the reference's val loader hands to the model for one scan (datasets/data_StreamMOS.py:565-574,
-    models/StreamMOS.py:86-93): T pose-aligned frames of 7-channel point features, BEV and range-view quantised
-    coordinates — plus the stand-ins for network intermediates this harness cannot produce (predicted labels,
-    deformable-attention sampling locations / weights). The 64-channel point features are computed ON THE DEVICE
-    by the PointNet stem (HotPath.point_pre), as in the reference: they never cross PCIe."""
+class _FlatBatch:
+    """Batches whose tensors can live in one flat buffer (pack()) so that a scan moves host -> device with ONE copy:
+    several separate H2D copies of 0.1-10 MB leave PCIe idle between them."""
 
-    FIELDS = ("pcds_xyzi", "pcds_coord", "pcds_sphere_coord", "pred", "loc", "attn")
+    FIELDS = ()
+    _flat = None
 
     def __init__(self, **kw):
         for f in self.FIELDS:
             setattr(self, f, kw[f])
-
-    coord_bev = property(lambda self: self.pcds_coord[:, :, :2])          # StreamMOS.py:102 (view, no copy)
-    coord_rv = property(lambda self: self.pcds_sphere_coord[:1])          # :99
-    _flat = None
 
     def nbytes(self):
         if self._flat is not None:  # packed: the whole flat buffer (alignment padding included) is what moves
@@ -99,12 +93,10 @@ class LoaderBatch:
         return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self.FIELDS)
 
     def to(self, device, non_blocking=True):
-        return LoaderBatch(**{f: getattr(self, f).to(device, non_blocking=non_blocking) for f in self.FIELDS})
+        return type(self)(**{f: getattr(self, f).to(device, non_blocking=non_blocking) for f in self.FIELDS})
 
     def copy_from(self, other):
-        # batches packed into one flat buffer (pack()) move with ONE copy: six separate H2D copies of 0.1-10 MB leave
-        # PCIe idle between them
-        if getattr(self, "_flat", None) is not None and getattr(other, "_flat", None) is not None:
+        if self._flat is not None and other._flat is not None:
             self._flat.copy_(other._flat, non_blocking=True)
             return
         for f in self.FIELDS:
@@ -127,9 +119,31 @@ class LoaderBatch:
             v = flat[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
             v.copy_(t)
             views[f] = v
-        out = LoaderBatch(**views)
+        out = type(self)(**views)
         out._flat = flat
         return out
+
+
+class LoaderBatch(_FlatBatch):
+    """What the reference's val loader hands to the model for one scan (datasets/data_StreamMOS.py:565-574,
+    models/StreamMOS.py:86-93): T pose-aligned frames of 7-channel point features, BEV and range-view quantised
+    coordinates — plus the stand-ins for network intermediates this harness cannot produce (predicted labels,
+    deformable-attention sampling locations / weights). The 64-channel point features are computed ON THE DEVICE
+    by the PointNet stem (HotPath.point_pre), as in the reference: they never cross PCIe."""
+
+    FIELDS = ("pcds_xyzi", "pcds_coord", "pcds_sphere_coord", "pred", "loc", "attn")
+    coord_bev = property(lambda self: self.pcds_coord[:, :, :2])          # StreamMOS.py:102 (view, no copy)
+    coord_rv = property(lambda self: self.pcds_sphere_coord[:1])          # :99
+
+
+class RawBatch(_FlatBatch):
+    """One scan as the loader has it BEFORE form_batch (datasets/data_StreamMOS.py:565-574): the raw, range filtered
+    and padded points of the T frames, plus the range-view coordinates of the current frame (SphereQuantize stays a
+    loader output: numpy's float32 arctan2 / arcsin cannot be matched bit for bit on the device) and the same
+    stand-ins as LoaderBatch. Quantize + make_point_feat run on the device (ops.form_batch, bit-exact)."""
+
+    FIELDS = ("points", "sphere_cur", "pred", "loc", "attn")
+    coord_rv = property(lambda self: self.sphere_cur)
 
 
 def make_host_loader_scan(seed, n_points=120000, t_frames=3, pin=True):
@@ -138,15 +152,28 @@ def make_host_loader_scan(seed, n_points=120000, t_frames=3, pin=True):
     s = synthetic.make_scan(seed, n_points, t_frames)
     rng = np.random.default_rng(seed + 7919)
     xyzi = s["xyzi"]                                                           # (T, N, 4)
-    dist = np.sqrt((xyzi[..., :3].astype(np.float64) ** 2).sum(-1)) + 1e-12
+    x, y, z = xyzi[..., 0], xyzi[..., 1], xyzi[..., 2]
+    dist = np.sqrt(x ** 2 + y ** 2 + z ** 2) + 1e-12          # float32, as make_point_feat computes it
     c = s["pcds_coord"][..., 0]                                                # (T, N, 3)
-    feat7 = np.stack((xyzi[..., 0], xyzi[..., 1], xyzi[..., 2], xyzi[..., 3], dist.astype(np.float32),
+    feat7 = np.stack((x, y, z, xyzi[..., 3], dist.astype(np.float32),
                       c[..., 0] - np.floor(c[..., 0]), c[..., 1] - np.floor(c[..., 1])), 1)  # (T, 7, N)
     other = make_host_scan(seed, n_points, t_frames, channels=1, pin=False)   # same pred / loc / attn stand-ins
     out = LoaderBatch(pcds_xyzi=torch.from_numpy(np.ascontiguousarray(feat7[..., None].astype(np.float32))),
                       pcds_coord=torch.from_numpy(np.ascontiguousarray(s["pcds_coord"])),
                       pcds_sphere_coord=torch.from_numpy(np.ascontiguousarray(s["pcds_sphere_coord"])),
                       pred=other.pred, loc=other.loc, attn=other.attn)
+    if pin and torch.cuda.is_available():
+        out = out.pack(pin=True)
+    return out
+
+
+def make_host_raw_scan(seed, n_points=120000, t_frames=3, pin=True):
+    """Synthetic RawBatch of one scan (same scan as make_host_loader_scan(seed): the two produce identical steps)."""
+    s = synthetic.make_scan(seed, n_points, t_frames)
+    other = make_host_scan(seed, n_points, t_frames, channels=1, pin=False)
+    out = RawBatch(points=torch.from_numpy(np.ascontiguousarray(s["xyzi"])),
+                   sphere_cur=torch.from_numpy(np.ascontiguousarray(s["pcds_sphere_coord"][:1])),
+                   pred=other.pred, loc=other.loc, attn=other.attn)
     if pin and torch.cuda.is_available():
         out = out.pack(pin=True)
     return out
@@ -253,9 +280,13 @@ class HotPath:
         Data dependencies (models/StreamMOS.py:101-105, mve.py:393-417): pool #1 and gather #5 depend on the
         coordinates only; gather1 -> pool2 -> gather2 -> pool3 and gather3 -> pool4 -> gather4 -> pool5 are two
         chains. With `branches` the four run as parallel branches (results are identical)."""
-        coord_bev = b.coord_bev
+        if hasattr(b, "points"):      # raw scan: Quantize + make_point_feat on the device (SURVEY 8f rank 2), then the stem
+            feat7, coord = ops.form_batch(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, self.size)
+            coord_bev, feat = coord[:, :, :2], self.point_pre(feat7)
+        else:
+            coord_bev = b.coord_bev
+            feat = b.feat if hasattr(b, "feat") else self.point_pre(b.pcds_xyzi)
         cur_bev, cur_rv = coord_bev[:1], b.coord_rv
-        feat = b.feat if hasattr(b, "feat") else self.point_pre(b.pcds_xyzi)
         # all five pooling plans of the scan depend on the coordinates only: four launches build them all
         if self.batch_plans:
             pl = ops.pool_plan_multi([(coord_bev, (512, 512), (1.0, 1.0)), (cur_rv, (32, 1024), (0.5, 0.5)),
@@ -313,7 +344,10 @@ class HotPath:
         """Voxel voting over 8 history scans + the current one, then per-instance votes."""
         cur = HISTORY
         # raw points of the current frame: loader batches carry them as the first 4 channels of pcds_xyzi
-        xyzi = b.xyzi if hasattr(b, "xyzi") else b.pcds_xyzi[0, :4, :, 0].t().contiguous()
+        if hasattr(b, "points"):
+            xyzi = b.points[0]
+        else:
+            xyzi = b.xyzi if hasattr(b, "xyzi") else b.pcds_xyzi[0, :4, :, 0].t().contiguous()
         if self.device.type == "cuda":
             # the previous scan moves from the current slot into its ring slot and the new scan takes the current
             # slot: one kernel (the window slides exactly as voxel_voting.py:182 walks it)

@@ -687,6 +687,41 @@ def test_point_stem_sizes_vs_oracle(B, Cin, N):
 
 
 # ------------------------------------------------------------------------------------------------
+# Model input tensors from raw scans (next: SURVEY §8f rank 2, exact part)
+# ------------------------------------------------------------------------------------------------
+def test_form_batch_golden_and_config_size(golden):
+    from streammos_b200 import ops, synthetic
+    g = golden("form_batch_a")
+    rng_ = ((-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0))
+    for tag, (xs, ys) in {"pp": (1, 1), "mp": (-1, 1)}.items():
+        feat, coord = ops.form_batch(t(g["points"]), *rng_, (512, 512, 30), xs, ys)
+        assert feat.shape == (3, 7, 3000, 1) and coord.shape == (3, 3000, 3, 1)
+        assert np.array_equal(feat[..., 0].cpu().numpy(), g["feat_" + tag])      # bit-exact with the reference's numpy
+        assert np.array_equal(coord[..., 0].cpu().numpy(), g["coord_" + tag])
+    s = synthetic.make_scan(77, 120000, 3)                                      # config size, vs the oracle
+    feat, coord = ops.form_batch(t(s["xyzi"]), *rng_, (512, 512, 30))
+    rf, rc = O.form_batch(s["xyzi"], *rng_, (512, 512, 30))
+    assert np.array_equal(feat[..., 0].cpu().numpy(), rf) and np.array_equal(coord[..., 0].cpu().numpy(), rc)
+    assert np.array_equal(rc[..., None], s["pcds_coord"])                       # = the harness's own loader restatement
+    with pytest.raises(RuntimeError):
+        ops.form_batch(t(s["xyzi"]).cpu(), *rng_, (512, 512, 30))
+
+
+def test_step_from_raw_scan_matches_step_from_loader_tensors():
+    """RawBatch (Quantize + make_point_feat on the device) and LoaderBatch (done by the host) give the same step."""
+    from streammos_b200 import stream
+    n = 20000
+    a, b = stream.HotPath(dev(), n_points=n, seed=4), stream.HotPath(dev(), n_points=n, seed=4)
+    with torch.no_grad():
+        for i in range(2):
+            la, sa, pa = a.step(stream.make_host_loader_scan(800 + i, n, pin=False).to(dev()))
+            lb, sb, pb = b.step(stream.make_host_raw_scan(800 + i, n, pin=False).to(dev()))
+            assert torch.equal(la, lb) and torch.equal(sa, sb)
+            for x, y in zip(pa, pb):
+                assert torch.equal(x, y)
+
+
+# ------------------------------------------------------------------------------------------------
 # Whole hot path: streaming harness on the GPU vs the CPU restatement of the same sequence
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("point_major", [True, False])

@@ -144,3 +144,14 @@ def test_point_stem_matches_reference_module(golden):
     assert np.abs(ref[..., pads] - ref64[..., pads]).max() > 1e-4
     np.testing.assert_allclose(y[..., pads], ref64[..., pads], rtol=1e-5, atol=1e-3)
     assert 0.2 < (ref > 0).mean() < 0.8   # both sides of the ReLU are exercised
+
+
+def test_form_batch_bit_exact(golden):
+    """Quantize + make_point_feat of the loader's form_batch (datasets/utils.py:151-169, data_StreamMOS.py:25-50,
+    471-513), both TTA sign pairs of the fixture: float32 arithmetic replayed exactly."""
+    g = golden("form_batch_a")
+    for tag, (xs, ys) in {"pp": (1, 1), "mp": (-1, 1)}.items():
+        feat, coord = O.form_batch(g["points"], (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), (512, 512, 30), xs, ys)
+        assert np.array_equal(feat, g["feat_" + tag]) and np.array_equal(coord, g["coord_" + tag])
+    assert float(g["feat_pp"][:, 4].min()) == np.float32(1e-12)          # points at the sensor origin
+    assert (g["coord_pp"][..., 0] == 0).any() and (g["coord_pp"] < 0).any()  # lower bound hit, pads out of range

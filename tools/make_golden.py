@@ -9,6 +9,7 @@ What runs, unmodified:
   * voxel_voting.py / voxel_instance_voting.py functions, extracted with `ast` because the scripts run
     argparse at import time (voxel_voting.py:128-136)
   * networks/backbone.py:PointNetStacker(7, 64, pre_bn=True, stack_num=2).eval()   (the stem of models/StreamMOS.py:77)
+  * datasets/utils.py Quantize / SphereQuantize + datasets/data_StreamMOS.py make_point_feat (the loader's form_batch)
 
     python tools/make_golden.py [--ref /root/reference]
 """
@@ -364,6 +365,44 @@ def gen_point_stem(ref, rng):
     return ["point_stem_a"]
 
 
+def gen_form_batch(ref, rng):
+    """The val loader's form_batch (datasets/data_StreamMOS.py:471-493) with the reference's own utils.Quantize,
+    utils.SphereQuantize and make_point_feat (AST-extracted: the module imports the dataset stack) on raw, range
+    filtered and padded float32 points of T frames, for two TTA sign pairs (form_batch_tta :495-513)."""
+    du = load_by_path("ref_dutils", os.path.join(ref, "datasets", "utils.py"))
+    g = {"np": np}
+    extract_functions(os.path.join(ref, "datasets", "data_StreamMOS.py"), ["make_point_feat"], g)
+
+    class Voxel:  # config/StreamMOS.py:11-19
+        RV_theta = (-25.0, 3.0)
+        range_x, range_y, range_z = (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0)
+        bev_shape, rv_shape = (512, 512, 30), (64, 2048)
+
+    T, N, n_valid = 3, 3000, 2700
+    r = np.abs(rng.standard_normal((T, N))) * 18.0
+    th = rng.uniform(0, 2 * np.pi, (T, N))
+    pts = np.stack([np.clip(r * np.cos(th), -49.99, 49.99), np.clip(r * np.sin(th), -49.99, 49.99),
+                    np.clip(rng.normal(-1.5, 0.6, (T, N)), -3.99, 1.99), rng.uniform(0, 1, (T, N))], -1).astype(np.float32)
+    pts[:, :10, :3] = 0.0                                  # the sensor origin: dist = 1e-12 exactly
+    pts[:, 10:20, 0] = np.float32(-50.0)                   # exactly on the lower bound -> x_quan = 0
+    pts[:, n_valid:, :] = -1000.0                          # loader pads (data_StreamMOS.py:568-571)
+    pts[:, n_valid:, 2] = -4000.0
+    out = {}
+    for tag, (xs, ys) in {"pp": (1, 1), "mp": (-1, 1)}.items():
+        total = pts.reshape(T * N, 4).copy()
+        total[:, 0] *= xs
+        total[:, 1] *= ys
+        xyzi = total[:, :4]
+        coord = du.Quantize(xyzi, range_x=Voxel.range_x, range_y=Voxel.range_y, range_z=Voxel.range_z, size=Voxel.bev_shape)
+        sphere = du.SphereQuantize(xyzi, phi_range=(-180.0, 180.0), theta_range=Voxel.RV_theta, size=Voxel.rv_shape)
+        feat = g["make_point_feat"](xyzi, coord, sphere, Voxel)
+        assert feat.dtype == np.float32 and coord.dtype == np.float32
+        out["feat_" + tag] = np.ascontiguousarray(feat.reshape(T, N, 7).transpose(0, 2, 1))   # (T, 7, N)
+        out["coord_" + tag] = coord.reshape(T, N, 3)
+    np.savez_compressed(os.path.join(GOLD, "form_batch_a.npz"), points=pts, **out)
+    return ["form_batch_a"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -374,8 +413,9 @@ def main():
     torch.set_num_threads(1)
     rng = np.random.default_rng(20261018)
     made = []
-    if a.only == "point_stem":
-        made += gen_point_stem(a.ref, np.random.default_rng(99))
+    if a.only in ("point_stem", "form_batch"):
+        made += gen_point_stem(a.ref, np.random.default_rng(99)) if a.only == "point_stem" else \
+            gen_form_batch(a.ref, np.random.default_rng(55))
         for m in made:
             print("%-28s %8.1f KB" % (m, os.path.getsize(os.path.join(GOLD, m + ".npz")) / 1024))
         return
@@ -386,6 +426,7 @@ def main():
     made += gen_instance(a.ref, rng)
     made += gen_stream_vote(a.ref, np.random.default_rng(77))
     made += gen_point_stem(a.ref, np.random.default_rng(99))
+    made += gen_form_batch(a.ref, np.random.default_rng(55))
     for m in made:
         p = os.path.join(GOLD, m + ".npz")
         print("%-28s %8.1f KB" % (m, os.path.getsize(p) / 1024))
