@@ -16,6 +16,9 @@ constexpr int kStemPts = 128;     // points per CTA
 constexpr int kStemThreads = 128;  // 4 warps: one thread per point in layer 1, 16 channels x 4 points per thread in layer 2
 constexpr int kStemC = 64;        // C1 == C2 == 64 (the only configuration StreamMOS builds)
 constexpr int kStemCinMax = 16;
+#ifndef SMOS_STEM_MIN_CTAS
+#define SMOS_STEM_MIN_CTAS 3  // four CTAs per SM (128 registers) spill with the packed accumulators: 98.8 vs 90.6 us
+#endif
 
 struct StemSmem {
   float h[kStemC][kStemPts];      // hidden activations, [channel][point]
@@ -27,7 +30,7 @@ struct StemSmem {
 };
 
 template <int CIN>
-__global__ void __launch_bounds__(kStemThreads)
+__global__ void __launch_bounds__(kStemThreads, SMOS_STEM_MIN_CTAS)
 point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B, int64_t x_sb, int64_t x_sc, int64_t x_sn,
                   const float* __restrict__ a0, const float* __restrict__ b0, const float* __restrict__ w1,
                   const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ w2,
@@ -93,25 +96,34 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
     // wavefronts) — with 8 channels per warp the kernel sat at 79 % of the shared-memory pipe and 52 % of the FMA pipe
     constexpr int CW = 16;
     const int c0 = wid * CW;
-    float acc[CW][4];
+    // accumulators as channel PAIRS: fma.rn.f32x2 (sm_100 packed fp32 FMA, two round-to-nearest FMAs per instruction:
+    // bit-identical to two scalar FMAs) halves the issue slots of the inner loop
+    float2 acc2[CW / 2][4];
 #pragma unroll
-    for (int j = 0; j < CW; ++j)
+    for (int j = 0; j < CW / 2; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+      for (int i = 0; i < 4; ++i) acc2[j][i] = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int k = 0; k < kStemC; ++k) {
       const float4 hv = *reinterpret_cast<const float4*>(&S.h[k][lane * 4]);
-      const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+      const float2 hh[4] = {make_float2(hv.x, hv.x), make_float2(hv.y, hv.y), make_float2(hv.z, hv.z),
+                            make_float2(hv.w, hv.w)};
 #pragma unroll
       for (int jq = 0; jq < CW / 4; ++jq) {
         const float4 wv = *reinterpret_cast<const float4*>(&S.w2t[k][c0 + 4 * jq]);
-        const float w[4] = {wv.x, wv.y, wv.z, wv.w};
+        const float2 wa = make_float2(wv.x, wv.y), wb = make_float2(wv.z, wv.w);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[4 * jq + j][i] = fmaf(w[j], hh[i], acc[4 * jq + j][i]);
+        for (int i = 0; i < 4; ++i) {
+          acc2[2 * jq][i] = __ffma2_rn(wa, hh[i], acc2[2 * jq][i]);
+          acc2[2 * jq + 1][i] = __ffma2_rn(wb, hh[i], acc2[2 * jq + 1][i]);
+        }
       }
     }
+    float acc[CW][4];
+#pragma unroll
+    for (int j = 0; j < CW / 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[2 * j][i] = acc2[j][i].x; acc[2 * j + 1][i] = acc2[j][i].y; }
     const int32_t n = n0 + lane * 4;
     const bool vec = (n + 3 < N) && ((y_sc & 3) == 0) && ((y_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
 #pragma unroll
@@ -158,7 +170,12 @@ extern "C" int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, i
   }
   // persistent CTAs: 4 per SM (53 KB of shared memory each), each walks the 128-point tiles with a grid stride
   const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kStemPts)) * B;
-  const int64_t want = static_cast<int64_t>(SMOS_SM_COUNT) * 4;
+  int per_sm = 0;
+  cudaError_t oe = Cin == 7
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<7>, kStemThreads, sizeof(StemSmem))
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<0>, kStemThreads, sizeof(StemSmem));
+  if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t want = static_cast<int64_t>(SMOS_SM_COUNT) * per_sm;  // one wave of persistent CTAs
   dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));
   if ((reinterpret_cast<uintptr_t>(w2) & 15) != 0) return SMOS_EINVAL;
   if (Cin == 7)  // the StreamMOS stem: x, y, z, intensity, dist, diff_x, diff_y
