@@ -195,6 +195,28 @@ def test_pool_channel_major_permute_paths_random_shapes(path, monkeypatch):
         assert np.array_equal(out.cpu().numpy(), ref), (path, B, C, N, size)
 
 
+def test_pool_and_gather_val_loader_tta_shape():
+    """The largest shapes the reference feeds the path: the val loader pads every frame to 160 000 points
+    (config/StreamMOS.py:46) and test-time augmentation stacks 4 flips (datasets/data_StreamMOS.py:495-513), so
+    VoxelMaxPool #1 sees B' = 4 x 3 = 12 batch entries. Forward bit-exact against the oracle, then a batched
+    cell-order gather back (B = 4)."""
+    from streammos_b200 import deep_point, ops
+    rng = np.random.default_rng(160000)
+    Bp, C, N, size = 12, 64, 160000, (512, 512)
+    ind = synth_scan(rng, Bp, N, size[0], size[1], (1.0, 1.0), n_valid=121000)
+    feat = np.maximum(rng.standard_normal((Bp, C, N, 1)).astype(np.float32), 0)
+    out = deep_point.VoxelMaxPool(t(feat), t(ind), size, (1.0, 1.0))
+    ref = O.voxel_maxpool_forward(feat, ind, size, (1.0, 1.0))
+    assert out.shape == (Bp, C, 512, 512) and np.array_equal(out.cpu().numpy(), ref)
+    del out
+    B, Cg, H, W, scale = 4, 32, 256, 256, (0.5, 0.5)
+    grid = rng.standard_normal((B, Cg, H, W)).astype(np.float32)
+    co = ind[:B]
+    plan = ops.pool_plan(t(co), (H, W), scale)
+    got = ops.bilinear_gather_forward(t(grid), t(co), scale, True, order=plan)
+    np.testing.assert_allclose(got[..., 0].cpu().numpy(), O.bilinear_sample(grid, co, scale), rtol=RTOL, atol=ATOL)
+
+
 def test_pool_rejects_cpu_tensors():
     from streammos_b200 import deep_point
     with pytest.raises(RuntimeError):
