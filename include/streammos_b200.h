@@ -256,6 +256,16 @@ int smos_form_batch(const float* points, int64_t T, int64_t N, int64_t row_strid
                     float min_x, float min_y, float min_z, float dx, float dy, float dz,
                     float* pcds_xyzi, float* pcds_coord, void* stream);
 
+/* smos_form_batch followed by smos_point_stem_forward as ONE kernel (the (T, 7, N) tensor never exists): raw points
+ * in, pcds_coord (T, N, 3) and the 64-channel features y (T, C2, N) out; results bit-identical to the two calls. */
+int smos_point_stem_forward_raw(const float* points, int64_t T, int64_t N, int64_t row_stride,
+                                float x_sign, float y_sign, float min_x, float min_y, float min_z,
+                                float dx, float dy, float dz,
+                                const float* bn0_alpha, const float* bn0_beta, const float* w1,
+                                const float* bn1_alpha, const float* bn1_beta, const float* w2,
+                                const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
+                                float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* (C) Long-term-memory voting.                                               */
 /* ------------------------------------------------------------------------- */

@@ -29,9 +29,20 @@ struct StemSmem {
   float a0[kStemCinMax], b0[kStemCinMax];
 };
 
-template <int CIN>
+// RAW: the 7 input channels are built on the fly from raw points (x, y, z, intensity): the loader's Quantize +
+// make_point_feat (see form_batch.cu, same float32 sequence, bit-exact), and the (B, N, 3) quantised coordinates leave
+// as a side output — the (B, 7, N) tensor never exists.
+struct StemRaw {
+  const float* pts;  // (B*N, rs) raw points, or null
+  int64_t rs;
+  float sx, sy, mx, my, mz, dx, dy, dz;
+  float* coord;      // (B, N, 3) out
+};
+
+template <int CIN, bool RAW>
 __global__ void __launch_bounds__(kStemThreads, SMOS_STEM_MIN_CTAS)
 point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B, int64_t x_sb, int64_t x_sc, int64_t x_sn,
+                  const __grid_constant__ StemRaw raw,
                   const float* __restrict__ a0, const float* __restrict__ b0, const float* __restrict__ w1,
                   const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ w2,
                   const float* __restrict__ a2, const float* __restrict__ b2, float* __restrict__ y, int64_t y_sb,
@@ -61,7 +72,35 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
   // raw inputs of my point in tile t (one point per thread), fetched one tile ahead of their use
   auto fetch = [&](int32_t t, float (&xr)[KI]) {
     const int32_t b = t / tiles_per_b;
-    const int32_t n = min((t - b * tiles_per_b) * kStemPts + tid, N - 1);
+    const int32_t nn = (t - b * tiles_per_b) * kStemPts + tid;
+    const int32_t n = min(nn, N - 1);
+    if (RAW) {
+      const float* p = raw.pts + (static_cast<int64_t>(b) * N + n) * raw.rs;
+      float px, py, pz, pw;
+      if (raw.rs == 4 && (reinterpret_cast<uintptr_t>(raw.pts) & 15) == 0) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        px = q.x; py = q.y; pz = q.z; pw = q.w;
+      } else {
+        px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2); pw = __ldg(p + 3);
+      }
+      px = __fmul_rn(px, raw.sx);
+      py = __fmul_rn(py, raw.sy);
+      const float qx = __fdiv_rn(__fsub_rn(px, raw.mx), raw.dx);
+      const float qy = __fdiv_rn(__fsub_rn(py, raw.my), raw.dy);
+      const float qz = __fdiv_rn(__fsub_rn(pz, raw.mz), raw.dz);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz));
+      xr[0] = px; xr[1] = py; xr[2] = pz; xr[3] = pw;
+      xr[4] = __fadd_rn(__fsqrt_rn(d2), 1e-12f);
+      xr[5] = __fsub_rn(qx, floorf(qx));
+      xr[6] = __fsub_rn(qy, floorf(qy));
+#pragma unroll
+      for (int ci = 7; ci < KI; ++ci) xr[ci] = 0.f;
+      if (nn < N) {
+        float* c = raw.coord + (static_cast<int64_t>(b) * N + n) * 3;
+        c[0] = qx; c[1] = qy; c[2] = qz;
+      }
+      return;
+    }
 #pragma unroll
     for (int ci = 0; ci < KI; ++ci)
       xr[ci] = ci < Cin ? __ldg(x + b * x_sb + ci * x_sc + static_cast<int64_t>(n) * x_sn) : 0.f;
@@ -148,43 +187,71 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
 
 }  // namespace
 
+static int stem_launch(const float* x, int64_t B, int32_t Cin, int64_t N, int64_t x_sb, int64_t x_sc, int64_t x_sn,
+                       const StemRaw& raw, const float* bn0_alpha, const float* bn0_beta, const float* w1,
+                       const float* bn1_alpha, const float* bn1_beta, const float* w2, const float* bn2_alpha,
+                       const float* bn2_beta, int32_t C1, int32_t C2, float* y, int64_t y_sb, int64_t y_sc, void* stream) {
+  if (B <= 0 || N < 0 || Cin <= 0) return SMOS_EINVAL;
+  if (N == 0) return SMOS_OK;
+  if ((!x && !raw.pts) || !w1 || !bn1_alpha || !bn1_beta || !w2 || !bn2_alpha || !bn2_beta || !y) return SMOS_EINVAL;
+  if ((bn0_alpha == nullptr) != (bn0_beta == nullptr)) return SMOS_EINVAL;
+  if (C1 != kStemC || C2 != kStemC || Cin > kStemCinMax || B > 65535 || N >= (int64_t(1) << 31)) return SMOS_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(w2) & 15) != 0) return SMOS_EINVAL;
+  const bool is_raw = raw.pts != nullptr;
+  if (is_raw && (Cin != 7 || raw.coord == nullptr || raw.rs < 4)) return SMOS_EINVAL;
+  static bool opt_in[64] = {};
+  int device = 0;
+  cudaGetDevice(&device);
+  if (device >= 0 && device < 64 && !opt_in[device]) {
+    cudaError_t e = cudaFuncSetAttribute(point_stem_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(point_stem_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(point_stem_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    opt_in[device] = true;
+  }
+  // persistent CTAs, one wave (3 per SM: 53 KB of shared memory and ~140 registers each), walking the 128-point tiles
+  const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kStemPts)) * B;
+  int per_sm = 0;
+  cudaError_t oe = is_raw ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<7, true>, kStemThreads, sizeof(StemSmem))
+                  : Cin == 7 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<7, false>, kStemThreads, sizeof(StemSmem))
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<0, false>, kStemThreads, sizeof(StemSmem));
+  if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int64_t want = static_cast<int64_t>(SMOS_SM_COUNT) * per_sm;
+  dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));
+  const int32_t Ni = static_cast<int32_t>(N), Bi = static_cast<int32_t>(B);
+  cudaStream_t st = smos_stream(stream);
+  if (is_raw)
+    point_stem_kernel<7, true><<<grid, kStemThreads, sizeof(StemSmem), st>>>(
+        x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc);
+  else if (Cin == 7)  // the StreamMOS stem: x, y, z, intensity, dist, diff_x, diff_y
+    point_stem_kernel<7, false><<<grid, kStemThreads, sizeof(StemSmem), st>>>(
+        x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc);
+  else
+    point_stem_kernel<0, false><<<grid, kStemThreads, sizeof(StemSmem), st>>>(
+        x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc);
+  return smos_launch_status();
+}
+
 extern "C" int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, int64_t N, int64_t x_sb, int64_t x_sc,
                                        int64_t x_sn, const float* bn0_alpha, const float* bn0_beta, const float* w1,
                                        const float* bn1_alpha, const float* bn1_beta, const float* w2,
                                        const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2, float* y,
                                        int64_t y_sb, int64_t y_sc, void* stream) {
-  if (B <= 0 || N < 0 || Cin <= 0) return SMOS_EINVAL;
-  if (N == 0) return SMOS_OK;
-  if (!x || !w1 || !bn1_alpha || !bn1_beta || !w2 || !bn2_alpha || !bn2_beta || !y) return SMOS_EINVAL;
-  if ((bn0_alpha == nullptr) != (bn0_beta == nullptr)) return SMOS_EINVAL;
-  if (C1 != kStemC || C2 != kStemC || Cin > kStemCinMax || B > 65535 || N >= (int64_t(1) << 31)) return SMOS_EUNSUPPORTED;
-  static bool opt_in[64] = {};
-  int device = 0;
-  cudaGetDevice(&device);
-  if (device >= 0 && device < 64 && !opt_in[device]) {
-    cudaError_t e = cudaFuncSetAttribute(point_stem_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    e = cudaFuncSetAttribute(point_stem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    opt_in[device] = true;
-  }
-  // persistent CTAs: 4 per SM (53 KB of shared memory each), each walks the 128-point tiles with a grid stride
-  const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kStemPts)) * B;
-  int per_sm = 0;
-  cudaError_t oe = Cin == 7
-      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<7>, kStemThreads, sizeof(StemSmem))
-      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<0>, kStemThreads, sizeof(StemSmem));
-  if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
-  const int64_t want = static_cast<int64_t>(SMOS_SM_COUNT) * per_sm;  // one wave of persistent CTAs
-  dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));
-  if ((reinterpret_cast<uintptr_t>(w2) & 15) != 0) return SMOS_EINVAL;
-  if (Cin == 7)  // the StreamMOS stem: x, y, z, intensity, dist, diff_x, diff_y
-    point_stem_kernel<7><<<grid, kStemThreads, sizeof(StemSmem), smos_stream(stream)>>>(
-        x, Cin, static_cast<int32_t>(N), static_cast<int32_t>(B), x_sb, x_sc, x_sn, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
-        bn2_beta, y, y_sb, y_sc);
-  else
-    point_stem_kernel<0><<<grid, kStemThreads, sizeof(StemSmem), smos_stream(stream)>>>(
-        x, Cin, static_cast<int32_t>(N), static_cast<int32_t>(B), x_sb, x_sc, x_sn, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
-        bn2_beta, y, y_sb, y_sc);
-  return smos_launch_status();
+  StemRaw raw = {};
+  return stem_launch(x, B, Cin, N, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
+                     bn2_beta, C1, C2, y, y_sb, y_sc, stream);
+}
+
+// smos_form_batch + smos_point_stem_forward in one kernel: raw points in, 64-channel features and the quantised
+// coordinates out (same arithmetic as the two calls: bit-identical results).
+extern "C" int smos_point_stem_forward_raw(const float* points, int64_t T, int64_t N, int64_t row_stride, float x_sign,
+                                           float y_sign, float min_x, float min_y, float min_z, float dx, float dy,
+                                           float dz, const float* bn0_alpha, const float* bn0_beta, const float* w1,
+                                           const float* bn1_alpha, const float* bn1_beta, const float* w2,
+                                           const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
+                                           float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, void* stream) {
+  if (!points || !pcds_coord) return SMOS_EINVAL;
+  StemRaw raw = {points, row_stride, x_sign, y_sign, min_x, min_y, min_z, dx, dy, dz, pcds_coord};
+  return stem_launch(nullptr, T, 7, N, 0, 0, 0, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta,
+                     C1, C2, y, y_sb, y_sc, stream);
 }

@@ -326,6 +326,43 @@ def point_stem_forward(x, bn0, w1, bn1, w2, bn2, out=None):
     return out
 
 
+def point_stem_forward_raw(points, range_x, range_y, range_z, size, bn0, w1, bn1, w2, bn2, x_sign=1.0, y_sign=1.0):
+    """form_batch + point_stem_forward in one kernel: points (T, N, >=4) float32 CUDA raw scans ->
+    (features (T, 64, N, 1), pcds_coord (T, N, 3, 1)); bit-identical to the two separate calls."""
+    import numpy as np
+    _need_cuda(points, "points")
+    _need_f32(points, "points")
+    assert points.dim() == 3 and points.size(2) >= 4 and points.stride(2) == 1 and points.stride(0) == points.size(1) * points.stride(1)
+    T, N = int(points.size(0)), int(points.size(1))
+    for name, w in (("w1", w1), ("w2", w2)):
+        _need_cuda(w, name)
+        _need_f32(w, name)
+    w1 = w1.reshape(w1.shape[0], -1).contiguous()
+    w2 = w2.reshape(w2.shape[0], -1).contiguous()
+    if w1.shape[1] != 7 or w2.shape[1] != w1.shape[0]:
+        raise RuntimeError("point_stem_forward_raw: the stem must take the 7 loader channels")
+    vecs = [t for t in ((bn0 or (None, None)) + tuple(bn1) + tuple(bn2)) if t is not None]
+    for v in vecs:
+        _need_cuda(v, "BatchNorm affine")
+        _need_f32(v, "BatchNorm affine")
+    vecs = [v.contiguous() for v in vecs]
+    a0, b0 = (vecs[0], vecs[1]) if bn0 is not None else (None, None)
+    a1, b1, a2, b2 = vecs[-4:]
+    d = [float(np.float32((r[1] - r[0]) / s_)) for r, s_ in zip((range_x, range_y, range_z), size)]
+    C1, C2 = int(w1.shape[0]), int(w2.shape[0])
+    out = torch.empty((T, C2, N, 1), dtype=torch.float32, device=points.device)
+    coord = torch.empty((T, N, 3, 1), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        rc = _lib.load().smos_point_stem_forward_raw(
+            _ptr(points), T, N, points.stride(1) if N > 1 else points.size(2), float(x_sign), float(y_sign),
+            float(range_x[0]), float(range_y[0]), float(range_z[0]), d[0], d[1], d[2], _ptr(a0), _ptr(b0), _ptr(w1),
+            _ptr(a1), _ptr(b1), _ptr(w2), _ptr(a2), _ptr(b2), C1, C2, _ptr(coord), _ptr(out), out.stride(0), out.stride(1),
+            _stream())
+    _lib.check(rc, "smos_point_stem_forward_raw")
+    _count(1)
+    return out, coord
+
+
 # ----------------------------------------------------------------------------------------------
 # MSDeformAttn
 # ----------------------------------------------------------------------------------------------

@@ -185,12 +185,13 @@ class HotPath:
 
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
                  batch_plans=True, grids_channels_last=False, overlap_voting=False, branches=True,
-                 ordered_gathers=True, ordered_rv=False, gather_taps=False):
+                 ordered_gathers=True, ordered_rv=False, gather_taps=False, fuse_form_batch=False):
         self.device = torch.device(device)
         self.overlap_voting = overlap_voting
         self.branches = branches and self.device.type == "cuda"
         self.ordered_gathers, self.ordered_rv = ordered_gathers, ordered_rv
         self.gather_taps = gather_taps and ordered_gathers and point_major and batch_plans
+        self.fuse_form_batch = fuse_form_batch
         self._side = None
         self._branch_streams = []
         self.batch_plans = batch_plans
@@ -281,8 +282,13 @@ class HotPath:
         coordinates only; gather1 -> pool2 -> gather2 -> pool3 and gather3 -> pool4 -> gather4 -> pool5 are two
         chains. With `branches` the four run as parallel branches (results are identical)."""
         if hasattr(b, "points"):      # raw scan: Quantize + make_point_feat on the device (SURVEY 8f rank 2), then the stem
-            feat7, coord = ops.form_batch(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, self.size)
-            coord_bev, feat = coord[:, :, :2], self.point_pre(feat7)
+            if self.fuse_form_batch:  # one kernel: raw points -> 64-channel features + quantised coordinates
+                feat, coord = ops.point_stem_forward_raw(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z,
+                                                         self.size, *self.stem.fused_parameters())
+            else:
+                feat7, coord = ops.form_batch(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, self.size)
+                feat = self.point_pre(feat7)
+            coord_bev = coord[:, :, :2]
         else:
             coord_bev = b.coord_bev
             feat = b.feat if hasattr(b, "feat") else self.point_pre(b.pcds_xyzi)

@@ -729,6 +729,25 @@ def test_form_batch_golden_and_config_size(golden):
         ops.form_batch(t(s["xyzi"]).cpu(), *rng_, (512, 512, 30))
 
 
+def test_point_stem_from_raw_points_equals_form_batch_then_stem(golden):
+    """The fused raw-point stem (smos_point_stem_forward_raw) is bit-identical to form_batch followed by the stem."""
+    from streammos_b200 import ops, synthetic
+    g = golden("point_stem_a")
+    bn = [O.bn_affine(g["bn%d_weight" % i], g["bn%d_bias" % i], g["bn%d_mean" % i], g["bn%d_var" % i],
+                      float(g["bn%d_eps" % i])) for i in range(3)]
+    tt = lambda pair: (t(pair[0]), t(pair[1]))
+    rng_ = ((-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0))
+    for n, (xs, ys) in ((120000, (1, 1)), (4099 * 4, (-1, 1)), (1, (1, -1))):
+        pts = synthetic.make_scan(5, max(n, 64), 3)["xyzi"][:, :n]
+        f7, c = ops.form_batch(t(pts), *rng_, (512, 512, 30), xs, ys)
+        want = ops.point_stem_forward(f7, tt(bn[0]), t(g["w1"]), tt(bn[1]), t(g["w2"]), tt(bn[2]))
+        got, gc = ops.point_stem_forward_raw(t(pts), *rng_, (512, 512, 30), tt(bn[0]), t(g["w1"]), tt(bn[1]), t(g["w2"]),
+                                             tt(bn[2]), xs, ys)
+        assert torch.equal(got, want) and torch.equal(gc, c)
+    rf, rc = O.form_batch(pts, *rng_, (512, 512, 30), xs, ys)
+    assert np.array_equal(got[..., 0].cpu().numpy(), O.point_stem(rf, bn[0], g["w1"], bn[1], g["w2"], bn[2]))
+
+
 def test_step_from_raw_scan_matches_step_from_loader_tensors():
     """RawBatch (Quantize + make_point_feat on the device) and LoaderBatch (done by the host) give the same step."""
     from streammos_b200 import stream
