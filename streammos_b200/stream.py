@@ -185,7 +185,7 @@ class HotPath:
 
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
                  batch_plans=True, grids_channels_last=False, overlap_voting=False, branches=True,
-                 ordered_gathers=True, ordered_rv=False, gather_taps=False, fuse_form_batch=False):
+                 ordered_gathers=True, ordered_rv=False, gather_taps=False, fuse_form_batch=True):
         self.device = torch.device(device)
         self.overlap_voting = overlap_voting
         self.branches = branches and self.device.type == "cuda"
