@@ -71,10 +71,10 @@ int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N,
                          int64_t* voxel_max_idx, int64_t idx_batch_stride,
                          void* plan, void* stream);
 
-/* Several plans in one go (three kernel launches for all of them instead of three each): a scan
+/* Several plans in one go (four kernel launches for all of them instead of four each): a scan
  * needs five — BEV at scales 1, 1/2, 1/4 and range view at 1/2, 1/4. Same semantics per entry as
  * smos_pool_plan_build. n <= 8. If the plan buffers are carved out of one allocation they are
- * cleared with a single memset. */
+ * cleared by the first of the four kernels (no memset nodes). */
 typedef struct smos_pool_plan_desc {
   const float* pcds_ind;
   int64_t B, N, ind_sb, ind_sn, ind_sd;

@@ -6,17 +6,20 @@
 // in one BEV cell next to the sensor, >90 % of the cells empty), so neither per-cell atomics
 // nor per-tile ownership balance. Here:
 //
-//   plan  (3 small kernels, coordinates only, shared by forward and backward)
-//         cell index -> per-cell counting sort: `sorted` lists the valid points grouped by
-//         cell; count[cell] / start[cell] locate each group.
-//   reduce (phase A) one warp per 32 consecutive sorted points, whatever cells they fall in:
-//         perfectly balanced. Inside its 32 points a warp reduces each run of equal cells (a
-//         "piece") and writes ONE row of C maxima per piece into a scratch row buffer, indexed
-//         by the position of the piece's first point. No atomics, no initialisation.
-//   write (phase B) one thread per 4 adjacent output cells x 8 channels: empty cells store
-//         zeros, occupied cells combine their <= 1 + count/32 piece rows. Every output element
-//         is written exactly once with 128-bit stores: the 201 MB zero-fill of the reference
-//         is fused away and HBM traffic stays at the algorithmic minimum.
+//   plan  (4 small kernels, coordinates only, shared by forward, backward and cell-order gathers; up to 8
+//         plans per launch) zero the counters -> cell index + per-cell ranks (one atomic per run of equal
+//         cells) -> segment allocation (one cursor atomic per CTA) -> scatter: `sorted` lists the valid points
+//         grouped by cell, out-of-grid points at its tail; count[cell] / start[cell] locate each group.
+//   permute (channel-major input only) 64-point x C tiles through shared memory: one row of C run-maxima per
+//         run of equal cells, written at the run's sorted position (LDG tiles by default, tiled-TMA pipeline
+//         behind SMOS_PERM_LDG=0).
+//   reduce one warp per 32 consecutive sorted positions, whatever cells they fall in: perfectly balanced.
+//         Inside its window a warp reduces each run of equal cells (a "piece") and writes ONE row of C maxima
+//         per piece into the row buffer, at the position of the piece's first point. No atomics.
+//   combine one warp per cell whose segment crosses a multiple of 32: folds its pieces into its first row.
+//   write one thread per 4 adjacent output cells x all channel groups: empty cells store zeros, occupied cells
+//         read their one row. Every output element is written exactly once with 128-bit stores: the 201 MB
+//         zero-fill of the reference is fused away.
 #include <cuda.h>
 
 #include <cstdlib>

@@ -157,7 +157,7 @@ def test_pool_permutation_invariant():
 
 
 def test_pool_batched_plans_match_single_plans():
-    """ops.pool_plan_multi (three launches for all five pooling calls of a scan) gives the same grids."""
+    """ops.pool_plan_multi (four launches for all five pooling calls of a scan) gives the same grids."""
     from streammos_b200 import deep_point, ops
     rng = np.random.default_rng(3)
     N = 50000

@@ -52,7 +52,7 @@ with torch.no_grad():
     specs = lambda b: [(b.coord_bev, (512, 512), (1.0, 1.0)), (b.coord_rv, (32, 1024), (0.5, 0.5)),
                        (b.coord_bev[:1], (256, 256), (0.5, 0.5)), (b.coord_rv, (16, 512), (0.25, 0.25)),
                        (b.coord_bev[:1], (128, 128), (0.25, 0.25))]
-    timeit("plan x5 (3 kernels)", lambda i: ops.pool_plan_multi(specs(S(i))))
+    timeit("plan x5 (4 kernels)", lambda i: ops.pool_plan_multi(specs(S(i))))
     timeit("plan x5 + gather taps x4", lambda i: ops.pool_plan_multi(specs(S(i)), gather_taps=[False, True, True, True, True]))
     plans = [ops.pool_plan_multi(specs(s)) for s in scans]
     tplans = [ops.pool_plan_multi(specs(s), gather_taps=[False, True, True, True, True]) for s in scans]
