@@ -9,8 +9,10 @@
  * golden vectors for these ops (its only test, deformattn/test.py, compares the CUDA op with
  * ms_deform_attn_core_pytorch at run time), so this oracle is pinned against OUTPUTS OF THE
  * REFERENCE ITSELF, generated in the build container by tools/make_golden.py (the reference's
- * point_deep.cpp compiled unmodified, its ms_deform_attn_core_pytorch, its BilinearSample module
- * and its voting functions) and committed under tests/golden/.
+ * point_deep.cpp compiled unmodified, its ms_deform_attn_core_pytorch, its BilinearSample module,
+ * its voting functions and one whole frame of the voxel_voting.py loop body with its Trans and Crop,
+ * its PointNetStacker module, its utils.Quantize / SphereQuantize / make_point_feat) and committed
+ * under tests/golden/. Status: pinned (tests/test_oracle_golden.py).
  *
  * Third-party arithmetic restated here: torch's grid_sampler_2d (bilinear, zeros padding) —
  * the reference pins torch 1.11.0 (README.md:65,79); the algorithm restated is ATen's

@@ -101,3 +101,21 @@ def test_bilinear_sample_signature():
     assert m.scale_rate == (0.5, 0.5)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 2, 4, 4), torch.zeros(1, 3, 2, 1))
+
+
+def test_flat_batches_pack_into_one_buffer():
+    """Raw / loader batches packed into one flat buffer: same tensors, 256-byte aligned fields, one copy moves all."""
+    from streammos_b200 import stream
+    for make in (stream.make_host_raw_scan, stream.make_host_loader_scan):
+        a = make(3, 2000, pin=False)
+        p = a.pack()
+        assert p._flat is not None and p.nbytes() == p._flat.numel() >= a.nbytes()
+        for f in a.FIELDS:
+            assert torch.equal(getattr(a, f), getattr(p, f)) and getattr(p, f).data_ptr() % 256 == p._flat.data_ptr() % 256
+        q = make(4, 2000, pin=False).pack()
+        q.copy_from(p)
+        assert torch.equal(q._flat, p._flat)
+    raw, lo = stream.make_host_raw_scan(3, 2000, pin=False), stream.make_host_loader_scan(3, 2000, pin=False)
+    assert torch.equal(raw.points[0].t(), lo.pcds_xyzi[0, :4, :, 0])          # same scan in both forms
+    assert torch.equal(raw.sphere_cur, lo.pcds_sphere_coord[:1]) and raw.nbytes() < lo.nbytes() / 2
+    assert not lo.coord_bev.is_contiguous() and lo.coord_bev.shape == (3, 2000, 2, 1)
