@@ -30,7 +30,7 @@
 namespace {
 
 constexpr int kPlanThreads = 256;
-constexpr int kReduceWarps = 8;   // warps per CTA in phase A
+constexpr int kReduceWarps = 4;   // warps per CTA in phase A
 constexpr int kWriteThreads = 256;
 constexpr int kCG = 8;            // channels per thread in phase B
 // A point that continues a run of equal cells begun by the lane before it (same 16-point segment, hence
