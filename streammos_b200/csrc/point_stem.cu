@@ -8,6 +8,8 @@
 // per-channel affine torch applies (y = x * alpha + beta, alpha = weight / sqrt(var + eps), beta = bias - mean *
 // alpha), kept separate from the convolutions so the arithmetic follows the reference's sequence. fp32 FMA on the
 // CUDA cores: TF32 tensor-core products would miss the 1e-5 parity bar.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -29,6 +31,36 @@ struct StemSmem {
   float a0[kStemCinMax], b0[kStemCinMax];
 };
 
+// Tensor-core variant of layer 2 (SMOS_STEM_TC=1): 3xTF32 split products on mma.sync.m16n8k8 (a = a_hi + a_lo with
+// a_hi = tf32(a), a_lo = tf32(a - a_hi); a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulation): relative error
+// ~1e-6, inside the 1e-5 parity bar but no longer bit-identical to the scalar FMA order. Row pitches = 8 mod 32 floats
+// make every fragment load (8 consecutive elements x 4 rows per warp) bank-conflict free.
+constexpr int kHPitchTC = kStemPts + 8;   // 136
+constexpr int kWPitchTC = kStemC + 8;     // 72
+struct StemSmemTC {
+  float h[kStemC][kHPitchTC];      // hidden activations, [k][point]
+  float w2hi[kStemC][kWPitchTC];   // tf32(W2) transposed: [k][c]
+  float w2lo[kStemC][kWPitchTC];   // tf32(W2 - tf32(W2))
+  float w1[kStemC][kStemCinMax];
+  float2 ab1[kStemC];
+  float a2[kStemC], b2[kStemC];
+  float a0[kStemCinMax], b0[kStemCinMax];
+};
+
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
 // RAW: the 7 input channels are built on the fly from raw points (x, y, z, intensity): the loader's Quantize +
 // make_point_feat (see form_batch.cu, same float32 sequence, bit-exact), and the (B, N, 3) quantised coordinates leave
 // as a side output — the (B, 7, N) tensor never exists.
@@ -39,7 +71,7 @@ struct StemRaw {
   float* coord;      // (B, N, 3) out
 };
 
-template <int CIN, bool RAW>
+template <int CIN, bool RAW, bool TC>
 __global__ void __launch_bounds__(kStemThreads, SMOS_STEM_MIN_CTAS)
 point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B, int64_t x_sb, int64_t x_sc, int64_t x_sn,
                   const __grid_constant__ StemRaw raw,
@@ -48,7 +80,8 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
                   const float* __restrict__ a2, const float* __restrict__ b2, float* __restrict__ y, int64_t y_sb,
                   int64_t y_sc) {
   extern __shared__ __align__(16) unsigned char stem_raw[];
-  StemSmem& S = *reinterpret_cast<StemSmem*>(stem_raw);
+  using Smem = typename std::conditional<TC, StemSmemTC, StemSmem>::type;
+  Smem& S = *reinterpret_cast<Smem*>(stem_raw);
   constexpr int KI = CIN > 0 ? (CIN + 3) / 4 * 4 : kStemCinMax;  // inputs rounded up to whole float4 (zero weights)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // parameters -> shared memory, ONCE per CTA (the CTAs are persistent and walk the 128-point tiles). W2 is kept
@@ -57,7 +90,17 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
   for (int i = tid; i < kStemC * (kStemC / 4); i += kStemThreads) {
     const int c = i & (kStemC - 1), kq = i >> 6;
     const float4 v = __ldg(reinterpret_cast<const float4*>(w2 + c * kStemC) + kq);
-    S.w2t[4 * kq][c] = v.x; S.w2t[4 * kq + 1][c] = v.y; S.w2t[4 * kq + 2][c] = v.z; S.w2t[4 * kq + 3][c] = v.w;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if constexpr (TC) {
+        const float hi = tf32_rna(vv[q]);
+        S.w2hi[4 * kq + q][c] = hi;
+        S.w2lo[4 * kq + q][c] = tf32_rna(vv[q] - hi);
+      } else {
+        S.w2t[4 * kq + q][c] = vv[q];
+      }
+    }
   }
   for (int i = tid; i < kStemC * kStemCinMax; i += kStemThreads) {
     const int c = i / kStemCinMax, ci = i % kStemCinMax;
@@ -131,54 +174,106 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
     }
     if (t + gridDim.x < ntiles) fetch(t + gridDim.x, xr);  // in flight during layer 2
     __syncthreads();
-    // layer 2: warp = 16 output channels, lane = 4 consecutive points: 64 FMAs per 5 shared-memory loads (8
-    // wavefronts) — with 8 channels per warp the kernel sat at 79 % of the shared-memory pipe and 52 % of the FMA pipe
-    constexpr int CW = 16;
-    const int c0 = wid * CW;
-    // accumulators as channel PAIRS: fma.rn.f32x2 (sm_100 packed fp32 FMA, two round-to-nearest FMAs per instruction:
-    // bit-identical to two scalar FMAs) halves the issue slots of the inner loop
-    float2 acc2[CW / 2][4];
+    if constexpr (TC) {
+      // layer 2 on the tensor cores: warp = 32 points (2 m-tiles of 16) x all 64 output channels (8 n-tiles of 8),
+      // K = 64 in 8 steps; A = hidden activations (row = point, col = k), B = W2^T (row = k, col = channel)
+      const int g = lane >> 2, tq = lane & 3;
+      const int p0 = wid * 32;
+      float acc[2][8][4];
 #pragma unroll
-    for (int j = 0; j < CW / 2; ++j)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc2[j][i] = make_float2(0.f, 0.f);
-#pragma unroll 4
-    for (int k = 0; k < kStemC; ++k) {
-      const float4 hv = *reinterpret_cast<const float4*>(&S.h[k][lane * 4]);
-      const float2 hh[4] = {make_float2(hv.x, hv.x), make_float2(hv.y, hv.y), make_float2(hv.z, hv.z),
-                            make_float2(hv.w, hv.w)};
+        for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int jq = 0; jq < CW / 4; ++jq) {
-        const float4 wv = *reinterpret_cast<const float4*>(&S.w2t[k][c0 + 4 * jq]);
-        const float2 wa = make_float2(wv.x, wv.y), wb = make_float2(wv.z, wv.w);
+          for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
+#pragma unroll 2
+      for (int ks = 0; ks < 8; ++ks) {
+        const int k0 = ks * 8;
+        float ahi[2][4], alo[2][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc2[2 * jq][i] = __ffma2_rn(wa, hh[i], acc2[2 * jq][i]);
-          acc2[2 * jq + 1][i] = __ffma2_rn(wb, hh[i], acc2[2 * jq + 1][i]);
+        for (int mt = 0; mt < 2; ++mt) {
+          const int m = p0 + mt * 16 + g;
+          const float a[4] = {S.h[k0 + tq][m], S.h[k0 + tq][m + 8], S.h[k0 + tq + 4][m], S.h[k0 + tq + 4][m + 8]};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) { ahi[mt][r] = tf32_rna(a[r]); alo[mt][r] = tf32_rna(a[r] - ahi[mt][r]); }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int n = nt * 8 + g;
+          const float bh0 = S.w2hi[k0 + tq][n], bh1 = S.w2hi[k0 + tq + 4][n];
+          const float bl0 = S.w2lo[k0 + tq][n], bl1 = S.w2lo[k0 + tq + 4][n];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma_tf32(acc[mt][nt], alo[mt], bh0, bh1);  // small terms first
+            mma_tf32(acc[mt][nt], ahi[mt], bl0, bl1);
+            mma_tf32(acc[mt][nt], ahi[mt], bh0, bh1);
+          }
         }
       }
-    }
-    float acc[CW][4];
+      // epilogue: c0:(point g, channel 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1) of every 16 x 8 tile
 #pragma unroll
-    for (int j = 0; j < CW / 2; ++j)
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + 2 * tq;
+        const float al0 = S.a2[c], be0 = S.b2[c], al1 = S.a2[c + 1], be1 = S.b2[c + 1];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { acc[2 * j][i] = acc2[j][i].x; acc[2 * j + 1][i] = acc2[j][i].y; }
-    const int32_t n = n0 + lane * 4;
-    const bool vec = (n + 3 < N) && ((y_sc & 3) == 0) && ((y_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-#pragma unroll
-    for (int j = 0; j < CW; ++j) {
-      const int c = c0 + j;
-      const float al = S.a2[c], be = S.b2[c];
-      float o[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = fmaxf(fmaf(acc[j][i], al, be), 0.f);
-      float* dst = y + b * y_sb + c * y_sc + n;
-      if (vec) {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (n + i < N) dst[i] = o[i];
+        for (int mt = 0; mt < 2; ++mt) {
+          const int32_t n = n0 + p0 + mt * 16 + g;
+          float* d0 = y + b * y_sb + c * y_sc + n;
+          float* d1 = d0 + y_sc;
+          if (n < N) { d0[0] = fmaxf(fmaf(acc[mt][nt][0], al0, be0), 0.f); d1[0] = fmaxf(fmaf(acc[mt][nt][1], al1, be1), 0.f); }
+          if (n + 8 < N) { d0[8] = fmaxf(fmaf(acc[mt][nt][2], al0, be0), 0.f); d1[8] = fmaxf(fmaf(acc[mt][nt][3], al1, be1), 0.f); }
+        }
+      }
+    } else {
+      // layer 2: warp = 16 output channels, lane = 4 consecutive points: 64 FMAs per 5 shared-memory loads (8
+      // wavefronts) — with 8 channels per warp the kernel sat at 79 % of the shared-memory pipe and 52 % of the FMA pipe
+      constexpr int CW = 16;
+      const int c0 = wid * CW;
+      // accumulators as channel PAIRS: fma.rn.f32x2 (sm_100 packed fp32 FMA, two round-to-nearest FMAs per instruction:
+      // bit-identical to two scalar FMAs) halves the issue slots of the inner loop
+      float2 acc2[CW / 2][4];
+  #pragma unroll
+      for (int j = 0; j < CW / 2; ++j)
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) acc2[j][i] = make_float2(0.f, 0.f);
+  #pragma unroll 4
+      for (int k = 0; k < kStemC; ++k) {
+        const float4 hv = *reinterpret_cast<const float4*>(&S.h[k][lane * 4]);
+        const float2 hh[4] = {make_float2(hv.x, hv.x), make_float2(hv.y, hv.y), make_float2(hv.z, hv.z),
+                              make_float2(hv.w, hv.w)};
+  #pragma unroll
+        for (int jq = 0; jq < CW / 4; ++jq) {
+          const float4 wv = *reinterpret_cast<const float4*>(&S.w2t[k][c0 + 4 * jq]);
+          const float2 wa = make_float2(wv.x, wv.y), wb = make_float2(wv.z, wv.w);
+  #pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc2[2 * jq][i] = __ffma2_rn(wa, hh[i], acc2[2 * jq][i]);
+            acc2[2 * jq + 1][i] = __ffma2_rn(wb, hh[i], acc2[2 * jq + 1][i]);
+          }
+        }
+      }
+      float acc[CW][4];
+  #pragma unroll
+      for (int j = 0; j < CW / 2; ++j)
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[2 * j][i] = acc2[j][i].x; acc[2 * j + 1][i] = acc2[j][i].y; }
+      const int32_t n = n0 + lane * 4;
+      const bool vec = (n + 3 < N) && ((y_sc & 3) == 0) && ((y_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  #pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        const int c = c0 + j;
+        const float al = S.a2[c], be = S.b2[c];
+        float o[4];
+  #pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = fmaxf(fmaf(acc[j][i], al, be), 0.f);
+        float* dst = y + b * y_sb + c * y_sc + n;
+        if (vec) {
+          *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+  #pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (n + i < N) dst[i] = o[i];
+        }
       }
     }
     __syncthreads();  // every warp is done reading h: the next tile's layer 1 may overwrite it
@@ -199,36 +294,36 @@ static int stem_launch(const float* x, int64_t B, int32_t Cin, int64_t N, int64_
   if ((reinterpret_cast<uintptr_t>(w2) & 15) != 0) return SMOS_EINVAL;
   const bool is_raw = raw.pts != nullptr;
   if (is_raw && (Cin != 7 || raw.coord == nullptr || raw.rs < 4)) return SMOS_EINVAL;
-  static bool opt_in[64] = {};
-  int device = 0;
-  cudaGetDevice(&device);
-  if (device >= 0 && device < 64 && !opt_in[device]) {
-    cudaError_t e = cudaFuncSetAttribute(point_stem_kernel<7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(point_stem_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(point_stem_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(StemSmem)));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    opt_in[device] = true;
-  }
-  // persistent CTAs, one wave (3 per SM: 53 KB of shared memory and ~140 registers each), walking the 128-point tiles
-  const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kStemPts)) * B;
-  int per_sm = 0;
-  cudaError_t oe = is_raw ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<7, true>, kStemThreads, sizeof(StemSmem))
-                  : Cin == 7 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<7, false>, kStemThreads, sizeof(StemSmem))
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, point_stem_kernel<0, false>, kStemThreads, sizeof(StemSmem));
-  if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
-  const int64_t want = static_cast<int64_t>(SMOS_SM_COUNT) * per_sm;
-  dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));
+  // SMOS_STEM_TC=1: layer 2 as 3xTF32 split products on the tensor cores (mma.sync), see StemSmemTC
+  const bool tc = smos_env_int("SMOS_STEM_TC", 0) != 0;
   const int32_t Ni = static_cast<int32_t>(N), Bi = static_cast<int32_t>(B);
   cudaStream_t st = smos_stream(stream);
-  if (is_raw)
-    point_stem_kernel<7, true><<<grid, kStemThreads, sizeof(StemSmem), st>>>(
-        x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc);
-  else if (Cin == 7)  // the StreamMOS stem: x, y, z, intensity, dist, diff_x, diff_y
-    point_stem_kernel<7, false><<<grid, kStemThreads, sizeof(StemSmem), st>>>(
-        x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc);
-  else
-    point_stem_kernel<0, false><<<grid, kStemThreads, sizeof(StemSmem), st>>>(
-        x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc);
+  const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kStemPts)) * B;
+#define SMOS_STEM_LAUNCH(CINV, RAWV, TCV)                                                                             \
+  do {                                                                                                                \
+    auto kern = point_stem_kernel<CINV, RAWV, TCV>;                                                                   \
+    const size_t smem = TCV ? sizeof(StemSmemTC) : sizeof(StemSmem);                                                   \
+    static bool opt_in[64] = {};                                                                                      \
+    int device = 0;                                                                                                   \
+    cudaGetDevice(&device);                                                                                           \
+    if (device >= 0 && device < 64 && !opt_in[device]) {                                                              \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+      if (e != cudaSuccess) return static_cast<int>(e);                                                               \
+      opt_in[device] = true;                                                                                          \
+    }                                                                                                                 \
+    /* persistent CTAs, one wave, walking the 128-point tiles with a grid stride */                                   \
+    int per_sm = 0;                                                                                                   \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStemThreads, smem) != cudaSuccess || per_sm < 1) \
+      per_sm = 1;                                                                                                     \
+    const int64_t want = static_cast<int64_t>(SMOS_SM_COUNT) * per_sm;                                                \
+    dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));                                                  \
+    kern<<<grid, kStemThreads, smem, st>>>(x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha,   \
+                                           bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc);                          \
+  } while (0)
+  if (is_raw) { if (tc) SMOS_STEM_LAUNCH(7, true, true); else SMOS_STEM_LAUNCH(7, true, false); }
+  else if (Cin == 7) { if (tc) SMOS_STEM_LAUNCH(7, false, true); else SMOS_STEM_LAUNCH(7, false, false); }
+  else { if (tc) SMOS_STEM_LAUNCH(0, false, true); else SMOS_STEM_LAUNCH(0, false, false); }
+#undef SMOS_STEM_LAUNCH
   return smos_launch_status();
 }
 

@@ -729,6 +729,32 @@ def test_form_batch_golden_and_config_size(golden):
         ops.form_batch(t(s["xyzi"]).cpu(), *rng_, (512, 512, 30))
 
 
+def test_point_stem_tensor_core_variant(golden, monkeypatch):
+    """SMOS_STEM_TC=1: layer 2 as 3xTF32 split products on mma.sync. Not bit-identical to the scalar FMA order, but
+    inside the same 1e-5 bar against the reference module and the oracle (fixture + config size, raw and loader input)."""
+    from streammos_b200 import ops, synthetic
+    g = golden("point_stem_a")
+    bn0, w1, bn1, w2, bn2 = _stem_params(g)
+    tt = lambda pair: (t(pair[0]), t(pair[1]))
+    scalar = ops.point_stem_forward(t(g["x"]), tt(bn0), t(w1), tt(bn1), t(w2), tt(bn2))
+    monkeypatch.setenv("SMOS_STEM_TC", "1")
+    y = ops.point_stem_forward(t(g["x"]), tt(bn0), t(w1), tt(bn1), t(w2), tt(bn2))
+    body, pads = slice(0, -50), slice(-50, None)
+    np.testing.assert_allclose(y[:, :, body, 0].cpu().numpy(), g["out"][:, :, body, 0], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(y[:, :, pads, 0].cpu().numpy(), g["out64"][:, :, pads, 0], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(y[:, :, body].cpu().numpy(), scalar[:, :, body].cpu().numpy(), rtol=1e-5, atol=1e-5)
+    rng_ = ((-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0))
+    pts = synthetic.make_scan(6, 120000, 3)["xyzi"]
+    got, gc = ops.point_stem_forward_raw(t(pts), *rng_, (512, 512, 30), tt(bn0), t(w1), tt(bn1), t(w2), tt(bn2))
+    rf, rc = O.form_batch(pts, *rng_, (512, 512, 30))
+    ref = O.point_stem(rf, bn0, w1, bn1, w2, bn2)
+    valid = np.abs(pts[..., 0]) < 100                                           # loader pads: see the golden test
+    gn = got[..., 0].cpu().numpy()
+    np.testing.assert_allclose(gn.transpose(0, 2, 1)[valid], ref.transpose(0, 2, 1)[valid], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(gn, ref, rtol=1e-5, atol=2e-3)
+    assert np.array_equal(gc[..., 0].cpu().numpy(), rc)
+
+
 def test_point_stem_from_raw_points_equals_form_batch_then_stem(golden):
     """The fused raw-point stem (smos_point_stem_forward_raw) is bit-identical to form_batch followed by the stem."""
     from streammos_b200 import ops, synthetic
