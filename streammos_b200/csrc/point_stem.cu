@@ -159,7 +159,7 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
       float xin[KI];
 #pragma unroll
       for (int ci = 0; ci < KI; ++ci) xin[ci] = ci < Cin ? fmaf(xr[ci], S.a0[ci], S.b0[ci]) : 0.f;
-#pragma unroll 4
+#pragma unroll 16  // 16 independent 8-FMA chains in flight: the layer is a dependent-FMA / LDS latency chain otherwise
       for (int c = 0; c < kStemC; ++c) {
         float acc = 0.f;
 #pragma unroll
