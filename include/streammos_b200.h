@@ -348,6 +348,27 @@ int smos_instance_vote(const float* points, int64_t P, int64_t row_stride,
                        const int64_t* pred, const float* box_lo, const float* box_hi,
                        int32_t K, int64_t* sums, void* stream);
 
+/* Instance clustering — cluster() of voxel_instance_voting.py:144-175 up to the vote block:
+ * foreground = points with pred_bf == 2 (:145), DBSCAN(eps, min_samples) over their xyz (:150-153; scikit-learn's
+ * labels, reproduced by an order-free formulation — see csrc/cluster.cu), clusters with more than
+ * min_cluster_points points kept in label order (:160-166), one axis-aligned box per kept cluster with the floor
+ * lifted by z_lift in float32 (:169-175). The boxes feed smos_instance_vote; smos_cluster_apply then writes the
+ * voted label to every point of a kept cluster (:184-191). No host synchronisation; eight kernels.
+ *   points (n, row_stride>=3) f32 ; pred_bf (n,) int32
+ *   workspace : smos_cluster_workspace_bytes(n) bytes, 16-byte aligned, kept until smos_cluster_apply
+ *   fg_index  (n,) int32 : indices of the foreground points, ascending (first M entries)
+ *   fg_label  (n,) int32 : DBSCAN label of foreground point i (first M entries; -1 = noise)
+ *   counts    (3,) int32 : M, number of clusters, number of kept clusters K
+ *   box_lo, box_hi (Kcap, 3) f32, kept_label (Kcap,) int32, Kcap >= n / (min_cluster_points + 1) + 1 */
+int64_t smos_cluster_workspace_bytes(int64_t n);
+int smos_cluster_boxes(const float* points, int64_t n, int64_t row_stride, const int32_t* pred_bf, double eps,
+                       int32_t min_samples, int32_t min_cluster_points, float z_lift, void* workspace,
+                       int32_t* fg_index, int32_t* fg_label, int32_t* counts, float* box_lo, float* box_hi,
+                       int32_t* kept_label, void* stream);
+/* sums (K, 2) int64 from smos_instance_vote over the K kept boxes; pred (n,) int64 is updated in place. */
+int smos_cluster_apply(int64_t n, void* workspace, const int32_t* fg_index, const int32_t* fg_label,
+                       const int32_t* counts, const int64_t* sums, int64_t* pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -314,6 +314,72 @@ API void oracle_instance_vote(const float* pts, int64_t P, int64_t row_stride, c
 }
 
 /* ---------------------------------------------------------------------------------------- */
+/* DBSCAN as cluster() runs it (voxel_instance_voting.py:150-153:                              */
+/*   DBSCAN(eps=0.3, min_samples=5).fit_predict(foreground_points), float32 xyz).               */
+/* The algorithm lives in a third-party dependency that is not vendored in the reference:      */
+/* scikit-learn (requirements.txt names it without a version; this image has 1.9.0). Restated   */
+/* from its published sources:                                                                  */
+/*   sklearn/cluster/_dbscan.py  fit(): neighborhoods = radius_neighbors(X, eps) (a point is    */
+/*     its own neighbour), core = n_neighbors >= min_samples;                                   */
+/*   sklearn/neighbors (KDTree, float64): a point is a neighbour when the reduced distance      */
+/*     ((0 + dx*dx) + dy*dy) + dz*dz, accumulated in float64 in that order, is <= eps*eps;      */
+/*   sklearn/cluster/_dbscan_inner.pyx  dbscan_inner(): depth-first expansion with a stack,     */
+/*     seeds visited in index order, label_num incremented after each expansion.                */
+/* Pinned by tests/golden/cluster_a.npz (labels produced by sklearn through the reference's      */
+/* own cluster()) and, where sklearn is importable, against fit_predict directly.               */
+/* ---------------------------------------------------------------------------------------- */
+static int dbscan_near(const float* a, const float* b, double r2) {
+  const double dx = (double)a[0] - (double)b[0], dy = (double)a[1] - (double)b[1], dz = (double)a[2] - (double)b[2];
+  double d = 0.0;
+  d += dx * dx;
+  d += dy * dy;
+  d += dz * dz;
+  return d <= r2;
+}
+
+API int oracle_dbscan(const float* pts, int64_t M, int64_t row_stride, double eps, int64_t min_samples,
+                      int32_t* labels) {
+  const double r2 = eps * eps;
+  int64_t* begin = (int64_t*)calloc((size_t)M + 1, sizeof(int64_t));
+  if (!begin) return 1;
+  for (int64_t i = 0; i < M; ++i) {
+    int64_t c = 0;
+    for (int64_t j = 0; j < M; ++j) c += dbscan_near(pts + i * row_stride, pts + j * row_stride, r2);
+    begin[i + 1] = begin[i] + c;
+  }
+  const int64_t nnz = begin[M];
+  int32_t* nbr = (int32_t*)malloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t));
+  int32_t* stack = (int32_t*)malloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t));
+  if (!nbr || !stack) { free(nbr); free(stack); free(begin); return 1; }
+  for (int64_t i = 0; i < M; ++i) {
+    int64_t w = begin[i];
+    for (int64_t j = 0; j < M; ++j)
+      if (dbscan_near(pts + i * row_stride, pts + j * row_stride, r2)) nbr[w++] = (int32_t)j;
+  }
+  for (int64_t i = 0; i < M; ++i) labels[i] = -1;
+  int32_t label_num = 0;
+  for (int64_t seed = 0; seed < M; ++seed) {
+    if (labels[seed] != -1 || begin[seed + 1] - begin[seed] < min_samples) continue;
+    int64_t top = 0, i = seed;
+    for (;;) { /* dbscan_inner: label, push unlabelled neighbours of core points, pop */
+      if (labels[i] == -1) {
+        labels[i] = label_num;
+        if (begin[i + 1] - begin[i] >= min_samples)
+          for (int64_t k = begin[i]; k < begin[i + 1]; ++k)
+            if (labels[nbr[k]] == -1) stack[top++] = nbr[k];
+      }
+      if (top == 0) break;
+      i = stack[--top];
+    }
+    label_num += 1;
+  }
+  free(stack);
+  free(nbr);
+  free(begin);
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------- */
 /* Streaming long-term voting, one frame — the loop body of voxel_voting.py:176-244:          */
 /*   Trans (datasets/utils.py:116-126): float64 pose_diff . (x,y,z,1) -> float32 (numpy's dgemm */
 /*   accumulates the four products in k order with FMAs; restated as an fma chain);            */

@@ -1,0 +1,367 @@
+// Instance clustering of the long-term voting stage: the part of cluster()
+// (voxel_instance_voting.py:144-175) that precedes the vote block — foreground selection, DBSCAN(eps 0.3,
+// min_samples 5), the >30-point cut, and one axis-aligned box per cluster with its floor lifted by 0.2 — and the
+// write-back that follows it (:189-191).
+//
+// The reference runs scikit-learn's DBSCAN on the host: a KD-tree radius query per point and a sequential
+// depth-first expansion whose border-point labels depend on the visiting order. Here the same labels come from an
+// order-free formulation that maps to the GPU:
+//   * neighbour test: ((dx*dx) + dy*dy) + dz*dz <= eps*eps in float64 without contraction (what the KD-tree's
+//     reduced distance evaluates), brute force over M^2 pairs in shared-memory tiles with a float32 reject first
+//     (M = moving points of one scan, a few thousand);
+//   * core points: >= min_samples neighbours, the point itself included;
+//   * clusters: connected components of core points under the neighbour relation — lock-free union-find whose
+//     root is the smallest index of the component; sklearn numbers clusters in the order of their first core
+//     point, i.e. by that root, so cluster id = rank of the root among roots;
+//   * border points: sklearn expands cluster 0 completely, then cluster 1, ...; a border point therefore takes the
+//     smallest cluster id among its core neighbours; points without a core neighbour are noise (-1).
+// Ordered compactions (foreground indices ascending, root ranks, kept clusters in id order) use per-CTA counts
+// and a sum over the preceding CTAs, so every result is deterministic.
+//
+// Nothing here synchronises: M and the cluster counts stay on the device; every kernel is launched for the upper
+// bound n and reads the actual count.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kClThreads = 256;
+constexpr int kClWarps = kClThreads / 32;
+
+struct ClusterWs {
+  float4* xyz;        // [n] foreground points (x, y, z, -)
+  int32_t* nnb;       // [n] neighbour count, then core flag
+  int32_t* parent;    // [n] union-find over core points (-1 for non-core)
+  int32_t* rootlab;   // [n] cluster id of a root
+  int32_t* cl_cnt;    // [n] points per cluster
+  int32_t* cl_min;    // [3n] ordered-int keys of the per-cluster minima
+  int32_t* cl_max;    // [3n]
+  int32_t* slot;      // [n] cluster id -> index among the kept clusters, or -1
+  int32_t* blk;       // [2 * ceil(n / 256)] per-CTA counts of the two ordered compactions
+};
+
+__host__ __device__ inline int64_t cl_align(int64_t x) { return (x + 255) / 256 * 256; }
+
+inline int64_t cluster_ws_layout(int64_t n, char* base, ClusterWs* w) {
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { char* p = base ? base + off : nullptr; off += cl_align(bytes); return p; };
+  const int64_t nb = (n + kClThreads - 1) / kClThreads;
+  ClusterWs t;
+  t.xyz = reinterpret_cast<float4*>(take(n * 16));
+  t.nnb = reinterpret_cast<int32_t*>(take(n * 4));
+  t.parent = reinterpret_cast<int32_t*>(take(n * 4));
+  t.rootlab = reinterpret_cast<int32_t*>(take(n * 4));
+  t.cl_cnt = reinterpret_cast<int32_t*>(take(n * 4));
+  t.cl_min = reinterpret_cast<int32_t*>(take(n * 12));
+  t.cl_max = reinterpret_cast<int32_t*>(take(n * 12));
+  t.slot = reinterpret_cast<int32_t*>(take(n * 4));
+  t.blk = reinterpret_cast<int32_t*>(take(nb * 8));
+  if (w) *w = t;
+  return off;
+}
+
+__device__ __forceinline__ int cl_key(float f) {  // monotonic float -> int
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float cl_unkey(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// exclusive position of this thread's flag inside the CTA and the CTA total; s_warp: kClWarps ints
+__device__ __forceinline__ int cl_block_scan(bool flag, int* s_warp, int* total) {
+  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = __popc(ballot);
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < kClWarps; ++k) {
+    const int c = s_warp[k];
+    base += k < warp ? c : 0;
+    tot += c;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + __popc(ballot & smos_lanemask_lt());
+}
+
+// sum of the counts of the CTAs before this one (blk has gridDim.x entries)
+__device__ __forceinline__ int cl_blocks_before(const int32_t* __restrict__ blk, int* s_red) {
+  int part = 0;
+  for (int c = threadIdx.x; c < static_cast<int>(blockIdx.x); c += kClThreads) part += blk[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int k = 0; k < kClWarps; ++k) base += s_red[k];
+  __syncthreads();
+  return base;
+}
+
+// ---- foreground selection (voxel_instance_voting.py:145-148): indices where pred_bf == 2, ascending ----------
+__global__ void __launch_bounds__(kClThreads)
+cl_fg_count_kernel(const int32_t* __restrict__ bf, int64_t n, ClusterWs w) {
+  __shared__ int s_warp[kClWarps];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kClThreads + threadIdx.x;
+  if (i < n) {  // per-cluster accumulators, reset for this call
+    w.cl_cnt[i] = 0;
+    w.cl_min[3 * i] = w.cl_min[3 * i + 1] = w.cl_min[3 * i + 2] = 0x7fffffff;
+    w.cl_max[3 * i] = w.cl_max[3 * i + 1] = w.cl_max[3 * i + 2] = static_cast<int>(0x80000000u);
+    w.slot[i] = -1;
+  }
+  int total;
+  cl_block_scan(i < n && bf[i] == 2, s_warp, &total);
+  if (threadIdx.x == 0) w.blk[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kClThreads)
+cl_fg_write_kernel(const int32_t* __restrict__ bf, const float* __restrict__ pts, int64_t n, int64_t rs,
+                   ClusterWs w, int32_t* __restrict__ fg_index, int32_t* __restrict__ fg_label,
+                   int32_t* __restrict__ counts) {
+  __shared__ int s_warp[kClWarps];
+  const int base = cl_blocks_before(w.blk, s_warp);
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kClThreads + threadIdx.x;
+  const bool fg = i < n && bf[i] == 2;
+  int total;
+  const int pos = base + cl_block_scan(fg, s_warp, &total);
+  if (fg) {
+    const float* p = pts + i * rs;
+    fg_index[pos] = static_cast<int32_t>(i);
+    w.xyz[pos] = make_float4(p[0], p[1], p[2], 0.f);
+  }
+  if (i < n) fg_label[i] = -1;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    counts[0] = base + total;  // M
+    counts[1] = 0;
+    counts[2] = 0;
+  }
+}
+
+// ---- the pair sweep --------------------------------------------------------------------------------------------
+// sklearn's KD-tree compares the reduced distance in float64: d = 0; d += dx*dx; d += dy*dy; d += dz*dz; d <= r*r
+__device__ __forceinline__ bool cl_near(float xi, float yi, float zi, float4 q, float reject, double r2) {
+  // float32 reject: |xi - xj| rounded is within 2^-24 relative of the exact difference; reject carries a 1e-3 margin
+  if (fabsf(xi - q.x) > reject || fabsf(yi - q.y) > reject || fabsf(zi - q.z) > reject) return false;
+  const double dx = static_cast<double>(xi) - static_cast<double>(q.x);
+  const double dy = static_cast<double>(yi) - static_cast<double>(q.y);
+  const double dz = static_cast<double>(zi) - static_cast<double>(q.z);
+  double d = __dmul_rn(dx, dx);
+  d = __dadd_rn(d, __dmul_rn(dy, dy));
+  d = __dadd_rn(d, __dmul_rn(dz, dz));
+  return d <= r2;
+}
+
+__device__ __forceinline__ int cl_find(int32_t* parent, int x) {
+  volatile int32_t* p = parent;
+  for (;;) {
+    const int a = p[x];
+    if (a == x) return x;
+    const int g = p[a];
+    if (g != a) p[x] = g;  // path halving; only ever lowers a non-root's pointer towards its root
+    x = a;
+  }
+}
+
+__device__ __forceinline__ void cl_unite(int32_t* parent, int a, int b) {
+  for (;;) {
+    a = cl_find(parent, a);
+    b = cl_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    if (atomicCAS(&parent[a], a, b) == a) return;  // the larger root hangs under the smaller one
+  }
+}
+
+enum { CL_COUNT = 0, CL_UNION = 1, CL_LABEL = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(kClThreads)
+cl_pairs_kernel(ClusterWs w, const int32_t* __restrict__ counts, float reject, double r2, int32_t min_samples,
+                int32_t* __restrict__ fg_label) {
+  __shared__ float4 s_q[kClThreads];
+  __shared__ int32_t s_aux[kClThreads];
+  const int M = counts[0];
+  const int row0 = blockIdx.x * kClThreads;
+  if (row0 >= M) return;
+  const int i = row0 + threadIdx.x;
+  const bool live = i < M;
+  float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool core = false;
+  if (live) {
+    me = w.xyz[i];
+    if (MODE != CL_COUNT) core = w.nnb[i] != 0;
+  }
+  // which rows work, which columns are needed
+  const bool work = MODE == CL_COUNT ? live : MODE == CL_UNION ? (live && core) : (live && !core);
+  const int col_end = MODE == CL_UNION ? min(M, row0 + kClThreads) : M;  // unions only with j < i
+  int acc = MODE == CL_LABEL ? 0x7fffffff : 0;
+  for (int j0 = 0; j0 < col_end; j0 += kClThreads) {
+    const int j = j0 + threadIdx.x;
+    __syncthreads();
+    if (j < M) {
+      s_q[threadIdx.x] = w.xyz[j];
+      if (MODE == CL_UNION) s_aux[threadIdx.x] = w.nnb[j];                                   // core flag
+      if (MODE == CL_LABEL) s_aux[threadIdx.x] = w.nnb[j] ? w.rootlab[w.parent[j]] : -1;      // cluster id of a core j
+    }
+    __syncthreads();
+    if (!work) continue;
+    const int jn = min(kClThreads, M - j0);
+    for (int t = 0; t < jn; ++t) {
+      if (MODE == CL_UNION && (j0 + t >= i || !s_aux[t])) continue;
+      if (MODE == CL_LABEL && s_aux[t] < 0) continue;
+      if (!cl_near(me.x, me.y, me.z, s_q[t], reject, r2)) continue;
+      if (MODE == CL_COUNT) acc += 1;
+      if (MODE == CL_UNION) cl_unite(w.parent, i, j0 + t);
+      if (MODE == CL_LABEL) acc = min(acc, s_aux[t]);
+    }
+  }
+  if (!live) return;
+  if (MODE == CL_COUNT) {
+    const bool c = acc >= min_samples;
+    w.nnb[i] = c ? 1 : 0;
+    w.parent[i] = c ? i : -1;
+  }
+  if (MODE == CL_LABEL) {
+    // core points: the id of their component; border points: the smallest id among core neighbours; else noise
+    const int lab = core ? w.rootlab[w.parent[i]] : (acc == 0x7fffffff ? -1 : acc);
+    fg_label[i] = lab;
+    if (lab >= 0) {
+      atomicAdd(&w.cl_cnt[lab], 1);
+      atomicMin(&w.cl_min[3 * lab], cl_key(me.x)); atomicMax(&w.cl_max[3 * lab], cl_key(me.x));
+      atomicMin(&w.cl_min[3 * lab + 1], cl_key(me.y)); atomicMax(&w.cl_max[3 * lab + 1], cl_key(me.y));
+      atomicMin(&w.cl_min[3 * lab + 2], cl_key(me.z)); atomicMax(&w.cl_max[3 * lab + 2], cl_key(me.z));
+    }
+  }
+}
+
+// ---- cluster ids: rank of each root among the roots (sklearn numbers clusters by their first core point) ------
+__global__ void __launch_bounds__(kClThreads)
+cl_root_count_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t* __restrict__ blk) {
+  __shared__ int s_warp[kClWarps];
+  const int M = counts[0];
+  const int i = blockIdx.x * kClThreads + threadIdx.x;
+  bool root = false;
+  if (i < M && w.nnb[i]) {
+    const int r = cl_find(w.parent, i);
+    root = r == i;
+    if (!root) w.parent[i] = r;  // flatten: the label kernel reads parent[j] directly
+  }
+  int total;
+  cl_block_scan(root, s_warp, &total);
+  if (threadIdx.x == 0) blk[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kClThreads)
+cl_root_label_kernel(ClusterWs w, int32_t* __restrict__ counts, const int32_t* __restrict__ blk) {
+  __shared__ int s_warp[kClWarps];
+  const int M = counts[0];
+  const int base = cl_blocks_before(blk, s_warp);
+  const int i = blockIdx.x * kClThreads + threadIdx.x;
+  const bool root = i < M && w.nnb[i] && w.parent[i] == i;
+  int total;
+  const int pos = base + cl_block_scan(root, s_warp, &total);
+  if (root) w.rootlab[i] = pos;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) counts[1] = base + total;  // clusters
+}
+
+// ---- boxes of the clusters with more than min_points points, in id order (:157-175) ----------------------------
+__global__ void __launch_bounds__(kClThreads)
+cl_boxes_kernel(ClusterWs w, int32_t* __restrict__ counts, int32_t min_points, float z_lift,
+                float* __restrict__ box_lo, float* __restrict__ box_hi, int32_t* __restrict__ kept_label) {
+  __shared__ int s_warp[kClWarps];
+  const int C = counts[1];
+  int base = 0;
+  for (int c0 = 0; c0 < C; c0 += kClThreads) {
+    const int c = c0 + threadIdx.x;
+    const bool keep = c < C && w.cl_cnt[c] > min_points;
+    int total;
+    const int k = base + cl_block_scan(keep, s_warp, &total);
+    if (keep) {
+      w.slot[c] = k;
+      kept_label[k] = c;
+      const float zmin = cl_unkey(w.cl_min[3 * c + 2]), zmax = cl_unkey(w.cl_max[3 * c + 2]);
+      // corners whose z equals the minimum get += 0.2 in float32 (:172-174); the box is then spanned by the
+      // lifted floor and the ceiling, whichever is lower (a cluster thinner than the lift flips them)
+      const float lift = __fadd_rn(zmin, z_lift);
+      const float zl = zmin == zmax ? lift : fminf(lift, zmax);
+      const float zh = zmin == zmax ? lift : fmaxf(lift, zmax);
+      box_lo[3 * k] = cl_unkey(w.cl_min[3 * c]);
+      box_lo[3 * k + 1] = cl_unkey(w.cl_min[3 * c + 1]);
+      box_lo[3 * k + 2] = zl;
+      box_hi[3 * k] = cl_unkey(w.cl_max[3 * c]);
+      box_hi[3 * k + 1] = cl_unkey(w.cl_max[3 * c + 1]);
+      box_hi[3 * k + 2] = zh;
+    }
+    base += total;
+  }
+  if (threadIdx.x == 0) counts[2] = base;
+}
+
+// ---- write-back (:184-191): every point of a kept cluster takes the label its box voted -------------------------
+__global__ void __launch_bounds__(kClThreads)
+cl_apply_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ fg_index,
+                const int32_t* __restrict__ fg_label, const int32_t* __restrict__ slot,
+                const int64_t* __restrict__ sums, int64_t* __restrict__ pred) {
+  const int M = counts[0];
+  const int i = blockIdx.x * kClThreads + threadIdx.x;
+  if (i >= M) return;
+  const int lab = fg_label[i];
+  if (lab < 0) return;
+  const int k = slot[lab];
+  if (k < 0) return;
+  // static_points_num = sum(pred[pred==1]), dynamic_points_num = sum(pred[pred==2]); 2 if dynamic > static else 1
+  pred[fg_index[i]] = sums[2 * k + 1] > sums[2 * k] ? 2 : 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t smos_cluster_workspace_bytes(int64_t n) {
+  if (n < 0) return -1;
+  return cluster_ws_layout(n > 0 ? n : 1, nullptr, nullptr);
+}
+
+int smos_cluster_boxes(const float* points, int64_t n, int64_t row_stride, const int32_t* pred_bf, double eps,
+                       int32_t min_samples, int32_t min_cluster_points, float z_lift, void* workspace,
+                       int32_t* fg_index, int32_t* fg_label, int32_t* counts, float* box_lo, float* box_hi,
+                       int32_t* kept_label, void* stream) {
+  if (n < 0 || n > 0x7fffffff || row_stride < 3 || !(eps > 0.0) || min_samples < 1 ||
+      min_cluster_points < 0)
+    return SMOS_EINVAL;
+  if (!counts) return SMOS_EINVAL;
+  cudaStream_t st = smos_stream(stream);
+  if (n == 0) return static_cast<int>(cudaMemsetAsync(counts, 0, 3 * sizeof(int32_t), st));
+  if (!points || !pred_bf || !workspace || !fg_index || !fg_label || !box_lo || !box_hi || !kept_label)
+    return SMOS_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return SMOS_EINVAL;
+  ClusterWs w;
+  cluster_ws_layout(n, static_cast<char*>(workspace), &w);
+  const int grid = smos_ceil_div(n, kClThreads);
+  const float reject = static_cast<float>(eps * 1.001);
+  const double r2 = eps * eps;
+  int32_t* blk_roots = w.blk + grid;
+  cl_fg_count_kernel<<<grid, kClThreads, 0, st>>>(pred_bf, n, w);
+  cl_fg_write_kernel<<<grid, kClThreads, 0, st>>>(pred_bf, points, n, row_stride, w, fg_index, fg_label, counts);
+  cl_pairs_kernel<CL_COUNT><<<grid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples, fg_label);
+  cl_pairs_kernel<CL_UNION><<<grid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples, fg_label);
+  cl_root_count_kernel<<<grid, kClThreads, 0, st>>>(w, counts, blk_roots);
+  cl_root_label_kernel<<<grid, kClThreads, 0, st>>>(w, counts, blk_roots);
+  cl_pairs_kernel<CL_LABEL><<<grid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples, fg_label);
+  cl_boxes_kernel<<<1, kClThreads, 0, st>>>(w, counts, min_cluster_points, z_lift, box_lo, box_hi, kept_label);
+  return smos_launch_status();
+}
+
+int smos_cluster_apply(int64_t n, void* workspace, const int32_t* fg_index, const int32_t* fg_label,
+                       const int32_t* counts, const int64_t* sums, int64_t* pred, void* stream) {
+  if (n < 0 || n > 0x7fffffff) return SMOS_EINVAL;
+  if (n == 0) return SMOS_OK;
+  if (!workspace || !fg_index || !fg_label || !counts || !sums || !pred) return SMOS_EINVAL;
+  ClusterWs w;
+  cluster_ws_layout(n, static_cast<char*>(workspace), &w);
+  cl_apply_kernel<<<smos_ceil_div(n, kClThreads), kClThreads, 0, smos_stream(stream)>>>(counts, fg_index, fg_label,
+                                                                                       w.slot, sums, pred);
+  return smos_launch_status();
+}
+
+}  // extern "C"

@@ -586,3 +586,57 @@ def instance_vote(points, pred, box_lo, box_hi):
     _lib.check(rc, "smos_instance_vote")
     _count(1)
     return sums
+
+
+def cluster_boxes(points, pred_bf, eps=0.3, min_samples=5, min_cluster_points=30, z_lift=0.2):
+    """Foreground selection + DBSCAN + kept-cluster boxes of cluster() (voxel_instance_voting.py:144-175).
+    points (n, >=3) f32 CUDA, pred_bf (n,) integer CUDA. Returns a dict of device tensors: fg_index (n,) int32,
+    fg_label (n,) int32, counts (3,) int32 [M, clusters, kept], box_lo / box_hi (Kcap, 3) f32, kept_label (Kcap,)
+    int32, and the workspace smos_cluster_apply needs. No host synchronisation."""
+    _need_cuda(points, "points")
+    _need_f32(points, "points")
+    assert points.dim() == 2 and points.size(1) >= 3 and points.stride(1) == 1
+    n = int(points.size(0))
+    if pred_bf.numel() != n:
+        raise RuntimeError("pred_bf must have one entry per point")
+    bf = pred_bf.reshape(-1).to(torch.int32).contiguous()
+    dev = points.device
+    lib = _lib.load()
+    kcap = n // (int(min_cluster_points) + 1) + 1
+    st = {
+        "n": n,
+        "fg_index": torch.empty((max(n, 1),), dtype=torch.int32, device=dev),
+        "fg_label": torch.empty((max(n, 1),), dtype=torch.int32, device=dev),
+        "counts": torch.empty((3,), dtype=torch.int32, device=dev),
+        "box_lo": torch.empty((kcap, 3), dtype=torch.float32, device=dev),
+        "box_hi": torch.empty((kcap, 3), dtype=torch.float32, device=dev),
+        "kept_label": torch.empty((kcap,), dtype=torch.int32, device=dev),
+        "workspace": torch.empty((int(lib.smos_cluster_workspace_bytes(n)),), dtype=torch.uint8, device=dev),
+    }
+    with torch.cuda.device(dev):
+        rc = lib.smos_cluster_boxes(_ptr(points), n, points.stride(0) if n > 1 else points.size(1), _ptr(bf),
+                                    float(eps), int(min_samples), int(min_cluster_points), float(z_lift),
+                                    _ptr(st["workspace"]), _ptr(st["fg_index"]), _ptr(st["fg_label"]),
+                                    _ptr(st["counts"]), _ptr(st["box_lo"]), _ptr(st["box_hi"]),
+                                    _ptr(st["kept_label"]), _stream())
+    _lib.check(rc, "smos_cluster_boxes")
+    _count(8 if n else 0)
+    return st
+
+
+def cluster_apply(state, sums, pred):
+    """Write-back of cluster() (voxel_instance_voting.py:184-191): pred (n,) int64 CUDA, updated in place."""
+    if pred.dtype != torch.int64 or not pred.is_contiguous() or not pred.is_cuda:
+        raise RuntimeError("pred must be a contiguous int64 CUDA tensor")
+    if sums.dtype != torch.int64 or not sums.is_contiguous():
+        raise RuntimeError("sums must be a contiguous int64 tensor")
+    n = state["n"]
+    if pred.numel() != n:
+        raise RuntimeError("pred must have one entry per point")
+    with torch.cuda.device(pred.device):
+        rc = _lib.load().smos_cluster_apply(n, _ptr(state["workspace"]), _ptr(state["fg_index"]),
+                                            _ptr(state["fg_label"]), _ptr(state["counts"]), _ptr(sums), _ptr(pred),
+                                            _stream())
+    _lib.check(rc, "smos_cluster_apply")
+    _count(1 if n else 0)
+    return pred

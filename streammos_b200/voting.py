@@ -61,6 +61,34 @@ def instance_vote_counts(local_map_points, local_map_prediction, cluster_corners
     return stat, dyn, label
 
 
+def dbscan_fit_predict(points, eps=0.3, min_samples=5):
+    """sklearn.cluster.DBSCAN(eps, min_samples).fit_predict(points[:, :3]) on the device (the call at
+    voxel_instance_voting.py:150-153): (M, >=3) f32 CUDA -> (M,) int32 labels, -1 = noise, same numbering."""
+    m = int(points.size(0))
+    st = ops.cluster_boxes(points, torch.full((m,), 2, dtype=torch.int32, device=points.device), eps, min_samples)
+    return st["fg_label"][:m]
+
+
+def cluster(current_points_orin, current_pred_result_orin, current_pred_bf_result_orin, local_map_points,
+            local_map_prediction, eps=0.3, min_samples=5):
+    """cluster() of voxel_instance_voting.py:144-193 on the device, same argument order: DBSCAN over the points the
+    per-frame prediction calls moving (pred_bf == 2), one lifted axis-aligned box per cluster of more than 30
+    points, votes of the local map inside each box, and the voted label written to the cluster's points.
+    All tensors CUDA; current_pred_result_orin int64, modified in place and returned like the reference does.
+    One host read (the number of kept clusters) sits between the clustering and the vote."""
+    pred = current_pred_result_orin
+    if pred.dtype != torch.int64 or not pred.is_contiguous():
+        raise RuntimeError("current_pred_result_orin must be a contiguous int64 tensor")
+    if int(current_points_orin.size(0)) == 0:
+        return pred
+    st = ops.cluster_boxes(current_points_orin, current_pred_bf_result_orin, eps, min_samples)
+    kept = int(st["counts"][2].item())
+    if kept == 0:                      # no moving point (:146-147) or no cluster above the cut
+        return pred
+    sums = ops.instance_vote(local_map_points, local_map_prediction, st["box_lo"][:kept], st["box_hi"][:kept])
+    return ops.cluster_apply(st, sums, pred)
+
+
 class StreamingVoter:
     """GPU-resident long-term memory for one scan stream: the loop body of voxel_voting.py:176-244 without the
     per-frame reload of 8 scans + predictions, the numpy pose transform, the crop and the .cuda() round trip.

@@ -519,6 +519,101 @@ def test_instance_vote_golden(golden):
     assert np.array_equal(label.cpu().numpy(), g["label"])
 
 
+def test_cluster_golden(golden):
+    """cluster() of voxel_instance_voting.py:144-193 on the device against the reference's own run (sklearn DBSCAN +
+    scipy hull / Delaunay): DBSCAN labels, and the relabelled prediction, bit-exact."""
+    from streammos_b200 import voting
+    g = golden("cluster_a")
+    fg = np.where(g["cur_bf"] == 2)[0]
+    labels = voting.dbscan_fit_predict(t(g["cur_pts"][fg]))
+    assert labels.dtype == torch.int32
+    assert np.array_equal(labels.cpu().numpy(), g["fg_labels"])
+    for name in ("cluster_a", "instance_a"):
+        g = golden(name)
+        pred = t(g["cur_pred"])
+        out = voting.cluster(t(g["cur_pts"]), pred, t(g["cur_bf"].astype(np.int64)), t(g["local_pts"]),
+                             t(g["local_pred"]))
+        assert out.data_ptr() == pred.data_ptr()                 # in place, like the reference
+        assert np.array_equal(out.cpu().numpy(), g["cluster_out"]), name
+
+
+def _blobs(rng, n_blobs, n_noise, spread=8.0, lo=5, hi=400):
+    parts = [rng.uniform(-spread, spread, 3) + rng.uniform(-1, 1, (int(rng.integers(lo, hi)), 3)) *
+             rng.uniform(0.2, 1.4, 3) for _ in range(n_blobs)]
+    parts.append(rng.uniform(-spread - 2, spread + 2, (n_noise, 3)))
+    x = np.concatenate(parts).astype(np.float32)
+    return x[rng.permutation(len(x))]
+
+
+@pytest.mark.parametrize("seed,n_blobs,n_noise", [(0, 1, 0), (1, 4, 300), (2, 9, 1500), (3, 0, 777), (4, 12, 40),
+                                                  (5, 30, 3000)])
+def test_dbscan_vs_oracle(seed, n_blobs, n_noise):
+    """Labels identical to the sequential scikit-learn algorithm (oracle): core points, cluster numbering by first
+    core point, border points to the lowest-numbered adjacent cluster, noise."""
+    from streammos_b200 import voting
+    x = _blobs(np.random.default_rng(seed), n_blobs, n_noise)
+    got = voting.dbscan_fit_predict(t(x)).cpu().numpy()
+    want = O.dbscan(x)
+    assert np.array_equal(got, want)
+
+
+def test_dbscan_edges():
+    from streammos_b200 import ops, voting
+    z = torch.zeros((7, 3), device=dev())
+    assert voting.dbscan_fit_predict(z).tolist() == [0] * 7                  # coincident points: one cluster
+    assert voting.dbscan_fit_predict(z[:4]).tolist() == [-1] * 4             # below min_samples: noise
+    assert voting.dbscan_fit_predict(z[:1]).tolist() == [-1]
+    # one dense blob larger than several CTAs: every point neighbours hundreds of others (union-find contention)
+    rng = np.random.default_rng(9)
+    x = (rng.uniform(-1, 1, (3000, 3)) * np.array([1.0, 0.5, 0.3])).astype(np.float32)
+    assert np.array_equal(voting.dbscan_fit_predict(t(x)).cpu().numpy(), O.dbscan(x))
+    # row stride 4, foreground interleaved with the rest, sizes that are not multiples of the CTA
+    n = 5003
+    pts = np.concatenate([_blobs(rng, 6, 200), rng.uniform(-20, 20, (n, 3)).astype(np.float32)])[:n]
+    pts = np.concatenate([pts, rng.uniform(0, 1, (n, 1)).astype(np.float32)], 1)[rng.permutation(n)]
+    bf = rng.integers(0, 4, n).astype(np.int32)
+    st = ops.cluster_boxes(t(pts), t(bf))
+    fg = np.where(bf == 2)[0]
+    m, n_clusters, n_kept = st["counts"].cpu().tolist()
+    want = O.dbscan(pts[fg])
+    kept, lo, hi = O.cluster_boxes(pts[fg], want)
+    assert m == len(fg) and n_clusters == want.max() + 1 and n_kept == len(kept)
+    assert np.array_equal(st["fg_index"][:m].cpu().numpy(), fg)
+    assert np.array_equal(st["fg_label"][:m].cpu().numpy(), want)
+    assert np.array_equal(st["kept_label"][:n_kept].cpu().numpy(), kept)
+    assert np.array_equal(st["box_lo"][:n_kept].cpu().numpy(), lo)
+    assert np.array_equal(st["box_hi"][:n_kept].cpu().numpy(), hi)
+
+
+def test_cluster_vs_oracle_and_no_foreground():
+    from streammos_b200 import voting
+    rng = np.random.default_rng(21)
+    objs = [rng.uniform(-30, 30, 3) * np.array([1, 1, 0.03]) + rng.uniform(-1, 1, (int(rng.integers(20, 300)), 3)) *
+            np.array([0.8, 0.4, 0.3]) for _ in range(25)]
+    objs.append(np.array([3.0, 3.0, -1.0]) + rng.uniform(-1, 1, (120, 3)) * np.array([0.8, 0.5, 0.04]))   # thin
+    objs.append(np.array([-9.0, 4.0, -1.5]) + rng.uniform(-1, 1, (80, 3)) * np.array([0.5, 0.5, 0.0]))    # flat
+    fgp = np.concatenate(objs)
+    bg = rng.uniform(-40, 40, (20000, 3)) * np.array([1, 1, 0.05])
+    cur = np.concatenate([fgp, bg]).astype(np.float32)
+    bf = np.concatenate([np.full(len(fgp), 2), rng.integers(0, 2, len(bg))]).astype(np.int64)
+    pred = rng.integers(0, 3, len(cur)).astype(np.int64)
+    perm = rng.permutation(len(cur))
+    cur, bf, pred = np.concatenate([cur, np.zeros((len(cur), 1), np.float32)], 1)[perm], bf[perm], pred[perm]
+    local = np.concatenate([fgp + rng.normal(0, 0.05, fgp.shape) for _ in range(4)] +
+                           [rng.uniform(-40, 40, (50000, 3)) * np.array([1, 1, 0.05])]).astype(np.float32)
+    local = np.concatenate([local, np.zeros((len(local), 1), np.float32)], 1)
+    lpred = rng.integers(0, 3, len(local)).astype(np.int64)
+    want = O.cluster(cur, pred, bf, local, lpred)
+    assert (want != pred).sum() > 500 and {1, 2} <= set(want[bf == 2].tolist())
+    got = voting.cluster(t(cur), t(pred), t(bf), t(local), t(lpred))
+    assert np.array_equal(got.cpu().numpy(), want)
+    # no moving point: returned unchanged (voxel_instance_voting.py:146-147)
+    same = voting.cluster(t(cur), t(pred), t(np.zeros_like(bf)), t(local), t(lpred))
+    assert np.array_equal(same.cpu().numpy(), pred)
+    with pytest.raises(RuntimeError):
+        voting.cluster(t(cur), t(pred).to(torch.int32), t(bf), t(local), t(lpred))
+
+
 def test_instance_vote_many_boxes_vs_oracle():
     from streammos_b200 import ops
     rng = np.random.default_rng(9)

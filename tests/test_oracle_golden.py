@@ -96,6 +96,44 @@ def test_instance_vote_bit_exact(golden):
     assert set(label.tolist()) == {1, 2}  # the fixture exercises both outcomes
 
 
+def test_cluster_matches_reference(golden):
+    """DBSCAN labels as sklearn gave them inside the reference's cluster(), and cluster()'s relabelled output."""
+    g = golden("cluster_a")
+    fg = np.where(g["cur_bf"] == 2)[0]
+    labels = O.dbscan(g["cur_pts"][fg])
+    assert np.array_equal(labels, g["fg_labels"])
+    sizes = np.bincount(labels[labels >= 0])
+    assert (sizes <= 30).any() and (sizes == 31).any() and (labels == -1).any()   # both sides of the >30 cut
+    out = O.cluster(g["cur_pts"], g["cur_pred"], g["cur_bf"], g["local_pts"], g["local_pred"])
+    assert np.array_equal(out, g["cluster_out"])
+    assert (out != g["cur_pred"]).sum() > 100
+    # the older fixture carries a full cluster() run as well
+    g = golden("instance_a")
+    out = O.cluster(g["cur_pts"], g["cur_pred"], g["cur_bf"], g["local_pts"], g["local_pred"])
+    assert np.array_equal(out, g["cluster_out"])
+    # no moving point -> unchanged (voxel_instance_voting.py:146-147)
+    none = O.cluster(g["cur_pts"], g["cur_pred"], np.zeros_like(g["cur_bf"]), g["local_pts"], g["local_pred"])
+    assert np.array_equal(none, g["cur_pred"])
+
+
+def test_dbscan_oracle_against_sklearn():
+    """The third-party algorithm itself, where it is importable: random clouds with touching blobs, so that border
+    points adjacent to two clusters and stolen-border clusters occur."""
+    sk = pytest.importorskip("sklearn.cluster")
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        blobs = [rng.uniform(-6, 6, 3) + rng.uniform(-1, 1, (int(rng.integers(5, 400)), 3)) * rng.uniform(0.2, 1.4, 3)
+                 for _ in range(int(rng.integers(1, 7)))]
+        blobs.append(rng.uniform(-8, 8, (int(rng.integers(0, 1500)), 3)))
+        x = np.concatenate(blobs).astype(np.float32)
+        x = x[rng.permutation(len(x))]
+        want = sk.DBSCAN(eps=0.3, min_samples=5).fit_predict(x)
+        assert np.array_equal(O.dbscan(x), want), trial
+    assert O.dbscan(np.zeros((0, 3), np.float32)).shape == (0,)
+    assert np.array_equal(O.dbscan(np.zeros((7, 3), np.float32)), np.zeros(7, np.int32))   # coincident points
+    assert np.array_equal(O.dbscan(np.zeros((4, 3), np.float32)), np.full(4, -1, np.int32))
+
+
 def _stream_vote_setup(g):
     """(scans, crop_lo, crop_hi, mins, deltas, size) of the fixture, thresholds as StreamingVoter derives them."""
     size = tuple(int(s) for s in g["size"])

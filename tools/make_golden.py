@@ -403,6 +403,54 @@ def gen_form_batch(ref, rng):
     return ["form_batch_a"]
 
 
+def gen_cluster(ref, rng):
+    """cluster() of voxel_instance_voting.py:144-193 end to end (sklearn DBSCAN + scipy hull/Delaunay through the
+    reference's own code) on a scan whose moving points are interleaved with the rest: objects of several sizes and
+    densities (some below the 30-point cut, some touching, one thinner than the 0.2 floor lift), loose noise."""
+    import scipy
+    from scipy.spatial import ConvexHull, Delaunay
+    from sklearn.cluster import DBSCAN
+    g = {"np": np, "scipy": scipy, "Delaunay": Delaunay, "ConvexHull": ConvexHull, "DBSCAN": DBSCAN}
+    extract_functions(os.path.join(ref, "voxel_instance_voting.py"), ["in_hull", "min_bounding_box_3d", "cluster"], g)
+    objs = []
+    for k in range(14):
+        c = np.array([rng.uniform(-35, 35), rng.uniform(-35, 35), rng.uniform(-1.6, -0.2)])
+        n = int(rng.choice([8, 20, 28, 31, 45, 90, 200, 420, 700]))
+        ext = np.array([rng.uniform(0.2, 1.2), rng.uniform(0.2, 0.6), rng.uniform(0.15, 0.5)]) * (n / 200.0) ** (1 / 3) * (2.0 if k % 2 else 1.0)
+        objs.append(c + rng.uniform(-1, 1, (n, 3)) * ext)
+    objs.append(objs[5][:60] + np.array([0.35, 0.0, 0.0]))                      # touches object 5
+    objs.append(np.array([12.0, -7.0, -1.0]) + rng.uniform(-1, 1, (150, 3)) * np.array([1.2, 0.6, 0.05]))  # thin
+    noise = np.stack([rng.uniform(-40, 40, 900), rng.uniform(-40, 40, 900), rng.uniform(-3, 1, 900)], -1)
+    fg = np.concatenate(objs + [noise])
+    bg = np.stack([rng.uniform(-50, 50, 16000), rng.uniform(-50, 50, 16000), rng.uniform(-4, 2, 16000)], -1)
+    cur = np.concatenate([fg, bg])
+    bf = np.concatenate([np.full(len(fg), 2, np.uint32), rng.integers(0, 2, len(bg)).astype(np.uint32)])
+    pred = np.concatenate([rng.integers(1, 3, len(fg)), rng.integers(0, 3, len(bg))]).astype(np.int64)
+    perm = rng.permutation(len(cur))
+    cur, bf, pred = cur[perm].astype(np.float32), bf[perm], pred[perm]
+    cur = np.concatenate([cur, rng.uniform(0, 1, (len(cur), 1)).astype(np.float32)], 1)
+    # local map = 3 jittered copies of the objects with per-object dynamic rates + background
+    lm, lp = [], []
+    for k, o in enumerate(objs):
+        p_dyn = rng.choice([0.15, 0.3, 0.36, 0.5, 0.7])
+        for rep in range(3):
+            lm.append(o + rng.normal(0, 0.05, o.shape))
+            lp.append(np.where(rng.uniform(0, 1, len(o)) < p_dyn, 2, 1))
+    lm.append(np.stack([rng.uniform(-50, 50, 40000), rng.uniform(-50, 50, 40000), rng.uniform(-4, 2, 40000)], -1))
+    lp.append(rng.integers(0, 3, 40000))
+    local_pts = np.concatenate(lm).astype(np.float32)
+    local_pts = np.concatenate([local_pts, np.zeros((len(local_pts), 1), np.float32)], 1)
+    local_pred = np.concatenate(lp).astype(np.int64)
+    fg_index = np.where(bf == 2)[0]
+    fg_labels = DBSCAN(eps=0.3, min_samples=5).fit_predict(cur[fg_index][:, :3])       # :150-153
+    out = g["cluster"](cur.copy(), pred.copy(), bf, local_pts, local_pred)
+    assert (out != pred).sum() > 100 and len(np.unique(fg_labels)) > 10
+    np.savez_compressed(os.path.join(GOLD, "cluster_a.npz"), cur_pts=cur, cur_pred=pred, cur_bf=bf,
+                        local_pts=local_pts, local_pred=local_pred, fg_labels=fg_labels.astype(np.int32),
+                        cluster_out=out)
+    return ["cluster_a"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -413,9 +461,9 @@ def main():
     torch.set_num_threads(1)
     rng = np.random.default_rng(20261018)
     made = []
-    if a.only in ("point_stem", "form_batch"):
-        made += gen_point_stem(a.ref, np.random.default_rng(99)) if a.only == "point_stem" else \
-            gen_form_batch(a.ref, np.random.default_rng(55))
+    single = {"point_stem": (gen_point_stem, 99), "form_batch": (gen_form_batch, 55), "cluster": (gen_cluster, 33)}
+    if a.only in single:
+        made += single[a.only][0](a.ref, np.random.default_rng(single[a.only][1]))
         for m in made:
             print("%-28s %8.1f KB" % (m, os.path.getsize(os.path.join(GOLD, m + ".npz")) / 1024))
         return
@@ -427,6 +475,7 @@ def main():
     made += gen_stream_vote(a.ref, np.random.default_rng(77))
     made += gen_point_stem(a.ref, np.random.default_rng(99))
     made += gen_form_batch(a.ref, np.random.default_rng(55))
+    made += gen_cluster(a.ref, np.random.default_rng(33))
     for m in made:
         p = os.path.join(GOLD, m + ".npz")
         print("%-28s %8.1f KB" % (m, os.path.getsize(p) / 1024))
