@@ -348,12 +348,19 @@ int smos_instance_vote(const float* points, int64_t P, int64_t row_stride,
                        const int64_t* pred, const float* box_lo, const float* box_hi,
                        int32_t K, int64_t* sums, void* stream);
 
+/* Same, with the number of boxes read on the device: K = min(*K_dev, K_cap). For boxes produced by
+ * smos_cluster_boxes (K_dev = counts + 2), so that clustering, vote and write-back need no host read in between.
+ * sums (K_cap, 2) int64 zero-filled by the caller. */
+int smos_instance_vote_counted(const float* points, int64_t P, int64_t row_stride,
+                               const int64_t* pred, const float* box_lo, const float* box_hi,
+                               int32_t K_cap, const int32_t* K_dev, int64_t* sums, void* stream);
+
 /* Instance clustering — cluster() of voxel_instance_voting.py:144-175 up to the vote block:
  * foreground = points with pred_bf == 2 (:145), DBSCAN(eps, min_samples) over their xyz (:150-153; scikit-learn's
  * labels, reproduced by an order-free formulation — see csrc/cluster.cu), clusters with more than
  * min_cluster_points points kept in label order (:160-166), one axis-aligned box per kept cluster with the floor
- * lifted by z_lift in float32 (:169-175). The boxes feed smos_instance_vote; smos_cluster_apply then writes the
- * voted label to every point of a kept cluster (:184-191). No host synchronisation; eight kernels.
+ * lifted by z_lift in float32 (:169-175). The boxes feed smos_instance_vote[_counted]; smos_cluster_apply then writes the
+ * voted label to every point of a kept cluster (:184-191). No host synchronisation; nine kernels.
  *   points (n, row_stride>=3) f32 ; pred_bf (n,) int32
  *   workspace : smos_cluster_workspace_bytes(n) bytes, 16-byte aligned, kept until smos_cluster_apply
  *   fg_index  (n,) int32 : indices of the foreground points, ascending (first M entries)

@@ -70,6 +70,7 @@ SIGNATURES = {
                                                    _vp]),
     "smos_memory_push": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "smos_instance_vote": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "smos_instance_vote_counted": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "smos_cluster_workspace_bytes": (ctypes.c_int64, [_i64]),
     "smos_cluster_boxes": (ctypes.c_int, [_vp, _i64, _i64, _vp, ctypes.c_double, _i32, _i32, ctypes.c_float, _vp,
                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -29,8 +29,9 @@ constexpr int kClWarps = kClThreads / 32;
 
 struct ClusterWs {
   float4* xyz;        // [n] foreground points (x, y, z, -)
-  int32_t* nnb;       // [n] neighbour count, then core flag
-  int32_t* parent;    // [n] union-find over core points (-1 for non-core)
+  int32_t* nnb;       // [n] neighbour count (the point itself included); core = nnb >= min_samples
+  int32_t* minlab;    // [n] smallest cluster id among the core neighbours of a non-core point
+  int32_t* parent;    // [n] union-find over core points
   int32_t* rootlab;   // [n] cluster id of a root
   int32_t* cl_cnt;    // [n] points per cluster
   int32_t* cl_min;    // [3n] ordered-int keys of the per-cluster minima
@@ -48,6 +49,7 @@ inline int64_t cluster_ws_layout(int64_t n, char* base, ClusterWs* w) {
   ClusterWs t;
   t.xyz = reinterpret_cast<float4*>(take(n * 16));
   t.nnb = reinterpret_cast<int32_t*>(take(n * 4));
+  t.minlab = reinterpret_cast<int32_t*>(take(n * 4));
   t.parent = reinterpret_cast<int32_t*>(take(n * 4));
   t.rootlab = reinterpret_cast<int32_t*>(take(n * 4));
   t.cl_cnt = reinterpret_cast<int32_t*>(take(n * 4));
@@ -108,6 +110,9 @@ cl_fg_count_kernel(const int32_t* __restrict__ bf, int64_t n, ClusterWs w) {
     w.cl_min[3 * i] = w.cl_min[3 * i + 1] = w.cl_min[3 * i + 2] = 0x7fffffff;
     w.cl_max[3 * i] = w.cl_max[3 * i + 1] = w.cl_max[3 * i + 2] = static_cast<int>(0x80000000u);
     w.slot[i] = -1;
+    w.nnb[i] = 0;
+    w.minlab[i] = 0x7fffffff;
+    w.parent[i] = static_cast<int32_t>(i);
   }
   int total;
   cl_block_scan(i < n && bf[i] == 2, s_warp, &total);
@@ -173,75 +178,105 @@ __device__ __forceinline__ void cl_unite(int32_t* parent, int a, int b) {
 }
 
 enum { CL_COUNT = 0, CL_UNION = 1, CL_LABEL = 2 };
+constexpr int kClColSplit = 16;  // grid.y: column tiles are dealt round-robin to this many CTAs per row tile
 
+// One CTA = one tile of 256 rows against the column tiles y, y + 16, ... (the launch is sized for the upper bound
+// n; CTAs beyond the M x M problem exit at once). Partial results meet in global atomics.
+//   CL_COUNT: nnb[i] += neighbours in these columns          (nnb zeroed by cl_fg_count_kernel)
+//   CL_UNION: core i, core j < i, near -> unite(i, j)        (column tiles up to the row tile only)
+//   CL_LABEL: non-core i: minlab[i] = min(cluster id of near core j)
 template <int MODE>
 __global__ void __launch_bounds__(kClThreads)
-cl_pairs_kernel(ClusterWs w, const int32_t* __restrict__ counts, float reject, double r2, int32_t min_samples,
-                int32_t* __restrict__ fg_label) {
+cl_pairs_kernel(ClusterWs w, const int32_t* __restrict__ counts, float reject, double r2, int32_t min_samples) {
   __shared__ float4 s_q[kClThreads];
   __shared__ int32_t s_aux[kClThreads];
   const int M = counts[0];
   const int row0 = blockIdx.x * kClThreads;
   if (row0 >= M) return;
+  const int tile_end = MODE == CL_UNION ? static_cast<int>(blockIdx.x) + 1 : (M + kClThreads - 1) / kClThreads;
+  if (static_cast<int>(blockIdx.y) >= tile_end) return;
   const int i = row0 + threadIdx.x;
   const bool live = i < M;
   float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
   bool core = false;
   if (live) {
     me = w.xyz[i];
-    if (MODE != CL_COUNT) core = w.nnb[i] != 0;
+    if (MODE != CL_COUNT) core = w.nnb[i] >= min_samples;
   }
-  // which rows work, which columns are needed
   const bool work = MODE == CL_COUNT ? live : MODE == CL_UNION ? (live && core) : (live && !core);
-  const int col_end = MODE == CL_UNION ? min(M, row0 + kClThreads) : M;  // unions only with j < i
   int acc = MODE == CL_LABEL ? 0x7fffffff : 0;
-  for (int j0 = 0; j0 < col_end; j0 += kClThreads) {
+  // the action for one candidate column t of the tile at j0
+  auto visit = [&](int j0, int t, float4 q) {
+    if (MODE == CL_UNION && (j0 + t >= i || !s_aux[t])) return;
+    if (MODE == CL_LABEL && s_aux[t] < 0) return;
+    if (!cl_near(me.x, me.y, me.z, q, reject, r2)) return;
+    if (MODE == CL_COUNT) acc += 1;
+    if (MODE == CL_UNION) cl_unite(w.parent, i, j0 + t);
+    if (MODE == CL_LABEL) acc = min(acc, s_aux[t]);
+  };
+  auto far = [&](float4 q) {  // Chebyshev distance in float32: above `reject` means certainly not a neighbour
+    return fmaxf(fmaxf(fabsf(me.x - q.x), fabsf(me.y - q.y)), fabsf(me.z - q.z));
+  };
+  for (int tj = blockIdx.y; tj < tile_end; tj += gridDim.y) {
+    const int j0 = tj * kClThreads;
     const int j = j0 + threadIdx.x;
     __syncthreads();
     if (j < M) {
       s_q[threadIdx.x] = w.xyz[j];
-      if (MODE == CL_UNION) s_aux[threadIdx.x] = w.nnb[j];                                   // core flag
-      if (MODE == CL_LABEL) s_aux[threadIdx.x] = w.nnb[j] ? w.rootlab[w.parent[j]] : -1;      // cluster id of a core j
+      if (MODE == CL_UNION) s_aux[threadIdx.x] = w.nnb[j] >= min_samples;
+      if (MODE == CL_LABEL) s_aux[threadIdx.x] = w.nnb[j] >= min_samples ? w.rootlab[w.parent[j]] : -1;
     }
     __syncthreads();
     if (!work) continue;
     const int jn = min(kClThreads, M - j0);
-    for (int t = 0; t < jn; ++t) {
-      if (MODE == CL_UNION && (j0 + t >= i || !s_aux[t])) continue;
-      if (MODE == CL_LABEL && s_aux[t] < 0) continue;
-      if (!cl_near(me.x, me.y, me.z, s_q[t], reject, r2)) continue;
-      if (MODE == CL_COUNT) acc += 1;
-      if (MODE == CL_UNION) cl_unite(w.parent, i, j0 + t);
-      if (MODE == CL_LABEL) acc = min(acc, s_aux[t]);
+    int t = 0;
+    for (; t + 4 <= jn; t += 4) {  // four columns per step: nearly all of them fail the float32 test together
+      const float4 q0 = s_q[t], q1 = s_q[t + 1], q2 = s_q[t + 2], q3 = s_q[t + 3];
+      const float m0 = far(q0), m1 = far(q1), m2 = far(q2), m3 = far(q3);
+      if (fminf(fminf(m0, m1), fminf(m2, m3)) > reject) continue;
+      if (m0 <= reject) visit(j0, t, q0);
+      if (m1 <= reject) visit(j0, t + 1, q1);
+      if (m2 <= reject) visit(j0, t + 2, q2);
+      if (m3 <= reject) visit(j0, t + 3, q3);
+    }
+    for (; t < jn; ++t) {
+      const float4 q = s_q[t];
+      if (far(q) <= reject) visit(j0, t, q);
     }
   }
-  if (!live) return;
-  if (MODE == CL_COUNT) {
-    const bool c = acc >= min_samples;
-    w.nnb[i] = c ? 1 : 0;
-    w.parent[i] = c ? i : -1;
-  }
-  if (MODE == CL_LABEL) {
-    // core points: the id of their component; border points: the smallest id among core neighbours; else noise
-    const int lab = core ? w.rootlab[w.parent[i]] : (acc == 0x7fffffff ? -1 : acc);
-    fg_label[i] = lab;
-    if (lab >= 0) {
-      atomicAdd(&w.cl_cnt[lab], 1);
-      atomicMin(&w.cl_min[3 * lab], cl_key(me.x)); atomicMax(&w.cl_max[3 * lab], cl_key(me.x));
-      atomicMin(&w.cl_min[3 * lab + 1], cl_key(me.y)); atomicMax(&w.cl_max[3 * lab + 1], cl_key(me.y));
-      atomicMin(&w.cl_min[3 * lab + 2], cl_key(me.z)); atomicMax(&w.cl_max[3 * lab + 2], cl_key(me.z));
-    }
+  if (MODE == CL_COUNT && live && acc) atomicAdd(&w.nnb[i], acc);
+  if (MODE == CL_LABEL && work && acc != 0x7fffffff) atomicMin(&w.minlab[i], acc);
+}
+
+// final label of every foreground point and the per-cluster size / extent
+__global__ void __launch_bounds__(kClThreads)
+cl_stats_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t min_samples,
+                int32_t* __restrict__ fg_label) {
+  const int M = counts[0];
+  const int i = blockIdx.x * kClThreads + threadIdx.x;
+  if (i >= M) return;
+  // core points: the id of their component; border points: the smallest id among core neighbours; else noise
+  const int ml = w.minlab[i];
+  const int lab = w.nnb[i] >= min_samples ? w.rootlab[w.parent[i]] : (ml == 0x7fffffff ? -1 : ml);
+  fg_label[i] = lab;
+  if (lab >= 0) {
+    const float4 me = w.xyz[i];
+    atomicAdd(&w.cl_cnt[lab], 1);
+    atomicMin(&w.cl_min[3 * lab], cl_key(me.x)); atomicMax(&w.cl_max[3 * lab], cl_key(me.x));
+    atomicMin(&w.cl_min[3 * lab + 1], cl_key(me.y)); atomicMax(&w.cl_max[3 * lab + 1], cl_key(me.y));
+    atomicMin(&w.cl_min[3 * lab + 2], cl_key(me.z)); atomicMax(&w.cl_max[3 * lab + 2], cl_key(me.z));
   }
 }
 
 // ---- cluster ids: rank of each root among the roots (sklearn numbers clusters by their first core point) ------
 __global__ void __launch_bounds__(kClThreads)
-cl_root_count_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t* __restrict__ blk) {
+cl_root_count_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t min_samples,
+                     int32_t* __restrict__ blk) {
   __shared__ int s_warp[kClWarps];
   const int M = counts[0];
   const int i = blockIdx.x * kClThreads + threadIdx.x;
   bool root = false;
-  if (i < M && w.nnb[i]) {
+  if (i < M && w.nnb[i] >= min_samples) {
     const int r = cl_find(w.parent, i);
     root = r == i;
     if (!root) w.parent[i] = r;  // flatten: the label kernel reads parent[j] directly
@@ -252,12 +287,13 @@ cl_root_count_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t* _
 }
 
 __global__ void __launch_bounds__(kClThreads)
-cl_root_label_kernel(ClusterWs w, int32_t* __restrict__ counts, const int32_t* __restrict__ blk) {
+cl_root_label_kernel(ClusterWs w, int32_t* __restrict__ counts, int32_t min_samples,
+                     const int32_t* __restrict__ blk) {
   __shared__ int s_warp[kClWarps];
   const int M = counts[0];
   const int base = cl_blocks_before(blk, s_warp);
   const int i = blockIdx.x * kClThreads + threadIdx.x;
-  const bool root = i < M && w.nnb[i] && w.parent[i] == i;
+  const bool root = i < M && w.nnb[i] >= min_samples && w.parent[i] == i;
   int total;
   const int pos = base + cl_block_scan(root, s_warp, &total);
   if (root) w.rootlab[i] = pos;
@@ -343,11 +379,13 @@ int smos_cluster_boxes(const float* points, int64_t n, int64_t row_stride, const
   int32_t* blk_roots = w.blk + grid;
   cl_fg_count_kernel<<<grid, kClThreads, 0, st>>>(pred_bf, n, w);
   cl_fg_write_kernel<<<grid, kClThreads, 0, st>>>(pred_bf, points, n, row_stride, w, fg_index, fg_label, counts);
-  cl_pairs_kernel<CL_COUNT><<<grid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples, fg_label);
-  cl_pairs_kernel<CL_UNION><<<grid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples, fg_label);
-  cl_root_count_kernel<<<grid, kClThreads, 0, st>>>(w, counts, blk_roots);
-  cl_root_label_kernel<<<grid, kClThreads, 0, st>>>(w, counts, blk_roots);
-  cl_pairs_kernel<CL_LABEL><<<grid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples, fg_label);
+  const dim3 pgrid(grid, kClColSplit);
+  cl_pairs_kernel<CL_COUNT><<<pgrid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples);
+  cl_pairs_kernel<CL_UNION><<<pgrid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples);
+  cl_root_count_kernel<<<grid, kClThreads, 0, st>>>(w, counts, min_samples, blk_roots);
+  cl_root_label_kernel<<<grid, kClThreads, 0, st>>>(w, counts, min_samples, blk_roots);
+  cl_pairs_kernel<CL_LABEL><<<pgrid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples);
+  cl_stats_kernel<<<grid, kClThreads, 0, st>>>(w, counts, min_samples, fg_label);
   cl_boxes_kernel<<<1, kClThreads, 0, st>>>(w, counts, min_cluster_points, z_lift, box_lo, box_hi, kept_label);
   return smos_launch_status();
 }

@@ -177,13 +177,15 @@ __device__ __forceinline__ int iv_cell(float v, float lo, float inv) {
 __global__ void __launch_bounds__(kVoteThreads)
 instance_vote_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const int64_t* __restrict__ pred,
                      const float* __restrict__ lo, const float* __restrict__ hi, int32_t K,
-                     unsigned long long* __restrict__ sums) {
+                     const int32_t* __restrict__ k_dev, unsigned long long* __restrict__ sums) {
   __shared__ float4 s_box[kBoxChunk * 2];  // (lo.x, lo.y, lo.z, hi.x) (hi.y, hi.z, -, -)
   __shared__ unsigned int s_cnt[kBoxChunk * 2];
   __shared__ unsigned int s_mask[kIvGrid * kIvGrid][kIvWords];
   __shared__ int s_ext[4];  // ordered-int keys of min x, min y, max x, max y
-  const int32_t k0 = blockIdx.y * kBoxChunk;
-  const int32_t kn = min(kBoxChunk, K - k0);
+  // the number of boxes may live on the device (boxes produced by smos_cluster_boxes): no host read in between
+  const int32_t Kt = k_dev ? min(__ldg(k_dev), K) : K;
+  for (int32_t k0 = blockIdx.y * kBoxChunk; k0 < Kt; k0 += gridDim.y * kBoxChunk) {
+  const int32_t kn = min(kBoxChunk, Kt - k0);
   if (threadIdx.x == 0) { s_ext[0] = s_ext[1] = 0x7fffffff; s_ext[2] = s_ext[3] = static_cast<int>(0x80000000u); }
   for (int i = threadIdx.x; i < kIvGrid * kIvGrid * kIvWords; i += kVoteThreads) (&s_mask[0][0])[i] = 0u;
   for (int i = threadIdx.x; i < kn * 2; i += kVoteThreads) s_cnt[i] = 0u;
@@ -243,6 +245,8 @@ instance_vote_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const
     const unsigned int c = s_cnt[i];
     // sum(pred[pred==2]) counts 2 per dynamic point (voxel_instance_voting.py:182-184)
     if (c) atomicAdd(&sums[k0 * 2 + i], static_cast<unsigned long long>(c) * ((i & 1) ? 2ull : 1ull));
+  }
+  __syncthreads();  // the shared tables are rebuilt for the next chunk of boxes
   }
 }
 
@@ -499,7 +503,21 @@ int smos_instance_vote(const float* points, int64_t P, int64_t row_stride, const
   if (gx > 8 * SMOS_SM_COUNT) gx = 8 * SMOS_SM_COUNT;  // persistent-style grid-stride loop
   dim3 grid(gx, smos_ceil_div(K, kBoxChunk));
   instance_vote_kernel<<<grid, kVoteThreads, 0, smos_stream(stream)>>>(
-      points, P, row_stride, pred, box_lo, box_hi, K, reinterpret_cast<unsigned long long*>(sums));
+      points, P, row_stride, pred, box_lo, box_hi, K, nullptr, reinterpret_cast<unsigned long long*>(sums));
+  return smos_launch_status();
+}
+
+int smos_instance_vote_counted(const float* points, int64_t P, int64_t row_stride, const int64_t* pred,
+                               const float* box_lo, const float* box_hi, int32_t K_cap, const int32_t* K_dev,
+                               int64_t* sums, void* stream) {
+  if (P < 0 || K_cap < 0 || row_stride < 3 || !K_dev) return SMOS_EINVAL;
+  if (K_cap == 0 || P == 0) return SMOS_OK;
+  if (!points || !pred || !box_lo || !box_hi || !sums) return SMOS_EINVAL;
+  int gx = smos_ceil_div(P, kVoteThreads * 4);
+  if (gx > 8 * SMOS_SM_COUNT) gx = 8 * SMOS_SM_COUNT;
+  // one grid row: every CTA walks the chunks of boxes that exist (usually one), none when *K_dev == 0
+  instance_vote_kernel<<<dim3(gx, 1), kVoteThreads, 0, smos_stream(stream)>>>(
+      points, P, row_stride, pred, box_lo, box_hi, K_cap, K_dev, reinterpret_cast<unsigned long long*>(sums));
   return smos_launch_status();
 }
 

@@ -567,9 +567,10 @@ def memory_push(points, pred, cur_points, cur_pred, hist_points=None, hist_pred=
     _count(1)
 
 
-def instance_vote(points, pred, box_lo, box_hi):
+def instance_vote(points, pred, box_lo, box_hi, count=None):
     """points (P, >=3) f32, pred (P,) int64, box_lo/box_hi (K, 3) f32 -> sums (K, 2) int64
-    [static_sum, dynamic_sum] with dynamic points weighted 2."""
+    [static_sum, dynamic_sum] with dynamic points weighted 2. count: optional (1,) int32 CUDA tensor holding the
+    number of valid boxes (rows beyond it stay zero) — read by the kernel, not by the host."""
     _need_cuda(points, "points")
     _need_f32(points, "points")
     if pred.dtype != torch.int64:
@@ -581,8 +582,16 @@ def instance_vote(points, pred, box_lo, box_hi):
     P, K = int(points.size(0)), int(box_lo.size(0))
     sums = torch.zeros((K, 2), dtype=torch.int64, device=points.device)
     with torch.cuda.device(points.device):
-        rc = _lib.load().smos_instance_vote(_ptr(points), P, points.stride(0) if P > 1 else points.size(1),
-                                            _ptr(pred), _ptr(box_lo), _ptr(box_hi), K, _ptr(sums), _stream())
+        if count is None:
+            rc = _lib.load().smos_instance_vote(_ptr(points), P, points.stride(0) if P > 1 else points.size(1),
+                                                _ptr(pred), _ptr(box_lo), _ptr(box_hi), K, _ptr(sums), _stream())
+        else:
+            if count.dtype != torch.int32 or not count.is_cuda:
+                raise RuntimeError("count must be an int32 CUDA tensor")
+            rc = _lib.load().smos_instance_vote_counted(_ptr(points), P,
+                                                        points.stride(0) if P > 1 else points.size(1), _ptr(pred),
+                                                        _ptr(box_lo), _ptr(box_hi), K, _ptr(count), _ptr(sums),
+                                                        _stream())
     _lib.check(rc, "smos_instance_vote")
     _count(1)
     return sums
@@ -620,7 +629,7 @@ def cluster_boxes(points, pred_bf, eps=0.3, min_samples=5, min_cluster_points=30
                                     _ptr(st["counts"]), _ptr(st["box_lo"]), _ptr(st["box_hi"]),
                                     _ptr(st["kept_label"]), _stream())
     _lib.check(rc, "smos_cluster_boxes")
-    _count(8 if n else 0)
+    _count(9 if n else 0)
     return st
 
 

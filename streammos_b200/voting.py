@@ -75,17 +75,16 @@ def cluster(current_points_orin, current_pred_result_orin, current_pred_bf_resul
     per-frame prediction calls moving (pred_bf == 2), one lifted axis-aligned box per cluster of more than 30
     points, votes of the local map inside each box, and the voted label written to the cluster's points.
     All tensors CUDA; current_pred_result_orin int64, modified in place and returned like the reference does.
-    One host read (the number of kept clusters) sits between the clustering and the vote."""
+    Eleven kernel launches and no host synchronisation: the number of clusters stays on the device."""
     pred = current_pred_result_orin
     if pred.dtype != torch.int64 or not pred.is_contiguous():
         raise RuntimeError("current_pred_result_orin must be a contiguous int64 tensor")
     if int(current_points_orin.size(0)) == 0:
         return pred
     st = ops.cluster_boxes(current_points_orin, current_pred_bf_result_orin, eps, min_samples)
-    kept = int(st["counts"][2].item())
-    if kept == 0:                      # no moving point (:146-147) or no cluster above the cut
-        return pred
-    sums = ops.instance_vote(local_map_points, local_map_prediction, st["box_lo"][:kept], st["box_hi"][:kept])
+    # no moving point (:146-147) or no cluster above the cut: counts[2] == 0 and both kernels do nothing
+    sums = ops.instance_vote(local_map_points, local_map_prediction, st["box_lo"], st["box_hi"],
+                             count=st["counts"][2:3])
     return ops.cluster_apply(st, sums, pred)
 
 

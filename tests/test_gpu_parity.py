@@ -625,7 +625,13 @@ def test_instance_vote_many_boxes_vs_oracle():
     half = rng.uniform(0.5, 4, (K, 3))
     lo, hi = (c - half).astype(np.float32), (c + half).astype(np.float32)
     sums = ops.instance_vote(t(pts), t(pred), t(lo), t(hi))
-    assert np.array_equal(sums.cpu().numpy(), O.instance_vote(pts, pred, lo, hi))
+    want = O.instance_vote(pts, pred, lo, hi)
+    assert np.array_equal(sums.cpu().numpy(), want)
+    # number of boxes read on the device: all of them (two chunks in one grid row), some, none
+    for k in (K, 257, 40, 0):
+        count = torch.tensor([k], dtype=torch.int32, device=dev())
+        got = ops.instance_vote(t(pts), t(pred), t(lo), t(hi), count=count).cpu().numpy()
+        assert np.array_equal(got[:k], want[:k]) and not got[k:].any(), k
 
 
 # ------------------------------------------------------------------------------------------------

@@ -120,3 +120,33 @@ with torch.no_grad():
     timeit("point stem 3x7xN -> 3x64xN (fused)", lambda i: hot.point_pre(lscans[i % 4].pcds_xyzi), (4 * 3 * 7 * N + 4 * 3 * 64 * N) / 1e6)
     timeit("point stem (torch layers)", lambda i: hot.stem.layer(lscans[i % 4].pcds_xyzi), (4 * 3 * 7 * N + 4 * 3 * 64 * N) / 1e6)
     timeit("whole step (eager, serial)", lambda i: hot.step(S(i)))
+    # instance clustering: cluster() of voxel_instance_voting.py on a scan with ~30 moving objects
+    import time
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for n_obj, per_obj in ((30, 100), (60, 400)):
+        objs = [np.array([rng.uniform(-40, 40), rng.uniform(-40, 40), rng.uniform(-1.5, -0.5)]) +
+                rng.uniform(-1, 1, (per_obj, 3)) * np.array([1.0, 0.5, 0.4]) for _ in range(n_obj)]
+        fgp = np.concatenate(objs + [np.stack([rng.uniform(-50, 50, 300), rng.uniform(-50, 50, 300),
+                                               rng.uniform(-3, 1, 300)], -1)]).astype(np.float32)
+        M = len(fgp)
+        cur = pts[8 * N:].clone()
+        idx = torch.from_numpy(rng.permutation(N)[:M]).to(dev)
+        cur[idx, :3] = torch.from_numpy(fgp).to(dev)
+        bf = torch.zeros(N, dtype=torch.int32, device=dev)
+        bf[idx] = 2
+        pred = torch.randint(0, 3, (N,), device=dev)
+        tag = "cluster M=%d" % M
+        timeit(tag + " dbscan+boxes (9 kernels)", lambda i: ops.cluster_boxes(cur, bf))
+        timeit(tag + " cluster() whole", lambda i: voting.cluster(cur, pred, bf, pts, labels))
+        try:
+            from sklearn.cluster import DBSCAN
+            x = cur[bf == 2][:, :3].cpu().numpy()
+            t0 = time.perf_counter()
+            ref = DBSCAN(eps=0.3, min_samples=5).fit_predict(x)
+            dt = time.perf_counter() - t0
+            same = np.array_equal(ref, ops.cluster_boxes(cur, bf)["fg_label"][:M].cpu().numpy())
+            print("%-34s %8.1f us   (sklearn DBSCAN alone on the host, %d clusters, labels identical: %s)"
+                  % (tag + " [host]", dt * 1e6, ref.max() + 1, same), flush=True)
+        except ImportError:
+            pass
