@@ -172,8 +172,9 @@ int smos_bilinear_gather_forward_taps(const float* grid, int64_t B, int64_t C, i
                                       const void* taps, int64_t N,
                                       float* out, int64_t o_sb, int64_t o_sc, int64_t o_sn, void* stream);
 
-/* grad_grid (B, C, H, W) NCHW-contiguous must be ZERO-FILLED by the caller;
- * contributions are accumulated with fp32 atomics (grid_sampler backward). */
+/* Gradient wrt the grid (grid_sampler backward). grad_grid (B, C, H, W) NCHW-contiguous; the function zero-fills
+ * it itself (no fill by the caller) and accumulates the contributions with fp32 atomics, so sums are exact up to
+ * fp32 addition order like the reference's. Two kernels. */
 int smos_bilinear_gather_backward(const float* grad_out, int64_t B, int64_t C, int64_t N,
                                   int64_t go_sb, int64_t go_sc, int64_t go_sn,
                                   const float* coord,

@@ -253,7 +253,7 @@ def bilinear_gather_backward(grad_out, grid_coord, scale_rate, H, W):
     else:
         co = grid_coord.permute(0, 1, 3, 2).reshape(B, N * S, 2)
         go = grad_out.reshape(B, C, N * S)
-    grad_grid = torch.zeros((B, C, H, W), dtype=torch.float32, device=grad_out.device)
+    grad_grid = torch.empty((B, C, H, W), dtype=torch.float32, device=grad_out.device)   # every element is written
     with torch.cuda.device(grad_out.device):
         rc = _lib.load().smos_bilinear_gather_backward(
             _ptr(go), B, C, N * S, go.stride(0), go.stride(1), go.stride(2), _ptr(co), co.stride(0), co.stride(1),

@@ -306,6 +306,29 @@ def test_bilinear_cell_order_matches_scan_order(C, H, W, scale):
         ops.bilinear_gather_forward(t(grid)[:1], t(coord)[:1], scale, True, order=plans[0])
 
 
+@pytest.mark.parametrize("C,H,W,scale,N", [(64, 128, 128, (0.25, 0.25), 120000), (32, 256, 256, (0.5, 0.5), 60000),
+                                          (32, 32, 1024, (0.5, 0.5), 60000), (3, 53, 47, (1.0, 1.0), 5000),
+                                          (2, 3, 12500, (1.0, 1.0), 4000)])
+def test_bilinear_backward_vs_oracle(C, H, W, scale, N):
+    """Gradient wrt the grid against the float64-accumulating oracle: row bands in shared memory (several bands per
+    plane, a ragged last band), and the global-atomics path for rows wider than a band (W = 12500)."""
+    from streammos_b200 import ops
+    rng = np.random.default_rng(C * H + W)
+    B = 2 if C <= 3 else 1
+    coord = np.concatenate([synth_scan(rng, 1, N, H, W, scale, n_valid=N - N // 50) for _ in range(B)])
+    gout = rng.standard_normal((B, C, N, 1)).astype(np.float32)
+    want = O.bilinear_sample_backward(gout, coord, scale, H, W)
+    tol = 1e-5 * np.abs(want).max() + 1e-5
+    got = ops.bilinear_gather_backward(t(gout), t(coord), scale, H, W)
+    assert got.shape == (B, C, H, W) and bool(torch.isfinite(got).all())
+    assert np.abs(got.cpu().numpy() - want).max() <= 4 * tol
+    # point-major gradient rows (channels_last strides) take the same path
+    gpm = t(gout).permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+    assert gpm.stride(1) == 1
+    got2 = ops.bilinear_gather_backward(gpm, t(coord), scale, H, W)
+    assert np.abs(got2.cpu().numpy() - want).max() <= 4 * tol
+
+
 def test_bilinear_multi_sample_dim_and_linearity():
     from streammos_b200 import ops
     rng = np.random.default_rng(5)

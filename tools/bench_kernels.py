@@ -150,3 +150,15 @@ with torch.no_grad():
                   % (tag + " [host]", dt * 1e6, ref.max() + 1, same), flush=True)
         except ImportError:
             pass
+    # training-side kernels: not on the streaming path, timed here for the record
+    go1 = torch.randn(3, 64, 512, 512, device=dev)
+    mb_b1 = (4 * 3 * 64 * 512 * 512 + 4 * 3 * 64 * N * 2 + 8 * 3 * N) / 1e6
+    timeit("bwd pool1 (3x64xN <- 3x64x512^2)", lambda i: ops.voxel_maxpool_backward(S(i).feat, plans[i % 4][0], out1, go1), mb_b1)
+    gp = torch.randn(1, 64, N, 1, device=dev)
+    timeit("bwd gather5 64ch@256^2", lambda i: ops.bilinear_gather_backward(gp, S(i).coord_bev[:1], (0.5, 0.5), 256, 256),
+           (4 * 64 * 256 * 256 + 8 * N + 4 * 64 * N) / 1e6)
+    gq = torch.randn(1, 64, N, 1, device=dev)
+    timeit("bwd gather3 64ch@128^2", lambda i: ops.bilinear_gather_backward(gq, S(i).coord_bev[:1], (0.25, 0.25), 128, 128),
+           (4 * 64 * 128 * 128 + 8 * N + 4 * 64 * N) / 1e6)
+    gout = torch.randn(1, 4096, 128, device=dev)
+    timeit("bwd msda (one layer)", lambda i: MSDA.ms_deform_attn_backward(value, hot.shapes, hot.lsi, S(i).loc[0], S(i).attn[0], gout, 256), 12.3)
