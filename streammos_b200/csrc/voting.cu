@@ -185,68 +185,68 @@ instance_vote_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const
   // the number of boxes may live on the device (boxes produced by smos_cluster_boxes): no host read in between
   const int32_t Kt = k_dev ? min(__ldg(k_dev), K) : K;
   for (int32_t k0 = blockIdx.y * kBoxChunk; k0 < Kt; k0 += gridDim.y * kBoxChunk) {
-  const int32_t kn = min(kBoxChunk, Kt - k0);
-  if (threadIdx.x == 0) { s_ext[0] = s_ext[1] = 0x7fffffff; s_ext[2] = s_ext[3] = static_cast<int>(0x80000000u); }
-  for (int i = threadIdx.x; i < kIvGrid * kIvGrid * kIvWords; i += kVoteThreads) (&s_mask[0][0])[i] = 0u;
-  for (int i = threadIdx.x; i < kn * 2; i += kVoteThreads) s_cnt[i] = 0u;
-  __syncthreads();
-  auto key = [](float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; };  // monotonic
-  auto unkey = [](int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); };
-  for (int i = threadIdx.x; i < kn; i += kVoteThreads) {
-    const float* l = lo + static_cast<int64_t>(k0 + i) * 3;
-    const float* h = hi + static_cast<int64_t>(k0 + i) * 3;
-    s_box[2 * i] = make_float4(l[0], l[1], l[2], h[0]);
-    s_box[2 * i + 1] = make_float4(h[1], h[2], 0.f, 0.f);
-    atomicMin(&s_ext[0], key(l[0])); atomicMin(&s_ext[1], key(l[1]));
-    atomicMax(&s_ext[2], key(h[0])); atomicMax(&s_ext[3], key(h[1]));
-  }
-  __syncthreads();
-  const float gx0 = unkey(s_ext[0]), gy0 = unkey(s_ext[1]);
-  const float ex = unkey(s_ext[2]) - gx0, ey = unkey(s_ext[3]) - gy0;
-  const float invx = ex > 0.f ? static_cast<float>(kIvGrid) / ex : 0.f;
-  const float invy = ey > 0.f ? static_cast<float>(kIvGrid) / ey : 0.f;
-  for (int i = threadIdx.x; i < kn; i += kVoteThreads) {
-    const float4 a = s_box[2 * i], bb = s_box[2 * i + 1];
-    const int x0 = iv_cell(a.x, gx0, invx), x1 = iv_cell(a.w, gx0, invx);
-    const int y0 = iv_cell(a.y, gy0, invy), y1 = iv_cell(bb.x, gy0, invy);
-    for (int y = y0; y <= y1; ++y)
-      for (int x = x0; x <= x1; ++x) atomicOr(&s_mask[y * kIvGrid + x][i >> 5], 1u << (i & 31));
-  }
-  __syncthreads();
-  const int nwords = (kn + 31) >> 5;
-  const bool vec = (rs == 4) && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0);
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x; i < P;
-       i += static_cast<int64_t>(gridDim.x) * kVoteThreads) {
-    const int64_t pr = __ldg(pred + i);
-    if (pr != 1 && pr != 2) continue;
-    float x, y, z;
-    if (vec) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(pts) + i);
-      x = q.x; y = q.y; z = q.z;
-    } else {
-      const float* q = pts + i * rs;
-      x = q[0]; y = q[1]; z = q[2];
+    const int32_t kn = min(kBoxChunk, Kt - k0);
+    if (threadIdx.x == 0) { s_ext[0] = s_ext[1] = 0x7fffffff; s_ext[2] = s_ext[3] = static_cast<int>(0x80000000u); }
+    for (int i = threadIdx.x; i < kIvGrid * kIvGrid * kIvWords; i += kVoteThreads) (&s_mask[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < kn * 2; i += kVoteThreads) s_cnt[i] = 0u;
+    __syncthreads();
+    auto key = [](float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; };  // monotonic
+    auto unkey = [](int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); };
+    for (int i = threadIdx.x; i < kn; i += kVoteThreads) {
+      const float* l = lo + static_cast<int64_t>(k0 + i) * 3;
+      const float* h = hi + static_cast<int64_t>(k0 + i) * 3;
+      s_box[2 * i] = make_float4(l[0], l[1], l[2], h[0]);
+      s_box[2 * i + 1] = make_float4(h[1], h[2], 0.f, 0.f);
+      atomicMin(&s_ext[0], key(l[0])); atomicMin(&s_ext[1], key(l[1]));
+      atomicMax(&s_ext[2], key(h[0])); atomicMax(&s_ext[3], key(h[1]));
     }
-    const unsigned int* m = s_mask[iv_cell(y, gy0, invy) * kIvGrid + iv_cell(x, gx0, invx)];
-    for (int w = 0; w < nwords; ++w) {
-      unsigned int bits = m[w];
-      while (bits) {
-        const int k = (w << 5) + __ffs(bits) - 1;
-        bits &= bits - 1;
-        const float4 a = s_box[2 * k], bb = s_box[2 * k + 1];
-        // inclusive AABB test == in_hull of the 8 corners (voxel_instance_voting.py:62-76,177)
-        if (x >= a.x && x <= a.w && y >= a.y && y <= bb.x && z >= a.z && z <= bb.y)
-          atomicAdd(&s_cnt[k * 2 + static_cast<int>(pr) - 1], 1u);
+    __syncthreads();
+    const float gx0 = unkey(s_ext[0]), gy0 = unkey(s_ext[1]);
+    const float ex = unkey(s_ext[2]) - gx0, ey = unkey(s_ext[3]) - gy0;
+    const float invx = ex > 0.f ? static_cast<float>(kIvGrid) / ex : 0.f;
+    const float invy = ey > 0.f ? static_cast<float>(kIvGrid) / ey : 0.f;
+    for (int i = threadIdx.x; i < kn; i += kVoteThreads) {
+      const float4 a = s_box[2 * i], bb = s_box[2 * i + 1];
+      const int x0 = iv_cell(a.x, gx0, invx), x1 = iv_cell(a.w, gx0, invx);
+      const int y0 = iv_cell(a.y, gy0, invy), y1 = iv_cell(bb.x, gy0, invy);
+      for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) atomicOr(&s_mask[y * kIvGrid + x][i >> 5], 1u << (i & 31));
+    }
+    __syncthreads();
+    const int nwords = (kn + 31) >> 5;
+    const bool vec = (rs == 4) && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x; i < P;
+         i += static_cast<int64_t>(gridDim.x) * kVoteThreads) {
+      const int64_t pr = __ldg(pred + i);
+      if (pr != 1 && pr != 2) continue;
+      float x, y, z;
+      if (vec) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(pts) + i);
+        x = q.x; y = q.y; z = q.z;
+      } else {
+        const float* q = pts + i * rs;
+        x = q[0]; y = q[1]; z = q[2];
+      }
+      const unsigned int* m = s_mask[iv_cell(y, gy0, invy) * kIvGrid + iv_cell(x, gx0, invx)];
+      for (int w = 0; w < nwords; ++w) {
+        unsigned int bits = m[w];
+        while (bits) {
+          const int k = (w << 5) + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float4 a = s_box[2 * k], bb = s_box[2 * k + 1];
+          // inclusive AABB test == in_hull of the 8 corners (voxel_instance_voting.py:62-76,177)
+          if (x >= a.x && x <= a.w && y >= a.y && y <= bb.x && z >= a.z && z <= bb.y)
+            atomicAdd(&s_cnt[k * 2 + static_cast<int>(pr) - 1], 1u);
+        }
       }
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kn * 2; i += kVoteThreads) {
-    const unsigned int c = s_cnt[i];
-    // sum(pred[pred==2]) counts 2 per dynamic point (voxel_instance_voting.py:182-184)
-    if (c) atomicAdd(&sums[k0 * 2 + i], static_cast<unsigned long long>(c) * ((i & 1) ? 2ull : 1ull));
-  }
-  __syncthreads();  // the shared tables are rebuilt for the next chunk of boxes
+    __syncthreads();
+    for (int i = threadIdx.x; i < kn * 2; i += kVoteThreads) {
+      const unsigned int c = s_cnt[i];
+      // sum(pred[pred==2]) counts 2 per dynamic point (voxel_instance_voting.py:182-184)
+      if (c) atomicAdd(&sums[k0 * 2 + i], static_cast<unsigned long long>(c) * ((i & 1) ? 2ull : 1ull));
+    }
+    __syncthreads();  // the shared tables are rebuilt for the next chunk of boxes
   }
 }
 
