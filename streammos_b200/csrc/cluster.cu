@@ -167,14 +167,19 @@ __device__ __forceinline__ int cl_find(int32_t* parent, int x) {
   }
 }
 
-__device__ __forceinline__ void cl_unite(int32_t* parent, int a, int b) {
-  for (;;) {
+// Joins the sets of i and j. `ri` is the caller's running guess of i's root (an ancestor of i, kept in a register
+// across the neighbours of i): most neighbours of a point already hang under it, and one load of parent[j] settles
+// those without walking any chain. Returns the new guess.
+__device__ __forceinline__ int cl_unite(int32_t* parent, int ri, int j) {
+  if (static_cast<volatile int32_t*>(parent)[j] == ri) return ri;
+  int a = cl_find(parent, ri), b = cl_find(parent, j);
+  while (a != b) {
+    if (a < b) { const int t = a; a = b; b = t; }
+    if (atomicCAS(&parent[a], a, b) == a) return b;  // the larger root hangs under the smaller one
     a = cl_find(parent, a);
     b = cl_find(parent, b);
-    if (a == b) return;
-    if (a < b) { const int t = a; a = b; b = t; }
-    if (atomicCAS(&parent[a], a, b) == a) return;  // the larger root hangs under the smaller one
   }
+  return a;
 }
 
 enum { CL_COUNT = 0, CL_UNION = 1, CL_LABEL = 2 };
@@ -205,13 +210,14 @@ cl_pairs_kernel(ClusterWs w, const int32_t* __restrict__ counts, float reject, d
   }
   const bool work = MODE == CL_COUNT ? live : MODE == CL_UNION ? (live && core) : (live && !core);
   int acc = MODE == CL_LABEL ? 0x7fffffff : 0;
+  int root = i;  // CL_UNION: running guess of i's root
   // the action for one candidate column t of the tile at j0
   auto visit = [&](int j0, int t, float4 q) {
     if (MODE == CL_UNION && (j0 + t >= i || !s_aux[t])) return;
     if (MODE == CL_LABEL && s_aux[t] < 0) return;
     if (!cl_near(me.x, me.y, me.z, q, reject, r2)) return;
     if (MODE == CL_COUNT) acc += 1;
-    if (MODE == CL_UNION) cl_unite(w.parent, i, j0 + t);
+    if (MODE == CL_UNION) root = cl_unite(w.parent, root, j0 + t);
     if (MODE == CL_LABEL) acc = min(acc, s_aux[t]);
   };
   auto far = [&](float4 q) {  // Chebyshev distance in float32: above `reject` means certainly not a neighbour
