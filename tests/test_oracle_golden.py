@@ -129,6 +129,13 @@ def test_dbscan_oracle_against_sklearn():
         x = x[rng.permutation(len(x))]
         want = sk.DBSCAN(eps=0.3, min_samples=5).fit_predict(x)
         assert np.array_equal(O.dbscan(x), want), trial
+    # lattices whose axis distances sit right at eps (2 x 0.15f, 3 x 0.1f): the float64 reduced distance decides
+    for step, depth, frac in ((0.15, 4, 0.55), (0.1, 3, 0.12)):
+        g = np.arange(15, dtype=np.float32) * np.float32(step)
+        x = np.stack(np.meshgrid(g, g, g[:depth], indexing="ij"), -1).reshape(-1, 3)
+        x = x[rng.uniform(0, 1, len(x)) < frac]
+        x = x[rng.permutation(len(x))]
+        assert np.array_equal(O.dbscan(x), sk.DBSCAN(eps=0.3, min_samples=5).fit_predict(x)), step
     assert O.dbscan(np.zeros((0, 3), np.float32)).shape == (0,)
     assert np.array_equal(O.dbscan(np.zeros((7, 3), np.float32)), np.zeros(7, np.int32))   # coincident points
     assert np.array_equal(O.dbscan(np.zeros((4, 3), np.float32)), np.full(4, -1, np.int32))
