@@ -2,7 +2,7 @@
 """Benchmark of the StreamMOS hot path on B200 (BASELINE.json metric: scans/s at ~120k points, % of HBM roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a kernels
-    python bench.py --impl reference [...]                          # the reference's CPU path (oracle/cpu_path.py)
+    python bench.py --impl reference [...]                          # torch-CPU port of the reference ops (oracle/cpu_path.py)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W                      # one rank per GPU, independent scan streams
 
@@ -44,8 +44,14 @@ def parse_args():
     ap.add_argument("--no-variants", action="store_true", help="skip the extra layout/API variant measurement")
     ap.add_argument("--in-flight", type=int, default=2, help="scans in flight per stream (projection streams)")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-operator table to stderr")
-    ap.add_argument("--no-branches", action="store_true",
-                    help="capture each graph as one chain instead of parallel branches for independent operators")
+    ap.add_argument("--branches", action="store_true",
+                    help="experiment: run the four independent operator groups of the projection (independent only because "
+                         "the CNN outputs are resident stand-ins) as parallel graph branches; the default is the "
+                         "reference's serial chain")
+    ap.add_argument("--no-branches", action="store_true", help="accepted for compatibility; the serial chain is the default")
+    ap.add_argument("--explicit-plans", action="store_true",
+                    help="call the operators with the explicit plan API (plan= / order=, five plans per batch of launches) "
+                         "instead of the reference's signatures + plan cache")
     ap.add_argument("--no-ordered-gathers", action="store_true",
                     help="BEV gathers visit the points in scan order instead of the pooling plan's cell order")
     ap.add_argument("--ordered-rv", action="store_true", help="range-view gathers in cell order too")
@@ -160,8 +166,9 @@ def cpu_state(hot):
 
 
 def time_cpu_path(state, scans, n_scans, warmup=1, budget_s=120.0):
-    """The reference's CPU path (oracle/cpu_path.py) on the host cores: scans/s over a bounded sample
-    (at most `n_scans` scans and at most `budget_s` seconds)."""
+    """A torch-CPU port of the reference operators (oracle/cpu_path.py: scatter_reduce pooling, F.grid_sample,
+    ms_deform_attn_core_pytorch, torch voting) on the host cores: scans/s over a bounded sample (at most `n_scans` scans
+    and at most `budget_s` seconds). A reported baseline, not a target."""
     import torch
     from oracle.cpu_path import CpuHotPath
     cores = os.cpu_count() or 1
@@ -213,8 +220,13 @@ def workload_config(args, graph, world):
             "pipeline": "3 graphs per scan (projection / temporal fusion / voting), %d scans in flight on %d CUDA streams; "
                         "cross-scan dependencies (short-term memory, voting ring) enforced with events; %s"
                         % (args.in_flight, args.in_flight + 1,
-                           "chains only" if args.no_branches else "independent operators of a scan are parallel graph "
+                           "operators in the reference's serial order" if not args.branches else
+                           "independent operators of a scan are parallel graph "
                            "branches (pool #1 | half-scale chain | quarter-scale chain | gather #5; voxel | instance votes)"),
+            "operator_api": "explicit plan API (plan= / order=)" if args.explicit_plans else
+                            "reference signatures only (VoxelMaxPool(feat, ind, size, scale), BilinearSample(grid, coord), "
+                            "MSDA.ms_deform_attn_forward, Quantize / determine_voxel_labels / get_point_labels_from_voxel_labels); "
+                            "plans shared through the plan cache as under the unmodified reference model",
             "gather_order": "scan order" if args.no_ordered_gathers else
                             ("cell order of the shared pooling plan (BEV%s)%s" % (
                                 " + RV" if (args.ordered_rv or args.gather_taps) else "",
@@ -234,7 +246,7 @@ def run_b200(args, world, rank, local):
     use_graph = not args.no_graph
     hot = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
                          vote_api=args.vote_api, overlap_voting=False,
-                         grids_channels_last=args.grids_channels_last, branches=not args.no_branches,
+                         grids_channels_last=args.grids_channels_last, branches=args.branches, batch_plans=args.explicit_plans,
                          ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv,
                          gather_taps=args.gather_taps)
     host = [stream.make_host_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
@@ -334,7 +346,7 @@ def run_b200(args, world, rank, local):
         def hot_like():
             return stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
                                   vote_api=args.vote_api, grids_channels_last=args.grids_channels_last,
-                                  branches=not args.no_branches, ordered_gathers=not args.no_ordered_gathers,
+                                  branches=args.branches, batch_plans=args.explicit_plans, ordered_gathers=not args.no_ordered_gathers,
                                   ordered_rv=args.ordered_rv, gather_taps=args.gather_taps)
 
         # (2) the LOADER's tensors in host memory, as in the reference (models/StreamMOS.py:86-103): 7-channel point
@@ -398,44 +410,62 @@ def run_b200(args, world, rank, local):
         torch.cuda.synchronize()
         pool1_ms = p0.elapsed_time(p1) / ksteps
         breakdown = op_breakdown(hot, devb, compute, min(args.steps, 50)) if (rank == 0) else None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        families = family_breakdown(hot, devb, dev, peak, max(3, min(args.steps, 30))) if rank == 0 else None
 
         # ---- variant (reported beside the headline, not instead of it): what a channels_last model and the fused
         # streaming voting API buy on the same workload ------------------------------------------
         variants = None
-        if rank == 0 and world == 1 and not args.no_variants and use_graph and \
-                not (args.grids_channels_last and args.vote_api == "fused"):
+        if rank == 0 and world == 1 and not args.no_variants and use_graph:
             del pipe
-            hot2 = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
-                                  vote_api="fused", grids_channels_last=True, branches=not args.no_branches,
-                                  ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv,
-                         gather_taps=args.gather_taps)
-            pipe2 = pipeline.ScanPipeline(hot2, devb, use_graphs=True, scans_in_flight=args.in_flight)
-            vsteps = min(args.steps, 500)
-            for i in range(20):
-                pipe2.submit()
-            torch.cuda.synchronize()
-            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            v0.record(compute)
-            for st in pipe2.streams():
-                st.wait_event(v0)
-            for i in range(vsteps):
-                pipe2.submit()
-            pipe2.join(compute)
-            v1.record(compute)
-            torch.cuda.synchronize()
-            vms = v0.elapsed_time(v1) / vsteps
-            variants = {"channels_last_cnn_grids+fused_voting_api": {
-                "value": 1000.0 / vms, "unit": "scans/s", "ms_per_step": vms,
-                "note": "same kernels; gathers read channels_last feature maps (model.to(memory_format=channels_last)) "
-                        "and voting takes float xyz + uint8 labels (smos_vote_fused) instead of the int64 staging of "
-                        "voxel_voting.py:234-243; results identical (tests)"}}
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+            def measure_variant(**kw):
+                base = dict(n_points=args.points, seed=rank, point_major=not args.channel_major, vote_api=args.vote_api,
+                            grids_channels_last=args.grids_channels_last, branches=args.branches,
+                            batch_plans=args.explicit_plans, ordered_gathers=not args.no_ordered_gathers,
+                            ordered_rv=args.ordered_rv, gather_taps=args.gather_taps)
+                base.update(kw)
+                hot2 = stream.HotPath(dev, **base)
+                pipe2 = pipeline.ScanPipeline(hot2, devb, use_graphs=True, scans_in_flight=args.in_flight)
+                vsteps = min(args.steps, 400)
+                for i in range(20):
+                    pipe2.submit()
+                torch.cuda.synchronize()
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                v0.record(compute)
+                for st in pipe2.streams():
+                    st.wait_event(v0)
+                for i in range(vsteps):
+                    pipe2.submit()
+                pipe2.join(compute)
+                v1.record(compute)
+                torch.cuda.synchronize()
+                vms = v0.elapsed_time(v1) / vsteps
+                del pipe2, hot2
+                return {"value": 1000.0 / vms, "unit": "scans/s", "ms_per_step": vms}
+
+            variants = {}
+            if not (args.grids_channels_last and args.vote_api == "fused"):
+                variants["channels_last_cnn_grids+fused_voting_api"] = dict(
+                    measure_variant(vote_api="fused", grids_channels_last=True),
+                    note="same kernels; gathers read channels_last feature maps (model.to(memory_format=channels_last)) and "
+                         "voting takes float xyz + uint8 labels (smos_vote_fused) instead of the int64 staging of "
+                         "voxel_voting.py:234-243; results identical (tests)")
+            variants["explicit_plan_api" if not args.explicit_plans else "reference_signatures"] = dict(
+                measure_variant(batch_plans=not args.explicit_plans),
+                note="same workload through the other operator API (explicit: five plans per batch of launches, plan= / order=; "
+                     "reference: the reference's arguments only + plan cache)")
+            if not args.branches:
+                variants["parallel_branches"] = dict(
+                    measure_variant(branches=True, batch_plans=True),
+                    note="experiment: pool #1 | half-scale chain | quarter-scale chain | gather #5 as parallel graph branches — "
+                         "possible only because the CNN outputs are resident stand-ins; NOT the reference's data flow")
+
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     # algorithmic bytes of the writer per launch: the dense output (4*B'*C*H*W) + count/start per cell (8*B'*H*W);
     # the rows of occupied cells are < 10 % more and are not counted
@@ -446,7 +476,8 @@ def run_b200(args, world, rank, local):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))["bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "pool_write_kernel (dense writer of VoxelMaxPool #1: 3x64x512x512 fp32)",
+    roofline = {"bound": "hbm", "kernel": "pool_write_kernel (dense writer of VoxelMaxPool #1: 3x64x512x512 fp32; the largest "
+                                          "single byte mover of the path, 30 % of its algorithmic bytes)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": kern_ms, "traffic": traffic,
                 "voxelmaxpool1_op": {"algorithmic_bytes": ab["pool"][0], "ms": pool1_ms,
@@ -455,7 +486,20 @@ def run_b200(args, world, rank, local):
                                      "note": "eager launches: plan (4 kernels) + permute + reduce + combine + write"},
                 "whole_path": {"algorithmic_bytes_per_scan": ab["total"],
                                "achieved": ab["total"] / (ms_step * 1e-3) / 1e9,
-                               "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak}}
+                               "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak,
+                               "note": "pipelined wall time per scan (ms_per_step): kernels of 2 scans in flight overlap"}}
+    if families:
+        # SURVEY 8d's own formula: algorithmic bytes / SUM of the hot-path kernel time (no overlap between families)
+        sum_us = sum(f["us_per_scan"] for f in families.values())
+        roofline["per_family"] = families
+        roofline["whole_path_sum_of_kernels"] = {"us_per_scan": sum_us, "algorithmic_bytes_per_scan": ab["total"],
+                                                 "achieved": ab["total"] / (sum_us * 1e-6) / 1e9,
+                                                 "frac": ab["total"] / (sum_us * 1e-6) / 1e9 / peak}
+        with_bytes = {k: f for k, f in families.items() if f.get("frac") is not None and k != "msda"}
+        lim = min(with_bytes, key=lambda k: with_bytes[k]["frac"])
+        roofline["limiter"] = {"family": lim, "frac": with_bytes[lim]["frac"],
+                               "note": "lowest fraction among the HBM-sized families (msda is 5 MB, L2 resident, latency bound); "
+                                       "`kernel` above is the single largest byte mover, not the limiter"}
     if rank != 0:
         return
     line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
@@ -463,7 +507,11 @@ def run_b200(args, world, rank, local):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, use_graph, world), "roofline": roofline, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-            "clocks": clocks, "breakdown_ms": breakdown, "variants": variants}
+            "clocks": clocks, "breakdown_ms": breakdown, "variants": variants,
+            "reference_signature": None if args.explicit_plans else {
+                "value": value, "unit": "scans/s",
+                "note": "`value` IS the reference-signature leg: every operator is called with the reference's arguments "
+                        "only; variants.explicit_plan_api is the same workload through plan= / order="}}
     if cpu_hot_state is not None:
         scans = [h for h in host[:4]]
         sps, ms, cores, done = time_cpu_path(cpu_hot_state, scans, args.cpu_scans, budget_s=30.0)
@@ -475,6 +523,95 @@ def run_b200(args, world, rank, local):
     if args.breakdown and breakdown:
         for k, v in breakdown.items():
             sys.stderr.write("%-28s %8.4f ms\n" % (k, v))
+
+
+def family_breakdown(hot, devb, dev, peak, iters):
+    """Per-family device time of the hot path (roofline = algorithmic bytes / sum of hot-path kernel time).
+
+    Each family's launches for all resident scans are captured into ONE CUDA graph (no host launch gaps) and the
+    graph is replayed `iters` times between two CUDA events on its stream; the ~100 MB of inputs per scan x 8 scans
+    rotate through L2 as in the stream. Consumers get pre-built plans, so plan building is its own family."""
+    import torch
+    from streammos_b200 import MultiScaleDeformableAttention as MSDA
+    from streammos_b200 import deep_point, ops, stream
+    ab = stream.algorithmic_bytes(hot.n_points)
+    nb = len(devb)
+    specs = lambda b: [(b.coord_bev, (512, 512), (1.0, 1.0)), (b.coord_rv, (32, 1024), (0.5, 0.5)),
+                       (b.coord_bev[:1], (256, 256), (0.5, 0.5)), (b.coord_rv, (16, 512), (0.25, 0.25)),
+                       (b.coord_bev[:1], (128, 128), (0.25, 0.25))]
+    st = torch.cuda.Stream(dev)
+    res = {}
+    with torch.cuda.stream(st), torch.no_grad():
+        P = [[ops.pool_plan(*sp) for sp in specs(b)] for b in devb]
+        keep = []
+        for b, pl in zip(devb, P):  # intermediates of the cascade, once per scan
+            cur, rv = b.coord_bev[:1], b.coord_rv
+            x0_pt = hot.g_half(hot.x0, cur, pl[2])
+            x0_rv = deep_point.VoxelMaxPool(x0_pt, rv, (32, 1024), (0.5, 0.5), pl[1])
+            x0_pt2 = hot.g_half(x0_rv, rv, pl[1])
+            x1_pt = hot.g_quarter(hot.x1, cur, pl[4])
+            x1_rv = deep_point.VoxelMaxPool(x1_pt, rv, (16, 512), (0.25, 0.25), pl[3])
+            x1_pt2 = hot.g_quarter(x1_rv, rv, pl[3])
+            keep.append((x0_pt, x0_rv, x0_pt2, x1_pt, x1_rv, x1_pt2))
+        value = hot.memory.view(1, stream.MEM_HW * stream.MEM_HW, stream.N_HEADS, stream.HEAD_DIM)
+
+        def f_plans(j):
+            if hot.batch_plans:
+                return ops.pool_plan_multi(specs(devb[j]))
+            return [ops.pool_plan(*sp) for sp in specs(devb[j])]
+
+        def f_pool1(j):
+            return deep_point.VoxelMaxPool(devb[j].feat, devb[j].coord_bev, (512, 512), (1.0, 1.0), P[j][0])
+
+        def f_pools(j):
+            b, k, pl = devb[j], keep[j], P[j]
+            cur, rv = b.coord_bev[:1], b.coord_rv
+            return (deep_point.VoxelMaxPool(k[0], rv, (32, 1024), (0.5, 0.5), pl[1]),
+                    deep_point.VoxelMaxPool(k[2], cur, (256, 256), (0.5, 0.5), pl[2]),
+                    deep_point.VoxelMaxPool(k[3], rv, (16, 512), (0.25, 0.25), pl[3]),
+                    deep_point.VoxelMaxPool(k[5], cur, (128, 128), (0.25, 0.25), pl[4]))
+
+        def f_gathers(j):
+            b, k, pl = devb[j], keep[j], P[j]
+            cur, rv = b.coord_bev[:1], b.coord_rv
+            return (hot.g_half(hot.x0, cur, pl[2]), hot.g_half(k[1], rv, pl[1]), hot.g_quarter(hot.x1, cur, pl[4]),
+                    hot.g_quarter(k[4], rv, pl[3]), hot.g_half(hot.dec, cur, pl[2]))
+
+        def f_msda(j):
+            b = devb[j]
+            h = MSDA.ms_deform_attn_forward(value, hot.shapes, hot.lsi, b.loc[0], b.attn[0], 256)
+            return MSDA.ms_deform_attn_forward(h.view_as(value), hot.shapes, hot.lsi, b.loc[1], b.attn[1], 256)
+
+        def f_vote(j):
+            hot.scan_index = j
+            return hot.long_term_voting(devb[j])
+
+        fams = [("plans", f_plans, 0), ("pool1", f_pool1, ab["pool"][0]), ("pools2-5", f_pools, sum(ab["pool"][1:])),
+                ("gathers", f_gathers, sum(ab["gather"])), ("msda", f_msda, ab["msda"]), ("voting", f_vote, ab["vote"])]
+        for name, fn, nbytes in fams:
+            for j in range(nb):
+                fn(j)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                outs = [fn(j) for j in range(nb)]
+            for _ in range(2):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(iters):
+                g.replay()
+            e1.record(st)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / (iters * nb)
+            ent = {"us_per_scan": ms * 1e3, "algorithmic_bytes": nbytes}
+            if nbytes:
+                ent["achieved"] = nbytes / (ms * 1e-3) / 1e9
+                ent["frac"] = ent["achieved"] / peak
+            res[name] = ent
+            del g, outs
+        hot.scan_index = 0
+    return res
 
 
 def deep_point_pool1(b):

@@ -33,10 +33,15 @@ extern "C" {
 #define SMOS_EINVAL (-1)       /* bad shape / null pointer / misaligned */
 #define SMOS_EUNSUPPORTED (-2) /* valid request the library does not implement */
 
-#define SMOS_ABI_VERSION 1
+#define SMOS_ABI_VERSION 2
 
 int smos_abi_version(void);
 const char* smos_error_string(int code);
+
+/* Identity of the CUDA-graph capture `stream` is currently part of (cudaStreamGetCaptureInfo): *id_host = 0 when
+ * the stream is not capturing, else the capture sequence's unique id. Host-side query, no synchronisation. The
+ * Python plan cache uses it so that a pooling plan built eagerly is never baked into a graph (and vice versa). */
+int smos_stream_capture_id(void* stream, uint64_t* id_host);
 
 /* ------------------------------------------------------------------------- */
 /* (A1) VoxelMaxPool — scatter-max of point features into a dense 2-D grid.   */
@@ -86,6 +91,10 @@ typedef struct smos_pool_plan_desc {
   void* gather_taps; /* may be NULL; else smos_gather_taps_bytes(B, N) bytes, 16-byte aligned: the BilinearSample
                         sampling state of every point for THIS grid and scale (networks/backbone.py:458-475), one
                         48-byte record per slot of the plan's cell order, for smos_bilinear_gather_forward_taps */
+  const float* scale_dev; /* may be NULL; else two float32 ON THE DEVICE that override scale_h / scale_w: the
+                             reference hands `scale_rate` to point_deep.cuda_kernel as a device tensor
+                             (deep_point/__init__.py:31, point_deep_cuda.cpp:22-37) — reading it on the device
+                             avoids a device->host copy and its synchronisation */
 } smos_pool_plan_desc;
 
 int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n, void* stream);
@@ -278,7 +287,7 @@ int smos_quantize(const float* pcds, int64_t P, int64_t row_stride,
                   float min_x, float min_y, float min_z,
                   float dx, float dy, float dz, float* out, void* stream);
 
-/* Bytes of scratch for smos_vote_voxel_labels. */
+/* Bytes of scratch for smos_vote_voxel_labels / smos_vote_fused / smos_vote_stream. */
 int64_t smos_vote_workspace_bytes(int64_t P, int32_t X, int32_t Y, int32_t Z, int32_t num_classes);
 
 /* determine_voxel_labels (voxel_voting.py:55-75): per-voxel class histogram over
@@ -338,6 +347,18 @@ int smos_vote_stream(const smos_vote_stream_scan* scans_host, int32_t n_scans, i
 int smos_memory_push(const float* points, const uint8_t* pred, int64_t n, int64_t row_floats,
                      float* cur_points, uint8_t* cur_pred, float* hist_points, uint8_t* hist_pred, void* stream);
 
+/* Staging for the reference's int64 voting API, one kernel (voxel_voting.py:234-241): for every point of the
+ * long-term memory ring, q = Quantize(point) (float32, as smos_quantize), coords = q.to(int64) (truncation) and
+ * labels = pred.to(int64) — the three tensors the script builds with Quantize and two `.to(torch.int64)` casts.
+ * Optionally performs smos_memory_push on the way (new_points / new_pred non-NULL): the scan in slot `cur_slot`
+ * moves to `hist_slot` (skipped if hist_slot < 0) and the new scan takes `cur_slot`, before anything is quantised.
+ *   ring_points (n_slots, n, row_floats) f32, ring_pred (n_slots, n) u8, slot major, updated in place when pushing
+ *   q_out (n_slots*n, 3) f32 or NULL ; coords_out (n_slots*n, 3) int64 ; labels_out (n_slots*n) int64 */
+int smos_vote_stage(float* ring_points, uint8_t* ring_pred, int32_t n_slots, int64_t n, int64_t row_floats,
+                    const float* new_points, const uint8_t* new_pred, int32_t cur_slot, int32_t hist_slot,
+                    float min_x, float min_y, float min_z, float dx, float dy, float dz,
+                    float* q_out, int64_t* coords_out, int64_t* labels_out, void* stream);
+
 /* Per-instance vote count (voxel_instance_voting.py:169-187, in_hull :62-76):
  * for each of K axis-aligned boxes count local-map points inside (inclusive
  * lo <= p <= hi) with prediction 1 (weight 1) and prediction 2 (weight 2).
@@ -355,6 +376,15 @@ int smos_instance_vote(const float* points, int64_t P, int64_t row_stride,
 int smos_instance_vote_counted(const float* points, int64_t P, int64_t row_stride,
                                const int64_t* pred, const float* box_lo, const float* box_hi,
                                int32_t K_cap, const int32_t* K_dev, int64_t* sums, void* stream);
+
+/* Same vote without a zero-filled output: the CTAs accumulate into `workspace` (smos_instance_vote_workspace_bytes(K_cap)
+ * bytes, 8-byte aligned, ZERO before its first use; every call leaves it zero again, so a stream can own one for its
+ * lifetime) and the last CTA to finish writes sums (K_cap, 2) — every element, no pre-fill. K_dev may be NULL (K = K_cap).
+ * Calls that share a workspace must be ordered on one stream. */
+int64_t smos_instance_vote_workspace_bytes(int32_t K);
+int smos_instance_vote_ws(const float* points, int64_t P, int64_t row_stride,
+                          const int64_t* pred, const float* box_lo, const float* box_hi,
+                          int32_t K_cap, const int32_t* K_dev, void* workspace, int64_t* sums, void* stream);
 
 /* Instance clustering — cluster() of voxel_instance_voting.py:144-175 up to the vote block:
  * foreground = points with pred_bf == 2 (:145), DBSCAN(eps, min_samples) over their xyz (:150-153; scikit-learn's

@@ -16,7 +16,7 @@ class PoolPlanDesc(ctypes.Structure):
     """struct smos_pool_plan_desc (include/streammos_b200.h)."""
     _fields_ = [("pcds_ind", _vp), ("B", _i64), ("N", _i64), ("ind_sb", _i64), ("ind_sn", _i64), ("ind_sd", _i64),
                 ("H", _i32), ("W", _i32), ("scale_h", _f32), ("scale_w", _f32), ("voxel_max_idx", _vp),
-                ("idx_batch_stride", _i64), ("plan", _vp), ("gather_taps", _vp)]
+                ("idx_batch_stride", _i64), ("plan", _vp), ("gather_taps", _vp), ("scale_dev", _vp)]
 
 
 class VoteStreamScan(ctypes.Structure):
@@ -29,6 +29,7 @@ class VoteStreamScan(ctypes.Structure):
 SIGNATURES = {
     "smos_abi_version": (ctypes.c_int, []),
     "smos_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "smos_stream_capture_id": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "smos_pool_plan_bytes": (_i64, [_i64, _i64, _i32, _i32]),
     "smos_pool_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "smos_pool_plan_build": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _f32, _f32, _vp, _i64,
@@ -68,15 +69,20 @@ SIGNATURES = {
     "smos_point_stem_forward_raw": (ctypes.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32,
                                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64,
                                                    _vp]),
+    "smos_vote_stage": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32,
+                                       _vp, _vp, _vp, _vp]),
     "smos_memory_push": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "smos_instance_vote": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
     "smos_instance_vote_counted": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "smos_instance_vote_workspace_bytes": (_i64, [_i32]),
+    "smos_instance_vote_ws": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "smos_cluster_workspace_bytes": (ctypes.c_int64, [_i64]),
     "smos_cluster_boxes": (ctypes.c_int, [_vp, _i64, _i64, _vp, ctypes.c_double, _i32, _i32, ctypes.c_float, _vp,
                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "smos_cluster_apply": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
+ABI_VERSION = 2  # SMOS_ABI_VERSION of include/streammos_b200.h
 _lib = None
 
 
@@ -94,7 +100,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.smos_abi_version() != 1:
+    if lib.smos_abi_version() != ABI_VERSION:
         raise RuntimeError("streammos_b200: ABI version mismatch")
     _lib = lib
     return lib

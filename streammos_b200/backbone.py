@@ -28,9 +28,16 @@ class BilinearSample(nn.Module):
     """forward(grid_feat (BS, C, H, W), grid_coord (BS, N, 2, S)) -> pc_feat (BS, C, N, S).
 
     `point_major_out=True` returns the same values in channels_last strides (each point's C features
-    contiguous) — the layout VoxelMaxPool consumes fastest; shapes and values are unchanged."""
+    contiguous) — the layout VoxelMaxPool consumes fastest; shapes and values are unchanged.
+
+    `auto_order`: with the reference signature (no `order=`) the points are visited in the cell order of the pooling
+    plan of (grid_coord, this grid's (H, W), scale_rate), taken from the plan cache — in the reference's cascade every
+    gather samples the grid a pooling call with exactly these coordinates, size and scale wrote or will write
+    (multi_view_encoder.py:395-417, StreamMOS.py:105), so the plan exists already or is built here for the pool that
+    follows. Same values, fewer cache lines per warp load."""
 
     point_major_out = False
+    auto_order = True
 
     def __init__(self, in_dim, scale_rate):
         super(BilinearSample, self).__init__()
@@ -39,6 +46,10 @@ class BilinearSample(nn.Module):
     def forward(self, grid_feat, grid_coord, order=None):
         """Reference signature plus an optional `order` (an ops.PoolPlan of the same coordinates, e.g. the one the
         neighbouring VoxelMaxPool uses): the points are then visited in cell order — same values, faster."""
+        if order is None and self.auto_order and self.point_major_out and grid_coord.is_cuda and \
+                grid_coord.dim() == 4 and grid_coord.size(3) == 1 and grid_coord.size(2) == 2 and \
+                grid_coord.dtype == torch.float32:
+            order = ops.cached_pool_plan(grid_coord, tuple(grid_feat.shape[2:]), tuple(self.scale_rate))
         return _BilinearSampleFunction.apply(grid_feat.float(), grid_coord, tuple(self.scale_rate),
                                              bool(self.point_major_out), order)
 

@@ -13,4 +13,14 @@ const char* smos_error_string(int code) {
   return "streammos_b200: unknown error";
 }
 
+int smos_stream_capture_id(void* stream, uint64_t* id_host) {
+  if (id_host == nullptr) return SMOS_EINVAL;
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  const cudaError_t e = cudaStreamGetCaptureInfo(smos_stream(stream), &status, &id);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  *id_host = status == cudaStreamCaptureStatusActive ? static_cast<uint64_t>(id) : 0;
+  return SMOS_OK;
+}
+
 }  // extern "C"

@@ -77,6 +77,7 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
                              float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
                              const int2* __restrict__ order, int32_t order_hw, int64_t order_len,
                              const TapsS* __restrict__ taps) {
+  SMOS_PDL_PROLOGUE();
   __shared__ TapsS s_taps[kGatherPts];
   extern __shared__ __align__(16) float s_out[];  // ROWS_OUT: [kGatherPts][C + 4]
   const int32_t n0 = blockIdx.x * kGatherPts;
@@ -165,6 +166,7 @@ gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H,
                            float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
                            const int2* __restrict__ order, int32_t order_hw, int64_t order_len,
                            const TapsS* __restrict__ taps) {
+  SMOS_PDL_PROLOGUE();
   __shared__ TapsS s_taps[kGatherPts];
   const int32_t n0 = blockIdx.x * kGatherPts;
   cta_taps<ORDERED, TAPS>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len,
@@ -210,11 +212,15 @@ gather_backward_kernel(const float* __restrict__ gout, int32_t C, int32_t N, int
                        int64_t go_sb, int64_t go_sc, int64_t go_sn, const float* __restrict__ coord,
                        int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
                        int32_t H, int32_t W, float* __restrict__ ggrid, int fast_n) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool valid = i < total;
   float v_nw = 0.f, v_ne = 0.f, v_sw = 0.f, v_se = 0.f;
   bool in_nw = false, in_ne = false, in_sw = false, in_se = false;
   float* g = nullptr;
+  // run key: (b, c, y0, x0) spelled out — the tap ADDRESS alone is not injective once x0 is clamped to [-2, W+1]
+  // ((y0, -1) aliases (y0 - 1, W - 1)), and lanes merged across such an alias would share the head's in-image flags
+  unsigned long long key = 0xffffffffffffff00ull | static_cast<unsigned>(threadIdx.x & 31);
   if (valid) {
     const int64_t cn = static_cast<int64_t>(C) * N;
     const int32_t b = static_cast<int32_t>(i / cn);
@@ -228,12 +234,12 @@ gather_backward_kernel(const float* __restrict__ gout, int32_t C, int32_t N, int
     g = ggrid + ((static_cast<int64_t>(b) * C + c) * H + t.y0) * W + t.x0;
     v_nw = go * t.w_nw; v_ne = go * t.w_ne; v_sw = go * t.w_sw; v_se = go * t.w_se;
     in_nw = t.in_nw; in_ne = t.in_ne; in_sw = t.in_sw; in_se = t.in_se;
+    key = (static_cast<unsigned long long>(static_cast<uint32_t>(b) * static_cast<uint32_t>(C) + static_cast<uint32_t>(c)) << 32) |
+          static_cast<uint32_t>((t.y0 + 2) * (W + 4) + (t.x0 + 2));
   }
   if (fast_n) {  // uniform: every lane of the warp takes part in the shuffles
     const int lane = threadIdx.x & 31;
-    // equal address <=> equal (b, c, y0, x0) <=> equal in-image flags; the products are each lane's own
-    const unsigned long long key = valid ? static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(g))
-                                         : (0xffffffffffffff00ull | static_cast<unsigned>(lane));
+    // equal key <=> equal (b, c, y0, x0) <=> equal in-image flags; the products are each lane's own
     const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
     const bool head = lane == 0 || key != prev;
     const unsigned heads = __ballot_sync(0xffffffffu, head);
@@ -278,15 +284,15 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
   const int32_t Ni = static_cast<int32_t>(N), Ci = static_cast<int32_t>(C);
   if (nhwc) {
     if (with_taps)
-      gather_forward_nhwc_kernel<true, true><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
+      SMOS_LAUNCH((gather_forward_nhwc_kernel<true, true>), g, kGatherThreads, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
                                                                             co_sb, co_sn, co_sd, scale_h, scale_w, out,
                                                                             o_sb, o_sc, o_sn, order, order_hw, order_len, taps);
     else if (ordered)
-      gather_forward_nhwc_kernel<true, false><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
+      SMOS_LAUNCH((gather_forward_nhwc_kernel<true, false>), g, kGatherThreads, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
                                                                              co_sb, co_sn, co_sd, scale_h, scale_w, out,
                                                                              o_sb, o_sc, o_sn, order, order_hw, order_len, nullptr);
     else
-      gather_forward_nhwc_kernel<false, false><<<g, kGatherThreads, 0, st>>>(grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord,
+      SMOS_LAUNCH((gather_forward_nhwc_kernel<false, false>), g, kGatherThreads, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord,
                                                                               Ni, co_sb, co_sn, co_sd, scale_h, scale_w, out,
                                                                               o_sb, o_sc, o_sn, nullptr, 1, 0, nullptr);
   } else {
@@ -297,7 +303,7 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
     const size_t smem = rows_out ? static_cast<size_t>(C + 4) * kGatherPts * 4 : 0;
     const bool dense = (gr_sw == 1 && gr_sh == W);
 #define SMOS_LAUNCH_PLANAR(D, R, O, T)                                                                       \
-    gather_forward_planar_kernel<D, R, O, T><<<g, kGatherThreads, smem, st>>>(                                 \
+    SMOS_LAUNCH((gather_forward_planar_kernel<D, R, O, T>), g, kGatherThreads, smem, st,                                  \
         grid, Ci, H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, Ni, co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb, \
         o_sc, o_sn, order, order_hw, order_len, taps)
     if (with_taps) {
@@ -374,7 +380,7 @@ int smos_bilinear_gather_backward(const float* grad_out, int64_t B, int64_t C, i
     return smos_launch_status();
   const int64_t total = B * C * N;
   const int fast_n = (go_sc == 1 && C > 1) ? 0 : 1;
-  gather_backward_kernel<<<smos_ceil_div(total, 256), 256, 0, smos_stream(stream)>>>(
+  SMOS_LAUNCH((gather_backward_kernel), smos_ceil_div(total, 256), 256, 0, smos_stream(stream), 
       grad_out, static_cast<int32_t>(C), static_cast<int32_t>(N), total, go_sb, go_sc, go_sn, coord, co_sb, co_sn,
       co_sd, scale_h, scale_w, H, W, grad_grid, fast_n);
   return smos_launch_status();

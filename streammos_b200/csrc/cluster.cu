@@ -31,8 +31,9 @@ struct ClusterWs {
   float4* xyz;        // [n] foreground points (x, y, z, -)
   int32_t* nnb;       // [n] neighbour count (the point itself included); core = nnb >= min_samples
   int32_t* minlab;    // [n] smallest cluster id among the core neighbours of a non-core point
-  int32_t* parent;    // [n] union-find over core points
-  int32_t* rootlab;   // [n] cluster id of a root
+  int32_t* parent;    // [n] union-find over core points (only the union sweep writes it)
+  int32_t* rootof;    // [n] root of a core point, written once the unions are complete (never touched by cl_find)
+  int32_t* rootlab;   // [n] cluster id of a root, -1 elsewhere
   int32_t* cl_cnt;    // [n] points per cluster
   int32_t* cl_min;    // [3n] ordered-int keys of the per-cluster minima
   int32_t* cl_max;    // [3n]
@@ -51,6 +52,7 @@ inline int64_t cluster_ws_layout(int64_t n, char* base, ClusterWs* w) {
   t.nnb = reinterpret_cast<int32_t*>(take(n * 4));
   t.minlab = reinterpret_cast<int32_t*>(take(n * 4));
   t.parent = reinterpret_cast<int32_t*>(take(n * 4));
+  t.rootof = reinterpret_cast<int32_t*>(take(n * 4));
   t.rootlab = reinterpret_cast<int32_t*>(take(n * 4));
   t.cl_cnt = reinterpret_cast<int32_t*>(take(n * 4));
   t.cl_min = reinterpret_cast<int32_t*>(take(n * 12));
@@ -103,6 +105,7 @@ __device__ __forceinline__ int cl_blocks_before(const int32_t* __restrict__ blk,
 // ---- foreground selection (voxel_instance_voting.py:145-148): indices where pred_bf == 2, ascending ----------
 __global__ void __launch_bounds__(kClThreads)
 cl_fg_count_kernel(const int32_t* __restrict__ bf, int64_t n, ClusterWs w) {
+  SMOS_PDL_PROLOGUE();
   __shared__ int s_warp[kClWarps];
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kClThreads + threadIdx.x;
   if (i < n) {  // per-cluster accumulators, reset for this call
@@ -113,6 +116,8 @@ cl_fg_count_kernel(const int32_t* __restrict__ bf, int64_t n, ClusterWs w) {
     w.nnb[i] = 0;
     w.minlab[i] = 0x7fffffff;
     w.parent[i] = static_cast<int32_t>(i);
+    w.rootof[i] = static_cast<int32_t>(i);
+    w.rootlab[i] = -1;
   }
   int total;
   cl_block_scan(i < n && bf[i] == 2, s_warp, &total);
@@ -123,6 +128,7 @@ __global__ void __launch_bounds__(kClThreads)
 cl_fg_write_kernel(const int32_t* __restrict__ bf, const float* __restrict__ pts, int64_t n, int64_t rs,
                    ClusterWs w, int32_t* __restrict__ fg_index, int32_t* __restrict__ fg_label,
                    int32_t* __restrict__ counts) {
+  SMOS_PDL_PROLOGUE();
   __shared__ int s_warp[kClWarps];
   const int base = cl_blocks_before(w.blk, s_warp);
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kClThreads + threadIdx.x;
@@ -167,6 +173,16 @@ __device__ __forceinline__ int cl_find(int32_t* parent, int x) {
   }
 }
 
+// Read-only walk to the root: for kernels that run after the union sweep, when parent[] no longer changes. No
+// path-halving stores, so concurrent readers of parent[] in the same launch always see a consistent forest.
+__device__ __forceinline__ int cl_find_ro(const int32_t* __restrict__ parent, int x) {
+  for (;;) {
+    const int a = parent[x];
+    if (a == x) return x;
+    x = a;
+  }
+}
+
 // Joins the sets of i and j. `ri` is the caller's running guess of i's root (an ancestor of i, kept in a register
 // across the neighbours of i): most neighbours of a point already hang under it, and one load of parent[j] settles
 // those without walking any chain. Returns the new guess.
@@ -193,6 +209,7 @@ constexpr int kClColSplit = 16;  // grid.y: column tiles are dealt round-robin t
 template <int MODE>
 __global__ void __launch_bounds__(kClThreads)
 cl_pairs_kernel(ClusterWs w, const int32_t* __restrict__ counts, float reject, double r2, int32_t min_samples) {
+  SMOS_PDL_PROLOGUE();
   __shared__ float4 s_q[kClThreads];
   __shared__ int32_t s_aux[kClThreads];
   const int M = counts[0];
@@ -230,7 +247,7 @@ cl_pairs_kernel(ClusterWs w, const int32_t* __restrict__ counts, float reject, d
     if (j < M) {
       s_q[threadIdx.x] = w.xyz[j];
       if (MODE == CL_UNION) s_aux[threadIdx.x] = w.nnb[j] >= min_samples;
-      if (MODE == CL_LABEL) s_aux[threadIdx.x] = w.nnb[j] >= min_samples ? w.rootlab[w.parent[j]] : -1;
+      if (MODE == CL_LABEL) s_aux[threadIdx.x] = w.nnb[j] >= min_samples ? w.rootlab[w.rootof[j]] : -1;
     }
     __syncthreads();
     if (!work) continue;
@@ -258,12 +275,14 @@ cl_pairs_kernel(ClusterWs w, const int32_t* __restrict__ counts, float reject, d
 __global__ void __launch_bounds__(kClThreads)
 cl_stats_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t min_samples,
                 int32_t* __restrict__ fg_label) {
+  SMOS_PDL_PROLOGUE();
   const int M = counts[0];
   const int i = blockIdx.x * kClThreads + threadIdx.x;
   if (i >= M) return;
   // core points: the id of their component; border points: the smallest id among core neighbours; else noise
   const int ml = w.minlab[i];
-  const int lab = w.nnb[i] >= min_samples ? w.rootlab[w.parent[i]] : (ml == 0x7fffffff ? -1 : ml);
+  int lab = w.nnb[i] >= min_samples ? w.rootlab[w.rootof[i]] : (ml == 0x7fffffff ? -1 : ml);
+  if (lab >= M) lab = -1;  // cannot happen (ids are ranks of roots); keeps the atomics below in bounds regardless
   fg_label[i] = lab;
   if (lab >= 0) {
     const float4 me = w.xyz[i];
@@ -278,14 +297,17 @@ cl_stats_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t min_sam
 __global__ void __launch_bounds__(kClThreads)
 cl_root_count_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t min_samples,
                      int32_t* __restrict__ blk) {
+  SMOS_PDL_PROLOGUE();
   __shared__ int s_warp[kClWarps];
   const int M = counts[0];
   const int i = blockIdx.x * kClThreads + threadIdx.x;
   bool root = false;
   if (i < M && w.nnb[i] >= min_samples) {
-    const int r = cl_find(w.parent, i);
+    // the forest is final here: a read-only walk, and the flattened root goes to its own array — storing it into
+    // parent[] would race with the walks of other threads of this launch
+    const int r = cl_find_ro(w.parent, i);
     root = r == i;
-    if (!root) w.parent[i] = r;  // flatten: the label kernel reads parent[j] directly
+    w.rootof[i] = r;
   }
   int total;
   cl_block_scan(root, s_warp, &total);
@@ -295,11 +317,12 @@ cl_root_count_kernel(ClusterWs w, const int32_t* __restrict__ counts, int32_t mi
 __global__ void __launch_bounds__(kClThreads)
 cl_root_label_kernel(ClusterWs w, int32_t* __restrict__ counts, int32_t min_samples,
                      const int32_t* __restrict__ blk) {
+  SMOS_PDL_PROLOGUE();
   __shared__ int s_warp[kClWarps];
   const int M = counts[0];
   const int base = cl_blocks_before(blk, s_warp);
   const int i = blockIdx.x * kClThreads + threadIdx.x;
-  const bool root = i < M && w.nnb[i] >= min_samples && w.parent[i] == i;
+  const bool root = i < M && w.nnb[i] >= min_samples && w.rootof[i] == i;
   int total;
   const int pos = base + cl_block_scan(root, s_warp, &total);
   if (root) w.rootlab[i] = pos;
@@ -310,6 +333,7 @@ cl_root_label_kernel(ClusterWs w, int32_t* __restrict__ counts, int32_t min_samp
 __global__ void __launch_bounds__(kClThreads)
 cl_boxes_kernel(ClusterWs w, int32_t* __restrict__ counts, int32_t min_points, float z_lift,
                 float* __restrict__ box_lo, float* __restrict__ box_hi, int32_t* __restrict__ kept_label) {
+  SMOS_PDL_PROLOGUE();
   __shared__ int s_warp[kClWarps];
   const int C = counts[1];
   int base = 0;
@@ -344,6 +368,7 @@ __global__ void __launch_bounds__(kClThreads)
 cl_apply_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ fg_index,
                 const int32_t* __restrict__ fg_label, const int32_t* __restrict__ slot,
                 const int64_t* __restrict__ sums, int64_t* __restrict__ pred) {
+  SMOS_PDL_PROLOGUE();
   const int M = counts[0];
   const int i = blockIdx.x * kClThreads + threadIdx.x;
   if (i >= M) return;
@@ -383,16 +408,16 @@ int smos_cluster_boxes(const float* points, int64_t n, int64_t row_stride, const
   const float reject = static_cast<float>(eps * 1.001);
   const double r2 = eps * eps;
   int32_t* blk_roots = w.blk + grid;
-  cl_fg_count_kernel<<<grid, kClThreads, 0, st>>>(pred_bf, n, w);
-  cl_fg_write_kernel<<<grid, kClThreads, 0, st>>>(pred_bf, points, n, row_stride, w, fg_index, fg_label, counts);
+  SMOS_LAUNCH((cl_fg_count_kernel), grid, kClThreads, 0, st, pred_bf, n, w);
+  SMOS_LAUNCH((cl_fg_write_kernel), grid, kClThreads, 0, st, pred_bf, points, n, row_stride, w, fg_index, fg_label, counts);
   const dim3 pgrid(grid, kClColSplit);
-  cl_pairs_kernel<CL_COUNT><<<pgrid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples);
-  cl_pairs_kernel<CL_UNION><<<pgrid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples);
-  cl_root_count_kernel<<<grid, kClThreads, 0, st>>>(w, counts, min_samples, blk_roots);
-  cl_root_label_kernel<<<grid, kClThreads, 0, st>>>(w, counts, min_samples, blk_roots);
-  cl_pairs_kernel<CL_LABEL><<<pgrid, kClThreads, 0, st>>>(w, counts, reject, r2, min_samples);
-  cl_stats_kernel<<<grid, kClThreads, 0, st>>>(w, counts, min_samples, fg_label);
-  cl_boxes_kernel<<<1, kClThreads, 0, st>>>(w, counts, min_cluster_points, z_lift, box_lo, box_hi, kept_label);
+  SMOS_LAUNCH((cl_pairs_kernel<CL_COUNT>), pgrid, kClThreads, 0, st, w, counts, reject, r2, min_samples);
+  SMOS_LAUNCH((cl_pairs_kernel<CL_UNION>), pgrid, kClThreads, 0, st, w, counts, reject, r2, min_samples);
+  SMOS_LAUNCH((cl_root_count_kernel), grid, kClThreads, 0, st, w, counts, min_samples, blk_roots);
+  SMOS_LAUNCH((cl_root_label_kernel), grid, kClThreads, 0, st, w, counts, min_samples, blk_roots);
+  SMOS_LAUNCH((cl_pairs_kernel<CL_LABEL>), pgrid, kClThreads, 0, st, w, counts, reject, r2, min_samples);
+  SMOS_LAUNCH((cl_stats_kernel), grid, kClThreads, 0, st, w, counts, min_samples, fg_label);
+  SMOS_LAUNCH((cl_boxes_kernel), 1, kClThreads, 0, st, w, counts, min_cluster_points, z_lift, box_lo, box_hi, kept_label);
   return smos_launch_status();
 }
 
@@ -403,7 +428,7 @@ int smos_cluster_apply(int64_t n, void* workspace, const int32_t* fg_index, cons
   if (!workspace || !fg_index || !fg_label || !counts || !sums || !pred) return SMOS_EINVAL;
   ClusterWs w;
   cluster_ws_layout(n, static_cast<char*>(workspace), &w);
-  cl_apply_kernel<<<smos_ceil_div(n, kClThreads), kClThreads, 0, smos_stream(stream)>>>(counts, fg_index, fg_label,
+  SMOS_LAUNCH((cl_apply_kernel), smos_ceil_div(n, kClThreads), kClThreads, 0, smos_stream(stream), counts, fg_index, fg_label,
                                                                                        w.slot, sums, pred);
   return smos_launch_status();
 }

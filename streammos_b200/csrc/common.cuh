@@ -7,13 +7,49 @@
 
 #include "../../include/streammos_b200.h"
 
-#define SMOS_SM_COUNT 148  // B200: 2 dies x 74 SMs
+#include <atomic>
+#include <utility>
+
+// SM count of the current device (B200: 148 = 2 dies x 74), queried once per device; thread safe.
+static inline int smos_sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool slot = dev >= 0 && dev < 64;
+  if (slot) {
+    const int v = cached[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
+  }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (slot) cached[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+#define SMOS_SM_COUNT smos_sm_count()
+
+// One-time opt-in of `kernel` to more than 48 KB of dynamic shared memory on the current device. `done` is one atomic
+// bit mask per kernel (bit = device index); concurrent host threads may both make the (idempotent) call, and devices
+// with an index >= 64 simply opt in on every launch.
+template <typename K>
+static inline cudaError_t smos_smem_opt_in(K kernel, std::atomic<unsigned long long>& done, int bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool slot = dev >= 0 && dev < 64;
+  if (slot && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && slot) done.fetch_or(1ull << dev, std::memory_order_release);
+  return e;
+}
 
 static inline cudaStream_t smos_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// Launch-error check that does not synchronise.
+// Launch-error check that does not synchronise. smos_launch_pdl records what cudaLaunchKernelEx returned (per host
+// thread and translation unit: a call launches and checks inside one .cu file).
+static thread_local cudaError_t smos_tls_launch_error = cudaSuccess;
 static inline int smos_launch_status() {
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = smos_tls_launch_error;
+  smos_tls_launch_error = cudaSuccess;
   return e == cudaSuccess ? SMOS_OK : static_cast<int>(e);
 }
 
@@ -22,6 +58,51 @@ static inline int smos_env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A scan is ~45 short dependent kernels on one stream; with plain launches each of them starts only after its
+// predecessor has drained AND the launch latency has passed. Every kernel of this library is launched with the
+// programmatic-stream-serialization attribute and begins with SMOS_PDL_PROLOGUE():
+//   griddepcontrol.launch_dependents  lets the NEXT kernel's CTAs be scheduled as soon as all of this kernel's CTAs
+//                                     have started (they fill the SMs this kernel's tail leaves idle);
+//   griddepcontrol.wait               blocks until the PREVIOUS kernel has completed and its writes are visible.
+// The wait comes before any global-memory access and before any early return, so a kernel never completes before
+// its predecessor: completion stays transitive along the stream and read-after-write as well as write-after-read
+// hazards are ordered exactly as with plain launches. What overlaps is launch latency, CTA scheduling and each
+// kernel's prologue. Works under stream capture (programmatic edges in the CUDA graph). SMOS_PDL=0 (read once)
+// falls back to plain launches.
+__device__ __forceinline__ void smos_pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#define SMOS_PDL_PROLOGUE() smos_pdl_prologue()
+
+static inline bool smos_pdl_enabled() {
+  static const bool on = smos_env_int("SMOS_PDL", 1) != 0;
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t smos_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = smos_pdl_enabled() ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (e != cudaSuccess) smos_tls_launch_error = e;
+  return e;
+}
+// SMOS_LAUNCH((kernel<T...>), grid, block, dynamic_smem_bytes, stream, args...) — errors surface through
+// smos_launch_status() (cudaGetLastError) as with <<<>>>
+#define SMOS_LAUNCH(kern, grid, block, smem, st, ...) \
+  ((void)smos_launch_pdl(kern, dim3(grid), dim3(block), static_cast<size_t>(smem), st, __VA_ARGS__))
 
 static inline int64_t smos_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -103,6 +184,7 @@ static inline PoolLayout smos_pool_layout(int64_t B, int64_t N, int32_t H, int32
 // the voting call (it is not a kernel ncu lists); 128-bit stores from a grid sized to the SM count run at the
 // HBM write rate.
 static __global__ void __launch_bounds__(256) smos_zero_kernel(uint4* __restrict__ p, int64_t n16) {
+  SMOS_PDL_PROLOGUE();
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < n16;
        i += static_cast<int64_t>(gridDim.x) * 256)
@@ -116,6 +198,6 @@ static inline cudaError_t smos_zero_async(void* p, size_t bytes, cudaStream_t st
   int64_t blocks = (n16 + 255) / 256;
   const int64_t cap = static_cast<int64_t>(SMOS_SM_COUNT) * 16;
   if (blocks > cap) blocks = cap;
-  smos_zero_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<uint4*>(p), n16);
+  SMOS_LAUNCH((smos_zero_kernel), static_cast<unsigned>(blocks), 256, 0, st, static_cast<uint4*>(p), n16);
   return cudaGetLastError();
 }

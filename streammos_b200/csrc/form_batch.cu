@@ -17,6 +17,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 form_batch_kernel(const float* __restrict__ pts, int64_t total, int64_t N, int64_t rs, float sx, float sy, float mx,
                   float my, float mz, float dx, float dy, float dz, float* __restrict__ feat, float* __restrict__ coord) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total) return;
   const float* p = pts + i * rs;
@@ -53,7 +54,7 @@ extern "C" int smos_form_batch(const float* points, int64_t T, int64_t N, int64_
   if (N == 0) return SMOS_OK;
   if (!points || !pcds_xyzi || !pcds_coord) return SMOS_EINVAL;
   const int64_t total = T * N;
-  form_batch_kernel<<<smos_ceil_div(total, 256), 256, 0, smos_stream(stream)>>>(
+  SMOS_LAUNCH((form_batch_kernel), smos_ceil_div(total, 256), 256, 0, smos_stream(stream), 
       points, total, N, row_stride, x_sign, y_sign, min_x, min_y, min_z, dx, dy, dz, pcds_xyzi, pcds_coord);
   return smos_launch_status();
 }

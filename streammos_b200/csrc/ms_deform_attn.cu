@@ -47,6 +47,7 @@ msda_forward_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
                     const int64_t* __restrict__ lsi, const T* __restrict__ loc,
                     const T* __restrict__ attn, int32_t S, int32_t M, int32_t D, int32_t L,
                     int32_t Q, int32_t P, int64_t n_groups, int32_t lpg, T* __restrict__ out) {
+  SMOS_PDL_PROLOGUE();
   // I = int32_t when every tensor has < 2^31 elements (always true for StreamMOS): halves the integer
   // instruction count of the address arithmetic, which dominated this latency-bound kernel
   const I tid = static_cast<I>(blockIdx.x) * kMsdaThreads + threadIdx.x;
@@ -126,6 +127,7 @@ msda_backward_kernel(const T* __restrict__ gout, const T* __restrict__ value,
                      const T* __restrict__ loc, const T* __restrict__ attn, int32_t S, int32_t M,
                      int32_t D, int32_t L, int32_t Q, int32_t P, int64_t n_groups, int32_t lpg,
                      T* __restrict__ gvalue, T* __restrict__ gloc, T* __restrict__ gattn) {
+  SMOS_PDL_PROLOGUE();
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * kMsdaThreads + threadIdx.x;
   const int64_t grp = tid / lpg;
   const int32_t gl = static_cast<int32_t>(tid - grp * lpg);
@@ -201,7 +203,7 @@ int forward_impl(const void* value, const int64_t* shapes, const int64_t* lsi, c
   const bool idx32 = static_cast<int64_t>(B) * S * M * D < (int64_t(1) << 31) &&
                      threads + kMsdaThreads < (int64_t(1) << 31) && n_groups * L * P * 2 < (int64_t(1) << 31);
 #define SMOS_MSDA_FWD(V, I)                                                                                         \
-  msda_forward_kernel<T, V, I><<<grid, kMsdaThreads, 0, st>>>(                                                       \
+  SMOS_LAUNCH((msda_forward_kernel<T, V, I>), grid, kMsdaThreads, 0, st,                                                        \
       static_cast<const T*>(value), shapes, lsi, static_cast<const T*>(loc), static_cast<const T*>(attn), S, M, D, L, \
       Q, P, n_groups, lpg, static_cast<T*>(out))
   if (vec && idx32) SMOS_MSDA_FWD(4, int32_t);
@@ -219,7 +221,7 @@ int backward_impl(const void* value, const int64_t* shapes, const int64_t* lsi, 
   const int64_t n_groups = static_cast<int64_t>(B) * Q * M;
   const int32_t lpg = pick_lpg(D);
   const int64_t threads = n_groups * lpg;
-  msda_backward_kernel<T><<<smos_ceil_div(threads, kMsdaThreads), kMsdaThreads, 0, st>>>(
+  SMOS_LAUNCH((msda_backward_kernel<T>), smos_ceil_div(threads, kMsdaThreads), kMsdaThreads, 0, st, 
       static_cast<const T*>(gout), static_cast<const T*>(value), shapes, lsi, static_cast<const T*>(loc),
       static_cast<const T*>(attn), S, M, D, L, Q, P, n_groups, lpg, static_cast<T*>(gvalue), static_cast<T*>(gloc),
       static_cast<T*>(gattn));

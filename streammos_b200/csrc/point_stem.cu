@@ -79,6 +79,7 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
                   const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ w2,
                   const float* __restrict__ a2, const float* __restrict__ b2, float* __restrict__ y, int64_t y_sb,
                   int64_t y_sc) {
+  SMOS_PDL_PROLOGUE();
   extern __shared__ __align__(16) unsigned char stem_raw[];
   using Smem = typename std::conditional<TC, StemSmemTC, StemSmem>::type;
   Smem& S = *reinterpret_cast<Smem*>(stem_raw);
@@ -303,21 +304,16 @@ static int stem_launch(const float* x, int64_t B, int32_t Cin, int64_t N, int64_
   do {                                                                                                                \
     auto kern = point_stem_kernel<CINV, RAWV, TCV>;                                                                   \
     const size_t smem = TCV ? sizeof(StemSmemTC) : sizeof(StemSmem);                                                   \
-    static bool opt_in[64] = {};                                                                                      \
-    int device = 0;                                                                                                   \
-    cudaGetDevice(&device);                                                                                           \
-    if (device >= 0 && device < 64 && !opt_in[device]) {                                                              \
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-      if (e != cudaSuccess) return static_cast<int>(e);                                                               \
-      opt_in[device] = true;                                                                                          \
-    }                                                                                                                 \
+    static std::atomic<unsigned long long> opted{0};                                                                  \
+    if (cudaError_t e = smos_smem_opt_in(kern, opted, static_cast<int>(smem)); e != cudaSuccess)                      \
+      return static_cast<int>(e);                                                                                     \
     /* persistent CTAs, one wave, walking the 128-point tiles with a grid stride */                                   \
     int per_sm = 0;                                                                                                   \
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStemThreads, smem) != cudaSuccess || per_sm < 1) \
       per_sm = 1;                                                                                                     \
     const int64_t want = static_cast<int64_t>(SMOS_SM_COUNT) * per_sm;                                                \
     dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));                                                  \
-    kern<<<grid, kStemThreads, smem, st>>>(x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha,   \
+    SMOS_LAUNCH((kern), grid, kStemThreads, smem, st, x, Cin, Ni, Bi, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha,   \
                                            bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc);                          \
   } while (0)
   if (is_raw) { if (tc) SMOS_STEM_LAUNCH(7, true, true); else SMOS_STEM_LAUNCH(7, true, false); }

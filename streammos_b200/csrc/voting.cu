@@ -20,20 +20,60 @@ constexpr int kMaxClasses = 64;
 
 bool use_packed(int64_t P, int32_t num_classes) { return num_classes <= 3 && P <= kPackMaxPoints; }
 
+// Packed counters of one voxel: three 21-bit fields at bits 1 / 22 / 43 holding the votes of class 2 / 1 / 0; bit 0 is
+// never set. A non-empty counter word is therefore even and >= 2, and the only one that is <= 2 is "one vote for
+// class 2", whose value (2) equals its own label: for the int64 label grid of the reference API (where the label slot
+// itself is the counter) a word <= 2 is always a valid final label, and a word > 2 is a counter still to be converted
+// — which makes the per-point conversion pass below idempotent and free of read/write hazards.
+__device__ __forceinline__ int vote_shift(int lab) { return 1 + kPackBits * (2 - lab); }
+
+__device__ __forceinline__ unsigned long long packed_argmax(unsigned long long w) {
+  const unsigned c2 = static_cast<unsigned>((w >> 1) & kPackMask);
+  const unsigned c1 = static_cast<unsigned>((w >> (1 + kPackBits)) & kPackMask);
+  const unsigned c0 = static_cast<unsigned>((w >> (1 + 2 * kPackBits)) & kPackMask);
+  unsigned long long best = 0ull;  // ties -> lowest class, empty -> 0 (torch.argmax)
+  unsigned bv = c0;
+  if (c1 > bv) { bv = c1; best = 1ull; }
+  if (c2 > bv) { bv = c2; best = 2ull; }
+  return best;
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kVoteThreads)
 vote_i64_kernel(const int64_t* __restrict__ coords, const int64_t* __restrict__ labels, int64_t P,
-                int32_t X, int32_t Y, int32_t Z, int32_t C, int packed, void* __restrict__ ws) {
+                int32_t X, int32_t Y, int32_t Z, int32_t C, int packed, void* __restrict__ ws,
+                uint32_t* __restrict__ lin_out) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   if (i >= P) return;
   const int64_t x = coords[i * 3], y = coords[i * 3 + 1], z = coords[i * 3 + 2];
   const int64_t lab = labels[i];
-  if (x < 0 || x >= X || y < 0 || y >= Y || z < 0 || z >= Z || lab < 0 || lab >= C) return;
-  const int64_t lin = (x * Y + y) * Z + z;
+  const bool ok = !(x < 0 || x >= X || y < 0 || y >= Y || z < 0 || z >= Z || lab < 0 || lab >= C);
+  const int64_t lin = ok ? (x * Y + y) * Z + z : -1;
+  if (lin_out != nullptr) lin_out[i] = static_cast<uint32_t>(lin);  // 0xffffffff: no vote
+  if (!ok) return;
   if (packed)
-    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << (kPackBits * static_cast<int>(lab)));
+    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << vote_shift(static_cast<int>(lab)));
   else
     atomicAdd(static_cast<unsigned int*>(ws) + lin * C + lab, 1u);
+}
+
+// Conversion of the voted slots of the int64 label grid, one thread per POINT instead of a pass over the whole grid
+// (63 MB for 512 x 512 x 30): a slot holding a counter word (> 2) becomes its label. Several points of one voxel may
+// convert it concurrently — they all compute the same label from the same final counts (the vote kernel has
+// completed) — and a point that finds a word <= 2 has nothing to do.
+__global__ void __launch_bounds__(kVoteThreads)
+vote_convert_points_kernel(const uint32_t* __restrict__ lin_in, int64_t P, unsigned long long* __restrict__ slots) {
+  SMOS_PDL_PROLOGUE();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= P) return;
+  const uint32_t lin = __ldg(lin_in + i);
+  if (lin == 0xffffffffu) return;
+  // adjacent points mostly share a voxel: one lane per run of equal voxels does the work
+  const uint32_t prev = __shfl_up_sync(__activemask(), lin, 1);
+  if ((threadIdx.x & 31) != 0 && prev == lin) return;
+  const unsigned long long w = __ldcg(slots + lin);
+  if (w > 2ull) slots[lin] = packed_argmax(w);
 }
 
 __device__ __forceinline__ float quant(float v, float lo, float d) { return __fdiv_rn(__fsub_rn(v, lo), d); }
@@ -54,13 +94,14 @@ __global__ void __launch_bounds__(kVoteThreads)
 vote_fused_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const uint8_t* __restrict__ labels,
                   float mx, float my, float mz, float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z,
                   int32_t C, int packed, void* __restrict__ ws) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   if (i >= P) return;
   const int lab = labels[i];
   int64_t lin;
   if (lab >= C || !quant_voxel(pts + i * rs, mx, my, mz, dx, dy, dz, X, Y, Z, &lin)) return;
   if (packed)
-    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << (kPackBits * lab));
+    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << vote_shift(lab));
   else
     atomicAdd(static_cast<unsigned int*>(ws) + lin * C + lab, 1u);
 }
@@ -69,19 +110,13 @@ vote_fused_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const ui
 template <typename OutT>
 __global__ void __launch_bounds__(kVoteThreads)
 vote_argmax_kernel(const void* __restrict__ ws, int64_t V, int32_t C, int packed, OutT* __restrict__ out) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   if (i >= V) return;
   int best = 0;
   if (packed) {
     const unsigned long long w = static_cast<const unsigned long long*>(ws)[i];
-    if (w != 0ull) {
-      const unsigned c0 = static_cast<unsigned>(w & kPackMask);
-      const unsigned c1 = static_cast<unsigned>((w >> kPackBits) & kPackMask);
-      const unsigned c2 = static_cast<unsigned>((w >> (2 * kPackBits)) & kPackMask);
-      unsigned bv = c0;
-      if (c1 > bv) { bv = c1; best = 1; }
-      if (c2 > bv) { bv = c2; best = 2; }
-    }
+    if (w != 0ull) best = static_cast<int>(packed_argmax(w));
   } else {
     const unsigned int* r = static_cast<const unsigned int*>(ws) + i * C;
     unsigned bv = r[0];
@@ -93,23 +128,11 @@ vote_argmax_kernel(const void* __restrict__ ws, int64_t V, int32_t C, int packed
   out[i] = static_cast<OutT>(best);
 }
 
-// In-place variant for the int64 label grid of the reference API: the 8-byte label slots themselves are the packed
-// counters (zero-filled, voted into with RED), and this pass turns every non-empty slot into its label. Empty
-// voxels already hold label 0 and are not written again: 63 MB read + a few MB written instead of a separate
-// 63 MB counter array (memset + read) plus a 63 MB label write.
-__device__ __forceinline__ unsigned long long packed_argmax(unsigned long long w) {
-  const unsigned c0 = static_cast<unsigned>(w & kPackMask);
-  const unsigned c1 = static_cast<unsigned>((w >> kPackBits) & kPackMask);
-  const unsigned c2 = static_cast<unsigned>((w >> (2 * kPackBits)) & kPackMask);
-  unsigned long long best = 0ull;
-  unsigned bv = c0;
-  if (c1 > bv) { bv = c1; best = 1ull; }
-  if (c2 > bv) { bv = c2; best = 2ull; }
-  return best;
-}
-
+// Dense in-place variant (grids with more than 2^32 - 2 voxels, where the per-point pass has no 32-bit voxel index):
+// one pass over the int64 label grid turns every non-empty counter word into its label.
 __global__ void __launch_bounds__(kVoteThreads)
 vote_argmax_inplace_kernel(unsigned long long* __restrict__ slots, int64_t V) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x) * 2;
   if (i >= V) return;
   if (i + 1 < V && (reinterpret_cast<uintptr_t>(slots) & 15) == 0) {
@@ -117,7 +140,7 @@ vote_argmax_inplace_kernel(unsigned long long* __restrict__ slots, int64_t V) {
     if ((w.x | w.y) == 0ull) return;
     w.x = packed_argmax(w.x);
     w.y = packed_argmax(w.y);
-    *reinterpret_cast<ulonglong2*>(slots + i) = w;
+    *reinterpret_cast<ulonglong2*>(slots + i) = w;  // (packed_argmax of 0 is 0)
   } else {
     for (int64_t k = i; k < V && k < i + 2; ++k) {
       const unsigned long long w = slots[k];
@@ -129,6 +152,7 @@ vote_argmax_inplace_kernel(unsigned long long* __restrict__ slots, int64_t V) {
 __global__ void __launch_bounds__(kVoteThreads)
 point_labels_i64_kernel(const int64_t* __restrict__ coords, int64_t Pc, const int64_t* __restrict__ vlabels,
                         int32_t X, int32_t Y, int32_t Z, int64_t* __restrict__ out) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   if (i >= Pc) return;
   const int64_t x = coords[i * 3], y = coords[i * 3 + 1], z = coords[i * 3 + 2];
@@ -141,6 +165,7 @@ __global__ void __launch_bounds__(kVoteThreads)
 point_labels_fused_kernel(const float* __restrict__ pts, int64_t Pc, int64_t rs, float mx, float my, float mz,
                           float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z,
                           const uint8_t* __restrict__ vlabels, int64_t* __restrict__ out) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   if (i >= Pc) return;
   int64_t lin;
@@ -152,12 +177,119 @@ point_labels_fused_kernel(const float* __restrict__ pts, int64_t Pc, int64_t rs,
 __global__ void __launch_bounds__(kVoteThreads)
 quantize_kernel(const float* __restrict__ pcds, int64_t P, int64_t rs, float mx, float my, float mz, float dx,
                 float dy, float dz, float* __restrict__ out) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   if (i >= P) return;
   const float* p = pcds + i * rs;
   out[i * 3] = quant(p[0], mx, dx);
   out[i * 3 + 1] = quant(p[1], my, dy);
   out[i * 3 + 2] = quant(p[2], mz, dz);
+}
+
+// ---- staging for the reference's int64 voting API (voxel_voting.py:234-241) ----------------------------------
+// The script quantises the local map (Quantize -> float32), casts the result and the predictions to int64
+// (`.to(torch.int64)`, truncation) and hands both to determine_voxel_labels. Here ONE kernel produces all three
+// tensors — q (float32), coords (int64) and labels (int64) — from the float points and uint8 predictions resident in
+// the long-term memory ring, and (optionally) performs the ring insert of the new scan on the way: thread i owns
+// point i of EVERY slot, so it can read the old "current" point before overwriting it (smos_memory_push fused in).
+// A warp parks its 32 x (3 int64 + 3 float) results in shared memory and writes them as whole 16-byte pieces of
+// contiguous 768- and 384-byte blocks.
+constexpr int kStageThreads = 128;
+
+struct StageArgs {
+  float* pts;            // (S, N, rs) ring, slot major
+  uint8_t* pred;         // (S, N)
+  const float* in_pts;   // (N, rs) new scan or null
+  const uint8_t* in_pred;
+  int64_t N, rs;
+  int32_t S, cur, hist;  // hist < 0: no history slot to fill
+  float mx, my, mz, dx, dy, dz;
+  float* q;              // (S*N, 3) or null
+  int64_t* coords;       // (S*N, 3)
+  int64_t* labels;       // (S*N)
+  int32_t vec_io;        // rs == 4 and 16-byte aligned point rows
+  int32_t vec_out;       // N % 4 == 0 and 16-byte aligned outputs: warp-staged 128-bit stores
+};
+
+__global__ void __launch_bounds__(kStageThreads)
+vote_stage_kernel(const __grid_constant__ StageArgs A) {
+  SMOS_PDL_PROLOGUE();
+  __shared__ __align__(16) long long s_c[kStageThreads / 32][32 * 3];
+  __shared__ __align__(16) float s_q[kStageThreads / 32][32 * 3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kStageThreads + threadIdx.x;
+  const int64_t i0 = i - lane;  // first point of my warp
+  if (i0 >= A.N) return;
+  const bool live = i < A.N;
+  const bool full = i0 + 32 <= A.N;  // whole warp in range
+  const bool push = A.in_pts != nullptr;
+  auto load_pt = [&](const float* base, float& x, float& y, float& z, float4& raw) {
+    if (A.vec_io) {
+      raw = *reinterpret_cast<const float4*>(base + i * 4);
+      x = raw.x; y = raw.y; z = raw.z;
+    } else {
+      const float* p = base + i * A.rs;
+      x = p[0]; y = p[1]; z = p[2];
+    }
+  };
+  auto copy_row = [&](float* dst, const float* src, const float4& raw) {
+    if (A.vec_io) {
+      *reinterpret_cast<float4*>(dst + i * 4) = raw;
+    } else {
+      for (int64_t k = 0; k < A.rs; ++k) dst[i * A.rs + k] = src[i * A.rs + k];
+    }
+  };
+  float ox = 0.f, oy = 0.f, oz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  uint8_t op = 0, np = 0;
+  if (push && live) {  // ring insert: old current -> history slot, new scan -> current slot
+    float4 oraw = make_float4(0.f, 0.f, 0.f, 0.f), nraw = oraw;
+    float* cur_pts = A.pts + static_cast<int64_t>(A.cur) * A.N * A.rs;
+    uint8_t* cur_pred = A.pred + static_cast<int64_t>(A.cur) * A.N;
+    load_pt(cur_pts, ox, oy, oz, oraw);
+    op = cur_pred[i];
+    load_pt(A.in_pts, nx, ny, nz, nraw);
+    np = A.in_pred[i];
+    if (A.hist >= 0) {
+      copy_row(A.pts + static_cast<int64_t>(A.hist) * A.N * A.rs, cur_pts, oraw);
+      A.pred[static_cast<int64_t>(A.hist) * A.N + i] = op;
+    }
+    copy_row(cur_pts, A.in_pts, nraw);
+    cur_pred[i] = np;
+  }
+  for (int32_t s = 0; s < A.S; ++s) {
+    float x = 0.f, y = 0.f, z = 0.f;
+    uint8_t lab = 0;
+    if (live) {
+      if (push && s == A.cur) { x = nx; y = ny; z = nz; lab = np; }
+      else if (push && s == A.hist) { x = ox; y = oy; z = oz; lab = op; }
+      else {
+        float4 raw;
+        load_pt(A.pts + static_cast<int64_t>(s) * A.N * A.rs, x, y, z, raw);
+        lab = A.pred[static_cast<int64_t>(s) * A.N + i];
+      }
+    }
+    const float qx = quant(x, A.mx, A.dx), qy = quant(y, A.my, A.dy), qz = quant(z, A.mz, A.dz);
+    // .to(torch.int64): truncation toward zero (voxel_voting.py:240)
+    const long long cx = static_cast<long long>(qx), cy = static_cast<long long>(qy), cz = static_cast<long long>(qz);
+    const int64_t g = static_cast<int64_t>(s) * A.N + i;
+    if (live) A.labels[g] = lab;
+    if (A.vec_out && full) {
+      __syncwarp();
+      s_c[wid][lane * 3] = cx; s_c[wid][lane * 3 + 1] = cy; s_c[wid][lane * 3 + 2] = cz;
+      if (A.q) { s_q[wid][lane * 3] = qx; s_q[wid][lane * 3 + 1] = qy; s_q[wid][lane * 3 + 2] = qz; }
+      __syncwarp();
+      const int64_t g0 = static_cast<int64_t>(s) * A.N + i0;
+      uint4* dc = reinterpret_cast<uint4*>(A.coords + g0 * 3);          // 768 contiguous bytes = 48 pieces
+      const uint4* sc = reinterpret_cast<const uint4*>(&s_c[wid][0]);
+      dc[lane] = sc[lane];
+      if (lane < 16) dc[32 + lane] = sc[32 + lane];
+      if (A.q && lane < 24)                                                // 384 contiguous bytes = 24 pieces
+        reinterpret_cast<uint4*>(A.q + g0 * 3)[lane] = reinterpret_cast<const uint4*>(&s_q[wid][0])[lane];
+    } else if (live) {
+      A.coords[g * 3] = cx; A.coords[g * 3 + 1] = cy; A.coords[g * 3 + 2] = cz;
+      if (A.q) { A.q[g * 3] = qx; A.q[g * 3 + 1] = qy; A.q[g * 3 + 2] = qz; }
+    }
+  }
 }
 
 // Instance vote. Testing every point against every box is O(P*K) compares (P ~ 1.08 M); almost all
@@ -177,7 +309,14 @@ __device__ __forceinline__ int iv_cell(float v, float lo, float inv) {
 __global__ void __launch_bounds__(kVoteThreads)
 instance_vote_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const int64_t* __restrict__ pred,
                      const float* __restrict__ lo, const float* __restrict__ hi, int32_t K,
-                     const int32_t* __restrict__ k_dev, unsigned long long* __restrict__ sums) {
+                     const int32_t* __restrict__ k_dev, unsigned long long* __restrict__ sums,
+                     unsigned long long* __restrict__ acc_ws, unsigned long long* __restrict__ out_ws) {
+  SMOS_PDL_PROLOGUE();
+  // acc_ws == null: the CTAs add straight into `sums` (zero-filled by the caller).
+  // acc_ws != null: they add into the persistent accumulator acc_ws[0 .. 2K) (zero on entry); the last CTA to finish
+  // (ticket in acc_ws[2K]) moves the totals to out_ws and leaves accumulator and ticket zero for the next call — no
+  // fill kernel in front of the vote.
+  if (acc_ws != nullptr) sums = acc_ws;
   __shared__ float4 s_box[kBoxChunk * 2];  // (lo.x, lo.y, lo.z, hi.x) (hi.y, hi.z, -, -)
   __shared__ unsigned int s_cnt[kBoxChunk * 2];
   __shared__ unsigned int s_mask[kIvGrid * kIvGrid][kIvWords];
@@ -248,6 +387,24 @@ instance_vote_kernel(const float* __restrict__ pts, int64_t P, int64_t rs, const
     }
     __syncthreads();  // the shared tables are rebuilt for the next chunk of boxes
   }
+  if (acc_ws != nullptr) {
+    __shared__ bool s_last;
+    __threadfence();  // my atomics are performed before my ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int* ticket = reinterpret_cast<unsigned int*>(acc_ws + 2 * static_cast<int64_t>(K));
+      s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1u;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int i = threadIdx.x; i < 2 * K; i += kVoteThreads) {
+        out_ws[i] = __ldcg(acc_ws + i);
+        acc_ws[i] = 0ull;
+      }
+      if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(acc_ws + 2 * static_cast<int64_t>(K)) = 0u;
+    }
+  }
 }
 
 // ---- streaming long-term memory -------------------------------------------------
@@ -288,6 +445,7 @@ __global__ void __launch_bounds__(kVoteThreads)
 vote_stream_kernel(const __grid_constant__ StreamScans S, int64_t rs, const __grid_constant__ CropBox box, float mx,
                    float my, float mz, float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z, int32_t C,
                    int packed, void* __restrict__ ws) {
+  SMOS_PDL_PROLOGUE();
   const int64_t g = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   if (g >= S.begin[S.n]) return;
   int j = 0;
@@ -299,7 +457,7 @@ vote_stream_kernel(const __grid_constant__ StreamScans S, int64_t rs, const __gr
   int64_t lin;
   if (lab >= C || !quant_voxel(q, mx, my, mz, dx, dy, dz, X, Y, Z, &lin)) return;
   if (packed)
-    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << (kPackBits * lab));
+    atomicAdd(static_cast<unsigned long long*>(ws) + lin, 1ull << vote_shift(lab));
   else
     atomicAdd(static_cast<unsigned int*>(ws) + lin * C + lab, 1u);
 }
@@ -310,6 +468,7 @@ __global__ void __launch_bounds__(kVoteThreads)
 stream_point_labels_kernel(const __grid_constant__ StreamScans S, int cur, int64_t rs, const __grid_constant__ CropBox box,
                            float mx, float my, float mz, float dx, float dy, float dz, int32_t X, int32_t Y, int32_t Z,
                            const uint8_t* __restrict__ vlabels, int64_t* __restrict__ out) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   if (i >= S.begin[cur + 1] - S.begin[cur]) return;
   float q[3];
@@ -328,6 +487,7 @@ __global__ void __launch_bounds__(kVoteThreads)
 memory_push_kernel(const float* __restrict__ pts_in, const uint8_t* __restrict__ pred_in, int64_t nfloat, int64_t n,
                    float* __restrict__ cur_pts, uint8_t* __restrict__ cur_pred, float* __restrict__ hist_pts,
                    uint8_t* __restrict__ hist_pred, int vec) {
+  SMOS_PDL_PROLOGUE();
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
   const int64_t nthreads = static_cast<int64_t>(gridDim.x) * kVoteThreads;
   if (vec) {  // every pointer 16-byte aligned, nfloat % 4 == 0, n % 16 == 0
@@ -353,7 +513,10 @@ memory_push_kernel(const float* __restrict__ pts_in, const uint8_t* __restrict__
 }
 
 int64_t ws_bytes(int64_t P, int64_t V, int32_t C) {
-  return use_packed(P, C) ? V * 8 : V * static_cast<int64_t>(C) * 4;
+  // packed: V counter words (the fused / streaming calls) or P 32-bit voxel indices (the int64 API, whose label grid
+  // holds the counters itself), whichever is larger
+  if (use_packed(P, C)) return V * 8 > P * 4 ? V * 8 : P * 4;
+  return V * static_cast<int64_t>(C) * 4;
 }
 
 }  // namespace
@@ -365,7 +528,7 @@ int smos_quantize(const float* pcds, int64_t P, int64_t row_stride, float min_x,
   if (P < 0 || row_stride < 3) return SMOS_EINVAL;
   if (P == 0) return SMOS_OK;
   if (!pcds || !out) return SMOS_EINVAL;
-  quantize_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, smos_stream(stream)>>>(
+  SMOS_LAUNCH((quantize_kernel), smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, smos_stream(stream), 
       pcds, P, row_stride, min_x, min_y, min_z, dx, dy, dz, out);
   return smos_launch_status();
 }
@@ -386,10 +549,16 @@ int smos_vote_voxel_labels(const int64_t* voxel_coords, const int64_t* semantic_
   if (packed) {  // the label slots double as the packed counters (workspace untouched)
     cudaError_t e = smos_zero_async(voxel_labels, static_cast<size_t>(V) * 8, st);
     if (e != cudaSuccess) return static_cast<int>(e);
-    if (P > 0) {
-      vote_i64_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st>>>(voxel_coords, semantic_labels, P, X, Y,
-                                                                               Z, num_classes, 1, voxel_labels);
-      vote_argmax_inplace_kernel<<<smos_ceil_div((V + 1) / 2, kVoteThreads), kVoteThreads, 0, st>>>(
+    if (P > 0 && V < 0xffffffffll) {
+      uint32_t* lin = static_cast<uint32_t*>(workspace);
+      SMOS_LAUNCH((vote_i64_kernel), smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st, voxel_coords, semantic_labels, P, X, Y,
+                                                                               Z, num_classes, 1, voxel_labels, lin);
+      SMOS_LAUNCH((vote_convert_points_kernel), smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st, 
+          lin, P, reinterpret_cast<unsigned long long*>(voxel_labels));
+    } else if (P > 0) {
+      SMOS_LAUNCH((vote_i64_kernel), smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st, voxel_coords, semantic_labels, P, X, Y,
+                                                                               Z, num_classes, 1, voxel_labels, nullptr);
+      SMOS_LAUNCH((vote_argmax_inplace_kernel), smos_ceil_div((V + 1) / 2, kVoteThreads), kVoteThreads, 0, st, 
           reinterpret_cast<unsigned long long*>(voxel_labels), V);
     }
     return smos_launch_status();
@@ -397,9 +566,9 @@ int smos_vote_voxel_labels(const int64_t* voxel_coords, const int64_t* semantic_
   cudaError_t e = smos_zero_async(workspace, static_cast<size_t>(ws_bytes(P, V, num_classes)), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (P > 0)
-    vote_i64_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st>>>(voxel_coords, semantic_labels, P, X, Y,
-                                                                             Z, num_classes, 0, workspace);
-  vote_argmax_kernel<int64_t><<<smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st>>>(workspace, V, num_classes,
+    SMOS_LAUNCH((vote_i64_kernel), smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st, voxel_coords, semantic_labels, P, X, Y,
+                                                                             Z, num_classes, 0, workspace, nullptr);
+  SMOS_LAUNCH((vote_argmax_kernel<int64_t>), smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st, workspace, V, num_classes,
                                                                                        0, voxel_labels);
   return smos_launch_status();
 }
@@ -409,7 +578,7 @@ int smos_vote_point_labels(const int64_t* new_voxel_coords, int64_t Pc, const in
   if (Pc < 0 || X <= 0 || Y <= 0 || Z <= 0) return SMOS_EINVAL;
   if (Pc == 0) return SMOS_OK;
   if (!new_voxel_coords || !voxel_labels || !point_labels) return SMOS_EINVAL;
-  point_labels_i64_kernel<<<smos_ceil_div(Pc, kVoteThreads), kVoteThreads, 0, smos_stream(stream)>>>(
+  SMOS_LAUNCH((point_labels_i64_kernel), smos_ceil_div(Pc, kVoteThreads), kVoteThreads, 0, smos_stream(stream), 
       new_voxel_coords, Pc, voxel_labels, X, Y, Z, point_labels);
   return smos_launch_status();
 }
@@ -429,12 +598,12 @@ int smos_vote_fused(const float* points, int64_t P, int64_t row_stride, const ui
   cudaError_t e = smos_zero_async(workspace, static_cast<size_t>(ws_bytes(P, V, num_classes)), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (P > 0)
-    vote_fused_kernel<<<smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st>>>(
+    SMOS_LAUNCH((vote_fused_kernel), smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, st, 
         points, P, row_stride, labels, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, num_classes, packed, workspace);
-  vote_argmax_kernel<uint8_t><<<smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st>>>(workspace, V, num_classes,
+  SMOS_LAUNCH((vote_argmax_kernel<uint8_t>), smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st, workspace, V, num_classes,
                                                                                        packed, voxel_labels_u8);
   if (Pc > 0)
-    point_labels_fused_kernel<<<smos_ceil_div(Pc, kVoteThreads), kVoteThreads, 0, st>>>(
+    SMOS_LAUNCH((point_labels_fused_kernel), smos_ceil_div(Pc, kVoteThreads), kVoteThreads, 0, st, 
         points + (P - Pc) * row_stride, Pc, row_stride, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, voxel_labels_u8,
         point_labels);
   return smos_launch_status();
@@ -467,14 +636,35 @@ int smos_vote_stream(const smos_vote_stream_scan* scans_host, int32_t n_scans, i
   cudaError_t e = smos_zero_async(workspace, static_cast<size_t>(ws_bytes(total, V, num_classes)), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (total > 0)
-    vote_stream_kernel<<<smos_ceil_div(total, kVoteThreads), kVoteThreads, 0, st>>>(
+    SMOS_LAUNCH((vote_stream_kernel), smos_ceil_div(total, kVoteThreads), kVoteThreads, 0, st, 
         S, row_stride, box, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, num_classes, packed, workspace);
-  vote_argmax_kernel<uint8_t><<<smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st>>>(workspace, V, num_classes,
+  SMOS_LAUNCH((vote_argmax_kernel<uint8_t>), smos_ceil_div(V, kVoteThreads), kVoteThreads, 0, st, workspace, V, num_classes,
                                                                                        packed, voxel_labels_u8);
   const int64_t nc = scans_host[current].n;
   if (nc > 0)
-    stream_point_labels_kernel<<<smos_ceil_div(nc, kVoteThreads), kVoteThreads, 0, st>>>(
+    SMOS_LAUNCH((stream_point_labels_kernel), smos_ceil_div(nc, kVoteThreads), kVoteThreads, 0, st, 
         S, current, row_stride, box, min_x, min_y, min_z, dx, dy, dz, X, Y, Z, voxel_labels_u8, point_labels);
+  return smos_launch_status();
+}
+
+int smos_vote_stage(float* ring_points, uint8_t* ring_pred, int32_t n_slots, int64_t n, int64_t row_floats,
+                    const float* new_points, const uint8_t* new_pred, int32_t cur_slot, int32_t hist_slot,
+                    float min_x, float min_y, float min_z, float dx, float dy, float dz,
+                    float* q_out, int64_t* coords_out, int64_t* labels_out, void* stream) {
+  if (n_slots <= 0 || n < 0 || row_floats < 3) return SMOS_EINVAL;
+  if (n == 0) return SMOS_OK;
+  if (!ring_points || !ring_pred || !coords_out || !labels_out) return SMOS_EINVAL;
+  if ((new_points == nullptr) != (new_pred == nullptr)) return SMOS_EINVAL;
+  if (new_points && (cur_slot < 0 || cur_slot >= n_slots || hist_slot >= n_slots || hist_slot == cur_slot)) return SMOS_EINVAL;
+  auto a16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  StageArgs A;
+  A.pts = ring_points; A.pred = ring_pred; A.in_pts = new_points; A.in_pred = new_pred;
+  A.N = n; A.rs = row_floats; A.S = n_slots; A.cur = cur_slot; A.hist = new_points ? hist_slot : -1;
+  A.mx = min_x; A.my = min_y; A.mz = min_z; A.dx = dx; A.dy = dy; A.dz = dz;
+  A.q = q_out; A.coords = coords_out; A.labels = labels_out;
+  A.vec_io = (row_floats == 4 && a16(ring_points) && a16(new_points)) ? 1 : 0;
+  A.vec_out = ((n & 3) == 0 && a16(q_out) && a16(coords_out)) ? 1 : 0;
+  SMOS_LAUNCH((vote_stage_kernel), smos_ceil_div(n, kStageThreads), kStageThreads, 0, smos_stream(stream), A);
   return smos_launch_status();
 }
 
@@ -489,7 +679,7 @@ int smos_memory_push(const float* points, const uint8_t* pred, int64_t n, int64_
                    (nfloat & 3) == 0 && (n & 15) == 0) ? 1 : 0;
   int64_t blocks = smos_ceil_div(vec ? (nfloat >> 2) : nfloat, kVoteThreads);
   if (blocks > SMOS_SM_COUNT * 8) blocks = SMOS_SM_COUNT * 8;
-  memory_push_kernel<<<static_cast<unsigned>(blocks), kVoteThreads, 0, smos_stream(stream)>>>(
+  SMOS_LAUNCH((memory_push_kernel), static_cast<unsigned>(blocks), kVoteThreads, 0, smos_stream(stream), 
       points, pred, nfloat, n, cur_points, cur_pred, hist_points, hist_pred, vec);
   return smos_launch_status();
 }
@@ -502,8 +692,31 @@ int smos_instance_vote(const float* points, int64_t P, int64_t row_stride, const
   int gx = smos_ceil_div(P, kVoteThreads * 4);
   if (gx > 8 * SMOS_SM_COUNT) gx = 8 * SMOS_SM_COUNT;  // persistent-style grid-stride loop
   dim3 grid(gx, smos_ceil_div(K, kBoxChunk));
-  instance_vote_kernel<<<grid, kVoteThreads, 0, smos_stream(stream)>>>(
-      points, P, row_stride, pred, box_lo, box_hi, K, nullptr, reinterpret_cast<unsigned long long*>(sums));
+  SMOS_LAUNCH((instance_vote_kernel), grid, kVoteThreads, 0, smos_stream(stream), 
+      points, P, row_stride, pred, box_lo, box_hi, K, nullptr, reinterpret_cast<unsigned long long*>(sums), nullptr,
+      nullptr);
+  return smos_launch_status();
+}
+
+int64_t smos_instance_vote_workspace_bytes(int32_t K) {
+  if (K < 0) return SMOS_EINVAL;
+  return (2 * static_cast<int64_t>(K) + 2) * 8;
+}
+
+int smos_instance_vote_ws(const float* points, int64_t P, int64_t row_stride, const int64_t* pred,
+                          const float* box_lo, const float* box_hi, int32_t K_cap, const int32_t* K_dev,
+                          void* workspace, int64_t* sums, void* stream) {
+  if (P < 0 || K_cap < 0 || row_stride < 3) return SMOS_EINVAL;
+  if (K_cap == 0) return SMOS_OK;
+  if (!sums || !workspace || (reinterpret_cast<uintptr_t>(workspace) & 7) != 0) return SMOS_EINVAL;
+  if (P > 0 && (!points || !pred || !box_lo || !box_hi)) return SMOS_EINVAL;
+  int gx = smos_ceil_div(P > 0 ? P : 1, kVoteThreads * 4);
+  if (gx > 8 * SMOS_SM_COUNT) gx = 8 * SMOS_SM_COUNT;
+  // one grid row when the box count lives on the device (every CTA walks the chunks that exist)
+  dim3 grid(gx, K_dev ? 1 : smos_ceil_div(K_cap, kBoxChunk));
+  SMOS_LAUNCH((instance_vote_kernel), grid, kVoteThreads, 0, smos_stream(stream), 
+      points, P, row_stride, pred, box_lo, box_hi, K_cap, K_dev, nullptr,
+      static_cast<unsigned long long*>(workspace), reinterpret_cast<unsigned long long*>(sums));
   return smos_launch_status();
 }
 
@@ -516,8 +729,9 @@ int smos_instance_vote_counted(const float* points, int64_t P, int64_t row_strid
   int gx = smos_ceil_div(P, kVoteThreads * 4);
   if (gx > 8 * SMOS_SM_COUNT) gx = 8 * SMOS_SM_COUNT;
   // one grid row: every CTA walks the chunks of boxes that exist (usually one), none when *K_dev == 0
-  instance_vote_kernel<<<dim3(gx, 1), kVoteThreads, 0, smos_stream(stream)>>>(
-      points, P, row_stride, pred, box_lo, box_hi, K_cap, K_dev, reinterpret_cast<unsigned long long*>(sums));
+  SMOS_LAUNCH((instance_vote_kernel), dim3(gx, 1), kVoteThreads, 0, smos_stream(stream), 
+      points, P, row_stride, pred, box_lo, box_hi, K_cap, K_dev, reinterpret_cast<unsigned long long*>(sums), nullptr,
+      nullptr);
   return smos_launch_status();
 }
 

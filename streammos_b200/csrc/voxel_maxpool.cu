@@ -62,6 +62,7 @@ struct PlanDev {
   int64_t quad_begin;  // first global cell-quad index (warp aligned)
   int32_t N, H, W, hw, cells, bn;
   float sh, sw;
+  const float* scale_dev;  // optional: {scale_h, scale_w} on the device (overrides sh / sw)
 };
 
 struct PlanBatch {
@@ -73,6 +74,7 @@ struct PlanBatch {
 // ---- plan 0: clear count[cells] and the four cursors of every plan (thread = 4 cells) -----------
 __global__ void __launch_bounds__(kPlanThreads)
 pool_zero_counts_kernel(const __grid_constant__ PlanBatch pb) {
+  SMOS_PDL_PROLOGUE();
   const int64_t gq = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gq >= pb.quad_total) return;
   int j = 0;
@@ -95,6 +97,7 @@ pool_zero_counts_kernel(const __grid_constant__ PlanBatch pb) {
 // ---- plan 1: cell index + warp-aggregated per-cell histogram -------------------------------
 __global__ void __launch_bounds__(kPlanThreads)
 pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
+  SMOS_PDL_PROLOGUE();
   const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   int32_t* target = nullptr;  // &count[gcell] of my plan; the out-of-grid cursor for invalid points; null past the end
   int32_t* rank_out = nullptr;
@@ -108,8 +111,9 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
     const int32_t n = static_cast<int32_t>(i - static_cast<int64_t>(b) * P.N);
     const float* q = P.ind + b * P.ind_sb + n * P.ind_sn;
     // fp32 multiply then C-cast truncation toward zero (reference .cu:40)
-    const float fh = __fmul_rn(q[0], P.sh);
-    const float fw = __fmul_rn(q[P.ind_sd], P.sw);
+    const float sh = P.scale_dev ? __ldg(P.scale_dev) : P.sh, sw = P.scale_dev ? __ldg(P.scale_dev + 1) : P.sw;
+    const float fh = __fmul_rn(q[0], sh);
+    const float fw = __fmul_rn(q[P.ind_sd], sw);
     const long long ih = static_cast<long long>(fh);
     const long long iw = static_cast<long long>(fw);
     int32_t cell = -1;
@@ -148,6 +152,7 @@ pool_cell_index_kernel(const __grid_constant__ PlanBatch pb) {
 // global cursor replaces a device-wide prefix scan. thread = 4 cells; a warp never straddles two plans.
 __global__ void __launch_bounds__(kPlanThreads)
 pool_cell_alloc_kernel(const __grid_constant__ PlanBatch pb) {
+  SMOS_PDL_PROLOGUE();
   __shared__ int32_t s_tot[kPlanThreads / 32], s_plan[kPlanThreads / 32], s_base;
   const int64_t gq = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool active = gq < pb.quad_total;  // whole warps only (quad ranges are warp aligned)
@@ -229,6 +234,7 @@ pool_cell_alloc_kernel(const __grid_constant__ PlanBatch pb) {
 // ---- plan 3: place every valid point in its cell's segment -----------------------------------
 __global__ void __launch_bounds__(kPlanThreads)
 pool_cell_scatter_kernel(const __grid_constant__ PlanBatch pb) {
+  SMOS_PDL_PROLOGUE();
   const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gi >= pb.pt_total) return;
   int j = 0;
@@ -273,6 +279,7 @@ constexpr int kPermThreads = 256;
 __global__ void __launch_bounds__(kPermThreads)
 pool_permute_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64_t f_sb, int64_t f_sc, int64_t f_sn,
                     const int32_t* __restrict__ pos, float* __restrict__ rows) {
+  SMOS_PDL_PROLOGUE();
   extern __shared__ float tile[];  // [kPermPts][C + 1]
   __shared__ int32_t s_pos[kPermPts];
   const int32_t b = blockIdx.y;
@@ -370,6 +377,7 @@ template <int CPL>
 __global__ void __launch_bounds__(kPermThreads)
 pool_permute_ldg_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64_t f_sb, int64_t f_sc,
                         const int32_t* __restrict__ pos, float* __restrict__ rows) {
+  SMOS_PDL_PROLOGUE();
   constexpr int PTS = kPermPts;
   constexpr int kPitch = PTS + 4;
   extern __shared__ __align__(16) float ltile[];  // [C][kPitch]
@@ -447,6 +455,7 @@ __global__ void __launch_bounds__(kPermThreads)
 pool_permute_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ feat, int32_t C, int32_t N,
                         int32_t B, int64_t f_sb, int64_t f_sc, const int32_t* __restrict__ pos,
                         float* __restrict__ rows) {
+  SMOS_PDL_PROLOGUE();
   constexpr int PTS = kTmPts;
   constexpr int kBoxes = PTS / kTmBox;            // TMA boxes per tile (32 points x 32 channels, 4 KB each)
   constexpr int kBoxFloats = kTmCh * kTmBox;      // 1024 floats: boxes stay 1024-byte aligned
@@ -569,16 +578,15 @@ typedef CUresult (*smos_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuui
                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static smos_encode_tiled_fn encode_tiled() {
-  static smos_encode_tiled_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // function-local static: initialised once, thread safe (C++11)
+  static const smos_encode_tiled_fn fn = []() -> smos_encode_tiled_fn {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<smos_encode_tiled_fn>(p);
-  }
+      return reinterpret_cast<smos_encode_tiled_fn>(p);
+    return nullptr;
+  }();
   return fn;
 }
 
@@ -597,12 +605,10 @@ static int launch_permute_tma(const float* feat, int32_t C, int64_t N, int64_t B
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return SMOS_EUNSUPPORTED;
   const size_t smem = static_cast<size_t>(STAGES) * kTmPts * kTmCh * 4 + 1024;
-  static bool opt_in[64] = {};
-  if (device >= 0 && device < 64 && !opt_in[device]) {
-    cudaError_t e = cudaFuncSetAttribute(pool_permute_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    opt_in[device] = true;
-  }
+  static std::atomic<unsigned long long> opted{0};
+  (void)device;
+  if (cudaError_t e = smos_smem_opt_in(pool_permute_tma_kernel<STAGES>, opted, 200 * 1024); e != cudaSuccess)
+    return static_cast<int>(e);
   const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kTmPts)) * (C / kTmCh) * B;
   int ctas_per_sm = static_cast<int>((224 * 1024) / (smem + 2048));
   if (ctas_per_sm > 6) ctas_per_sm = 6;
@@ -611,16 +617,15 @@ static int launch_permute_tma(const float* feat, int32_t C, int64_t N, int64_t B
   if (want >= 1 && want < ctas_per_sm) ctas_per_sm = want;
   int64_t pgrid = static_cast<int64_t>(SMOS_SM_COUNT) * ctas_per_sm;
   if (pgrid > ntiles) pgrid = ntiles;
-  pool_permute_tma_kernel<STAGES><<<static_cast<unsigned>(pgrid), kPermThreads, smem, st>>>(
+  SMOS_LAUNCH((pool_permute_tma_kernel<STAGES>), static_cast<unsigned>(pgrid), kPermThreads, smem, st, 
       tm, feat, C, static_cast<int32_t>(N), static_cast<int32_t>(B), f_sb, f_sc, pos, rows);
   return SMOS_OK;
 }
 
 // pipeline depth of the TMA permute; SMOS_PERM_STAGES (2 / 3 / 4) overrides the default for experiments
 static int perm_stages() {
-  static int v = 0;
-  if (v == 0) { const int x = env_int("SMOS_PERM_STAGES", 0); v = (x >= 2 && x <= 4) ? x : 3; }
-  return v;
+  const int x = env_int("SMOS_PERM_STAGES", 0);
+  return (x >= 2 && x <= 4) ? x : 3;
 }
 
 // ---- phase A: piece maxima ------------------------------------------------------------------
@@ -653,6 +658,7 @@ template <int VEC, bool SORTED_ROWS>
 __global__ void __launch_bounds__(kReduceWarps * 32)
 pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int64_t f_sn, int32_t hw,
                    const int2* __restrict__ sorted, const int32_t* __restrict__ cursor, float* rows) {
+  SMOS_PDL_PROLOGUE();
   using V = typename VecT<VEC>::type;
   constexpr int kBatch = VEC == 4 ? 8 : 16;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -729,6 +735,7 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
 template <int VEC>
 __global__ void __launch_bounds__(kReduceWarps * 32)
 pool_combine_kernel(int32_t C, const int2* __restrict__ multi, const int32_t* __restrict__ cursor, float* rows) {
+  SMOS_PDL_PROLOGUE();
   using V = typename VecT<VEC>::type;
   constexpr int kBatch = VEC == 4 ? 8 : 16;
   const int lane = threadIdx.x & 31;
@@ -767,6 +774,7 @@ __global__ void __launch_bounds__(kWriteThreads)
 pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t groups_per_cta,
                   const int32_t* __restrict__ count, const int32_t* __restrict__ start,
                   float* __restrict__ out, int stream_out) {
+  SMOS_PDL_PROLOGUE();
   const int32_t b = blockIdx.z;
   const bool vec_rows = ((C & 7) == 0);
   constexpr int CPT = VEC4 ? 4 : 1;  // cells per thread
@@ -857,6 +865,7 @@ pool_backward_kernel(const float* __restrict__ feat, int32_t C, int32_t N, int64
                      const int32_t* __restrict__ cell_in, const float* __restrict__ vout,
                      const float* __restrict__ gout, float* __restrict__ gfeat,
                      int64_t g_sb, int64_t g_sc, int64_t g_sn, int fast_n) {
+  SMOS_PDL_PROLOGUE();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   int32_t b, c, n;
@@ -917,6 +926,8 @@ int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n,
     P.hw = static_cast<int32_t>(L.hw); P.cells = static_cast<int32_t>(L.cells);
     P.bn = static_cast<int32_t>(d.B * d.N);
     P.sh = d.scale_h; P.sw = d.scale_w;
+    P.scale_dev = d.scale_dev;
+    if (d.scale_dev != nullptr && d.gather_taps != nullptr) return SMOS_EUNSUPPORTED;  // the records need host scales
     P.pt_begin = pt; P.quad_begin = quad;
     pt += d.B * d.N;
     quad += smos_align_up((L.cells + 3) / 4, 32);
@@ -926,10 +937,10 @@ int smos_pool_plan_build_multi(const smos_pool_plan_desc* descs_host, int32_t n,
   cudaStream_t st = smos_stream(stream);
   // zero the per-cell counters and the cursors of every plan: one launch (a cudaMemsetAsync node per plan, or one
   // over the whole span of the plans, cost more than the three plan kernels together)
-  pool_zero_counts_kernel<<<smos_ceil_div(quad, kPlanThreads), kPlanThreads, 0, st>>>(pb);
-  if (pt > 0) pool_cell_index_kernel<<<smos_ceil_div(pt, kPlanThreads), kPlanThreads, 0, st>>>(pb);
-  pool_cell_alloc_kernel<<<smos_ceil_div(quad, kPlanThreads), kPlanThreads, 0, st>>>(pb);
-  if (pt > 0) pool_cell_scatter_kernel<<<smos_ceil_div(pt, kPlanThreads), kPlanThreads, 0, st>>>(pb);
+  SMOS_LAUNCH((pool_zero_counts_kernel), smos_ceil_div(quad, kPlanThreads), kPlanThreads, 0, st, pb);
+  if (pt > 0) SMOS_LAUNCH((pool_cell_index_kernel), smos_ceil_div(pt, kPlanThreads), kPlanThreads, 0, st, pb);
+  SMOS_LAUNCH((pool_cell_alloc_kernel), smos_ceil_div(quad, kPlanThreads), kPlanThreads, 0, st, pb);
+  if (pt > 0) SMOS_LAUNCH((pool_cell_scatter_kernel), smos_ceil_div(pt, kPlanThreads), kPlanThreads, 0, st, pb);
   return smos_launch_status();
 }
 
@@ -941,6 +952,7 @@ int smos_pool_plan_build(const float* pcds_ind, int64_t B, int64_t N, int64_t in
   d.H = H; d.W = W; d.scale_h = scale_h; d.scale_w = scale_w;
   d.voxel_max_idx = voxel_max_idx; d.idx_batch_stride = idx_batch_stride; d.plan = plan;
   d.gather_taps = nullptr;
+  d.scale_dev = nullptr;
   return smos_pool_plan_build_multi(&d, 1, stream);
 }
 
@@ -975,16 +987,13 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
     const bool point_major = (f_sc == 1 && C > 1);
     if (!point_major) {
       // channel-major: permute into sorted rows, then reduce those rows in place
-      static bool smem_opt_in[64] = {};
+      static std::atomic<unsigned long long> opted_generic{0}, opted_ldg1{0}, opted_ldg2{0};
       int device = 0;
       cudaGetDevice(&device);
       const size_t smem = static_cast<size_t>(kPermPts) * (C + 1) * 4;
       if (smem > 200 * 1024) return SMOS_EUNSUPPORTED;
-      if (device >= 0 && device < 64 && !smem_opt_in[device]) {
-        cudaError_t e = cudaFuncSetAttribute(pool_permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        smem_opt_in[device] = true;
-      }
+      if (cudaError_t e = smos_smem_opt_in(pool_permute_kernel, opted_generic, 200 * 1024); e != cudaSuccess)
+        return static_cast<int>(e);
       const int depth = perm_stages();
       const bool tma_ok = f_sn == 1 && (N & 3) == 0 && (f_sb & 3) == 0 && (f_sc & 3) == 0 && (C % kTmCh) == 0 &&
                           (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 && N >= kTmPts && encode_tiled() != nullptr;
@@ -992,20 +1001,16 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
                           (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 &&
                           static_cast<size_t>(C) * (kPermPts + 4) * 4 <= 200 * 1024;
       if (vec_ok && env_int("SMOS_PERM_LDG", 1)) {  // default; SMOS_PERM_LDG=0 selects the TMA pipeline below
-        static bool ldg_opt_in[64] = {};
-        if (device >= 0 && device < 64 && !ldg_opt_in[device]) {
-          cudaError_t e = cudaFuncSetAttribute(pool_permute_ldg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          if (e != cudaSuccess) return static_cast<int>(e);
-          e = cudaFuncSetAttribute(pool_permute_ldg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-          if (e != cudaSuccess) return static_cast<int>(e);
-          ldg_opt_in[device] = true;
-        }
+        if (cudaError_t e = smos_smem_opt_in(pool_permute_ldg_kernel<1>, opted_ldg1, 200 * 1024); e != cudaSuccess)
+          return static_cast<int>(e);
+        if (cudaError_t e = smos_smem_opt_in(pool_permute_ldg_kernel<2>, opted_ldg2, 200 * 1024); e != cudaSuccess)
+          return static_cast<int>(e);
         dim3 pg(smos_ceil_div(N, kPermPts), static_cast<unsigned>(B));
         const size_t lsmem = static_cast<size_t>(C) * (kPermPts + 4) * 4;
         if (C > 32)
-          pool_permute_ldg_kernel<2><<<pg, kPermThreads, lsmem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, pos, rows);
+          SMOS_LAUNCH((pool_permute_ldg_kernel<2>), pg, kPermThreads, lsmem, st, pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, pos, rows);
         else
-          pool_permute_ldg_kernel<1><<<pg, kPermThreads, lsmem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, pos, rows);
+          SMOS_LAUNCH((pool_permute_ldg_kernel<1>), pg, kPermThreads, lsmem, st, pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, pos, rows);
       } else if (tma_ok) {
         int rc;
         if (depth == 2) rc = launch_permute_tma<2>(pcds_feat, Ci, N, B, f_sb, f_sc, pos, rows, device, st);
@@ -1014,25 +1019,25 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
         if (rc != SMOS_OK) return rc;
       } else {
         dim3 pg(smos_ceil_div(N, kPermPts), static_cast<unsigned>(B));
-        pool_permute_kernel<<<pg, kPermThreads, smem, st>>>(pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, f_sn, pos, rows);
+        SMOS_LAUNCH((pool_permute_kernel), pg, kPermThreads, smem, st, pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, f_sn, pos, rows);
       }
       if (stages & SMOS_POOL_STAGE_NO_REDUCE) {}
-      else if ((C & 127) == 0) pool_reduce_kernel<4, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
-      else if ((C & 63) == 0) pool_reduce_kernel<2, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
-      else pool_reduce_kernel<1, true><<<grid, kReduceWarps * 32, 0, st>>>(rows, Ci, 0, 0, hw, sorted, cursor, rows);
+      else if ((C & 127) == 0) SMOS_LAUNCH((pool_reduce_kernel<4, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, cursor, rows);
+      else if ((C & 63) == 0) SMOS_LAUNCH((pool_reduce_kernel<2, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, cursor, rows);
+      else SMOS_LAUNCH((pool_reduce_kernel<1, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, cursor, rows);
     } else {
-      if ((C & 127) == 0 && aligned) pool_reduce_kernel<4, false><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
-      else if ((C & 63) == 0 && aligned) pool_reduce_kernel<2, false><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
-      else pool_reduce_kernel<1, false><<<grid, kReduceWarps * 32, 0, st>>>(pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
+      if ((C & 127) == 0 && aligned) SMOS_LAUNCH((pool_reduce_kernel<4, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
+      else if ((C & 63) == 0 && aligned) SMOS_LAUNCH((pool_reduce_kernel<2, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
+      else SMOS_LAUNCH((pool_reduce_kernel<1, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
     }
   }
   if (total >= 32 && (stages & SMOS_POOL_STAGE_COMBINE)) {
     // fold multi-piece cells (<= total/32 of them; the exact number is only known on the device)
     const int2* multi = reinterpret_cast<const int2*>(base + L.off_multi);
     const int cgrid = smos_ceil_div(total / 32 + 1, kReduceWarps);
-    if ((C & 127) == 0) pool_combine_kernel<4><<<cgrid, kReduceWarps * 32, 0, st>>>(Ci, multi, cursor, rows);
-    else if ((C & 63) == 0) pool_combine_kernel<2><<<cgrid, kReduceWarps * 32, 0, st>>>(Ci, multi, cursor, rows);
-    else pool_combine_kernel<1><<<cgrid, kReduceWarps * 32, 0, st>>>(Ci, multi, cursor, rows);
+    if ((C & 127) == 0) SMOS_LAUNCH((pool_combine_kernel<4>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows);
+    else if ((C & 63) == 0) SMOS_LAUNCH((pool_combine_kernel<2>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows);
+    else SMOS_LAUNCH((pool_combine_kernel<1>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows);
   }
   // outputs beyond L2 capacity are written with evict-first stores
   const int stream_out = (B * C * L.hw * 4 > (int64_t(96) << 20)) ? 1 : 0;
@@ -1048,9 +1053,9 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
   dim3 grid(gx, (ngroups + groups_per_cta - 1) / groups_per_cta, static_cast<unsigned>(B));
   if (stages & SMOS_POOL_STAGE_WRITE) {
     if (vec4)
-      pool_write_kernel<true><<<grid, kWriteThreads, 0, st>>>(rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
+      SMOS_LAUNCH((pool_write_kernel<true>), grid, kWriteThreads, 0, st, rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
     else
-      pool_write_kernel<false><<<grid, kWriteThreads, 0, st>>>(rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
+      SMOS_LAUNCH((pool_write_kernel<false>), grid, kWriteThreads, 0, st, rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
   }
   return smos_launch_status();
 }
@@ -1066,7 +1071,7 @@ int smos_voxel_maxpool_backward(const float* pcds_feat, int64_t B, int64_t C, in
   const int32_t* cell = reinterpret_cast<const int32_t*>(static_cast<const char*>(plan) + L.off_cell);
   const int64_t total = B * C * N;
   const int fast_n = (f_sc == 1 && C > 1) ? 0 : 1;
-  pool_backward_kernel<<<smos_ceil_div(total, 256), 256, 0, smos_stream(stream)>>>(
+  SMOS_LAUNCH((pool_backward_kernel), smos_ceil_div(total, 256), 256, 0, smos_stream(stream), 
       pcds_feat, static_cast<int32_t>(C), static_cast<int32_t>(N), total, f_sb, f_sc, f_sn, L.hw, cell, voxel_out,
       grad_voxel_out, grad_feat, g_sb, g_sc, g_sn, fast_n);
   return smos_launch_status();

@@ -3,7 +3,8 @@
 Same names, argument meaning and assertions: `VoxelMaxPool(pcds_feat, pcds_ind, output_size,
 scale_rate)` and `VoxelMaxPoolFunction`. Differences that do not change results: the output
 is produced by one output-stationary kernel (no zeros/full fills, no metadata uploads), the
-backward re-uses the forward's pooling plan instead of `voxel_max_idx`, and CPU tensors raise
+backward re-uses the forward's pooling plan instead of `voxel_max_idx`, plans are shared between
+calls that pass the same coordinate tensor (plan_cache.py), and CPU tensors raise
 (the reference silently ran its serial C++ loop on them, deep_point/__init__.py:38-40).
 
   pcds_feat  (BS, C, N, 1)      pcds_ind (BS, N, D=2, 1)
@@ -28,7 +29,9 @@ class VoxelMaxPoolFunction(Function):
             raise RuntimeError("deep_point.VoxelMaxPool: CPU tensors are not supported by the B200 build "
                                "(no CPU fallback); the CPU restatement lives in oracle/ for tests only")
         if plan is None:
-            plan = ops.pool_plan(pcds_ind, output_size, scale_rate)
+            # reference signature: the plan comes from the cache shared with the other pools / gathers of the scan
+            # that pass the same coordinate tensor (plan_cache.py); built here on a miss
+            plan = ops.cached_pool_plan(pcds_ind, output_size, scale_rate)
         else:
             assert (plan.B, plan.N, plan.H, plan.W) == (pcds_ind.size(0), pcds_ind.size(1), output_size[0],
                                                         output_size[1]), "plan does not match this call"

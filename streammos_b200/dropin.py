@@ -4,11 +4,15 @@ models/StreamMOS.py, networks/multi_view_encoder.py and deformattn/ run unmodifi
     import streammos_b200.dropin as dropin; dropin.install()
     # then:  import deep_point; import MultiScaleDeformableAttention; from networks import backbone
 
-(The reference has no plugin registry; its modules are found through sys.modules.)"""
+(The reference has no plugin registry; its modules are found through sys.modules.)
+
+`point_major_points` (default): BilinearSample returns its (B, C, N, 1) result with channels_last strides — same shape
+and values, each point's channels contiguous, the layout the next VoxelMaxPool and the 1x1 point convolutions read
+fastest. Pass False for (B, C, N, 1)-contiguous results as the reference produces them."""
 import sys
 
 
-def install(point_major_points=False):
+def install(point_major_points=True):
     from . import MultiScaleDeformableAttention as msda
     from . import backbone as b200_backbone
     from . import deep_point as b200_deep_point

@@ -102,6 +102,7 @@ def pool_plan_multi(specs, gather_taps=None):
         d.H, d.W, d.scale_h, d.scale_w = H, W, float(scale_rate[0]), float(scale_rate[1])
         d.voxel_max_idx, d.idx_batch_stride, d.plan = None, 0, buf.data_ptr()
         d.gather_taps = taps.data_ptr() if taps is not None else None
+        d.scale_dev = None
         plans.append(PoolPlan(buf, B, N, H, W, None, scale_rate, taps))
     with torch.cuda.device(device):
         rc = lib.smos_pool_plan_build_multi(descs, len(items), _stream())
@@ -110,9 +111,17 @@ def pool_plan_multi(specs, gather_taps=None):
     return plans
 
 
-def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=0):
+def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=0, scale_dev=None):
     """pcds_ind (B, N, 2[, 1]) float32 -> PoolPlan. `idx_out` (B, N) int64 receives the reference's
-    voxel_max_idx side product if given (deep_point/__init__.py:27)."""
+    voxel_max_idx side product if given (deep_point/__init__.py:27). `scale_dev`: a (2,) float32 CUDA tensor that
+    overrides `scale_rate` and is read by the kernels on the device (the reference hands the scales to
+    point_deep.cuda_kernel as a device tensor; no device->host copy, no synchronisation)."""
+    if scale_dev is not None:
+        _need_cuda(scale_dev, "scale_rate")
+        _need_f32(scale_dev, "scale_rate")
+        if scale_dev.numel() != 2 or not scale_dev.is_contiguous():
+            raise NotImplementedError("only 2-D grids (D == 2) are implemented — the shapes StreamMOS uses")
+        scale_rate = (0.0, 0.0)
     ind, B, N, H, W = _plan_inputs(pcds_ind, output_size, scale_rate)
     lib = _lib.load()
     nbytes = lib.smos_pool_plan_bytes(B, N, H, W)
@@ -122,13 +131,27 @@ def pool_plan(pcds_ind, output_size, scale_rate, idx_out=None, idx_batch_stride=
     if idx_out is not None:
         _need_cuda(idx_out, "voxel_max_idx")
         assert idx_out.dtype == torch.int64 and idx_out.is_contiguous() and idx_out.numel() == B * N
+    d = (_lib.PoolPlanDesc * 1)()
+    d[0].pcds_ind, d[0].B, d[0].N = ind.data_ptr(), B, N
+    d[0].ind_sb, d[0].ind_sn, d[0].ind_sd = ind.stride(0), ind.stride(1), ind.stride(2)
+    d[0].H, d[0].W, d[0].scale_h, d[0].scale_w = H, W, float(scale_rate[0]), float(scale_rate[1])
+    d[0].voxel_max_idx = idx_out.data_ptr() if idx_out is not None else None
+    d[0].idx_batch_stride, d[0].plan, d[0].gather_taps = int(idx_batch_stride), buf.data_ptr(), None
+    d[0].scale_dev = scale_dev.data_ptr() if scale_dev is not None else None
     with torch.cuda.device(ind.device):
-        rc = lib.smos_pool_plan_build(_ptr(ind), B, N, ind.stride(0), ind.stride(1), ind.stride(2), H, W,
-                                      float(scale_rate[0]), float(scale_rate[1]), _ptr(idx_out),
-                                      int(idx_batch_stride), _ptr(buf), _stream())
+        rc = lib.smos_pool_plan_build_multi(d, 1, _stream())
     _lib.check(rc, "smos_pool_plan_build")
     _count(4)  # zero counts + cell index + cell allocation + scatter
-    return PoolPlan(buf, B, N, H, W, idx_out, scale_rate)
+    return PoolPlan(buf, B, N, H, W, idx_out, None if scale_dev is not None else scale_rate)
+
+
+def cached_pool_plan(pcds_ind, output_size, scale_rate):
+    """pool_plan() through the plan cache (plan_cache.py): calls that pass the same coordinate tensor, grid and scale
+    — the reference's pools and gathers of one scan do — share one plan."""
+    from . import plan_cache
+    ind, B, N, H, W = _plan_inputs(pcds_ind, output_size, scale_rate)
+    return plan_cache.get(ind, (H, W), scale_rate, lambda: pool_plan(ind, (H, W), scale_rate),
+                          lambda geos: pool_plan_multi([(ind, (g[0], g[1]), (g[2], g[3])) for g in geos]))
 
 
 def _feat3(pcds_feat):
@@ -390,9 +413,17 @@ def _msda_check(value, spatial_shapes, level_start_index, sampling_loc, attn_wei
     return B, S, M, D, L, Q, P
 
 
-def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out=None):
+    """`out`: optional (B, Lq, M*D) contiguous tensor to write into (a stream keeps its short-term memory in place: the
+    second layer's output lands straight in the memory buffer the next scan reads). Must not alias `value`."""
     B, S, M, D, L, Q, P = _msda_check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
-    out = torch.empty((B, Q, M * D), dtype=value.dtype, device=value.device)
+    if out is None:
+        out = torch.empty((B, Q, M * D), dtype=value.dtype, device=value.device)
+    else:
+        if out.dtype != value.dtype or not out.is_contiguous() or out.numel() != B * Q * M * D or not out.is_cuda:
+            raise RuntimeError("out must be a contiguous (B, Lq, M*D) CUDA tensor of value's dtype")
+        if out.data_ptr() == value.data_ptr():
+            raise RuntimeError("out must not alias value")
     with torch.cuda.device(value.device):
         rc = _lib.load().smos_ms_deform_attn_forward(_DT[value.dtype], _ptr(value), _ptr(spatial_shapes),
                                                      _ptr(level_start_index), _ptr(sampling_loc),
@@ -436,6 +467,38 @@ def quantize(pcds, mins, deltas):
     return out
 
 
+def vote_stage(ring_points, ring_pred, mins, deltas, new_points=None, new_pred=None, cur_slot=0, hist_slot=-1,
+               want_q=True):
+    """Quantize + the two `.to(torch.int64)` casts of voxel_voting.py:234-241 in one kernel, straight from the
+    long-term memory ring: ring_points (S, N, r>=3) f32, ring_pred (S, N) u8 -> (q (S*N, 3) f32 or None,
+    coords (S*N, 3) int64, labels (S*N,) int64). With new_points / new_pred the ring insert (memory_push) happens in
+    the same kernel first: slot cur_slot moves to hist_slot (if >= 0) and the new scan takes cur_slot."""
+    _need_cuda(ring_points, "ring_points")
+    _need_f32(ring_points, "ring_points")
+    if ring_points.dim() != 3 or not ring_points.is_contiguous() or ring_pred.dtype != torch.uint8 or \
+            not ring_pred.is_contiguous() or ring_pred.shape != ring_points.shape[:2] or not ring_pred.is_cuda:
+        raise RuntimeError("vote_stage: ring_points (S, N, r) f32 / ring_pred (S, N) u8, contiguous CUDA tensors")
+    S, N, r = (int(v) for v in ring_points.shape)
+    if new_points is not None:
+        _need_cuda(new_points, "new_points")
+        _need_f32(new_points, "new_points")
+        if new_points.shape != (N, r) or not new_points.is_contiguous() or new_pred.dtype != torch.uint8 or \
+                new_pred.shape != (N,) or not new_pred.is_contiguous() or not new_pred.is_cuda:
+            raise RuntimeError("vote_stage: new_points (N, r) f32 / new_pred (N,) u8, contiguous CUDA tensors")
+    dev = ring_points.device
+    q = torch.empty((S * N, 3), dtype=torch.float32, device=dev) if want_q else None
+    coords = torch.empty((S * N, 3), dtype=torch.int64, device=dev)
+    labels = torch.empty((S * N,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().smos_vote_stage(_ptr(ring_points), _ptr(ring_pred), S, N, r, _ptr(new_points), _ptr(new_pred),
+                                         int(cur_slot), int(hist_slot), float(mins[0]), float(mins[1]), float(mins[2]),
+                                         float(deltas[0]), float(deltas[1]), float(deltas[2]), _ptr(q), _ptr(coords),
+                                         _ptr(labels), _stream())
+    _lib.check(rc, "smos_vote_stage")
+    _count(1)
+    return q, coords, labels
+
+
 def _vote_ws(P, X, Y, Z, C, device):
     n = _lib.load().smos_vote_workspace_bytes(P, X, Y, Z, C)
     if n < 0:
@@ -458,7 +521,7 @@ def vote_voxel_labels(voxel_coords, semantic_labels, dims, num_classes):
         rc = _lib.load().smos_vote_voxel_labels(_ptr(voxel_coords), _ptr(semantic_labels), P, X, Y, Z,
                                                 int(num_classes), _ptr(ws), _ptr(out), _stream())
     _lib.check(rc, "smos_vote_voxel_labels")
-    _count(3)  # zero + vote + argmax
+    _count(3)  # zero + vote + per-point conversion
     return out
 
 
@@ -567,10 +630,18 @@ def memory_push(points, pred, cur_points, cur_pred, hist_points=None, hist_pred=
     _count(1)
 
 
-def instance_vote(points, pred, box_lo, box_hi, count=None):
+def instance_vote_workspace(K, device):
+    """Persistent accumulator for instance_vote(..., workspace=): zero now, left zero by every call."""
+    n = int(_lib.load().smos_instance_vote_workspace_bytes(int(K)))
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def instance_vote(points, pred, box_lo, box_hi, count=None, workspace=None):
     """points (P, >=3) f32, pred (P,) int64, box_lo/box_hi (K, 3) f32 -> sums (K, 2) int64
     [static_sum, dynamic_sum] with dynamic points weighted 2. count: optional (1,) int32 CUDA tensor holding the
-    number of valid boxes (rows beyond it stay zero) — read by the kernel, not by the host."""
+    number of valid boxes (rows beyond it stay zero) — read by the kernel, not by the host.
+    workspace: instance_vote_workspace(K, device) owned by the calling stream — the vote then needs no zero fill of
+    `sums` in front of it (one launch instead of two)."""
     _need_cuda(points, "points")
     _need_f32(points, "points")
     if pred.dtype != torch.int64:
@@ -580,6 +651,19 @@ def instance_vote(points, pred, box_lo, box_hi, count=None):
     box_hi = box_hi.to(torch.float32).contiguous()
     assert points.dim() == 2 and points.size(1) >= 3 and points.stride(1) == 1
     P, K = int(points.size(0)), int(box_lo.size(0))
+    if workspace is not None:
+        if count is not None and (count.dtype != torch.int32 or not count.is_cuda):
+            raise RuntimeError("count must be an int32 CUDA tensor")
+        if workspace.numel() * workspace.element_size() < (2 * K + 2) * 8 or not workspace.is_cuda:
+            raise RuntimeError("workspace too small (ops.instance_vote_workspace)")
+        sums = torch.empty((K, 2), dtype=torch.int64, device=points.device)
+        with torch.cuda.device(points.device):
+            rc = _lib.load().smos_instance_vote_ws(_ptr(points), P, points.stride(0) if P > 1 else points.size(1),
+                                                   _ptr(pred), _ptr(box_lo), _ptr(box_hi), K, _ptr(count), _ptr(workspace),
+                                                   _ptr(sums), _stream())
+        _lib.check(rc, "smos_instance_vote_ws")
+        _count(1 if K else 0)
+        return sums
     sums = torch.zeros((K, 2), dtype=torch.int64, device=points.device)
     with torch.cuda.device(points.device):
         if count is None:

@@ -42,7 +42,7 @@ class ScanPipeline:
                 hot.scan_index = j
                 with torch.cuda.stream(self._pm_stream(j)):
                     self.proj[j] = hot.projection(dev_scans[j])
-                    hot.memory.copy_(hot.temporal_fusion(dev_scans[j]))
+                    hot.temporal_fusion(dev_scans[j])
                     self.out[j] = hot.long_term_voting(dev_scans[j])
                 torch.cuda.synchronize(dev)
             if use_graphs:
@@ -55,7 +55,7 @@ class ScanPipeline:
                         self.proj[j] = hot.projection(dev_scans[j])
                     self.gM[j] = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self.gM[j], pool=pools[id(s)], stream=s):
-                        hot.memory.copy_(hot.temporal_fusion(dev_scans[j]))
+                        hot.temporal_fusion(dev_scans[j])
                     hot.scan_index = j
                     self.gV[j] = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self.gV[j], pool=pool_c, stream=self.sC):
@@ -87,7 +87,7 @@ class ScanPipeline:
             if self.use_graphs:
                 self.gM[j].replay()
             else:
-                hot.memory.copy_(hot.temporal_fusion(self.scans[j]))
+                hot.temporal_fusion(self.scans[j])
             self.m_done[j].record(s)
         with torch.no_grad(), torch.cuda.stream(self.sC):
             if ready_event is not None:

@@ -2,8 +2,9 @@
 so the reference's own deep_point/__init__.py runs unmodified on top of the sm_100a kernels.
 
 The reference passes grid sizes/strides/scales as DEVICE tensors; sizes are taken from
-`voxel_out.shape`, the two scale factors need one small device->host read (the higher-level
-`streammos_b200.deep_point` boundary avoids it)."""
+`voxel_out.shape`, and the two scale factors are read by the plan kernel from the device tensor
+itself (smos_pool_plan_desc.scale_dev): no device->host copy, no synchronisation, so the
+unmodified reference path can be captured into a CUDA graph."""
 import torch
 
 from .. import ops
@@ -18,10 +19,9 @@ def _check_input(t, name):
 
 
 def _plan(pcds_ind, voxel_out, voxel_max_idx, scale_rate):
-    scale = [float(s) for s in scale_rate.detach().cpu().tolist()]
     out_size = tuple(voxel_out.shape[2:])
-    return ops.pool_plan(pcds_ind, out_size, scale, idx_out=voxel_max_idx,
-                         idx_batch_stride=voxel_out.stride(0))
+    return ops.pool_plan(pcds_ind, out_size, None, idx_out=voxel_max_idx, idx_batch_stride=voxel_out.stride(0),
+                         scale_dev=scale_rate.detach().to(torch.float32))
 
 
 def voxel_maxpooling_forward(pcds_feat, pcds_ind, voxel_out, voxel_max_idx, voxel_out_size, voxel_out_stride,

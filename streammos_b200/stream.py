@@ -184,8 +184,14 @@ class HotPath:
     returns the per-point labels after long-term voting plus the instance votes."""
 
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
-                 batch_plans=True, grids_channels_last=False, overlap_voting=False, branches=True,
+                 batch_plans=False, grids_channels_last=False, overlap_voting=False, branches=False,
                  ordered_gathers=True, ordered_rv=False, gather_taps=False, fuse_form_batch=True):
+        """batch_plans=False (default): every operator is called with the REFERENCE's arguments only
+        (VoxelMaxPool(feat, ind, size, scale), BilinearSample(grid, coord)); plans are shared through the plan cache
+        exactly as they are under the unmodified reference model. batch_plans=True: the explicit plan API (all five
+        plans of a scan built by one batch of launches, passed as plan= / order=).
+        branches=False (default): one serial chain, the reference's data flow (multi_view_encoder.py:393-417 feeds every
+        stage from the previous one through its CNN blocks)."""
         self.device = torch.device(device)
         self.overlap_voting = overlap_voting
         self.branches = branches and self.device.type == "cuda"
@@ -251,7 +257,9 @@ class HotPath:
         self.g_quarter = BilinearSample(in_dim=64, scale_rate=(0.25, 0.25))
         self.g_half.point_major_out = point_major
         self.g_quarter.point_major_out = point_major
+        self.g_half.auto_order = self.g_quarter.auto_order = bool(ordered_gathers) and not batch_plans
         self.scan_index = 0
+        self.iv_ws = None  # persistent accumulator of the instance votes (ops.instance_vote_workspace)
         self.size = synthetic.BEV_SHAPE
         self.mins = (synthetic.RANGE_X[0], synthetic.RANGE_Y[0], synthetic.RANGE_Z[0])
         self.deltas = tuple(float(np.float32((r[1] - r[0]) / s)) for r, s in
@@ -276,11 +284,11 @@ class HotPath:
         return main, sides
 
     def projection(self, b):
-        """Cascade projection: 5 x VoxelMaxPool + 5 x BilinearSample.
-
-        Data dependencies (models/StreamMOS.py:101-105, mve.py:393-417): pool #1 and gather #5 depend on the
-        coordinates only; gather1 -> pool2 -> gather2 -> pool3 and gather3 -> pool4 -> gather4 -> pool5 are two
-        chains. With `branches` the four run as parallel branches (results are identical)."""
+        """Cascade projection: 5 x VoxelMaxPool + 5 x BilinearSample, in the reference's order
+        (models/StreamMOS.py:101-105, mve.py:393-417). In the reference the stages form ONE chain (x0 = CNN(pool #1),
+        x1 = CNN(cat(x0, pool #3)), gather #5 reads the decoder output); here the CNN outputs are resident stand-ins, so
+        pool #1, the two pool/gather chains and gather #5 happen to be independent: `branches=True` (an experiment,
+        not the default) runs them as parallel graph branches."""
         if hasattr(b, "points"):      # raw scan: Quantize + make_point_feat on the device (SURVEY 8f rank 2), then the stem
             if self.fuse_form_batch:  # one kernel: raw points -> 64-channel features + quantised coordinates
                 feat, coord = ops.point_stem_forward_raw(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z,
@@ -339,48 +347,65 @@ class HotPath:
         return bev_in, x0_bev, x1_bev, x1_pt, pt_bev
 
     def temporal_fusion(self, b):
-        """Two deformable-attention layers sampling the short-term memory (mve.py:268-273, 313-321)."""
+        """Two deformable-attention layers sampling the short-term memory (mve.py:268-273, 313-321). The second
+        layer writes straight into the memory buffer (the first one has finished reading it): the attended feature
+        IS the next scan's query_embed_store (mve.py:456), no copy."""
         value = self.memory.view(1, MEM_HW * MEM_HW, N_HEADS, HEAD_DIM)
         h = MSDA.ms_deform_attn_forward(value, self.shapes, self.lsi, b.loc[0], b.attn[0], 256)
         value2 = h.view(1, MEM_HW * MEM_HW, N_HEADS, HEAD_DIM)
-        h = MSDA.ms_deform_attn_forward(value2, self.shapes, self.lsi, b.loc[1], b.attn[1], 256)
-        return h
+        if self.device.type != "cuda":
+            self.memory.copy_(MSDA.ms_deform_attn_forward(value2, self.shapes, self.lsi, b.loc[1], b.attn[1], 256))
+            return self.memory
+        return ops.ms_deform_attn_forward(value2, self.shapes, self.lsi, b.loc[1], b.attn[1], out=self.memory)
 
     def long_term_voting(self, b):
-        """Voxel voting over 8 history scans + the current one, then per-instance votes."""
+        """Voxel voting over 8 history scans + the current one, then per-instance votes. The reference functions
+        assume pre-cropped input (voxel_voting.py:225-231); synthetic scans lie inside the crop box and padded points
+        quantise out of range, so no crop is applied here (voting.StreamingVoter implements the script's crop)."""
         cur = HISTORY
         # raw points of the current frame: loader batches carry them as the first 4 channels of pcds_xyzi
         if hasattr(b, "points"):
             xyzi = b.points[0]
         else:
             xyzi = b.xyzi if hasattr(b, "xyzi") else b.pcds_xyzi[0, :4, :, 0].t().contiguous()
+        n = self.n_points
+        pts = self.local_pts.view(-1, 4)
+        prev = (self.scan_index - 1) % HISTORY
+        if self.device.type == "cuda" and self.vote_api == "reference":
+            # voxel_voting.py:234-243 through the reference's function signatures. One kernel inserts the new scan into
+            # the ring (the previous scan moves from the current slot into its history slot, exactly as :182 walks the
+            # window) and produces Quantize's float result together with the script's two int64 casts (:240-241)
+            q, coords, labels = voting.quantize_staged(self.local_pts, self.local_pred, synthetic.RANGE_X,
+                                                       synthetic.RANGE_Y, synthetic.RANGE_Z, self.size, new_points=xyzi,
+                                                       new_pred=b.pred, cur_slot=cur, hist_slot=prev)
+            if self.iv_ws is None:
+                self.iv_ws = ops.instance_vote_workspace(N_BOXES, self.device)
+            if self.branches:  # the instance votes do not depend on the voxel votes: a parallel branch
+                main, (side,) = self._fork(1)
+                with torch.cuda.stream(side):
+                    sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi, workspace=self.iv_ws)
+            vl = voting.determine_voxel_labels(coords, labels, self.size, num_classes=3)
+            point_labels = voting.get_point_labels_from_voxel_labels(coords[cur * n:], vl, self.size)
+            if self.branches:
+                main.wait_stream(side)
+            else:
+                sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi, workspace=self.iv_ws)
+            return point_labels, sums
         if self.device.type == "cuda":
-            # the previous scan moves from the current slot into its ring slot and the new scan takes the current
-            # slot: one kernel (the window slides exactly as voxel_voting.py:182 walks it)
-            prev = (self.scan_index - 1) % HISTORY
             ops.memory_push(xyzi, b.pred, self.local_pts[cur], self.local_pred[cur], self.local_pts[prev],
                             self.local_pred[prev])
         else:
             self.local_pts[cur].copy_(xyzi)
             self.local_pred[cur].copy_(b.pred)
-        pts = self.local_pts.view(-1, 4)
-        n = self.n_points
         labels = self.local_pred.view(-1).to(torch.int64)              # voxel_voting.py:241
-        if self.branches:  # the instance votes do not depend on the voxel votes: a parallel branch
-            main, (side,) = self._fork(1)
-            with torch.cuda.stream(side):
-                sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi)
-        if self.vote_api == "reference":
+        if self.vote_api == "reference":  # CPU harness state (tests)
             q = voting.Quantize(pts, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, self.size)
             coords = q.to(torch.int64)                                 # voxel_voting.py:240
             vl = voting.determine_voxel_labels(coords, labels, self.size, num_classes=3)
             point_labels = voting.get_point_labels_from_voxel_labels(coords[cur * n:], vl, self.size)
         else:  # fused streaming variant (SURVEY §8f rank 1): float xyz + uint8 labels in, no int64 staging
             _, point_labels = ops.vote_fused(pts, self.local_pred.view(-1), n, self.mins, self.deltas, self.size, 3)
-        if self.branches:
-            main.wait_stream(side)
-        else:
-            sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi)
+        sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi)
         if self.device.type != "cuda":  # CPU harness state (tests): the current scan becomes history at the end
             slot = self.scan_index % HISTORY
             self.local_pts[slot].copy_(self.local_pts[cur])
@@ -400,13 +425,11 @@ class HotPath:
             with torch.cuda.stream(self._side):
                 point_labels, sums = self.long_term_voting(b)
             proj = self.projection(b)
-            fused = self.temporal_fusion(b)
-            self.memory.copy_(fused)
+            self.temporal_fusion(b)
             main.wait_stream(self._side)
         else:
             proj = self.projection(b)
-            fused = self.temporal_fusion(b)
-            self.memory.copy_(fused)  # becomes the next scan's query_embed_store (mve.py:456)
+            self.temporal_fusion(b)  # the attended feature becomes the next scan's query_embed_store (mve.py:456)
             point_labels, sums = self.long_term_voting(b)
         self.scan_index += 1
         return point_labels, sums, proj

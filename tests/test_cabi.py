@@ -50,7 +50,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.smos_abi_version() == 1
+    assert lib.smos_abi_version() == 2
     assert lib.smos_error_string(0) == b"ok"
     assert b"invalid" in lib.smos_error_string(-1)
     assert lib.smos_pool_plan_bytes(3, 160000, 512, 512) > 3 * 160000 * 16

@@ -423,6 +423,22 @@ def test_msda_gradcheck_double(channels):
     assert gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, attn, 2))
 
 
+def test_msda_forward_into_caller_buffer():
+    from streammos_b200 import ops
+    rng = np.random.default_rng(5)
+    value = rng.standard_normal((1, 64 * 64, 4, 32)).astype(np.float32)
+    loc = rng.uniform(0, 1, (1, 4096, 4, 1, 4, 2)).astype(np.float32)
+    attn = rng.uniform(0, 1, (1, 4096, 4, 1, 4)).astype(np.float32)
+    shapes, lsi = np.array([[64, 64]], np.int64), np.array([0], np.int64)
+    args = [t(a) for a in (value, shapes, lsi, loc, attn)]
+    want = ops.ms_deform_attn_forward(*args)
+    buf = torch.full((1, 4096, 128), 7.0, device=dev())
+    got = ops.ms_deform_attn_forward(*args, out=buf)
+    assert got.data_ptr() == buf.data_ptr() and torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        ops.ms_deform_attn_forward(*args, out=args[0].view(1, 4096, 128))
+
+
 def test_msda_error_behaviour():
     from streammos_b200 import MultiScaleDeformableAttention as MSDA_mod
     rng = np.random.default_rng(0)
@@ -531,6 +547,86 @@ def test_memory_push_moves_current_into_history(n):
     assert float(ring_p[0].abs().sum()) == 0.0
     ops.memory_push(t(cur_p), t(cur_l), ring_p[2], ring_l[2])                            # no history slot: overwrite only
     assert np.array_equal(ring_p[2].cpu().numpy(), cur_p) and np.array_equal(ring_p[1].cpu().numpy(), cur_p)
+
+
+@pytest.mark.parametrize("S,n,push", [(9, 120000, True), (9, 4099, True), (3, 17, True), (2, 1, False), (4, 50000, False)])
+def test_vote_stage_equals_quantize_and_casts(S, n, push):
+    """smos_vote_stage = ring insert + Quantize + the script's two .to(int64) casts (voxel_voting.py:234-241): bit-exact
+    against the oracle's Quantize, numpy truncation and a plain ring update; odd n exercises the scalar stores."""
+    from streammos_b200 import voting
+    rng = np.random.default_rng(S * 1000 + n)
+    ring_p = np.concatenate([rng.uniform(-52, 52, (S, n, 2)), rng.uniform(-4.5, 2.5, (S, n, 1)), rng.uniform(0, 1, (S, n, 1))],
+                            -1).astype(np.float32)
+    ring_p[:, ::11] = -1000.0                                       # pads
+    ring_p[:, 1::13, 0] = np.float32(-50.0) - np.float32(1e-3)      # quantises into (-1, 0): truncates to 0
+    ring_l = rng.integers(0, 3, (S, n)).astype(np.uint8)
+    new_p = ring_p[0][::-1].copy() * np.float32(0.9)
+    new_l = rng.integers(0, 3, n).astype(np.uint8)
+    rx, ry, rz, size = (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), (512, 512, 30)
+    dp, dl = t(ring_p), t(ring_l)
+    cur, hist = S - 1, (S - 2 if S > 2 else -1)
+    want_p, want_l = ring_p.copy(), ring_l.copy()
+    if push:
+        if hist >= 0:
+            want_p[hist], want_l[hist] = ring_p[cur], ring_l[cur]
+        want_p[cur], want_l[cur] = new_p, new_l
+        q, coords, labels = voting.quantize_staged(dp, dl, rx, ry, rz, size, new_points=t(new_p), new_pred=t(new_l),
+                                                   cur_slot=cur, hist_slot=hist)
+    else:
+        q, coords, labels = voting.quantize_staged(dp, dl, rx, ry, rz, size)
+    assert np.array_equal(dp.cpu().numpy(), want_p) and np.array_equal(dl.cpu().numpy(), want_l)
+    want_q = O.quantize(want_p.reshape(-1, 4), rx, ry, rz, size)
+    assert np.array_equal(q.cpu().numpy(), want_q)
+    assert np.array_equal(coords.cpu().numpy(), want_q.astype(np.int64))      # numpy / torch casts truncate
+    assert np.array_equal(labels.cpu().numpy(), want_l.reshape(-1).astype(np.int64))
+    # and the separate reference-shaped calls agree
+    q2 = voting.Quantize(dp.view(-1, 4), rx, ry, rz, size)
+    assert torch.equal(q2, q) and torch.equal(q2.to(torch.int64), coords)
+
+
+def test_instance_vote_workspace_variant_needs_no_zero_fill():
+    from streammos_b200 import ops
+    rng = np.random.default_rng(19)
+    P, K = 200000, 40
+    pts = np.concatenate([rng.uniform(-50, 50, (P, 2)), rng.uniform(-4, 2, (P, 1)), rng.uniform(0, 1, (P, 1))],
+                         1).astype(np.float32)
+    pred = rng.integers(0, 3, P).astype(np.int64)
+    c = np.concatenate([rng.uniform(-45, 45, (K, 2)), rng.uniform(-3, 1, (K, 1))], 1)
+    half = rng.uniform(0.5, 4, (K, 3))
+    lo, hi = (c - half).astype(np.float32), (c + half).astype(np.float32)
+    want = O.instance_vote(pts, pred, lo, hi)
+    ws = ops.instance_vote_workspace(K, dev())
+    for rep in range(3):  # the workspace is left zero: repeated calls give the same totals
+        got = ops.instance_vote(t(pts), t(pred), t(lo), t(hi), workspace=ws)
+        assert np.array_equal(got.cpu().numpy(), want), rep
+        assert not ws.cpu().numpy().any()
+    for k in (K, 7, 0):
+        count = torch.tensor([k], dtype=torch.int32, device=dev())
+        got = ops.instance_vote(t(pts), t(pred), t(lo), t(hi), count=count, workspace=ws).cpu().numpy()
+        assert np.array_equal(got[:k], want[:k]) and not got[k:].any(), k
+    # more boxes than one shared-memory chunk
+    K2 = 300
+    c = np.concatenate([rng.uniform(-45, 45, (K2, 2)), rng.uniform(-3, 1, (K2, 1))], 1)
+    half = rng.uniform(0.5, 4, (K2, 3))
+    lo, hi = (c - half).astype(np.float32), (c + half).astype(np.float32)
+    ws2 = ops.instance_vote_workspace(K2, dev())
+    got = ops.instance_vote(t(pts), t(pred), t(lo), t(hi), workspace=ws2)
+    assert np.array_equal(got.cpu().numpy(), O.instance_vote(pts, pred, lo, hi))
+
+
+def test_voting_single_class2_vote_and_heavy_voxels():
+    """Counter words of the in-place int64 path: one vote for class 2 is the word 2 (= its own label), several points of
+    one voxel convert it concurrently, and ties resolve to the lowest class."""
+    from streammos_b200 import ops
+    size = (4, 4, 2)
+    coords = np.array([[0, 0, 0]] * 1 + [[1, 1, 1]] * 7 + [[2, 2, 0]] * 4000 + [[3, 3, 1]] * 6, np.int64)
+    labels = np.array([2] + [2] * 3 + [1] * 4 + list(np.arange(4000) % 3) + [0, 0, 1, 1, 2, 2], np.int64)
+    ref = O.determine_voxel_labels(coords, labels, size, 3)
+    assert ref[0, 0, 0] == 2 and ref[1, 1, 1] == 1 and ref[3, 3, 1] == 0
+    perm = np.random.default_rng(0).permutation(len(labels))
+    for order in (np.arange(len(labels)), perm):
+        vl = ops.vote_voxel_labels(t(coords[order]), t(labels[order]), size, 3)
+        assert np.array_equal(vl.cpu().numpy(), ref)
 
 
 def test_instance_vote_golden(golden):
