@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--ordered-rv", action="store_true", help="range-view gathers in cell order too")
     ap.add_argument("--gather-taps", action="store_true",
                     help="gathers read their sampling state from records the plan build emits (measured: no gain)")
+    ap.add_argument("--families-only", action="store_true",
+                    help="tuning aid: print only the per-family device times (not the contract's JSON line) and exit")
     return ap.parse_args()
 
 
@@ -254,6 +256,13 @@ def run_b200(args, world, rank, local):
     torch.cuda.synchronize()
     cpu_hot_state = cpu_state(hot) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
+    if args.families_only:
+        with torch.no_grad():
+            hot.step(devb[0])
+            hot.scan_index = 0
+            fam = family_breakdown(hot, devb, dev, 6451.8, max(3, min(args.steps, 30)))
+        print(json.dumps({k: round(v["us_per_scan"], 2) for k, v in fam.items()}), flush=True)
+        return
     compute = torch.cuda.Stream(dev)
     copy = torch.cuda.Stream(dev)
     launches_per_step = 0
@@ -558,7 +567,11 @@ def family_breakdown(hot, devb, dev, peak, iters):
         def f_plans(j):
             if hot.batch_plans:
                 return ops.pool_plan_multi(specs(devb[j]))
-            return [ops.pool_plan(*sp) for sp in specs(devb[j])]
+            # reference signatures: the plan cache builds what the cascade asks for, in the cascade's order — one by one
+            # on the first scan, then in the batches it learned (plan_cache.py); inside this capture every scan's
+            # coordinate tensors are new to the cache, as in the stream
+            sp = specs(devb[j])
+            return [ops.cached_pool_plan(*sp[i]) for i in (0, 2, 1, 4, 3)]
 
         def f_pool1(j):
             return deep_point.VoxelMaxPool(devb[j].feat, devb[j].coord_bev, (512, 512), (1.0, 1.0), P[j][0])

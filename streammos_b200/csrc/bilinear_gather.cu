@@ -62,75 +62,84 @@ __device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict_
   __syncthreads();
 }
 
+// Per-lane sampling state: slot `slot` of the launch (ORDERED: entry of a pooling plan's `sorted` list over all B*N
+// points; else point `slot` of batch b). Each lane computes (or, with TAPS, loads) the state of ITS point: lanes are
+// points in the planar kernel, so nothing needs to be shared between threads.
+template <bool ORDERED, bool TAPS>
+__device__ __forceinline__ TapsS lane_taps(int64_t slot, int32_t b, const float* __restrict__ coord, int32_t N,
+                                           int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw, int32_t H,
+                                           int32_t W, const int2* __restrict__ order, int32_t order_hw, int64_t order_len,
+                                           const TapsS* __restrict__ taps) {
+  if (TAPS) {
+    TapsS r;
+    const bool live = slot < order_len;
+    const uint4* src = reinterpret_cast<const uint4*>(taps + (live ? slot : order_len - 1));
+    uint4* dst = reinterpret_cast<uint4*>(&r);
+    dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
+    if (!live) r.n = -1;
+    return r;
+  }
+  int32_t n;
+  bool live;
+  if (ORDERED) {
+    live = slot < order_len;
+    const int2 e = __ldg(order + (live ? slot : order_len - 1));
+    n = static_cast<int32_t>(static_cast<uint32_t>(e.x) & 0x7fffffffu);  // bit 31: the plan's run-merge mark
+    b = e.y >= 0 ? e.y / order_hw : -1 - e.y;                            // out-of-grid entries carry -1 - b
+  } else {
+    live = slot < N;
+    n = static_cast<int32_t>(live ? slot : N - 1);
+  }
+  const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
+  return make_taps_record(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W, live ? n : -1, b);
+}
+
 // Planar (NCHW-like: arbitrary channel stride, contiguous H x W planes up to gr_sh / gr_sw) grid.
-// CTA = 32 consecutive points x all channels; lanes run over the points (in scan order the taps of a
-// warp fall into a handful of sectors per channel plane), the 4 warps split the channel groups. All
-// 4*kCPT tap loads of a step are UNCONDITIONAL (out-of-image taps read a clamped, valid pixel and are
-// zeroed by a select afterwards): predicated loads get serialised through one temporary register by
-// ptxas. For point-major outputs the kCPT results leave as one full 32-byte sector per thread.
+// One WARP = 32 consecutive slots x all channels, independent of every other warp (no block barrier anywhere): lanes
+// are points, the warp walks the channel groups of kCPT channels. A scan is then ONE wave of ~N/32 warps spread over
+// the whole GPU — every warp runs its latency chain (order entry -> coordinates -> sampling state -> tap loads ->
+// row stores) once, concurrently with all others, instead of 2.5 waves of CTAs each paying the chain plus two block
+// barriers (the round-1 kernel: 4 warps sharing 32 points through shared memory, 17 us for 32 ch @ 256^2).
+// All 4*kCPT tap loads of a step are UNCONDITIONAL (out-of-image taps read a clamped, valid pixel and are zeroed by a
+// select afterwards): predicated loads get serialised through one temporary register by ptxas. For point-major
+// outputs the warp parks its 32 x C results in its own slice of shared memory ([point][C + 4]: conflict-free 128-bit
+// stores) and the rows leave as whole 128-byte lines.
+constexpr int kGatherWarps = 2;  // independent warps per CTA
+
 template <bool DENSE, bool ROWS_OUT, bool ORDERED, bool TAPS>
-__global__ void __launch_bounds__(kGatherThreads, SMOS_GATHER_MIN_CTAS)
+__global__ void __launch_bounds__(kGatherWarps * 32, 14)  // <= 72 registers: room for the 32 loads of a step in flight
 gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                              int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
                              const float* __restrict__ coord, int32_t N,
                              int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
                              float* __restrict__ out, int64_t o_sb, int64_t o_sc, int64_t o_sn,
                              const int2* __restrict__ order, int32_t order_hw, int64_t order_len,
-                             const TapsS* __restrict__ taps) {
+                             const TapsS* __restrict__ taps, int32_t groups_per_warp) {
   SMOS_PDL_PROLOGUE();
-  __shared__ TapsS s_taps[kGatherPts];
-  extern __shared__ __align__(16) float s_out[];  // ROWS_OUT: [kGatherPts][C + 4]
-  const int32_t n0 = blockIdx.x * kGatherPts;
-  cta_taps<ORDERED, TAPS>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len,
-                          taps);
+  extern __shared__ __align__(16) float s_out_all[];  // ROWS_OUT: [kGatherWarps][32][C + 4]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const TapsS t = s_taps[lane];
+  const int64_t slot0 = (static_cast<int64_t>(blockIdx.x) * kGatherWarps + wid) * 32;
+  if (slot0 >= (ORDERED || TAPS ? order_len : static_cast<int64_t>(N))) return;  // whole warp past the end
+  const TapsS t = lane_taps<ORDERED, TAPS>(slot0 + lane, blockIdx.z, coord, N, co_sb, co_sn, co_sd, sh, sw, H, W, order,
+                                           order_hw, order_len, taps);
   const int32_t b = t.b;
   const int32_t n = t.n;  // < 0: slot without a point
-  // DENSE: planes are contiguous H x W images (gr_sh == W, gr_sw == 1): the shared offsets y*W+x are
-  // used as they are (32-bit); otherwise they are re-expressed in the tensor's strides
-  int64_t q_nw = t.o_nw, q_ne = t.o_ne, q_sw = t.o_sw, q_se = t.o_se;
-  if (!DENSE) {
-    q_nw = static_cast<int64_t>(t.o_nw / W) * gr_sh + static_cast<int64_t>(t.o_nw % W) * gr_sw;
-    q_ne = static_cast<int64_t>(t.o_ne / W) * gr_sh + static_cast<int64_t>(t.o_ne % W) * gr_sw;
-    q_sw = static_cast<int64_t>(t.o_sw / W) * gr_sh + static_cast<int64_t>(t.o_sw % W) * gr_sw;
-    q_se = static_cast<int64_t>(t.o_se / W) * gr_sh + static_cast<int64_t>(t.o_se % W) * gr_sw;
-  }
-  const bool i_nw = t.in_mask & 1u, i_ne = t.in_mask & 2u, i_sw = t.in_mask & 4u, i_se = t.in_mask & 8u;
+  // channel groups (kCPT channels each) of this warp: blockIdx.y splits the channels when there are few points
+  const int32_t ngroups = (C + kCPT - 1) / kCPT;
+  const int32_t cg_begin = blockIdx.y * groups_per_warp;
+  const int32_t cg_end = min(ngroups, cg_begin + groups_per_warp);
   const float* g = grid + b * gr_sb;
+  float* s_out = s_out_all + static_cast<size_t>(wid) * 32 * (C + 4);
   const bool vec_ok = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  const int32_t ngroups = (C + kCPT - 1) / kCPT;
-  for (int32_t cg = wid; cg < ngroups; cg += kGatherThreads / 32) {
-    const int32_t c0 = cg * kCPT;
-    const int32_t nch = min(kCPT, C - c0);
-    float v[kCPT][4];
-    const float* gc0 = g + static_cast<int64_t>(c0) * gr_sc;
-    const int64_t cstep = (nch == kCPT) ? gr_sc : 0;  // a partial last group re-reads its first channel
-#pragma unroll
-    for (int k = 0; k < kCPT; ++k) {
-      const float* gc = (nch == kCPT) ? gc0 + k * cstep : g + static_cast<int64_t>(min(c0 + k, C - 1)) * gr_sc;
-      v[k][0] = __ldg(gc + q_nw);
-      v[k][1] = __ldg(gc + q_ne);
-      v[k][2] = __ldg(gc + q_sw);
-      v[k][3] = __ldg(gc + q_se);
-    }
-    float acc[kCPT];
-#pragma unroll
-    for (int k = 0; k < kCPT; ++k) {
-      const float a = i_nw ? v[k][0] : 0.f, bq = i_ne ? v[k][1] : 0.f;
-      const float c = i_sw ? v[k][2] : 0.f, d = i_se ? v[k][3] : 0.f;
-      acc[k] = fmaf(d, t.w_se, fmaf(c, t.w_sw, fmaf(bq, t.w_ne, fmaf(a, t.w_nw, 0.f))));
-    }
+  float* const orow = out + b * o_sb + static_cast<int64_t>(n >= 0 ? n : 0) * o_sn;
+  auto emit = [&](int32_t c0, int32_t nch, const float (&acc)[kCPT]) {
     if (ROWS_OUT) {
-      // point-major output: park the results in shared memory ([point][C + 4]: the two 128-bit stores of a thread
-      // are conflict free) so that the rows leave as whole 128-byte lines, 4 lines per store instruction, instead of
-      // 32 different lines per instruction (one 16-byte piece per lane)
       float* so = s_out + lane * (C + 4) + c0;
       *reinterpret_cast<float4*>(so) = make_float4(acc[0], acc[1], acc[2], acc[3]);
       *reinterpret_cast<float4*>(so + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     } else if (n >= 0) {
-      float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(c0) * o_sc;
+      float* o = orow + static_cast<int64_t>(c0) * o_sc;
       if (vec_ok && nch == kCPT) {
         *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -140,17 +149,82 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
           if (k < nch) o[static_cast<int64_t>(k) * o_sc] = acc[k];
       }
     }
+  };
+  // Almost every warp has all four taps of all its points inside the image (only border pixels and the padded points
+  // at the tail of the cell order do not): then NE = NW + 1 pixel and SE = SW + 1 pixel, no tap needs zeroing, and a
+  // channel costs two address computations, four loads and four FMAs.
+  const bool all_in = DENSE && ((C & (kCPT - 1)) == 0) && __all_sync(0xffffffffu, t.in_mask == 0xfu);
+  if (all_in) {
+    const float* pn = g + t.o_nw;
+    const float* ps = g + t.o_sw;
+#pragma unroll 1
+    for (int32_t cg = cg_begin; cg < cg_end; ++cg) {
+      const int32_t c0 = cg * kCPT;
+      const float* an = pn + static_cast<int64_t>(c0) * gr_sc;
+      const float* as = ps + static_cast<int64_t>(c0) * gr_sc;
+      float v[kCPT][4];
+#pragma unroll
+      for (int k = 0; k < kCPT; ++k) {
+        v[k][0] = __ldg(an + k * gr_sc);
+        v[k][1] = __ldg(an + k * gr_sc + 1);
+        v[k][2] = __ldg(as + k * gr_sc);
+        v[k][3] = __ldg(as + k * gr_sc + 1);
+      }
+      float acc[kCPT];
+#pragma unroll
+      for (int k = 0; k < kCPT; ++k)
+        acc[k] = fmaf(v[k][3], t.w_se, fmaf(v[k][2], t.w_sw, fmaf(v[k][1], t.w_ne, fmaf(v[k][0], t.w_nw, 0.f))));
+      emit(c0, kCPT, acc);
+    }
+  } else {
+    // general path: any strides, taps clamped into the image and zeroed by a select (value AND weight: a clamped
+    // pixel may hold inf / NaN). All loads unconditional: predicated ones get serialised by ptxas.
+    int64_t q_nw = t.o_nw, q_ne = t.o_ne, q_sw = t.o_sw, q_se = t.o_se;
+    if (!DENSE) {
+      q_nw = static_cast<int64_t>(t.o_nw / W) * gr_sh + static_cast<int64_t>(t.o_nw % W) * gr_sw;
+      q_ne = static_cast<int64_t>(t.o_ne / W) * gr_sh + static_cast<int64_t>(t.o_ne % W) * gr_sw;
+      q_sw = static_cast<int64_t>(t.o_sw / W) * gr_sh + static_cast<int64_t>(t.o_sw % W) * gr_sw;
+      q_se = static_cast<int64_t>(t.o_se / W) * gr_sh + static_cast<int64_t>(t.o_se % W) * gr_sw;
+    }
+    const bool i_nw = t.in_mask & 1u, i_ne = t.in_mask & 2u, i_sw = t.in_mask & 4u, i_se = t.in_mask & 8u;
+#pragma unroll 1
+    for (int32_t cg = cg_begin; cg < cg_end; ++cg) {
+      const int32_t c0 = cg * kCPT;
+      const int32_t nch = min(kCPT, C - c0);
+      float v[kCPT][4];
+#pragma unroll
+      for (int k = 0; k < kCPT; ++k) {
+        const float* gc = g + static_cast<int64_t>(min(c0 + k, C - 1)) * gr_sc;  // a partial group re-reads its last channel
+        v[k][0] = __ldg(gc + q_nw);
+        v[k][1] = __ldg(gc + q_ne);
+        v[k][2] = __ldg(gc + q_sw);
+        v[k][3] = __ldg(gc + q_se);
+      }
+      float acc[kCPT];
+#pragma unroll
+      for (int k = 0; k < kCPT; ++k) {
+        const float a = i_nw ? v[k][0] : 0.f, bq = i_ne ? v[k][1] : 0.f;
+        const float c = i_sw ? v[k][2] : 0.f, d = i_se ? v[k][3] : 0.f;
+        acc[k] = fmaf(d, t.w_se, fmaf(c, t.w_sw, fmaf(bq, t.w_ne, fmaf(a, t.w_nw, 0.f))));
+      }
+      emit(c0, nch, acc);
+    }
   }
   if (ROWS_OUT) {
-    __syncthreads();
-    // C % 8 == 0 here: a row is C / 4 float4 pieces; thread t of the CTA moves piece t % q of row t / q
-    const int32_t q = C >> 2;
-    for (int32_t i = threadIdx.x; i < kGatherPts * q; i += kGatherThreads) {
-      const int32_t p = i / q, j = i - p * q;
-      const int32_t pn = s_taps[p].n;
-      if (pn < 0) continue;
-      const float4 r = *reinterpret_cast<const float4*>(s_out + p * (C + 4) + (j << 2));
-      *reinterpret_cast<float4*>(out + s_taps[p].b * o_sb + static_cast<int64_t>(pn) * o_sn + (j << 2)) = r;
+    __syncwarp();
+    // C % 8 == 0 here. This warp's channel range [c_lo, c_hi) of every row is q float4 pieces; lane l moves piece
+    // i % q of row i / q for i = l, l + 32, ...: each store instruction writes whole 32-byte sectors of 32 / q rows
+    const int32_t c_lo = cg_begin * kCPT, q = ((cg_end - cg_begin) * kCPT) >> 2;
+    const int64_t my_row = n >= 0 ? (b * o_sb + static_cast<int64_t>(n) * o_sn) : -1;
+    const bool pow2 = (q & (q - 1)) == 0;
+    const int32_t shq = 31 - __clz(q);
+    for (int32_t i = lane; i < 32 * q; i += 32) {
+      const int32_t p = pow2 ? (i >> shq) : i / q;
+      const int32_t j = i - p * q;
+      const int64_t rb = __shfl_sync(0xffffffffu, my_row, p);
+      if (rb < 0) continue;
+      const float4 r = *reinterpret_cast<const float4*>(s_out + p * (C + 4) + c_lo + (j << 2));
+      *reinterpret_cast<float4*>(out + rb + c_lo + (j << 2)) = r;
     }
   }
 }
@@ -281,6 +355,19 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
   const bool ordered = (order != nullptr && o_sc == 1 && C > 1) || with_taps;
   const int64_t order_len = B * N;
   dim3 g(smos_ceil_div(ordered ? order_len : N, kGatherPts), 1, ordered ? 1u : static_cast<unsigned>(B));
+  dim3 gp(smos_ceil_div(ordered ? order_len : N, 32 * kGatherWarps), 1, ordered ? 1u : static_cast<unsigned>(B));
+  // one warp = 32 slots x (all channels / split). The split adds warps (latency hiding) at the price of recomputing
+  // the sampling state per warp: by default aim at >= 48 resident warps per SM
+  const int32_t ngroups_p = static_cast<int32_t>((C + kCPT - 1) / kCPT);
+  int32_t split = smos_env_int("SMOS_GATHER_SPLIT", 0);
+  if (split <= 0) {
+    split = 1;
+    const int64_t warps = static_cast<int64_t>(gp.x) * gp.z * kGatherWarps;
+    while (split < 4 && split * 2 <= ngroups_p && warps * split < static_cast<int64_t>(48) * SMOS_SM_COUNT) split *= 2;
+  }
+  if (split > ngroups_p) split = ngroups_p;
+  const int32_t groups_per_warp = (ngroups_p + split - 1) / split;
+  gp.y = static_cast<unsigned>((ngroups_p + groups_per_warp - 1) / groups_per_warp);
   const int32_t Ni = static_cast<int32_t>(N), Ci = static_cast<int32_t>(C);
   if (nhwc) {
     if (with_taps)
@@ -299,13 +386,14 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
     // point-major output rows (C % 8 == 0, 16-byte aligned) are assembled in shared memory and leave as whole lines
     const bool rows_out = (o_sc == 1) && C > 1 && ((C & 7) == 0) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
                           ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
-                          (static_cast<size_t>(C + 4) * kGatherPts * 4 <= 40 * 1024) && smos_env_int("SMOS_GATHER_ROWS", 1);
-    const size_t smem = rows_out ? static_cast<size_t>(C + 4) * kGatherPts * 4 : 0;
+                          (static_cast<size_t>(C + 4) * 32 * 4 * kGatherWarps <= 46 * 1024) &&
+                          smos_env_int("SMOS_GATHER_ROWS", 1);
+    const size_t smem = rows_out ? static_cast<size_t>(C + 4) * 32 * 4 * kGatherWarps : 0;
     const bool dense = (gr_sw == 1 && gr_sh == W);
 #define SMOS_LAUNCH_PLANAR(D, R, O, T)                                                                       \
-    SMOS_LAUNCH((gather_forward_planar_kernel<D, R, O, T>), g, kGatherThreads, smem, st,                                  \
+    SMOS_LAUNCH((gather_forward_planar_kernel<D, R, O, T>), gp, kGatherWarps * 32, smem, st,                                  \
         grid, Ci, H, W, gr_sb, gr_sc, gr_sh, gr_sw, coord, Ni, co_sb, co_sn, co_sd, scale_h, scale_w, out, o_sb, \
-        o_sc, o_sn, order, order_hw, order_len, taps)
+        o_sc, o_sn, order, order_hw, order_len, taps, groups_per_warp)
     if (with_taps) {
       if (dense && rows_out) SMOS_LAUNCH_PLANAR(true, true, true, true);
       else if (dense) SMOS_LAUNCH_PLANAR(true, false, true, true);
