@@ -341,7 +341,15 @@ def run_b200(args, world, rank, local):
             torch.cuda.synchronize()
             barrier(world)
             ms = max_over_ranks(f0.elapsed_time(f1), world, dev) / nsteps
+            # host cost of submitting one scan (API calls of e2e_loop): a short burst that fits the launch queue, so the
+            # host never waits for the device
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_loop(2 * N_SCANS)
+            host_us = (time.perf_counter() - t0) / (2 * N_SCANS) * 1e6
+            torch.cuda.synchronize()
             return {"steps": nsteps, "value": world * 1000.0 / ms, "unit": "scans/s", "ms_per_step": ms,
+                    "host_submit_us_per_scan": max_over_ranks(host_us, world, dev),
                     "h2d_bytes_per_step": host_[0].nbytes(),
                     "d2h_bytes_per_step": h_labels[0].numel() * 8 + h_sums[0].numel() * 8}
 

@@ -369,11 +369,15 @@ def test_msda_golden(golden, name, dtype):
         gtol = dict(rtol=1e-6, atol=1e-9)
     else:                       # north_star: 1e-5 relative in fp32
         tol = dict(rtol=RTOL, atol=1e-6 * max(scale, 1e-3))
-        gtol = dict(rtol=2e-4, atol=2e-5 * max(1.0, np.abs(g["gloc"]).max()))
+        # fp32 gradients against the fp64 reference: rtol 1e-4 plus 1e-5 of each gradient's own scale. d/d(loc) is
+        # a difference of neighbouring pixels times the map size (cancellation of O(|value|) terms) and grad_value is
+        # accumulated with order-dependent fp32 atomics, so a pure 1e-5 relative bound is not attainable in fp32 —
+        # the reference's own float check uses rtol 1e-2 / atol 1e-3 (deformattn/test.py:56)
+        gtol = None
     np.testing.assert_allclose(out.detach().cpu().numpy(), g["out64"], **tol)
-    np.testing.assert_allclose(value.grad.cpu().numpy(), g["gvalue"], **gtol)
-    np.testing.assert_allclose(attn.grad.cpu().numpy(), g["gattn"], **gtol)
-    np.testing.assert_allclose(loc.grad.cpu().numpy(), g["gloc"], **gtol)
+    for got, want in ((value.grad, g["gvalue"]), (attn.grad, g["gattn"]), (loc.grad, g["gloc"])):
+        k = gtol if gtol is not None else dict(rtol=1e-4, atol=1e-5 * max(np.abs(want).max(), 1e-6))
+        np.testing.assert_allclose(got.cpu().numpy(), want, **k)
 
 
 def _streammos_msda_inputs(rng, B, Hs=64, Ws=64, M=4, D=32, P=4):
@@ -421,6 +425,34 @@ def test_msda_gradcheck_double(channels):
     attn = torch.rand(N, Lq, M, L, P, device=dev()) + 1e-5
     attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
     assert gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, attn, 2))
+
+
+@pytest.mark.parametrize("channels", [1025, 2048, 3096])
+def test_msda_gradcheck_double_large_channels(channels):
+    """The large channel counts of deformattn/test.py:85 (the reference routes D > 1024 to its multi-block reduction
+    kernels, ms_deform_im2col_cuda.cuh:1015-1130). Same shapes and seed; gradcheck in fast mode (random projections of
+    the Jacobian) because the full numerical Jacobian of a 186 k-element value tensor is 18 GB."""
+    from torch.autograd import gradcheck
+    from streammos_b200.functions import MSDeformAttnFunction
+    torch.manual_seed(3)
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=dev())
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = (torch.rand(N, S, M, channels, device=dev()) * 0.01).double().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2, device=dev()).double().requires_grad_(True)
+    attn = torch.rand(N, Lq, M, L, P, device=dev()) + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+    assert gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, attn, 2), fast_mode=True)
+    # and the analytical gradients equal torch autograd through the fp64 oracle formula, element for element
+    out = MSDeformAttnFunction.apply(value, shapes, lsi, loc, attn, 2)
+    gout = torch.rand_like(out)
+    out.backward(gout)
+    rv, rl, ra = O.ms_deform_attn_backward(value.detach().cpu().numpy(), shapes.cpu().numpy(), lsi.cpu().numpy(),
+                                           loc.detach().cpu().numpy(), attn.detach().cpu().numpy(), gout.cpu().numpy())
+    np.testing.assert_allclose(value.grad.cpu().numpy(), rv, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(loc.grad.cpu().numpy(), rl, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(attn.grad.cpu().numpy(), ra, rtol=1e-9, atol=1e-12)
 
 
 def test_msda_forward_into_caller_buffer():

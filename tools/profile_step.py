@@ -24,7 +24,7 @@ hot = stream.HotPath(dev, a.points, seed=0, branches=False, vote_api=a.vote_api)
 scans = [(stream.make_host_loader_scan if a.loader else stream.make_host_scan)(i, a.points).to(dev) for i in range(4)]
 fn = {"step": hot.step, "vote": hot.long_term_voting, "proj": hot.projection}[a.what]
 with torch.no_grad():
-    for i in range(3):
+    for i in range(8):  # the plan cache learns its prefetch batches on the first scans: profile the steady state
         fn(scans[i % 4])
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

@@ -4,7 +4,10 @@ minute under compute-sanitizer:
     compute-sanitizer --tool memcheck  --error-exitcode 1 python tools/sanitize_run.py
     compute-sanitizer --tool racecheck --error-exitcode 1 python tools/sanitize_run.py
 
-SURVEY §5: "new kernels must be compute-sanitizer --tool racecheck clean". The summaries are committed under profiles/.
+SURVEY §5: "new kernels must be compute-sanitizer --tool racecheck clean". On this pool compute-sanitizer is CLOSED
+(gpurun answers "compute-sanitizer is closed on this pool and stays closed", profiles/r2_compute_sanitizer_closed.txt), so
+the script is run plain — every result compared with the oracle — and the race / bounds arguments are made by construction
+in DESIGN.md §4.6.
 """
 import os
 import sys
@@ -54,7 +57,7 @@ assert np.array_equal(ops.voxel_maxpool_forward(t(feat), plans[0]).cpu().numpy()
 fx = t(feat).requires_grad_(True)
 out = deep_point.VoxelMaxPool(fx, t(ind), (H, W), (0.5, 0.5))
 out.backward(g3)
-assert np.array_equal(fx.grad.cpu().numpy(), O.voxel_maxpool_backward(feat, ind, want, g3.cpu().numpy(), (0.5, 0.5)))
+assert np.array_equal(fx.grad.cpu().numpy()[..., 0], O.voxel_maxpool_backward(feat, ind, want, g3.cpu().numpy(), (0.5, 0.5)))
 ok("batched plans with gather records, pooling backward")
 from streammos_b200.point_deep import cuda_kernel  # noqa: E402
 vo = torch.zeros(B, C, H, W, device=dev)
