@@ -240,13 +240,16 @@ int smos_ms_deform_attn_backward(int32_t dtype, const void* value,
 /*   x  : (B, Cin, N) float32, strides x_sb / x_sc / x_sn ; Cin <= 16
  *   w1 : (C1, Cin) row major ; w2 : (C2, C1) row major ; C1 == C2 == 64
  *   bn0_alpha / bn0_beta may both be NULL (no pre-BN)
- *   y  : (B, C2, N) float32, strides y_sb / y_sc, points contiguous; every element written. */
+ *   y  : (B, C2, N) float32, element strides y_sb / y_sc / y_sn (channel-major y_sn == 1, or point-major y_sc == 1: each
+ *        point's C2 features contiguous, what VoxelMaxPool reads without its permute stage); every element written.
+ * Layer 2 runs on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulation in TMEM): within 1e-5 of
+ * the fp32 reference. The environment variable SMOS_STEM_UMMA=0 selects the CUDA-core kernel (fixed FMA order, y_sn == 1). */
 int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, int64_t N,
                             int64_t x_sb, int64_t x_sc, int64_t x_sn,
                             const float* bn0_alpha, const float* bn0_beta, const float* w1,
                             const float* bn1_alpha, const float* bn1_beta, const float* w2,
                             const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
-                            float* y, int64_t y_sb, int64_t y_sc, void* stream);
+                            float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* (E, next: SURVEY 8f rank 2, exact part) model input tensors from raw scans. */
@@ -274,7 +277,7 @@ int smos_point_stem_forward_raw(const float* points, int64_t T, int64_t N, int64
                                 const float* bn0_alpha, const float* bn0_beta, const float* w1,
                                 const float* bn1_alpha, const float* bn1_beta, const float* w2,
                                 const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
-                                float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, void* stream);
+                                float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* (C) Long-term-memory voting.                                               */

@@ -281,12 +281,15 @@ point_stem_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int32_t B
   }
 }
 
+#include "point_stem_umma.cuh"
+
 }  // namespace
 
 static int stem_launch(const float* x, int64_t B, int32_t Cin, int64_t N, int64_t x_sb, int64_t x_sc, int64_t x_sn,
                        const StemRaw& raw, const float* bn0_alpha, const float* bn0_beta, const float* w1,
                        const float* bn1_alpha, const float* bn1_beta, const float* w2, const float* bn2_alpha,
-                       const float* bn2_beta, int32_t C1, int32_t C2, float* y, int64_t y_sb, int64_t y_sc, void* stream) {
+                       const float* bn2_beta, int32_t C1, int32_t C2, float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn,
+                       void* stream) {
   if (B <= 0 || N < 0 || Cin <= 0) return SMOS_EINVAL;
   if (N == 0) return SMOS_OK;
   if ((!x && !raw.pts) || !w1 || !bn1_alpha || !bn1_beta || !w2 || !bn2_alpha || !bn2_beta || !y) return SMOS_EINVAL;
@@ -300,6 +303,28 @@ static int stem_launch(const float* x, int64_t B, int32_t Cin, int64_t N, int64_
   const int32_t Ni = static_cast<int32_t>(N), Bi = static_cast<int32_t>(B);
   cudaStream_t st = smos_stream(stream);
   const int64_t ntiles = static_cast<int64_t>(smos_ceil_div(N, kStemPts)) * B;
+  // default: layer 2 on the 5th-generation tensor cores (tcgen05.mma, 3xTF32 split, accumulators in TMEM).
+  // SMOS_STEM_UMMA=0 selects the CUDA-core kernel below (bit-identical to the oracle's FMA order; channel-major
+  // output only), SMOS_STEM_TC=1 its mma.sync variant.
+  if (smos_env_int("SMOS_STEM_UMMA", 1) != 0 && !tc) {
+#define SMOS_STEM_UMMA_LAUNCH(CINV, RAWV)                                                                            \
+  do {                                                                                                                \
+    auto kern = point_stem_umma_kernel<CINV, RAWV>;                                                                   \
+    static std::atomic<unsigned long long> opted{0};                                                                  \
+    if (cudaError_t e = smos_smem_opt_in(kern, opted, static_cast<int>(sizeof(umma_stem::Smem) + 128)); e != cudaSuccess) \
+      return static_cast<int>(e);                                                                                     \
+    const int64_t want = SMOS_SM_COUNT; /* 165 KB of shared memory: one persistent CTA per SM */                      \
+    dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));                                                  \
+    SMOS_LAUNCH((kern), grid, umma_stem::kThreads, sizeof(umma_stem::Smem) + 128, st, x, Cin, Ni, Bi, x_sb, x_sc, x_sn, \
+                raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc, y_sn);     \
+  } while (0)
+    if (is_raw) SMOS_STEM_UMMA_LAUNCH(7, true);
+    else if (Cin == 7) SMOS_STEM_UMMA_LAUNCH(7, false);
+    else SMOS_STEM_UMMA_LAUNCH(0, false);
+#undef SMOS_STEM_UMMA_LAUNCH
+    return smos_launch_status();
+  }
+  if (y_sn != 1) return SMOS_EUNSUPPORTED;  // the CUDA-core kernels write channel-major rows
 #define SMOS_STEM_LAUNCH(CINV, RAWV, TCV)                                                                             \
   do {                                                                                                                \
     auto kern = point_stem_kernel<CINV, RAWV, TCV>;                                                                   \
@@ -327,10 +352,10 @@ extern "C" int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, i
                                        int64_t x_sn, const float* bn0_alpha, const float* bn0_beta, const float* w1,
                                        const float* bn1_alpha, const float* bn1_beta, const float* w2,
                                        const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2, float* y,
-                                       int64_t y_sb, int64_t y_sc, void* stream) {
+                                       int64_t y_sb, int64_t y_sc, int64_t y_sn, void* stream) {
   StemRaw raw = {};
   return stem_launch(x, B, Cin, N, x_sb, x_sc, x_sn, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha,
-                     bn2_beta, C1, C2, y, y_sb, y_sc, stream);
+                     bn2_beta, C1, C2, y, y_sb, y_sc, y_sn, stream);
 }
 
 // smos_form_batch + smos_point_stem_forward in one kernel: raw points in, 64-channel features and the quantised
@@ -340,9 +365,10 @@ extern "C" int smos_point_stem_forward_raw(const float* points, int64_t T, int64
                                            float dz, const float* bn0_alpha, const float* bn0_beta, const float* w1,
                                            const float* bn1_alpha, const float* bn1_beta, const float* w2,
                                            const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
-                                           float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, void* stream) {
+                                           float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn,
+                                           void* stream) {
   if (!points || !pcds_coord) return SMOS_EINVAL;
   StemRaw raw = {points, row_stride, x_sign, y_sign, min_x, min_y, min_z, dx, dy, dz, pcds_coord};
   return stem_launch(nullptr, T, 7, N, 0, 0, 0, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta,
-                     C1, C2, y, y_sb, y_sc, stream);
+                     C1, C2, y, y_sb, y_sc, y_sn, stream);
 }

@@ -6,7 +6,7 @@ models/StreamMOS.py, networks/multi_view_encoder.py and deformattn/ run unmodifi
 
 (The reference has no plugin registry; its modules are found through sys.modules.)
 
-`point_major_points` (default): BilinearSample returns its (B, C, N, 1) result with channels_last strides — same shape
+`point_major_points` (default): BilinearSample and the fused PointNetStacker return their (B, C, N, 1) results with channels_last strides — same shape
 and values, each point's channels contiguous, the layout the next VoxelMaxPool and the 1x1 point convolutions read
 fastest. Pass False for (B, C, N, 1)-contiguous results as the reference produces them."""
 import sys
@@ -24,6 +24,7 @@ def install(point_major_points=True):
     sys.modules["deep_point"] = b200_deep_point
     sys.modules["MultiScaleDeformableAttention"] = msda
     b200_backbone.BilinearSample.point_major_out = bool(point_major_points)
+    b200_backbone.PointNetStacker.point_major_out = bool(point_major_points)
     # networks.backbone.BilinearSample is looked up by name at model build time (backbone.py:37-43,
     # multi_view_encoder.py:377-378): replace the class if the reference package is importable.
     ref_backbone = sys.modules.get("networks.backbone")

@@ -313,9 +313,18 @@ def form_batch(points, range_x, range_y, range_z, size, x_sign=1.0, y_sign=1.0):
 # ----------------------------------------------------------------------------------------------
 # PointNet stem (next: SURVEY 8f rank 4)
 # ----------------------------------------------------------------------------------------------
-def point_stem_forward(x, bn0, w1, bn1, w2, bn2, out=None):
+def _stem_out(B, C2, N, device, point_major):
+    import os
+    if point_major and os.environ.get("SMOS_STEM_UMMA", "1") != "0" and os.environ.get("SMOS_STEM_TC", "0") == "0":
+        # same shape, channels_last strides: each point's C2 features contiguous (tensor-core kernel only)
+        return torch.empty((B, N, 1, C2), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+    return torch.empty((B, C2, N, 1), dtype=torch.float32, device=device)
+
+
+def point_stem_forward(x, bn0, w1, bn1, w2, bn2, out=None, point_major_out=False):
     """Fused eval-mode PointNetStacker(Cin, 64, pre_bn=True, stack_num=2): x (B, Cin, N[, 1]) float32 ->
-    (B, 64, N, 1) contiguous. bn* = (alpha, beta) per-channel affines of the eval BatchNorms (bn0 may be None);
+    (B, 64, N, 1), contiguous or (point_major_out) with channels_last strides — the layout VoxelMaxPool reads without its
+    permute stage. bn* = (alpha, beta) per-channel affines of the eval BatchNorms (bn0 may be None);
     w1 (64, Cin[, 1, 1]), w2 (64, 64[, 1, 1])."""
     _need_cuda(x, "x")
     _need_f32(x, "x")
@@ -337,19 +346,20 @@ def point_stem_forward(x, bn0, w1, bn1, w2, bn2, out=None):
     a0, b0 = (vecs[0], vecs[1]) if bn0 is not None else (None, None)
     a1, b1, a2, b2 = vecs[-4:]
     if out is None:
-        out = torch.empty((B, C2, N, 1), dtype=torch.float32, device=x.device)
+        out = _stem_out(B, C2, N, x.device, point_major_out)
     else:
-        assert out.is_contiguous() and out.shape == (B, C2, N, 1) and out.dtype == torch.float32
+        assert out.shape == (B, C2, N, 1) and out.dtype == torch.float32
     with torch.cuda.device(x.device):
         rc = _lib.load().smos_point_stem_forward(_ptr(x3), B, Cin, N, x3.stride(0), x3.stride(1), x3.stride(2), _ptr(a0),
                                                  _ptr(b0), _ptr(w1), _ptr(a1), _ptr(b1), _ptr(w2), _ptr(a2), _ptr(b2),
-                                                 C1, C2, _ptr(out), out.stride(0), out.stride(1), _stream())
+                                                 C1, C2, _ptr(out), out.stride(0), out.stride(1), out.stride(2), _stream())
     _lib.check(rc, "smos_point_stem_forward")
     _count(1)
     return out
 
 
-def point_stem_forward_raw(points, range_x, range_y, range_z, size, bn0, w1, bn1, w2, bn2, x_sign=1.0, y_sign=1.0):
+def point_stem_forward_raw(points, range_x, range_y, range_z, size, bn0, w1, bn1, w2, bn2, x_sign=1.0, y_sign=1.0,
+                           point_major_out=False):
     """form_batch + point_stem_forward in one kernel: points (T, N, >=4) float32 CUDA raw scans ->
     (features (T, 64, N, 1), pcds_coord (T, N, 3, 1)); bit-identical to the two separate calls."""
     import numpy as np
@@ -373,14 +383,14 @@ def point_stem_forward_raw(points, range_x, range_y, range_z, size, bn0, w1, bn1
     a1, b1, a2, b2 = vecs[-4:]
     d = [float(np.float32((r[1] - r[0]) / s_)) for r, s_ in zip((range_x, range_y, range_z), size)]
     C1, C2 = int(w1.shape[0]), int(w2.shape[0])
-    out = torch.empty((T, C2, N, 1), dtype=torch.float32, device=points.device)
+    out = _stem_out(T, C2, N, points.device, point_major_out)
     coord = torch.empty((T, N, 3, 1), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
         rc = _lib.load().smos_point_stem_forward_raw(
             _ptr(points), T, N, points.stride(1) if N > 1 else points.size(2), float(x_sign), float(y_sign),
             float(range_x[0]), float(range_y[0]), float(range_z[0]), d[0], d[1], d[2], _ptr(a0), _ptr(b0), _ptr(w1),
             _ptr(a1), _ptr(b1), _ptr(w2), _ptr(a2), _ptr(b2), C1, C2, _ptr(coord), _ptr(out), out.stride(0), out.stride(1),
-            _stream())
+            out.stride(2), _stream())
     _lib.check(rc, "smos_point_stem_forward_raw")
     _count(1)
     return out, coord

@@ -236,6 +236,7 @@ class HotPath:
             bn0.running_mean.copy_(torch.tensor([0.5, -0.3, -1.2, 0.3, 18.0, 0.5, 0.5]))
             bn0.running_var.copy_(torch.tensor([300.0, 280.0, 0.8, 0.05, 150.0, 0.08, 0.08]))
         self.stem.eval().to(self.device)
+        self.stem.point_major_out = point_major
         # short-term memory: previous scan's attended BEV feature, (1, 4096, 128) (mve.py:433-439)
         self.memory = torch.randn(1, MEM_HW * MEM_HW, N_HEADS * HEAD_DIM, generator=g).to(self.device)
         self.shapes = torch.tensor([[MEM_HW, MEM_HW]], dtype=torch.int64, device=self.device)
@@ -292,7 +293,8 @@ class HotPath:
         if hasattr(b, "points"):      # raw scan: Quantize + make_point_feat on the device, then the stem
             if self.fuse_form_batch:  # one kernel: raw points -> 64-channel features + quantised coordinates
                 feat, coord = ops.point_stem_forward_raw(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z,
-                                                         self.size, *self.stem.fused_parameters())
+                                                         self.size, *self.stem.fused_parameters(),
+                                                         point_major_out=self.point_major)
             else:
                 feat7, coord = ops.form_batch(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, self.size)
                 feat = self.point_pre(feat7)
