@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--ordered-rv", action="store_true", help="range-view gathers in cell order too")
     ap.add_argument("--gather-taps", action="store_true",
                     help="gathers read their sampling state from records the plan build emits (measured: no gain)")
+    ap.add_argument("--e2e-only", action="store_true", help="tuning aid: measure and print only the raw-scan e2e leg")
     ap.add_argument("--families-only", action="store_true",
                     help="tuning aid: print only the per-family device times (not the contract's JSON line) and exit")
     return ap.parse_args()
@@ -217,7 +218,8 @@ def workload_config(args, graph, world):
             "points_per_scan": args.points, "bev_shape": [512, 512, 30], "rv_shape": [64, 2048],
             "memory": [64, 64, 128], "streams": world, "parallelism": "1 independent scan stream per GPU, no collectives",
             "launch": "cuda-graph replay" if graph else "eager", "vote_api": args.vote_api,
-            "point_feature_layout": "channel-major" if args.channel_major else "point-major (channels_last strides)",
+            "point_feature_layout": "channel-major (reference layout: VoxelMaxPool #1 permutes)" if args.channel_major else
+                                    "point-major (channels_last strides), stem output included",
             "cnn_grid_layout": "channels_last" if args.grids_channels_last else "NCHW (reference default)",
             "pipeline": "3 graphs per scan (projection / temporal fusion / voting), %d scans in flight on %d CUDA streams; "
                         "cross-scan dependencies (short-term memory, voting ring) enforced with events; %s"
@@ -251,8 +253,13 @@ def run_b200(args, world, rank, local):
                          grids_channels_last=args.grids_channels_last, branches=args.branches, batch_plans=args.explicit_plans,
                          ordered_gathers=not args.no_ordered_gathers, ordered_rv=args.ordered_rv,
                          gather_taps=args.gather_taps)
-    host = [stream.make_host_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
+    # the 64-channel point features are what the PointNet stem hands to VoxelMaxPool #1; the drop-in stem
+    # (backbone.PointNetStacker, tcgen05 kernel) emits them point-major (channels_last strides), like every other
+    # point-feature tensor of the path. --channel-major keeps the reference's (B, C, N, 1)-contiguous layout.
+    host = [stream.make_host_scan(rank * 1000 + i, args.points, feat_point_major=not args.channel_major)
+            for i in range(N_SCANS)]
     devb = [h.to(dev) for h in host]
+    assert devb[0].feat.stride() == host[0].feat.stride()
     torch.cuda.synchronize()
     cpu_hot_state = cpu_state(hot) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
@@ -260,7 +267,10 @@ def run_b200(args, world, rank, local):
         with torch.no_grad():
             hot.step(devb[0])
             hot.scan_index = 0
-            fam = family_breakdown(hot, devb, dev, 6451.8, max(3, min(args.steps, 30)))
+            raw = None
+            if os.environ.get("SMOS_FAMILIES_RAW"):
+                raw = [stream.make_host_raw_scan(rank * 1000 + i, args.points, pin=False).to(dev) for i in range(N_SCANS)]
+            fam = family_breakdown(hot, devb, dev, 6451.8, max(3, min(args.steps, 30)), stem_scans=raw)
         print(json.dumps({k: round(v["us_per_scan"], 2) for k, v in fam.items()}), flush=True)
         return
     compute = torch.cuda.Stream(dev)
@@ -315,12 +325,14 @@ def run_b200(args, world, rank, local):
                         copy.wait_event(pipe_.m_done[j])
                         copy.wait_event(pipe_.v_done[j])
                         copy.wait_event(d2h[j])
-                        devb_[j].copy_from(host_[j])        # H2D of this scan's inputs (pinned -> HBM)
+                        if not os.environ.get("SMOS_E2E_NO_H2D"):  # experiment knob: how much of e2e is the copy
+                            devb_[j].copy_from(host_[j])    # H2D of this scan's inputs (pinned -> HBM)
                         ready[j].record(copy)
                     pipe_.submit(ready[j])
                     with torch.cuda.stream(sC):             # D2H of the step's result, behind the voting graph
-                        h_labels[j].copy_(outs_[j][0], non_blocking=True)
-                        h_sums[j].copy_(outs_[j][1], non_blocking=True)
+                        if not os.environ.get("SMOS_E2E_NO_D2H"):
+                            h_labels[j].copy_(outs_[j][0], non_blocking=True)
+                            h_sums[j].copy_(outs_[j][1], non_blocking=True)
                         d2h[j].record(sC)
 
             for j in range(N_SCANS):
@@ -353,6 +365,15 @@ def run_b200(args, world, rank, local):
                     "h2d_bytes_per_step": host_[0].nbytes(),
                     "d2h_bytes_per_step": h_labels[0].numel() * 8 + h_sums[0].numel() * 8}
 
+        if args.e2e_only:
+            hot_r = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
+                                   vote_api=args.vote_api, branches=args.branches, batch_plans=args.explicit_plans)
+            host_r = [stream.make_host_raw_scan(rank * 1000 + i, args.points) for i in range(N_SCANS)]
+            devb_r = [h.pack(device=dev) for h in host_r]
+            torch.cuda.synchronize()
+            pipe_r = pipeline.ScanPipeline(hot_r, devb_r, use_graphs=use_graph, scans_in_flight=args.in_flight)
+            print(json.dumps(measure_e2e(pipe_r, host_r, devb_r, args.steps)), flush=True)
+            return
         # (1) hot-path inputs themselves in host memory: the 64-channel point features (92 MB per scan) cross PCIe —
         #     something the reference never does (its PointNet stem produces them on the GPU)
         side_steps = min(args.steps, 300)
@@ -542,7 +563,7 @@ def run_b200(args, world, rank, local):
             sys.stderr.write("%-28s %8.4f ms\n" % (k, v))
 
 
-def family_breakdown(hot, devb, dev, peak, iters):
+def family_breakdown(hot, devb, dev, peak, iters, stem_scans=None):
     """Per-family device time of the hot path (roofline = algorithmic bytes / sum of hot-path kernel time).
 
     Each family's launches for all resident scans are captured into ONE CUDA graph (no host launch gaps) and the
@@ -581,8 +602,18 @@ def family_breakdown(hot, devb, dev, peak, iters):
             sp = specs(devb[j])
             return [ops.cached_pool_plan(*sp[i]) for i in (0, 2, 1, 4, 3)]
 
+        raw_feat = None
+        if stem_scans is not None:  # raw-scan path: the stem's output (point-major rows) is what pool #1 reads
+            from streammos_b200 import synthetic
+            stem_args = (synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, hot.size) + tuple(hot.stem.fused_parameters())
+            raw_feat = [ops.point_stem_forward_raw(r.points, *stem_args, point_major_out=hot.point_major)[0] for r in stem_scans]
+
+        def f_stem(j):
+            return ops.point_stem_forward_raw(stem_scans[j].points, *stem_args, point_major_out=hot.point_major)
+
         def f_pool1(j):
-            return deep_point.VoxelMaxPool(devb[j].feat, devb[j].coord_bev, (512, 512), (1.0, 1.0), P[j][0])
+            feat = raw_feat[j] if raw_feat is not None else devb[j].feat
+            return deep_point.VoxelMaxPool(feat, devb[j].coord_bev, (512, 512), (1.0, 1.0), P[j][0])
 
         def f_pools(j):
             b, k, pl = devb[j], keep[j], P[j]
@@ -607,7 +638,8 @@ def family_breakdown(hot, devb, dev, peak, iters):
             hot.scan_index = j
             return hot.long_term_voting(devb[j])
 
-        fams = [("plans", f_plans, 0), ("pool1", f_pool1, ab["pool"][0]), ("pools2-5", f_pools, sum(ab["pool"][1:])),
+        fams = ([("stem (raw-scan path only)", f_stem, 0)] if stem_scans is not None else []) + \
+               [("plans", f_plans, 0), ("pool1", f_pool1, ab["pool"][0]), ("pools2-5", f_pools, sum(ab["pool"][1:])),
                 ("gathers", f_gathers, sum(ab["gather"])), ("msda", f_msda, ab["msda"]), ("voting", f_vote, ab["vote"])]
         for name, fn, nbytes in fams:
             for j in range(nb):

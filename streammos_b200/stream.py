@@ -48,7 +48,7 @@ class ScanBatch:
         return ScanBatch(**{f: torch.empty_like(getattr(self, f), device=device) for f in self.FIELDS})
 
 
-def make_host_scan(seed, n_points=120000, t_frames=3, channels=64, pin=True):
+def make_host_scan(seed, n_points=120000, t_frames=3, channels=64, pin=True, feat_point_major=False):
     """Synthetic inputs of one scan: LiDAR-shaped coordinates, post-ReLU point features (the PointNet
     output of models/StreamMOS.py:101), predicted labels for the long-term memory and the sampling
     locations / attention weights the two deformable-attention layers receive."""
@@ -67,7 +67,10 @@ def make_host_scan(seed, n_points=120000, t_frames=3, channels=64, pin=True):
         rng.standard_normal((2, 1, q, N_HEADS, 1, N_POINTS, 2)) * (2.0 / MEM_HW)
     a = rng.standard_normal((2, 1, q, N_HEADS, N_POINTS))
     attn = (np.exp(a) / np.exp(a).sum(-1, keepdims=True)).reshape(2, 1, q, N_HEADS, 1, N_POINTS)
-    out = ScanBatch(feat=torch.from_numpy(feat), coord_bev=torch.from_numpy(coord_bev),
+    feat_t = torch.from_numpy(feat)
+    if feat_point_major:  # channels_last strides: each point's channels contiguous, as the drop-in PointNet stem emits them
+        feat_t = feat_t.contiguous(memory_format=torch.channels_last)
+    out = ScanBatch(feat=feat_t, coord_bev=torch.from_numpy(coord_bev),
                     coord_rv=torch.from_numpy(coord_rv), xyzi=torch.from_numpy(s["xyzi"][0].copy()),
                     pred=torch.from_numpy(pred), loc=torch.from_numpy(loc.astype(np.float32)),
                     attn=torch.from_numpy(attn.astype(np.float32)))
