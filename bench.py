@@ -247,6 +247,10 @@ def run_b200(args, world, rank, local):
     _lib.load()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # one process per GPU on one host: run next to the GPU (cores of its NUMA node) before any pinned buffer is
+    # allocated, so submits and H2D reads do not cross the socket link (SMOS_NO_PIN=1: leave the affinity alone)
+    from streammos_b200 import multi
+    pinned_cpus = None if os.environ.get("SMOS_NO_PIN") else multi.pin_rank_to_gpu(local, world)
     use_graph = not args.no_graph
     hot = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
                          vote_api=args.vote_api, overlap_voting=False,
@@ -543,7 +547,10 @@ def run_b200(args, world, rank, local):
     line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, use_graph, world), "roofline": roofline, "e2e": e2e,
+            "config": dict(workload_config(args, use_graph, world),
+                           host_affinity=("rank pinned to %d cores of its GPU's NUMA node" % len(pinned_cpus))
+                           if pinned_cpus else "unchanged"),
+            "roofline": roofline, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks, "breakdown_ms": breakdown, "variants": variants,
             "reference_signature": None if args.explicit_plans else {

@@ -216,6 +216,25 @@ int smos_ms_deform_attn_forward(int32_t dtype, const void* value,
                                 int32_t L, int32_t Q, int32_t P,
                                 void* output, void* stream);
 
+/* (next: SURVEY 8f rank 4, fusing) The same sampling core started one step    */
+/* earlier, at what the attention module computes in front of it               */
+/* (deformattn/modules/ms_deform_attn.py:96-108):                              */
+/*   attn_weight  = softmax(attn_logits over the L*P samples of a (b, q, m))   */
+/*   sampling_loc = reference_points[:, :, None, :, None, :]                    */
+/*                  + sampling_offsets / (W_l, H_l)                 (ref_dim 2) */
+/*                = ref[..., :2] + sampling_offsets / P * ref[..., 2:] * 0.5    */
+/*                                                                  (ref_dim 4) */
+/*   sampling_offsets : (B, Q, M, L, P, 2)   attn_logits : (B, Q, M, L*P)       */
+/*   reference_points : (B, Q, L, ref_dim)   all contiguous, value's dtype      */
+int smos_ms_deform_attn_fused_forward(int32_t dtype, const void* value,
+                                      const int64_t* spatial_shapes,
+                                      const int64_t* level_start_index,
+                                      const void* sampling_offsets, const void* attn_logits,
+                                      const void* reference_points, int32_t ref_dim,
+                                      int32_t B, int32_t S, int32_t M, int32_t D,
+                                      int32_t L, int32_t Q, int32_t P,
+                                      void* output, void* stream);
+
 /* grad_value must be ZERO-FILLED by the caller (atomic accumulation);
  * grad_sampling_loc and grad_attn_weight are fully written. */
 int smos_ms_deform_attn_backward(int32_t dtype, const void* value,

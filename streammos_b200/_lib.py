@@ -52,6 +52,8 @@ SIGNATURES = {
                                                      _f32, _f32, _i32, _i32, _vp, _vp]),
     "smos_ms_deform_attn_forward": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
                                                    _i32, _i32, _vp, _vp]),
+    "smos_ms_deform_attn_fused_forward": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
+                                                         _i32, _i32, _i32, _vp, _vp]),
     "smos_ms_deform_attn_backward": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                                     _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "smos_quantize": (ctypes.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),

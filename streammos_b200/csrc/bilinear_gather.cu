@@ -15,7 +15,13 @@ constexpr int kGatherThreads = 128;
 #define SMOS_GATHER_MIN_CTAS 10  // <= 42 registers: the kernel's speed follows the number of resident warps
 #endif
 constexpr int kGatherPts = 32;  // points per CTA
-constexpr int kCPT = 8;         // channels per thread-step in the planar kernel
+#ifndef SMOS_GATHER_CPT
+#define SMOS_GATHER_CPT 8
+#endif
+#ifndef SMOS_GATHER_PLANAR_MIN_CTAS
+#define SMOS_GATHER_PLANAR_MIN_CTAS 14  // <= 72 registers: room for the 32 loads of a step in flight
+#endif
+constexpr int kCPT = SMOS_GATHER_CPT;  // channels per thread-step in the planar kernel (4 or 8)
 
 // Per-point sampling state shared by all threads of a CTA: the replayed pixel arithmetic costs ~150
 // instructions (two IEEE divisions) and every channel of a point needs the same result, so it is
@@ -107,7 +113,7 @@ __device__ __forceinline__ TapsS lane_taps(int64_t slot, int32_t b, const float*
 constexpr int kGatherWarps = 2;  // independent warps per CTA
 
 template <bool DENSE, bool ROWS_OUT, bool ORDERED, bool TAPS>
-__global__ void __launch_bounds__(kGatherWarps * 32, 14)  // <= 72 registers: room for the 32 loads of a step in flight
+__global__ void __launch_bounds__(kGatherWarps * 32, SMOS_GATHER_PLANAR_MIN_CTAS)
 gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                              int64_t gr_sb, int64_t gr_sc, int64_t gr_sh, int64_t gr_sw,
                              const float* __restrict__ coord, int32_t N,
@@ -116,7 +122,7 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
                              const int2* __restrict__ order, int32_t order_hw, int64_t order_len,
                              const TapsS* __restrict__ taps, int32_t groups_per_warp) {
   SMOS_PDL_PROLOGUE();
-  extern __shared__ __align__(16) float s_out_all[];  // ROWS_OUT: [kGatherWarps][32][C + 4]
+  extern __shared__ __align__(16) float s_out_all[];  // ROWS_OUT: [kGatherWarps][32][channels of one warp + 4]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t slot0 = (static_cast<int64_t>(blockIdx.x) * kGatherWarps + wid) * 32;
   if (slot0 >= (ORDERED || TAPS ? order_len : static_cast<int64_t>(N))) return;  // whole warp past the end
@@ -129,20 +135,26 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
   const int32_t cg_begin = blockIdx.y * groups_per_warp;
   const int32_t cg_end = min(ngroups, cg_begin + groups_per_warp);
   const float* g = grid + b * gr_sb;
-  float* s_out = s_out_all + static_cast<size_t>(wid) * 32 * (C + 4);
+  // the staging slice holds only the channels THIS warp produces (a warp of a split launch used to reserve rows of
+  // all C channels: at 64 channels that capped the SM at 13 CTAs)
+  const int32_t c_lo0 = cg_begin * kCPT;
+  const int32_t ld_s = groups_per_warp * kCPT + 4;
+  float* s_out = s_out_all + static_cast<size_t>(wid) * 32 * ld_s;
   const bool vec_ok = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   float* const orow = out + b * o_sb + static_cast<int64_t>(n >= 0 ? n : 0) * o_sn;
   auto emit = [&](int32_t c0, int32_t nch, const float (&acc)[kCPT]) {
     if (ROWS_OUT) {
-      float* so = s_out + lane * (C + 4) + c0;
-      *reinterpret_cast<float4*>(so) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(so + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      float* so = s_out + lane * ld_s + (c0 - c_lo0);
+#pragma unroll
+      for (int k4 = 0; k4 < kCPT; k4 += 4)
+        *reinterpret_cast<float4*>(so + k4) = make_float4(acc[k4], acc[k4 + 1], acc[k4 + 2], acc[k4 + 3]);
     } else if (n >= 0) {
       float* o = orow + static_cast<int64_t>(c0) * o_sc;
       if (vec_ok && nch == kCPT) {
-        *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+        for (int k4 = 0; k4 < kCPT; k4 += 4)
+          *reinterpret_cast<float4*>(o + k4) = make_float4(acc[k4], acc[k4 + 1], acc[k4 + 2], acc[k4 + 3]);
       } else {
 #pragma unroll
         for (int k = 0; k < kCPT; ++k)
@@ -223,7 +235,7 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
       const int32_t j = i - p * q;
       const int64_t rb = __shfl_sync(0xffffffffu, my_row, p);
       if (rb < 0) continue;
-      const float4 r = *reinterpret_cast<const float4*>(s_out + p * (C + 4) + c_lo + (j << 2));
+      const float4 r = *reinterpret_cast<const float4*>(s_out + p * ld_s + (j << 2));
       *reinterpret_cast<float4*>(out + rb + c_lo + (j << 2)) = r;
     }
   }
@@ -384,11 +396,11 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
                                                                               o_sb, o_sc, o_sn, nullptr, 1, 0, nullptr);
   } else {
     // point-major output rows (C % 8 == 0, 16-byte aligned) are assembled in shared memory and leave as whole lines
+    const size_t smem_rows = static_cast<size_t>(groups_per_warp * kCPT + 4) * 32 * 4 * kGatherWarps;
     const bool rows_out = (o_sc == 1) && C > 1 && ((C & 7) == 0) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
-                          (static_cast<size_t>(C + 4) * 32 * 4 * kGatherWarps <= 46 * 1024) &&
+                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (smem_rows <= 46 * 1024) &&
                           smos_env_int("SMOS_GATHER_ROWS", 1);
-    const size_t smem = rows_out ? static_cast<size_t>(C + 4) * 32 * 4 * kGatherWarps : 0;
+    const size_t smem = rows_out ? smem_rows : 0;
     const bool dense = (gr_sw == 1 && gr_sh == W);
 #define SMOS_LAUNCH_PLANAR(D, R, O, T)                                                                       \
     SMOS_LAUNCH((gather_forward_planar_kernel<D, R, O, T>), gp, kGatherWarps * 32, smem, st,                                  \

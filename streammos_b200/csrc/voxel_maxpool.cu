@@ -657,20 +657,53 @@ template <> __device__ __forceinline__ float4 vneg_inf<4>() { return make_float4
 template <int VEC, bool SORTED_ROWS>
 __global__ void __launch_bounds__(kReduceWarps * 32)
 pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int64_t f_sn, int32_t hw,
-                   const int2* __restrict__ sorted, const int32_t* __restrict__ cursor, float* rows) {
+                   const int2* __restrict__ sorted, int32_t bn, float* rows) {
   SMOS_PDL_PROLOGUE();
   using V = typename VecT<VEC>::type;
   constexpr int kBatch = VEC == 4 ? 8 : 16;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int32_t total = *cursor;
+  // The valid entries of `sorted` are its first cursor[0] slots; every slot behind them holds an out-of-grid point
+  // (cell < 0, written by the plan's scatter kernel). The window therefore finds its own length from the entries
+  // it loads anyway instead of reading the cursor first: one dependent round trip less in a kernel that is a
+  // chain of four.
   const int32_t p0 = (blockIdx.x * kReduceWarps + wib) * 32;
-  if (p0 >= total) return;
-  const int32_t cnt = min(32, total - p0);
-  int2 e = make_int2(0, -1 - lane);  // distinct negative cells for lanes past the end
-  if (lane < cnt) e = sorted[p0 + lane];
+  if (p0 >= bn) return;
+  int2 e = make_int2(0, -1);
+  if (p0 + lane < bn) e = sorted[p0 + lane];
+  // Point-major input (no SORTED_ROWS): a cell whose segment runs over the end of this window for fewer than 32
+  // positions is FINISHED here — the warp also reads the next window's entries and folds that short tail into its
+  // last piece — and the next window's warp skips the same leading run (both sides decide from the entries alone:
+  // a leading run that continues the previous window's last cell and is shorter than the window belongs to the
+  // previous warp). Only cells that cover at least one whole further window are still reduced as several pieces
+  // ("rule B": pieces at `start` and at every window the segment covers completely, the last one including the short
+  // tail). In the small grids that makes multi-piece cells rare instead of the rule (avg 4-15 points per cell).
+  int2 e2 = make_int2(0, -1);
+  int32_t prev_cell = -1;
+  if (!SORTED_ROWS) {
+    if (p0 + 32 + lane < bn) e2 = sorted[p0 + 32 + lane];
+    if (p0 > 0) prev_cell = sorted[p0 - 1].y;
+  }
+  const int32_t cnt = __popc(__ballot_sync(0xffffffffu, e.y >= 0));  // valid entries are the leading ones
+  if (cnt == 0) return;
+  if (lane >= cnt) e = make_int2(0, -1 - lane);  // distinct negative cells for lanes past the end
   const int32_t prev = __shfl_up_sync(0xffffffffu, e.y, 1);
   const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || e.y != prev) &
                          (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+  int32_t lead = 0, tail_k = 0;
+  int64_t tail_off = 0;
+  if (!SORTED_ROWS) {
+    const unsigned same_prev = __ballot_sync(0xffffffffu, prev_cell >= 0 && e.y == prev_cell);
+    const int32_t j = same_prev == 0xffffffffu ? 32 : __ffs(~same_prev) - 1;  // leading run that continues the previous window
+    if (j < 32) lead = j;            // shorter than a window: the previous warp has folded it into its last piece
+    if (lead >= cnt) return;         // (a run that fills the whole window is a piece of its own: lead stays 0)
+    if (cnt == 32) {
+      const int32_t last_cell = __shfl_sync(0xffffffffu, e.y, 31);
+      const unsigned same_last = __ballot_sync(0xffffffffu, e2.y == last_cell);
+      const int32_t k = same_last == 0xffffffffu ? 32 : __ffs(~same_last) - 1;
+      if (k < 32) tail_k = k;        // my last cell ends inside the next window: finish it here
+    }
+    tail_off = (e2.y >= 0 ? e2.y / hw : 0) * f_sb + static_cast<int64_t>(static_cast<uint32_t>(e2.x) & ~kMergedN) * f_sn;
+  }
   // Entries to reduce, compacted to the low lanes: lane j holds the row offset (c = 0) of entry j and the position
   // of the piece it belongs to (the first position of its cell inside this window). Without SORTED_ROWS every
   // position is an entry. With SORTED_ROWS only the row owners are: a merged follower has no row (its value is
@@ -700,7 +733,7 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
     if (lead_empty && c_ok) *reinterpret_cast<V*>(rows + static_cast<int64_t>(p0) * C + c) = vneg_inf<VEC>();
     V acc;
     int32_t piece_pos = -1;
-    for (int32_t j0 = 0; j0 < m; j0 += kBatch) {
+    for (int32_t j0 = lead; j0 < m; j0 += kBatch) {
       V v[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
@@ -725,8 +758,29 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
         }
       }
     }
+    if (!SORTED_ROWS && tail_k > 0) {  // warp uniform: the short tail of my last cell in the next window
+      for (int32_t t0 = 0; t0 < tail_k; t0 += kBatch) {
+        V v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int64_t off = __shfl_sync(0xffffffffu, tail_off, min(t0 + u, tail_k - 1));
+          v[u] = __ldg(reinterpret_cast<const V*>(src + off + c_ld));
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) acc = vmax<VEC>(acc, v[u]);  // (re-read rows repeat: max is idempotent)
+      }
+    }
     if (c_ok && piece_pos >= 0) *reinterpret_cast<V*>(rows + static_cast<int64_t>(piece_pos) * C + c) = acc;
   }
+}
+
+// Number of piece rows a cell's segment [s, s + k) leaves behind the row at s. Rule A (channel-major path): one per
+// further window the segment touches. Rule B (point-major path, see pool_reduce_kernel): one per further window it
+// covers completely. A cell is "multi-piece" when this is > 0; its pieces sit at s and at first + 32 i.
+__device__ __forceinline__ int32_t pool_extra_pieces(int32_t s, int32_t k, bool rule_b) {
+  const int32_t first = (s & ~31) + 32, end = s + k;
+  if (k <= 0 || end <= first) return 0;
+  return rule_b ? (end - first) >> 5 : (end - first + 31) >> 5;
 }
 
 // ---- phase A2: fold the pieces of multi-piece cells into their first row ------------------------
@@ -734,7 +788,8 @@ pool_reduce_kernel(const float* __restrict__ feat, int32_t C, int64_t f_sb, int6
 // occupied cell's maxima sit in rows[start[cell]].
 template <int VEC>
 __global__ void __launch_bounds__(kReduceWarps * 32)
-pool_combine_kernel(int32_t C, const int2* __restrict__ multi, const int32_t* __restrict__ cursor, float* rows) {
+pool_combine_kernel(int32_t C, const int2* __restrict__ multi, const int32_t* __restrict__ cursor, float* rows,
+                    int rule_b) {
   SMOS_PDL_PROLOGUE();
   using V = typename VecT<VEC>::type;
   constexpr int kBatch = VEC == 4 ? 8 : 16;
@@ -742,9 +797,10 @@ pool_combine_kernel(int32_t C, const int2* __restrict__ multi, const int32_t* __
   const int32_t w = blockIdx.x * kReduceWarps + (threadIdx.x >> 5);
   if (w >= cursor[1]) return;
   const int2 sk = multi[w];
-  const int32_t s = sk.x, end = sk.x + sk.y;
+  const int32_t s = sk.x;
   const int32_t first_aligned = (s & ~31) + 32;
-  const int32_t npieces = 1 + (end - first_aligned + 31) / 32;  // end > first_aligned by construction
+  const int32_t npieces = 1 + pool_extra_pieces(s, sk.y, rule_b != 0);
+  if (npieces == 1) return;  // listed under rule A, single piece under rule B
   for (int32_t c0 = 0; c0 < C; c0 += 32 * VEC) {
     const int32_t c = c0 + lane * VEC;
     if (c >= C) continue;
@@ -764,21 +820,75 @@ pool_combine_kernel(int32_t C, const int2* __restrict__ multi, const int32_t* __
   }
 }
 
+// Fold of the multi-piece cells by the first CTAs of the writer launch (see pool_write_kernel).
+__device__ __forceinline__ void pool_fold_multi(const float* __restrict__ rows, int32_t C, int32_t hw,
+                                             const int32_t* __restrict__ count, float* __restrict__ out,
+                                             const int2* __restrict__ multi, const int2* __restrict__ sorted,
+                                             int32_t fold_ctas, int32_t multi_cap, int32_t bx, bool rule_b) {
+  constexpr int kBatch = 16;
+  const int lane = threadIdx.x & 31;
+  const int32_t nwarps = fold_ctas * (kWriteThreads / 32);
+  int32_t w = bx * (kWriteThreads / 32) + (threadIdx.x >> 5);
+  // the list entry is fetched together with the list length (the list has room for multi_cap entries; what
+  // lies behind the length is never used)
+  int2 sk = w < multi_cap ? __ldg(multi + w) : make_int2(0, 0);
+  const int32_t nmulti = __ldg(count + (static_cast<int64_t>(hw) * gridDim.z) + 1);  // cursor[1]
+  for (; w < nmulti; w += nwarps, sk = w < nmulti ? __ldg(multi + w) : sk) {
+    const int32_t s0 = sk.x;
+    const int32_t first = (s0 & ~31) + 32;
+    const int32_t npieces = 1 + pool_extra_pieces(s0, sk.y, rule_b);
+    if (npieces == 1) continue;  // listed under rule A, single piece under rule B: the writer thread has it
+    const int32_t gcell = __ldg(&sorted[s0].y);
+    const int32_t bb = gcell / hw, cell = gcell - bb * hw;
+    for (int32_t c0 = 0; c0 < C; c0 += 32) {
+      const int32_t c = min(c0 + lane, C - 1);
+      float acc = __ldg(rows + static_cast<int64_t>(s0) * C + c);
+      for (int32_t p0 = 1; p0 < npieces; p0 += kBatch) {
+        float v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)  // unconditional loads: the last piece is re-read past the end
+          v[u] = __ldg(rows + static_cast<int64_t>(first + (min(p0 + u, npieces - 1) - 1) * 32) * C + c);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) acc = fmaxf(acc, v[u]);
+      }
+      if (c0 + lane < C) out[(static_cast<int64_t>(bb) * C + c) * hw + cell] = acc;
+    }
+  }
+}
+
 // ---- phase B: dense writer --------------------------------------------------------------------
 // thread = 4 adjacent cells (along W); it walks the channel groups (kCG channels each) of its CTA's
 // channel range, so one read of count/start feeds up to C output stores. An occupied cell reads its
 // one row (rows[start]); all row loads of a channel group are issued together. Empty cells store zeros.
 // Every output element is written exactly once with 128-bit stores.
-template <bool VEC4>
+// FOLD (default): the first `fold_ctas` CTAs of the launch (blockIdx.y == blockIdx.z == 0) are not writers: their
+// warps walk the plan's list of multi-piece cells (segments that cross a multiple of 32, reduced as several pieces),
+// fold each cell's piece rows (lanes over channels, 16 rows in flight) and store the C maxima straight into the
+// output; the writer threads skip exactly those cells. This used to be a separate launch between the reduction and
+// the writer (pool_combine_kernel: 5-9 us of launch + a chain of dependent round trips per pooling call); inside
+// the writer launch it runs beside the dense stores and nothing waits for it. (Folding inside the writer THREADS was
+// measured and rejected: a thread owns 4 cells x 8 channels and a hot cell has up to 47 pieces — the small writers
+// went from 4 to 9-21 us, the big one from 42 to 76 us.)
+template <bool VEC4, bool FOLD>
 __global__ void __launch_bounds__(kWriteThreads)
 pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t groups_per_cta,
                   const int32_t* __restrict__ count, const int32_t* __restrict__ start,
-                  float* __restrict__ out, int stream_out) {
+                  float* __restrict__ out, int stream_out, const int2* __restrict__ multi,
+                  const int2* __restrict__ sorted, int32_t fold_ctas, int32_t multi_cap, int rule_b) {
   SMOS_PDL_PROLOGUE();
+  int32_t bx = blockIdx.x;
+  if (FOLD) {
+    if (bx < fold_ctas) {
+      if (blockIdx.y != 0 || blockIdx.z != 0) return;
+      pool_fold_multi(rows, C, hw, count, out, multi, sorted, fold_ctas, multi_cap, bx, rule_b != 0);
+      return;
+    }
+    bx -= fold_ctas;
+  }
   const int32_t b = blockIdx.z;
   const bool vec_rows = ((C & 7) == 0);
   constexpr int CPT = VEC4 ? 4 : 1;  // cells per thread
-  const int32_t cell0 = (blockIdx.x * kWriteThreads + threadIdx.x) * CPT;
+  const int32_t cell0 = (bx * kWriteThreads + threadIdx.x) * CPT;
   if (cell0 >= hw) return;
   const int32_t g0 = b * hw + cell0;
   int32_t k[CPT], s[CPT];
@@ -793,7 +903,9 @@ pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t
   bool any = false;
 #pragma unroll
   for (int q = 0; q < CPT; ++q) any |= k[q] > 0;
-  if (any) {
+  // outputs that fit L2 are latency bound: fetch `start` together with `count` (the HBM-bound big writer keeps the
+  // conditional second load — unconditional it was 39.5 -> 45.3 us)
+  if (any || !stream_out) {
     if (VEC4) {
       const int4 ss = __ldg(reinterpret_cast<const int4*>(start + g0));
       s[0] = ss.x; s[1 % CPT] = ss.y; s[2 % CPT] = ss.z; s[3 % CPT] = ss.w;
@@ -801,6 +913,13 @@ pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t
       s[0] = __ldg(start + g0);
     }
   }
+  unsigned multi_mask = 0u;  // cells of mine whose segment crosses a multiple of 32: written by the fold warps
+  if (FOLD) {
+#pragma unroll
+    for (int q = 0; q < CPT; ++q)
+      if (pool_extra_pieces(s[q], k[q], rule_b != 0) > 0) multi_mask |= 1u << q;
+  }
+  const bool any_multi = multi_mask != 0u;
   const int32_t ngroups = (C + kCG - 1) / kCG;
   const int32_t cg_begin = blockIdx.y * groups_per_cta;
   const int32_t cg_end = min(ngroups, cg_begin + groups_per_cta);
@@ -841,6 +960,16 @@ pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t
       }
     }
     float* ob = out + (static_cast<int64_t>(b) * C + c0) * hw + cell0;
+    if (FOLD && any_multi) {  // rare: cells owned by the fold warps are left alone, the others leave one by one
+#pragma unroll
+      for (int j = 0; j < kCG; ++j)
+        if (j < nch) {
+#pragma unroll
+          for (int q = 0; q < CPT; ++q)
+            if (!((multi_mask >> q) & 1u)) ob[static_cast<int64_t>(j) * hw + q] = v[q][j];
+        }
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < kCG; ++j) {
       if (j < nch) {
@@ -981,10 +1110,11 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
   const int32_t hw = static_cast<int32_t>(L.hw);
   const int32_t Ci = static_cast<int32_t>(C);
   const int64_t total = B * N;
+  const bool point_major = (f_sc == 1 && C > 1);
+  const int rule_b = point_major ? 1 : 0;  // which reduction produced the piece rows (pool_extra_pieces)
   if (total > 0 && (stages & SMOS_POOL_STAGE_REDUCE)) {
     const int grid = smos_ceil_div(total, kReduceWarps * 32);
     const bool aligned = (reinterpret_cast<uintptr_t>(pcds_feat) & 15) == 0 && (f_sb & 3) == 0 && (f_sn & 3) == 0;
-    const bool point_major = (f_sc == 1 && C > 1);
     if (!point_major) {
       // channel-major: permute into sorted rows, then reduce those rows in place
       static std::atomic<unsigned long long> opted_generic{0}, opted_ldg1{0}, opted_ldg2{0};
@@ -1022,22 +1152,25 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
         SMOS_LAUNCH((pool_permute_kernel), pg, kPermThreads, smem, st, pcds_feat, Ci, static_cast<int32_t>(N), f_sb, f_sc, f_sn, pos, rows);
       }
       if (stages & SMOS_POOL_STAGE_NO_REDUCE) {}
-      else if ((C & 127) == 0) SMOS_LAUNCH((pool_reduce_kernel<4, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, cursor, rows);
-      else if ((C & 63) == 0) SMOS_LAUNCH((pool_reduce_kernel<2, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, cursor, rows);
-      else SMOS_LAUNCH((pool_reduce_kernel<1, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, cursor, rows);
+      else if ((C & 127) == 0) SMOS_LAUNCH((pool_reduce_kernel<4, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, static_cast<int32_t>(total), rows);
+      else if ((C & 63) == 0) SMOS_LAUNCH((pool_reduce_kernel<2, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, static_cast<int32_t>(total), rows);
+      else SMOS_LAUNCH((pool_reduce_kernel<1, true>), grid, kReduceWarps * 32, 0, st, rows, Ci, 0, 0, hw, sorted, static_cast<int32_t>(total), rows);
     } else {
-      if ((C & 127) == 0 && aligned) SMOS_LAUNCH((pool_reduce_kernel<4, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
-      else if ((C & 63) == 0 && aligned) SMOS_LAUNCH((pool_reduce_kernel<2, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
-      else SMOS_LAUNCH((pool_reduce_kernel<1, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, cursor, rows);
+      if ((C & 127) == 0 && aligned) SMOS_LAUNCH((pool_reduce_kernel<4, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, static_cast<int32_t>(total), rows);
+      else if ((C & 63) == 0 && aligned) SMOS_LAUNCH((pool_reduce_kernel<2, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, static_cast<int32_t>(total), rows);
+      else SMOS_LAUNCH((pool_reduce_kernel<1, false>), grid, kReduceWarps * 32, 0, st, pcds_feat, Ci, f_sb, f_sn, hw, sorted, static_cast<int32_t>(total), rows);
     }
   }
-  if (total >= 32 && (stages & SMOS_POOL_STAGE_COMBINE)) {
+  // multi-piece cells: folded by dedicated CTAs of the writer launch (default) or by the separate combine kernel
+  // (SMOS_POOL_FOLD=0, kept for A/B runs)
+  const bool fold = env_int("SMOS_POOL_FOLD", 1) != 0 && total >= 32;
+  if (!fold && total >= 32 && (stages & SMOS_POOL_STAGE_COMBINE)) {
     // fold multi-piece cells (<= total/32 of them; the exact number is only known on the device)
     const int2* multi = reinterpret_cast<const int2*>(base + L.off_multi);
     const int cgrid = smos_ceil_div(total / 32 + 1, kReduceWarps);
-    if ((C & 127) == 0) SMOS_LAUNCH((pool_combine_kernel<4>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows);
-    else if ((C & 63) == 0) SMOS_LAUNCH((pool_combine_kernel<2>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows);
-    else SMOS_LAUNCH((pool_combine_kernel<1>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows);
+    if ((C & 127) == 0) SMOS_LAUNCH((pool_combine_kernel<4>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows, rule_b);
+    else if ((C & 63) == 0) SMOS_LAUNCH((pool_combine_kernel<2>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows, rule_b);
+    else SMOS_LAUNCH((pool_combine_kernel<1>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows, rule_b);
   }
   // outputs beyond L2 capacity are written with evict-first stores
   const int stream_out = (B * C * L.hw * 4 > (int64_t(96) << 20)) ? 1 : 0;
@@ -1050,12 +1183,33 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
   int32_t groups_per_cta = ngroups;
   while (groups_per_cta > 1 && static_cast<int64_t>(gx) * B * ((ngroups + groups_per_cta - 1) / groups_per_cta) < 3 * SMOS_SM_COUNT)
     groups_per_cta = (groups_per_cta + 1) / 2;
-  dim3 grid(gx, (ngroups + groups_per_cta - 1) / groups_per_cta, static_cast<unsigned>(B));
+  // fold CTAs come first in the launch (their chains are the longest): one warp per possible list entry (a warp that
+  // walks several entries pays the whole chain of dependent round trips once per entry), at most four CTAs per SM
+  const int32_t multi_cap = static_cast<int32_t>(total / 32 + 1);
+  int32_t fold_ctas = 0;
+  if (fold) {
+    fold_ctas = smos_ceil_div(multi_cap, (kWriteThreads / 32) * env_int("SMOS_FOLD_PER_WARP", 1));
+    if (fold_ctas > 4 * SMOS_SM_COUNT) fold_ctas = 4 * SMOS_SM_COUNT;
+    if (fold_ctas < 1) fold_ctas = 1;
+  }
+  const int2* multi_list = reinterpret_cast<const int2*>(base + L.off_multi);
+  dim3 grid(gx + fold_ctas, (ngroups + groups_per_cta - 1) / groups_per_cta, static_cast<unsigned>(B));
   if (stages & SMOS_POOL_STAGE_WRITE) {
-    if (vec4)
-      SMOS_LAUNCH((pool_write_kernel<true>), grid, kWriteThreads, 0, st, rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
-    else
-      SMOS_LAUNCH((pool_write_kernel<false>), grid, kWriteThreads, 0, st, rows, Ci, hw, groups_per_cta, count, start, voxel_out, stream_out);
+    // experiment knob: dynamic shared memory nobody uses caps the resident CTAs per SM of the HBM-bound big writer
+    const size_t wsmem = stream_out ? static_cast<size_t>(env_int("SMOS_WRITE_SMEM_KB", 0)) * 1024 : 0;
+    if (wsmem > 48 * 1024) {
+      static std::atomic<unsigned long long> o1{0}, o2{0};
+      if (cudaError_t e = smos_smem_opt_in(pool_write_kernel<true, true>, o1, 200 * 1024); e != cudaSuccess) return static_cast<int>(e);
+      if (cudaError_t e = smos_smem_opt_in(pool_write_kernel<true, false>, o2, 200 * 1024); e != cudaSuccess) return static_cast<int>(e);
+    }
+#define SMOS_LAUNCH_WRITE(V, F)                                                                                   \
+    SMOS_LAUNCH((pool_write_kernel<V, F>), grid, kWriteThreads, wsmem, st, rows, Ci, hw, groups_per_cta, count, start, \
+                voxel_out, stream_out, multi_list, sorted, fold_ctas, multi_cap, rule_b)
+    if (vec4 && fold) SMOS_LAUNCH_WRITE(true, true);
+    else if (vec4) SMOS_LAUNCH_WRITE(true, false);
+    else if (fold) SMOS_LAUNCH_WRITE(false, true);
+    else SMOS_LAUNCH_WRITE(false, false);
+#undef SMOS_LAUNCH_WRITE
   }
   return smos_launch_status();
 }

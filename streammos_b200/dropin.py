@@ -38,4 +38,14 @@ def install(point_major_points=True):
         # models/StreamMOS.py:77 builds `backbone.PointNetStacker(7, C, pre_bn=True, stack_num=2)`: same constructor and
         # parameter names, eval forward fused into one kernel (training / autograd keep the torch layers)
         ref_backbone.PointNetStacker = b200_backbone.PointNetStacker
+    # deformattn/modules/ms_deform_attn.py is pure Python around the compiled sampling core; its forward is swapped for
+    # the one that fuses softmax + sampling-location arithmetic into the kernel at inference (modules.py). Patching the
+    # method (not the class) also covers modules built before install() and `from deformattn.modules import MSDeformAttn`
+    # bindings made at import time (networks/multi_view_encoder.py:8).
+    try:
+        import deformattn.modules.ms_deform_attn as ref_msda_mod
+        from . import modules as b200_modules
+        ref_msda_mod.MSDeformAttn.forward = b200_modules.msdeformattn_forward
+    except Exception:
+        pass
     return True

@@ -187,7 +187,9 @@ def voxel_maxpool_forward(pcds_feat, plan, out=None, stages=POOL_STAGE_ALL, work
         rc = lib.smos_voxel_maxpool_forward_stages(_ptr(f), B, C, N, f.stride(0), f.stride(1), f.stride(2), plan.H,
                                                    plan.W, _ptr(plan.buf), _ptr(ws), _ptr(out), int(stages), _stream())
     _lib.check(rc, "smos_voxel_maxpool_forward")
-    _count((1 if point_major else 2) * bool(stages & 1) + bool(stages & 2) + bool(stages & 4))
+    import os
+    separate_combine = os.environ.get("SMOS_POOL_FOLD", "1") == "0" and B * N >= 32  # default: folded by the writer launch
+    _count((1 if point_major else 2) * bool(stages & 1) + (bool(stages & 2) and separate_combine) + bool(stages & 4))
     return out
 
 
@@ -439,6 +441,36 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
                                                      _ptr(level_start_index), _ptr(sampling_loc),
                                                      _ptr(attn_weight), B, S, M, D, L, Q, P, _ptr(out), _stream())
     _lib.check(rc, "smos_ms_deform_attn_forward")
+    _count(1)
+    return out
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                 reference_points, out=None):
+    """The sampling core plus what deformattn/modules/ms_deform_attn.py:96-108 computes in front of it, in one kernel:
+    softmax of `attn_logits` (B, Lq, M, L*P) over the L*P samples and sampling_locations = reference_points (B, Lq, L,
+    2 | 4) + normalised `sampling_offsets` (B, Lq, M, L, P, 2). -> (B, Lq, M*D). Forward only (inference)."""
+    B, S, M, D, L, Q, P = _msda_check(value, spatial_shapes, level_start_index, sampling_offsets,
+                                      attn_logits.view(attn_logits.shape[0], attn_logits.shape[1], attn_logits.shape[2],
+                                                       spatial_shapes.size(0), -1),
+                                      extra=[("reference_points", reference_points)])
+    if reference_points.dtype != value.dtype:
+        raise RuntimeError("ms_deform_attn: reference_points must have value's dtype")
+    rd = int(reference_points.shape[-1])
+    if rd not in (2, 4) or tuple(reference_points.shape[:3]) != (B, Q, L):
+        raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(rd))  # module :107
+    if tuple(sampling_offsets.shape) != (B, Q, M, L, P, 2) or attn_logits.numel() != B * Q * M * L * P:
+        raise RuntimeError("ms_deform_attn: sampling_offsets (B, Lq, M, L, P, 2) / attn_logits (B, Lq, M, L*P)")
+    if out is None:
+        out = torch.empty((B, Q, M * D), dtype=value.dtype, device=value.device)
+    elif out.dtype != value.dtype or not out.is_contiguous() or out.numel() != B * Q * M * D or not out.is_cuda or \
+            out.data_ptr() == value.data_ptr():
+        raise RuntimeError("out must be a contiguous (B, Lq, M*D) CUDA tensor of value's dtype that does not alias value")
+    with torch.cuda.device(value.device):
+        rc = _lib.load().smos_ms_deform_attn_fused_forward(
+            _DT[value.dtype], _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_offsets),
+            _ptr(attn_logits), _ptr(reference_points), rd, B, S, M, D, L, Q, P, _ptr(out), _stream())
+    _lib.check(rc, "smos_ms_deform_attn_fused_forward")
     _count(1)
     return out
 

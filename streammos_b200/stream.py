@@ -379,10 +379,11 @@ class HotPath:
         if self.device.type == "cuda" and self.vote_api == "reference":
             # voxel_voting.py:234-243 through the reference's function signatures. One kernel inserts the new scan into
             # the ring (the previous scan moves from the current slot into its history slot, exactly as :182 walks the
-            # window) and produces Quantize's float result together with the script's two int64 casts (:240-241)
+            # window) and produces the script's two int64 casts (:240-241); Quantize's float32 result is a temporary
+            # that dies at the cast, so it is not materialised (quantize_staged(want_q=True) returns it: tested)
             q, coords, labels = voting.quantize_staged(self.local_pts, self.local_pred, synthetic.RANGE_X,
                                                        synthetic.RANGE_Y, synthetic.RANGE_Z, self.size, new_points=xyzi,
-                                                       new_pred=b.pred, cur_slot=cur, hist_slot=prev)
+                                                       new_pred=b.pred, cur_slot=cur, hist_slot=prev, want_q=False)
             if self.iv_ws is None:
                 self.iv_ws = ops.instance_vote_workspace(N_BOXES, self.device)
             if self.branches:  # the instance votes do not depend on the voxel votes: a parallel branch

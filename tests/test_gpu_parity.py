@@ -380,6 +380,69 @@ def test_msda_golden(golden, name, dtype):
         np.testing.assert_allclose(got.cpu().numpy(), want, **k)
 
 
+@pytest.mark.parametrize("name", ["msda_module_streammos", "msda_module_boxes"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_msda_fused_forward_golden(golden, name, dtype):
+    """One kernel for softmax + sampling locations + sampling core against what the reference module
+    computed on the CPU (its own forward, core = ms_deform_attn_core_pytorch), 2-d and 4-d reference points."""
+    from streammos_b200 import ops
+    g = golden(name)
+    out = ops.ms_deform_attn_fused_forward(t(g["value"], dtype), t(g["shapes"]), t(g["lsi"]), t(g["offsets"], dtype),
+                                           t(g["logits"], dtype), t(g["ref"], dtype))
+    ref64 = O.ms_deform_attn_fused_forward(g["value"], g["shapes"], g["lsi"], g["offsets"], g["logits"], g["ref"])
+    scale = np.abs(ref64).max()
+    tol = dict(rtol=1e-7, atol=1e-10) if dtype == torch.float64 else dict(rtol=RTOL, atol=2e-6 * scale)
+    np.testing.assert_allclose(out.cpu().numpy(), ref64, **tol)
+    np.testing.assert_allclose(out.cpu().numpy(), g["core_out"], rtol=1e-4, atol=1e-5 * scale)
+    # and the unfused core on the module's own locations / weights agrees with the fused kernel
+    un = ops.ms_deform_attn_forward(t(g["value"], dtype), t(g["shapes"]), t(g["lsi"]), t(g["loc"], dtype),
+                                    t(g["attn"], dtype))
+    np.testing.assert_allclose(out.cpu().numpy(), un.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
+
+
+@pytest.mark.parametrize("name", ["msda_module_streammos", "msda_module_boxes"])
+def test_msdeformattn_module_golden(golden, name):
+    """streammos_b200.modules.MSDeformAttn (reference constructor and parameter names) loaded with the reference
+    module's weights: inference (fused kernel) and autograd (reference sequence) paths against the reference output."""
+    from streammos_b200.modules import MSDeformAttn
+    g = golden(name)
+    d_model, L, M, P = (int(v) for v in g["dims"])
+    m = MSDeformAttn(d_model, L, M, P)
+    sd = {k[2:].replace("__", "."): torch.from_numpy(np.asarray(g[k])) for k in list(g.keys()) if k.startswith("w_")}
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    args = (t(g["query"]), t(g["ref"]), t(g["src"]), t(g["shapes"]), t(g["lsi"]))
+    with torch.no_grad():
+        out = m(*args)
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=1e-4, atol=2e-5)
+    q = args[0].clone().requires_grad_(True)
+    out2 = m(q, *args[1:])
+    np.testing.assert_allclose(out2.detach().cpu().numpy(), g["out"], rtol=1e-4, atol=2e-5)
+    out2.sum().backward()
+    assert torch.isfinite(q.grad).all() and float(q.grad.abs().sum()) > 0
+    with pytest.raises(ValueError):
+        m(args[0], args[1][..., :1].repeat(1, 1, 1, 3), *args[2:])
+
+
+def test_msda_forward_many_samples_and_wide_heads():
+    """Shapes that exercise the sample batching of the forward kernel: L*P not a multiple of the batch or of the lane
+    group (3 levels x 3 points = 9 samples), D = 8 (two lanes per group), D = 160 (more channel quads than lanes),
+    and samples far outside the maps."""
+    from streammos_b200 import ops
+    rng = np.random.default_rng(77)
+    for D, M in ((8, 3), (160, 2), (5, 2)):
+        shapes = np.array([[7, 5], [4, 6], [3, 3]], np.int64)
+        lsi = np.concatenate(([0], np.cumsum(shapes.prod(1))[:-1])).astype(np.int64)
+        S, B, Q, L, P = int(shapes.prod(1).sum()), 2, 37, 3, 3
+        value = rng.standard_normal((B, S, M, D))
+        loc = rng.uniform(-0.4, 1.4, (B, Q, M, L, P, 2))
+        attn = rng.uniform(0, 1, (B, Q, M, L, P))
+        ref = O.ms_deform_attn_forward(value, shapes, lsi, loc, attn)
+        for dtype, tol in ((torch.float64, dict(rtol=1e-7, atol=1e-10)), (torch.float32, dict(rtol=RTOL, atol=1e-5))):
+            out = ops.ms_deform_attn_forward(t(value, dtype), t(shapes), t(lsi), t(loc, dtype), t(attn, dtype))
+            np.testing.assert_allclose(out.cpu().numpy(), ref, **tol)
+
+
 def _streammos_msda_inputs(rng, B, Hs=64, Ws=64, M=4, D=32, P=4):
     value = rng.standard_normal((B, Hs * Ws, M, D)).astype(np.float32)
     ys, xs = np.meshgrid(np.linspace(0.5, Hs - 0.5, Hs), np.linspace(0.5, Ws - 0.5, Ws), indexing="ij")
@@ -615,6 +678,9 @@ def test_vote_stage_equals_quantize_and_casts(S, n, push):
     # and the separate reference-shaped calls agree
     q2 = voting.Quantize(dp.view(-1, 4), rx, ry, rz, size)
     assert torch.equal(q2, q) and torch.equal(q2.to(torch.int64), coords)
+    # want_q=False (what the stream harness uses: the float tensor is a dead temporary in the script): same casts
+    q3, coords3, labels3 = voting.quantize_staged(dp, dl, rx, ry, rz, size, want_q=False)
+    assert q3 is None and torch.equal(coords3, coords) and torch.equal(labels3, labels)
 
 
 def test_instance_vote_workspace_variant_needs_no_zero_fill():

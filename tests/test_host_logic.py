@@ -119,3 +119,21 @@ def test_flat_batches_pack_into_one_buffer():
     assert torch.equal(raw.points[0].t(), lo.pcds_xyzi[0, :4, :, 0])          # same scan in both forms
     assert torch.equal(raw.sphere_cur, lo.pcds_sphere_coord[:1]) and raw.nbytes() < lo.nbytes()
     assert not lo.coord_bev.is_contiguous() and lo.coord_bev.shape == (3, 2000, 2, 1)
+
+
+def test_gpu_numa_affinity_helpers(tmp_path):
+    """bench.py pins each rank to the cores next to its GPU (multi.pin_rank_to_gpu): the sysfs parsing and the
+    per-rank split of a node's cores."""
+    from streammos_b200 import multi
+    assert multi.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert multi.parse_cpulist("") == []
+    d = tmp_path / "0000:1b:00.0"
+    d.mkdir()
+    (d / "local_cpulist").write_text("0-27,56-83\n")
+    cpus = multi.gpu_local_cpus("0000:1B:00.0", sysfs=str(tmp_path))
+    assert cpus == list(range(0, 28)) + list(range(56, 84))
+    assert multi.gpu_local_cpus("0000:ff:00.0", sysfs=str(tmp_path)) == []
+    shares = [multi.share_of_cpus(cpus, r, 4) for r in range(4)]
+    assert sorted(c for s in shares for c in s) == cpus and all(shares)     # disjoint, complete, never empty
+    assert multi.share_of_cpus([5], 3, 4) == [5]
+    assert multi.pin_rank_to_gpu(0, 1) is None                                 # single rank: nothing changes

@@ -70,6 +70,17 @@ def test_msda_backward(golden, name):
     np.testing.assert_allclose(gl, g["gloc"], rtol=1e-7, atol=1e-10)
 
 
+@pytest.mark.parametrize("name", ["msda_module_streammos", "msda_module_boxes"])
+def test_msda_fused_front_end(golden, name):
+    """Softmax + sampling-location arithmetic of the reference MODULE (ms_deform_attn.py:96-108), restated by
+    oracle.ms_deform_attn_fused_forward, against the tensors the module itself handed to its sampling core."""
+    g = golden(name)
+    out = O.ms_deform_attn_fused_forward(g["value"], g["shapes"], g["lsi"], g["offsets"], g["logits"], g["ref"])
+    np.testing.assert_allclose(out, g["core_out"], rtol=1e-4, atol=1e-5)   # fixture is the module's float32 run
+    ref = O.ms_deform_attn_forward(g["value"], g["shapes"], g["lsi"], g["loc"], g["attn"])
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-5)
+
+
 def test_voting_bit_exact(golden):
     g = golden("voting_a")
     size = tuple(int(s) for s in g["size"])

@@ -57,6 +57,11 @@ def test_attnet_infer_with_dropin_matches_reference_operators():
     import streammos_b200.backbone as b200_backbone
     assert isinstance(net.bev_grid2point, b200_backbone.BilinearSample)
     assert isinstance(net.point_pre, b200_backbone.PointNetStacker)
+    # and the reference's own MSDeformAttn modules run the forward that fuses softmax + sampling locations into the kernel
+    import deformattn.modules.ms_deform_attn as ref_msda_mod
+    from streammos_b200 import modules as b200_modules
+    assert ref_msda_mod.MSDeformAttn.forward is b200_modules.msdeformattn_forward
+    assert any(isinstance(m, ref_msda_mod.MSDeformAttn) for m in net.modules())
     plan_cache.clear()
     before = plan_cache.stats()
     legs["b200"] = refmodel.run_stream(net, dev, batches)

@@ -168,6 +168,57 @@ def gen_msda(ref, rng):
     return names
 
 
+def gen_msda_module(ref, rng):
+    """The reference's MSDeformAttn MODULE (deformattn/modules/ms_deform_attn.py) run on the CPU: its own forward with the
+    compiled sampling core replaced by the reference's ms_deform_attn_core_pytorch. Stores the module's weights, inputs,
+    the tensors it hands to the core (raw offsets, logits) and its output, for the 2-d (StreamMOS) and 4-d reference
+    point forms."""
+    sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import deformattn.modules.ms_deform_attn as mod
+    import deformattn.functions.ms_deform_attn_func as fn
+
+    class _Core:  # stands in for MSDeformAttnFunction: same positional call, the reference's CPU core
+        @staticmethod
+        def apply(value, shapes, lsi, loc, attn, im2col_step):
+            _Core.seen = (loc.detach().clone(), attn.detach().clone())
+            return fn.ms_deform_attn_core_pytorch(value, shapes, loc, attn)
+
+    mod.MSDeformAttnFunction = _Core
+    names = []
+    for name, d_model, L, M, P, shapes, ref_dim, N, Lq in (
+            ("msda_module_streammos", 128, 1, 4, 4, [(12, 12)], 2, 1, 96),   # CENet_Transformer: D_MODEL 128, 1 level
+            ("msda_module_boxes", 64, 2, 2, 3, [(6, 4), (3, 2)], 4, 1, 9)):
+        torch.manual_seed(11)
+        m = mod.MSDeformAttn(d_model, L, M, P).eval()
+        with torch.no_grad():  # the default init zeroes the offset / logit weights: give them life
+            m.sampling_offsets.weight.copy_(torch.randn_like(m.sampling_offsets.weight) * 0.05)
+            m.attention_weights.weight.copy_(torch.randn_like(m.attention_weights.weight) * 0.2)
+            m.attention_weights.bias.copy_(torch.randn_like(m.attention_weights.bias) * 0.2)
+        sh = torch.as_tensor(shapes, dtype=torch.long)
+        lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+        S = int(sh.prod(1).sum())
+        query = torch.randn(N, Lq, d_model)
+        src = torch.randn(N, S, d_model)
+        refp = torch.rand(N, Lq, L, ref_dim)
+        if ref_dim == 4:
+            refp[..., 2:] = refp[..., 2:] * 0.5 + 0.1
+        with torch.no_grad():
+            out = m(query, refp, src, sh, lsi)
+            value = m.value_proj(src).view(N, S, M, d_model // M)
+            offs = m.sampling_offsets(query).view(N, Lq, M, L, P, 2)
+            logits = m.attention_weights(query).view(N, Lq, M, L * P)
+            core = fn.ms_deform_attn_core_pytorch(value, sh, *_Core.seen)
+        sd = {"w_" + k.replace(".", "__"): v.numpy() for k, v in m.state_dict().items()}
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), query=query.numpy(), src=src.numpy(), ref=refp.numpy(),
+                            shapes=sh.numpy(), lsi=lsi.numpy(), out=out.numpy(), value=value.numpy(), offsets=offs.numpy(),
+                            logits=logits.numpy(), loc=_Core.seen[0].numpy(), attn=_Core.seen[1].numpy(),
+                            core_out=core.numpy(), dims=np.array([d_model, L, M, P]), **sd)
+        names.append(name)
+    return names
+
+
 def gen_voting(ref, rng):
     g = {"torch": torch, "np": np}
     extract_functions(os.path.join(ref, "voxel_voting.py"),
@@ -461,7 +512,8 @@ def main():
     torch.set_num_threads(1)
     rng = np.random.default_rng(20261018)
     made = []
-    single = {"point_stem": (gen_point_stem, 99), "form_batch": (gen_form_batch, 55), "cluster": (gen_cluster, 33)}
+    single = {"point_stem": (gen_point_stem, 99), "form_batch": (gen_form_batch, 55), "cluster": (gen_cluster, 33),
+              "msda_module": (gen_msda_module, 0)}
     if a.only in single:
         made += single[a.only][0](a.ref, np.random.default_rng(single[a.only][1]))
         for m in made:
@@ -476,6 +528,7 @@ def main():
     made += gen_point_stem(a.ref, np.random.default_rng(99))
     made += gen_form_batch(a.ref, np.random.default_rng(55))
     made += gen_cluster(a.ref, np.random.default_rng(33))
+    made += gen_msda_module(a.ref, None)  # last: it re-seeds torch's generator
     for m in made:
         p = os.path.join(GOLD, m + ".npz")
         print("%-28s %8.1f KB" % (m, os.path.getsize(p) / 1024))
