@@ -288,6 +288,30 @@ int smos_form_batch(const float* points, int64_t T, int64_t N, int64_t row_strid
                     float min_x, float min_y, float min_z, float dx, float dy, float dz,
                     float* pcds_xyzi, float* pcds_coord, void* stream);
 
+/* (next: SURVEY 8f rank 2) Scan ingestion: the loader steps in front of form_batch, per frame of the T-frame window
+ * (datasets/data_StreamMOS.py:515-574): utils.Trans (datasets/utils.py:116-126: float64 pose_diff . (x, y, z, 1) ->
+ * float32), utils.filter_pcds_mask (:107-113: lo <= p < hi on the aligned point), order-preserving compaction and
+ * padding to n_out rows with (pad_xy, pad_xy, pad_z, pad_xy) = (-1000, -1000, -4000, -1000). Bit-exact against those
+ * functions. Lets a stream keep the RAW scans of its window in HBM: only the new scan and the poses cross PCIe.
+ *   frame.points  : (n_cap, row_floats >= 4) float32 raw scan (x, y, z, intensity) in its own sensor frame
+ *   frame.n_dev   : DEVICE int32: rows of `points` that hold points (<= n_cap)        } read by the kernels, so the
+ *   frame.pose_dev: DEVICE 12 float64: rows 0..2 of pose_diff, row major; NULL = none } launches are graph-replayable
+ *   out_points    : (T, n_out, 4) float32, 16-byte aligned; out_src: (T, n_out) int32 raw row of each output row
+ *                   (-1 = padding) or NULL; out_count: (T) int32 points that passed the filter or NULL. The loader
+ *                   asserts count < n_out; here a frame that does not fit is truncated and out_count tells. T <= 8. */
+typedef struct smos_ingest_frame {
+  const float* points;
+  const int32_t* n_dev;
+  const double* pose_dev;
+  int64_t n_cap;
+} smos_ingest_frame;
+
+int64_t smos_ingest_workspace_bytes(int32_t T, int64_t n_cap_max, int64_t n_out);
+int smos_ingest_frames(const smos_ingest_frame* frames_host, int32_t T, int64_t row_floats,
+                       float x_lo, float x_hi, float y_lo, float y_hi, float z_lo, float z_hi,
+                       int64_t n_out, float pad_xy, float pad_z, void* workspace,
+                       float* out_points, int32_t* out_src, int32_t* out_count, void* stream);
+
 /* smos_form_batch followed by smos_point_stem_forward as ONE kernel (the (T, 7, N) tensor never exists): raw points
  * in, pcds_coord (T, N, 3) and the 64-channel features y (T, C2, N) out; results bit-identical to the two calls. */
 int smos_point_stem_forward_raw(const float* points, int64_t T, int64_t N, int64_t row_stride,

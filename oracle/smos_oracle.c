@@ -509,3 +509,43 @@ API void oracle_form_batch(const float* pts, int64_t T, int64_t N, int64_t rs, f
       c[0] = qx; c[1] = qy; c[2] = qz;
     }
 }
+
+/* ---------------------------------------------------------------------------------------- */
+/* Scan ingestion: one frame of the val loader's window,                   */
+/* datasets/data_StreamMOS.py:515-574:                                                         */
+/*   utils.Trans (datasets/utils.py:116-126): pcds_tmp = mat.dot([x, y, z, 1]) in float64      */
+/*   (numpy's dgemm: the four products accumulated in k order with FMAs), xyz stored back as  */
+/*   float32, intensity untouched;                                                             */
+/*   utils.filter_pcds_mask (:107-113): lo <= p < hi on the aligned float32 point;             */
+/*   pc_list[ht][valid_mask]: order-preserving compaction;                                     */
+/*   np.pad(..., constant_values=-1000) and [-pad_length:, 2] = -4000 (:566-571).              */
+/* pts (n, rs) -> out (n_out, 4), src (n_out) raw row of every output row (-1 = padding).     */
+/* Returns the number of points that passed the filter (the loader asserts it is < n_out).    */
+/* ---------------------------------------------------------------------------------------- */
+API int64_t oracle_ingest_frame(const float* pts, int64_t n, int64_t rs, const double* m, int transform,
+                                const float* lo, const float* hi, int64_t n_out, float pad_xy, float pad_z,
+                                float* out, int32_t* src) {
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const float* p = pts + i * rs;
+    float x = p[0], y = p[1], z = p[2];
+    if (transform) {
+      const double dx = x, dy = y, dz = z;
+      x = (float)fma(m[3], 1.0, fma(m[2], dz, fma(m[1], dy, m[0] * dx)));
+      y = (float)fma(m[7], 1.0, fma(m[6], dz, fma(m[5], dy, m[4] * dx)));
+      z = (float)fma(m[11], 1.0, fma(m[10], dz, fma(m[9], dy, m[8] * dx)));
+    }
+    if (x >= lo[0] && x < hi[0] && y >= lo[1] && y < hi[1] && z >= lo[2] && z < hi[2]) {
+      if (k < n_out) {
+        out[k * 4] = x; out[k * 4 + 1] = y; out[k * 4 + 2] = z; out[k * 4 + 3] = p[3];
+        if (src) src[k] = (int32_t)i;
+      }
+      ++k;
+    }
+  }
+  for (int64_t r = k; r < n_out; ++r) {
+    out[r * 4] = pad_xy; out[r * 4 + 1] = pad_xy; out[r * 4 + 2] = pad_z; out[r * 4 + 3] = pad_xy;
+    if (src) src[r] = -1;
+  }
+  return k;
+}

@@ -25,6 +25,11 @@ class VoteStreamScan(ctypes.Structure):
                 ("transform", _i32)]
 
 
+class IngestFrame(ctypes.Structure):
+    """struct smos_ingest_frame (include/streammos_b200.h)."""
+    _fields_ = [("points", _vp), ("n_dev", _vp), ("pose_dev", _vp), ("n_cap", _i64)]
+
+
 # name -> (restype, argtypes); mirrors include/streammos_b200.h one to one
 SIGNATURES = {
     "smos_abi_version": (ctypes.c_int, []),
@@ -68,6 +73,9 @@ SIGNATURES = {
     "smos_point_stem_forward": (ctypes.c_int, [_vp, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                _vp, _i32, _i32, _vp, _i64, _i64, _i64, _vp]),
     "smos_form_batch": (ctypes.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    "smos_ingest_workspace_bytes": (_i64, [_i32, _i64, _i64]),
+    "smos_ingest_frames": (ctypes.c_int, [ctypes.POINTER(IngestFrame), _i32, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _i64,
+                                          _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "smos_point_stem_forward_raw": (ctypes.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32,
                                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64,
                                                    _i64, _vp]),

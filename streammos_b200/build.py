@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libstreammos_b200.so")
 SOURCES = ["api.cu", "voxel_maxpool.cu", "bilinear_gather.cu", "ms_deform_attn.cu", "voting.cu", "point_stem.cu", "form_batch.cu",
-           "cluster.cu"]
+           "cluster.cu", "ingest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

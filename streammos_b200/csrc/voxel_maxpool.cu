@@ -1163,7 +1163,13 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
   }
   // multi-piece cells: folded by dedicated CTAs of the writer launch (default) or by the separate combine kernel
   // (SMOS_POOL_FOLD=0, kept for A/B runs)
-  const bool fold = env_int("SMOS_POOL_FOLD", 1) != 0 && total >= 32;
+  // Default (2): inside the writer launch for outputs that fit L2 (the latency-bound small grids, -0.5 us per call and
+  // one launch less); the HBM-bound 201 MB writer keeps the lean variant + the combine kernel — with the fold path
+  // compiled in, ptxas allocates 63 instead of 84 registers, 4 CTAs per SM become resident and the writer slows
+  // from 42 to 45 us (more CTAs per SM were measured slower before). 1: always, 0: never.
+  const int fold_mode = env_int("SMOS_POOL_FOLD", 2);
+  const bool big_out = B * C * L.hw * 4 > (int64_t(96) << 20);
+  const bool fold = (fold_mode == 1 || (fold_mode == 2 && !big_out)) && total >= 32;
   if (!fold && total >= 32 && (stages & SMOS_POOL_STAGE_COMBINE)) {
     // fold multi-piece cells (<= total/32 of them; the exact number is only known on the device)
     const int2* multi = reinterpret_cast<const int2*>(base + L.off_multi);
@@ -1173,7 +1179,7 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
     else SMOS_LAUNCH((pool_combine_kernel<1>), cgrid, kReduceWarps * 32, 0, st, Ci, multi, cursor, rows, rule_b);
   }
   // outputs beyond L2 capacity are written with evict-first stores
-  const int stream_out = (B * C * L.hw * 4 > (int64_t(96) << 20)) ? 1 : 0;
+  const int stream_out = big_out ? 1 : 0;
   const bool vec4 = ((hw & 3) == 0) && ((reinterpret_cast<uintptr_t>(voxel_out) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(count) & 15) == 0);
   const int cpt = vec4 ? 4 : 1;

@@ -188,7 +188,9 @@ def voxel_maxpool_forward(pcds_feat, plan, out=None, stages=POOL_STAGE_ALL, work
                                                    plan.W, _ptr(plan.buf), _ptr(ws), _ptr(out), int(stages), _stream())
     _lib.check(rc, "smos_voxel_maxpool_forward")
     import os
-    separate_combine = os.environ.get("SMOS_POOL_FOLD", "1") == "0" and B * N >= 32  # default: folded by the writer launch
+    mode = os.environ.get("SMOS_POOL_FOLD", "2")  # default: folded inside the writer launch unless the output exceeds L2
+    big_out = B * C * plan.H * plan.W * 4 > (96 << 20)
+    separate_combine = (mode == "0" or (mode == "2" and big_out)) and B * N >= 32
     _count((1 if point_major else 2) * bool(stages & 1) + (bool(stages & 2) and separate_combine) + bool(stages & 4))
     return out
 
@@ -310,6 +312,59 @@ def form_batch(points, range_x, range_y, range_z, size, x_sign=1.0, y_sign=1.0):
     _lib.check(rc, "smos_form_batch")
     _count(1)
     return feat, coord
+
+
+def ingest_frames(frames, range_x, range_y, range_z, n_out, pad_xy=-1000.0, pad_z=-4000.0, want_src=False,
+                  out=None, workspace=None):
+    """The loader steps in front of form_batch on the device (datasets/data_StreamMOS.py:515-574): per frame pose
+    alignment (utils.Trans), range filter (utils.filter_pcds_mask), order-preserving compaction and padding to `n_out`
+    rows. `frames`: list of (points (n_cap, >=4) f32 CUDA raw scan, n, pose) with n an int or a (1,) int32 CUDA tensor
+    (rows that hold points) and pose a 4x4 / 3x4 float64 array, a (12,) float64 CUDA tensor, or None.
+    -> (points (T, n_out, 4) f32, count (T,) int32 CUDA[, src (T, n_out) int32]); bit-exact with the loader."""
+    import numpy as np
+    lib = _lib.load()
+    T = len(frames)
+    dev = frames[0][0].device
+    descs = (_lib.IngestFrame * T)()
+    keep = []
+    n_cap_max, rs = 0, None
+    for d, (pts, n, pose) in zip(descs, frames):
+        _need_cuda(pts, "points")
+        _need_f32(pts, "points")
+        if pts.dim() != 2 or pts.size(1) < 4 or pts.stride(1) != 1:
+            raise RuntimeError("ingest_frames: points must be (n_cap, >=4) float32 rows")
+        r = pts.stride(0) if pts.size(0) > 1 else pts.size(1)
+        rs = r if rs is None else rs
+        if r != rs:
+            raise RuntimeError("ingest_frames: all frames must share a row stride")
+        if not isinstance(n, torch.Tensor):
+            n = torch.tensor([int(n)], dtype=torch.int32, device=dev)
+        if n.dtype != torch.int32 or not n.is_cuda:
+            raise RuntimeError("ingest_frames: n must be an int or an int32 CUDA tensor")
+        if pose is not None and not isinstance(pose, torch.Tensor):
+            m = np.asarray(pose, dtype=np.float64).reshape(-1, 4)[:3]
+            pose = torch.from_numpy(np.ascontiguousarray(m).reshape(12)).to(dev)
+        if pose is not None and (pose.dtype != torch.float64 or pose.numel() < 12 or not pose.is_cuda or
+                                 not pose.is_contiguous()):
+            raise RuntimeError("ingest_frames: pose must hold 12 contiguous float64 values on the device")
+        keep.append((n, pose))
+        d.points, d.n_dev, d.n_cap = pts.data_ptr(), n.data_ptr(), int(pts.size(0))
+        d.pose_dev = pose.data_ptr() if pose is not None else None
+        n_cap_max = max(n_cap_max, int(pts.size(0)))
+    n_out = int(n_out)
+    if out is None:
+        out = torch.empty((T, n_out, 4), dtype=torch.float32, device=dev)
+    count = torch.empty((T,), dtype=torch.int32, device=dev)
+    src = torch.empty((T, n_out), dtype=torch.int32, device=dev) if want_src else None
+    if workspace is None:
+        workspace = torch.empty(int(lib.smos_ingest_workspace_bytes(T, n_cap_max, n_out)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.smos_ingest_frames(descs, T, int(rs), float(range_x[0]), float(range_x[1]), float(range_y[0]),
+                                    float(range_y[1]), float(range_z[0]), float(range_z[1]), n_out, float(pad_xy),
+                                    float(pad_z), _ptr(workspace), _ptr(out), _ptr(src), _ptr(count), _stream())
+    _lib.check(rc, "smos_ingest_frames")
+    _count(2)
+    return (out, count, src) if want_src else (out, count)
 
 
 # ----------------------------------------------------------------------------------------------

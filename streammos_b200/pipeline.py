@@ -69,8 +69,9 @@ class ScanPipeline:
     def streams(self):
         return tuple(self.pm_streams) + (self.sC,)
 
-    def submit(self, ready_event=None):
-        """Enqueue the next scan (buffer index = scan number mod n). `ready_event`: its inputs are resident."""
+    def submit(self, ready_event=None, also_ready=()):
+        """Enqueue the next scan (buffer index = scan number mod n). `ready_event`: its inputs are resident;
+        `also_ready`: events of other buffers this scan reads (the older raw scans of a resident window)."""
         i = self.submitted
         j = i % self.n
         s = self._pm_stream(j)
@@ -78,6 +79,8 @@ class ScanPipeline:
         with torch.no_grad(), torch.cuda.stream(s):
             if ready_event is not None:
                 s.wait_event(ready_event)
+            for e in also_ready:
+                s.wait_event(e)
             if self.use_graphs:
                 self.gP[j].replay()
             else:

@@ -149,6 +149,59 @@ class RawBatch(_FlatBatch):
     coord_rv = property(lambda self: self.sphere_cur)
 
 
+class ResidentRawBatch(_FlatBatch):
+    """What has to reach the device for one scan when the stream keeps the RAW scans of its T-frame window resident in
+    HBM (smos_ingest_frames): the new raw scan exactly as read from the .bin file (own sensor frame,
+    no filter, no padding: `raw` (n_cap, 4) with `meta[0]` rows in use), the T pose_diff matrices of the window
+    (`poses` (T, 12) float64, datasets/data_StreamMOS.py:427-447), the range-view coordinates of the current frame
+    (SphereQuantize stays a loader output) and the stand-ins of RawBatch. The two older frames are the `raw` buffers of
+    the previous scans (`older`, set by link_window): pose alignment, range filter and padding of all T frames run on
+    the device, bit-exact with the loader (ops.ingest_frames)."""
+
+    FIELDS = ("raw", "meta", "poses", "sphere_cur", "pred", "loc", "attn")
+    coord_rv = property(lambda self: self.sphere_cur)
+    older = ()
+
+
+def link_window(batches, t_frames=3):
+    """Scan i of a cyclic list of device batches sees the raw scans of i-1, i-2, ... as the older frames of its window."""
+    n = len(batches)
+    for i, b in enumerate(batches):
+        b.older = tuple(batches[(i - k) % n] for k in range(1, t_frames))
+    return batches
+
+
+def make_host_resident_stream(seed, n_scans, n_points=120000, t_frames=3, n_cap=None, pin=True):
+    """`n_scans` consecutive scans of ONE synthetic drive, cyclic (scan 0 follows scan n_scans-1): the vehicle moves by
+    the same rigid motion every scan, so the window's pose_diff matrices are the same for every scan. Returns
+    (resident, raw): ResidentRawBatch per scan, and the RawBatch the HOST would build from the same drive today (its
+    numpy pose alignment + filter + padding of all T frames) — the two describe identical model inputs."""
+    raws = [synthetic.lidar_raw_scan(np.random.default_rng(seed * 7919 + 31 * i)) for i in range(n_scans)]
+    n_cap = n_cap or (max(len(r) for r in raws) + 255) // 256 * 256
+    diffs = synthetic.stream_pose_diffs(t_frames)
+    poses = np.stack([np.ascontiguousarray(d[:3]).reshape(12) for d in diffs])
+    resident, host_aligned = [], []
+    for i in range(n_scans):
+        frames = [synthetic.align_filter_pad(raws[(i - k) % n_scans], diffs[k], n_points)[0] for k in range(t_frames)]
+        other = make_host_scan(seed * 1000 + i, n_points, t_frames, channels=1, pin=False)
+        sphere = np.ascontiguousarray(synthetic.quantize_sphere(frames[0])[None, :, :, None])     # (1, N, 2, 1)
+        n_valid = int((frames[0][:, 0] > synthetic.PAD_XY).sum())
+        pred = other.pred.clone()
+        pred[n_valid:] = 0
+        buf = np.zeros((n_cap, 4), np.float32)
+        buf[: len(raws[i])] = raws[i]
+        r = ResidentRawBatch(raw=torch.from_numpy(buf), meta=torch.tensor([len(raws[i]), 0, 0, 0], dtype=torch.int32),
+                             poses=torch.from_numpy(poses.copy()), sphere_cur=torch.from_numpy(sphere), pred=pred,
+                             loc=other.loc, attn=other.attn)
+        h = RawBatch(points=torch.from_numpy(np.stack(frames)), sphere_cur=torch.from_numpy(sphere.copy()), pred=pred.clone(),
+                     loc=other.loc, attn=other.attn)
+        if pin and torch.cuda.is_available():
+            r, h = r.pack(pin=True), h.pack(pin=True)
+        resident.append(r)
+        host_aligned.append(h)
+    return resident, host_aligned
+
+
 def make_host_loader_scan(seed, n_points=120000, t_frames=3, pin=True):
     """Synthetic loader output of one scan (see LoaderBatch). Point features as make_point_feat builds them
     (data_StreamMOS.py:25-50): x, y, z, intensity, dist, diff_x, diff_y."""
@@ -293,6 +346,10 @@ class HotPath:
         x1 = CNN(cat(x0, pool #3)), gather #5 reads the decoder output); here the CNN outputs are resident stand-ins, so
         pool #1, the two pool/gather chains and gather #5 happen to be independent: `branches=True` (an experiment,
         not the default) runs them as parallel graph branches."""
+        if hasattr(b, "raw"):         # resident window: the loader's pose alignment + range filter + padding on the device
+            frames = [(b.raw, b.meta[:1], b.poses[0])] + [(o.raw, o.meta[:1], b.poses[k + 1]) for k, o in enumerate(b.older)]
+            b.points, b.n_valid = ops.ingest_frames(frames, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z,
+                                                    self.n_points, synthetic.PAD_XY, synthetic.PAD_Z)
         if hasattr(b, "points"):      # raw scan: Quantize + make_point_feat on the device (SURVEY 8f rank 2), then the stem
             if self.fuse_form_batch:  # one kernel: raw points -> 64-channel features + quantised coordinates
                 feat, coord = ops.point_stem_forward_raw(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z,

@@ -51,6 +51,66 @@ def lidar_scan(rng, n_points=120000, n_beams=64, ego_shift=(0.0, 0.0)):
     return out, len(valid)
 
 
+def lidar_raw_scan(rng, n_beams=64, n_az=1860):
+    """-> (n, 4) float32 RAW scan in its own sensor frame, as read from a KITTI .bin (no range filter, no padding):
+    ring-major / azimuth-minor, obstacles out to 58 m (so the loader's range filter has something to remove), ~1 % of
+    the beams without a return."""
+    elev = np.deg2rad(np.linspace(2.0, -24.8, n_beams))
+    az = np.linspace(-np.pi, np.pi, n_az, endpoint=False)
+    n_seg = 48
+    seg_r = rng.uniform(4.0, 58.0, n_seg)
+    seg_r[rng.uniform(0, 1, n_seg) < 0.3] = 58.0
+    obst = np.repeat(seg_r, int(np.ceil(n_az / n_seg)))[:n_az]
+    sensor_h = 1.73
+    pts = np.empty((n_beams, n_az, 4), np.float32)
+    for b in range(n_beams):
+        r_ground = sensor_h / np.tan(-elev[b]) if elev[b] < -1e-3 else 1e9
+        r = np.minimum(r_ground, obst) * (1.0 + rng.normal(0, 0.004, n_az))
+        r = np.maximum(r, 1.5)
+        a = az + rng.normal(0, 2e-4, n_az)
+        pts[b, :, 0] = r * np.cos(elev[b]) * np.cos(a)
+        pts[b, :, 1] = r * np.cos(elev[b]) * np.sin(a)
+        pts[b, :, 2] = r * np.sin(elev[b])
+        pts[b, :, 3] = rng.uniform(0, 1, n_az)
+    pts = pts.reshape(-1, 4)
+    return np.ascontiguousarray(pts[rng.uniform(0, 1, len(pts)) > 0.01])
+
+
+def stream_pose_diffs(t_frames=3, step=(0.62, 0.03, 0.0), yaw=0.004):
+    """pose_diff of the frames of a window as the loader computes them (datasets/data_StreamMOS.py:427-447):
+    inv(pose_cur).dot(pose_{cur - ht}) for a vehicle that advances by the same rigid motion every scan — the same
+    T matrices for every scan of the stream (ht = 0 is only NEARLY the identity, as in the loader)."""
+    c, s_ = np.cos(yaw), np.sin(yaw)
+    delta = np.eye(4)
+    delta[:2, :2] = [[c, -s_], [s_, c]]
+    delta[:3, 3] = step
+    poses = [np.eye(4)]
+    for _ in range(16):
+        poses.append(poses[-1].dot(delta))
+    cur = 12
+    cur_inv = np.linalg.inv(poses[cur])
+    return [cur_inv.dot(poses[cur - ht]) for ht in range(t_frames)]
+
+
+def align_filter_pad(raw, pose_diff, n_out):
+    """The loader's per-frame steps (datasets/data_StreamMOS.py:515-574 with utils.Trans / filter_pcds_mask of
+    datasets/utils.py:107-126) in numpy, as the host does them today: -> (n_out, 4) float32, number of valid points."""
+    pc = raw.copy()
+    if pose_diff is not None:
+        tmp = pc[:, :4].T.copy()
+        tmp[-1] = 1
+        tmp = np.asarray(pose_diff, np.float64).dot(tmp).T
+        pc[:, :3] = tmp[:, :3]
+    keep = ((pc[:, 0] >= RANGE_X[0]) & (pc[:, 0] < RANGE_X[1]) & (pc[:, 1] >= RANGE_Y[0]) & (pc[:, 1] < RANGE_Y[1]) &
+            (pc[:, 2] >= RANGE_Z[0]) & (pc[:, 2] < RANGE_Z[1]))
+    pc = pc[keep]
+    assert len(pc) < n_out, "frame does not fit (the loader asserts pad_length > 0)"
+    out = np.full((n_out, 4), PAD_XY, np.float32)
+    out[:, 2] = PAD_Z
+    out[: len(pc)] = pc
+    return out, len(pc)
+
+
 def quantize_bev(pcds):
     """datasets/utils.py:151-169 Quantize with the config ranges -> (N, 3) float32 (x_quan, y_quan, z_quan)."""
     d = [np.float32((r[1] - r[0]) / s) for r, s in zip((RANGE_X, RANGE_Y, RANGE_Z), BEV_SHAPE)]

@@ -1212,3 +1212,80 @@ def test_pipeline_matches_serial_step(use_graphs):
         assert torch.equal(wl, gl), "labels differ at scan %d" % i
         assert torch.equal(ws, gs), "instance votes differ at scan %d" % i
     torch.testing.assert_close(hot.memory, serial.memory, rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Scan ingestion: pose alignment + range filter + compaction + padding on the device
+# ------------------------------------------------------------------------------------------------
+def _ingest_inputs(g):
+    return [(g["raw"][tt, :int(g["n_raw"][tt])], None if np.isnan(g["pose_diff"][tt]).any() else g["pose_diff"][tt])
+            for tt in range(len(g["n_raw"]))]
+
+
+def test_ingest_frames_golden(golden):
+    """smos_ingest_frames against the loader's own utils.Trans / filter_pcds_mask / padding (tests/golden/ingest_a.npz),
+    bit for bit; frame capacities larger than the point counts (the counts are read on the device)."""
+    from streammos_b200 import ops
+    g = golden("ingest_a")
+    n_out = int(g["n_out"])
+    frames = [(t(g["raw"][k]), int(g["n_raw"][k]), p) for k, (_, p) in enumerate(_ingest_inputs(g))]
+    out, cnt, src = ops.ingest_frames(frames, (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), n_out, want_src=True)
+    assert np.array_equal(cnt.cpu().numpy(), g["count"])
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), g["out"].view(np.uint32))
+    want_out, want_cnt, want_src = O.ingest_frames(_ingest_inputs(g), (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), n_out)
+    assert np.array_equal(src.cpu().numpy(), want_src)
+
+
+@pytest.mark.parametrize("n_raw,n_out", [(131072, 120000), (1000, 4096), (5000, 1024), (1, 8), (4097, 4097)])
+def test_ingest_frames_vs_oracle(n_raw, n_out):
+    """Config size (131 k raw points -> 120 k rows), output longer / shorter than the input (a frame that does not fit
+    is truncated and the count says so), single point, tile edges; device-resident counts and poses."""
+    from streammos_b200 import ops
+    rng = np.random.default_rng(n_raw + n_out)
+    frames_np = []
+    for k in range(3):
+        n = max(1, n_raw - 37 * k)
+        raw = np.stack([rng.uniform(-60, 60, n), rng.uniform(-60, 60, n), rng.uniform(-5, 3, n), rng.uniform(0, 1, n)],
+                       -1).astype(np.float32)
+        if n_out >= 100000:   # LiDAR-like: most points inside the range, so that the frame fits as in the loader
+            raw[:, :2] *= np.float32(0.7)
+            raw[:, 2] = rng.uniform(-3.9, 1.9, n).astype(np.float32)
+        a = 0.01 * (k + 1)
+        pose = np.eye(4)
+        pose[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        pose[:3, 3] = (0.6 * k, -0.04 * k, 0.01 * k)
+        frames_np.append((raw, pose if k else None))
+    want_out, want_cnt, want_src = O.ingest_frames(frames_np, (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), n_out)
+    cap = n_raw + 100
+    frames = []
+    for raw, pose in frames_np:
+        buf = np.full((cap, 4), 7.0, np.float32)   # rows behind n hold in-range garbage that must be ignored
+        buf[:len(raw)] = raw
+        frames.append((t(buf), torch.tensor([len(raw)], dtype=torch.int32, device=dev()),
+                       None if pose is None else t(np.ascontiguousarray(pose[:3]).reshape(12))))
+    out, cnt, src = ops.ingest_frames(frames, (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), n_out, want_src=True)
+    assert np.array_equal(cnt.cpu().numpy(), want_cnt)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want_out.view(np.uint32))
+    assert np.array_equal(src.cpu().numpy(), want_src)
+
+
+def test_resident_window_step_matches_host_aligned_frames():
+    """The stream harness with the raw scans of the T-frame window resident in HBM (pose alignment + range filter +
+    padding on the device) gives exactly the step the host-aligned frames give: same pooled grids, same labels."""
+    from streammos_b200 import stream
+    n, scans = 120000, 4
+    resident, aligned = stream.make_host_resident_stream(3, scans, n, pin=False)
+    dres = stream.link_window([b.to(dev()) for b in resident])
+    dali = [b.to(dev()) for b in aligned]
+    hot_a = stream.HotPath(dev(), n, seed=5)
+    hot_b = stream.HotPath(dev(), n, seed=5)
+    with torch.no_grad():
+        for i in range(scans):
+            la, sa, pa = hot_a.step(dres[i])
+            lb, sb, pb = hot_b.step(dali[i])
+            assert torch.equal(dres[i].points, dali[i].points)          # the ingested frames ARE the loader's frames
+            assert int(dres[i].n_valid[0]) < n
+            assert torch.equal(la, lb) and torch.equal(sa, sb)
+            for x, y in zip(pa, pb):
+                assert torch.equal(x, y)
+    assert torch.equal(hot_a.memory, hot_b.memory)

@@ -211,3 +211,22 @@ def test_form_batch_bit_exact(golden):
         assert np.array_equal(feat, g["feat_" + tag]) and np.array_equal(coord, g["coord_" + tag])
     assert float(g["feat_pp"][:, 4].min()) == np.float32(1e-12)          # points at the sensor origin
     assert (g["coord_pp"][..., 0] == 0).any() and (g["coord_pp"] < 0).any()  # lower bound hit, pads out of range
+
+
+def _ingest_frames(g):
+    return [(g["raw"][t, :int(g["n_raw"][t])], None if np.isnan(g["pose_diff"][t]).any() else g["pose_diff"][t])
+            for t in range(len(g["n_raw"]))]
+
+
+def test_ingest_frames_bit_exact(golden):
+    """Pose alignment + range filter + ordered compaction + padding (datasets/data_StreamMOS.py:515-574) against the
+    loader's own utils.Trans / utils.filter_pcds_mask: every float32 of every frame, the counts and the masks."""
+    g = golden("ingest_a")
+    out, cnt, src = O.ingest_frames(_ingest_frames(g), (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), int(g["n_out"]))
+    assert np.array_equal(cnt, g["count"])
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))   # bit patterns, pads included
+    for t in range(len(cnt)):
+        assert np.array_equal(src[t, :cnt[t]], np.nonzero(g["mask"][t])[0]) and (src[t, cnt[t]:] == -1).all()
+    # the frame without a pose hits the bounds exactly: lower bounds are inside, upper bounds are not
+    keep = g["mask"][3][:8]
+    assert keep.tolist() == [True, False, True, True, True, False, True, False]

@@ -454,6 +454,66 @@ def gen_form_batch(ref, rng):
     return ["form_batch_a"]
 
 
+def gen_ingest(ref, rng):
+    """The val loader's per-frame steps in front of form_batch (datasets/data_StreamMOS.py:515-574) with the
+    reference's own utils.Trans and utils.filter_pcds_mask; the compaction and padding lines of __getitem__ (:551-571)
+    are restated here because they live inline in the Dataset class. Three raw frames of different lengths, pose_diff =
+    inv(pose_cur).dot(pose_ht) as the loader computes it (:427-447; the current frame's own pose_diff is only nearly
+    the identity), a fourth frame without any transform and with points exactly on the range bounds."""
+    du = load_by_path("ref_dutils", os.path.join(ref, "datasets", "utils.py"))
+    rx, ry, rz, n_out = (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), 6144
+
+    def pose(yaw, pitch, tx, ty, tz):
+        cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+        R = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]]) @ np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+        P = np.eye(4)
+        P[:3, :3], P[:3, 3] = R, (tx, ty, tz)
+        return P
+
+    poses = [pose(0.31, 0.004, 120.3, -45.2, 1.1), pose(0.295, 0.003, 119.5, -45.5, 1.08), pose(0.28, 0.002, 118.6, -45.7, 1.07)]
+    cur_inv = np.linalg.inv(poses[0])
+    raws, diffs = [], []
+    for ht, n in enumerate((5000, 5613, 4801)):
+        r = np.abs(rng.standard_normal(n)) * 22.0
+        th = rng.uniform(0, 2 * np.pi, n)
+        raw = np.stack([r * np.cos(th), r * np.sin(th), rng.normal(-1.2, 1.4, n), rng.uniform(0, 1, n)], -1).astype(np.float32)
+        raw[::97, 0] = rng.uniform(49.5, 50.5, len(raw[::97]))      # around the upper x bound after alignment
+        raw[5::89, 2] = rng.uniform(-4.3, -3.7, len(raw[5::89]))    # around the lower z bound
+        raws.append(raw)
+        diffs.append(cur_inv.dot(poses[ht]))
+    # frame without a pose (the product's "no transform" path): bounds hit exactly
+    raw = np.stack([rng.uniform(-55, 55, 3000), rng.uniform(-55, 55, 3000), rng.uniform(-5, 3, 3000), rng.uniform(0, 1, 3000)],
+                   -1).astype(np.float32)
+    raw[:8, 0] = [-50.0, 50.0, np.nextafter(np.float32(50.0), np.float32(0)), -50.0, 0, 0, 0, 0]
+    raw[:8, 1] = [0, 0, 0, 0, -50.0, 50.0, 0, 0]
+    raw[:8, 2] = [0, 0, 0, 0, 0, 0, -4.0, 2.0]
+    raws.append(raw)
+    diffs.append(None)
+    outs, counts, masks = [], [], []
+    for raw, d in zip(raws, diffs):
+        pc = du.Trans(raw, d) if d is not None else raw.copy()                                   # :522
+        mask = du.filter_pcds_mask(pc, range_x=rx, range_y=ry, range_z=rz)                       # :545-548
+        pc = pc[mask]                                                                            # :551
+        pad_length = n_out - pc.shape[0]                                                         # :558
+        assert pad_length > 0                                                                    # :559
+        pc = np.pad(pc, ((0, pad_length), (0, 0)), 'constant', constant_values=-1000)            # :560
+        pc[-pad_length:, 2] = -4000                                                              # :561
+        assert pc.dtype == np.float32
+        outs.append(pc)
+        counts.append(int(mask.sum()))
+        masks.append(mask)
+    nmax = max(len(r) for r in raws)
+    raw_pad = np.zeros((len(raws), nmax, 4), np.float32)
+    mask_pad = np.zeros((len(raws), nmax), bool)
+    for i, (r, m) in enumerate(zip(raws, masks)):
+        raw_pad[i, :len(r)] = r
+        mask_pad[i, :len(r)] = m
+    np.savez_compressed(os.path.join(GOLD, "ingest_a.npz"), raw=raw_pad, n_raw=np.array([len(r) for r in raws]),
+                        pose_diff=np.stack([d if d is not None else np.full((4, 4), np.nan) for d in diffs]),
+                        out=np.stack(outs), count=np.array(counts), mask=mask_pad, n_out=np.array(n_out))
+    return ["ingest_a"]
+
+
 def gen_cluster(ref, rng):
     """cluster() of voxel_instance_voting.py:144-193 end to end (sklearn DBSCAN + scipy hull/Delaunay through the
     reference's own code) on a scan whose moving points are interleaved with the rest: objects of several sizes and
@@ -513,7 +573,7 @@ def main():
     rng = np.random.default_rng(20261018)
     made = []
     single = {"point_stem": (gen_point_stem, 99), "form_batch": (gen_form_batch, 55), "cluster": (gen_cluster, 33),
-              "msda_module": (gen_msda_module, 0)}
+              "msda_module": (gen_msda_module, 0), "ingest": (gen_ingest, 66)}
     if a.only in single:
         made += single[a.only][0](a.ref, np.random.default_rng(single[a.only][1]))
         for m in made:
@@ -528,6 +588,7 @@ def main():
     made += gen_point_stem(a.ref, np.random.default_rng(99))
     made += gen_form_batch(a.ref, np.random.default_rng(55))
     made += gen_cluster(a.ref, np.random.default_rng(33))
+    made += gen_ingest(a.ref, np.random.default_rng(66))
     made += gen_msda_module(a.ref, None)  # last: it re-seeds torch's generator
     for m in made:
         p = os.path.join(GOLD, m + ".npz")
