@@ -224,7 +224,9 @@ def workload_config(args, graph, world):
             "pipeline": "3 graphs per scan (projection / temporal fusion / voting), %d scans in flight on %d CUDA streams; "
                         "cross-scan dependencies (short-term memory, voting ring) enforced with events; %s"
                         % (args.in_flight, args.in_flight + 1,
-                           "operators in the reference's serial order" if not args.branches else
+                           "operators of the network in the reference's serial order; the instance vote "
+                           "(voxel_instance_voting.py, an independent post-processing pass of the reference) runs beside the "
+                           "voxel vote (voxel_voting.py) as a second graph branch" if not args.branches else
                            "independent operators of a scan are parallel graph "
                            "branches (pool #1 | half-scale chain | quarter-scale chain | gather #5; voxel | instance votes)"),
             "operator_api": "explicit plan API (plan= / order=)" if args.explicit_plans else

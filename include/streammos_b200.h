@@ -399,10 +399,16 @@ int smos_memory_push(const float* points, const uint8_t* pred, int64_t n, int64_
  * Optionally performs smos_memory_push on the way (new_points / new_pred non-NULL): the scan in slot `cur_slot`
  * moves to `hist_slot` (skipped if hist_slot < 0) and the new scan takes `cur_slot`, before anything is quantised.
  *   ring_points (n_slots, n, row_floats) f32, ring_pred (n_slots, n) u8, slot major, updated in place when pushing
- *   q_out (n_slots*n, 3) f32 or NULL ; coords_out (n_slots*n, 3) int64 ; labels_out (n_slots*n) int64 */
+ *   q_out (n_slots*n, 3) f32 or NULL ; coords_out (n_slots*n, 3) int64 ; labels_out (n_slots*n) int64
+ *   crop_lo_host / crop_hi_host: 3 floats each or NULL. The script crops the local map to the open box
+ *   lo < p < hi (transforms.Crop, utils/transforms.py:151-161, thresholds fov -/+ eps compared in float32) BEFORE it
+ *   quantises (voxel_voting.py:225-231); tensors cannot shrink inside a captured launch, so a point outside the box
+ *   keeps its slot and gets coords (-1, -1, -1): it casts no vote and reads no voxel label, exactly as if it had
+ *   been removed (q keeps the plain quotient). */
 int smos_vote_stage(float* ring_points, uint8_t* ring_pred, int32_t n_slots, int64_t n, int64_t row_floats,
                     const float* new_points, const uint8_t* new_pred, int32_t cur_slot, int32_t hist_slot,
                     float min_x, float min_y, float min_z, float dx, float dy, float dz,
+                    const float* crop_lo_host, const float* crop_hi_host,
                     float* q_out, int64_t* coords_out, int64_t* labels_out, void* stream);
 
 /* Per-instance vote count (voxel_instance_voting.py:169-187, in_hull :62-76):

@@ -80,7 +80,7 @@ SIGNATURES = {
                                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64,
                                                    _i64, _vp]),
     "smos_vote_stage": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32,
-                                       _vp, _vp, _vp, _vp]),
+                                       ctypes.POINTER(_f32), ctypes.POINTER(_f32), _vp, _vp, _vp, _vp]),
     "smos_memory_push": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "smos_instance_vote": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
     "smos_instance_vote_counted": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),

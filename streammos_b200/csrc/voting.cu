@@ -204,6 +204,8 @@ struct StageArgs {
   int64_t N, rs;
   int32_t S, cur, hist;  // hist < 0: no history slot to fill
   float mx, my, mz, dx, dy, dz;
+  float clo[3], chi[3];  // open crop box (transforms.Crop); used when `crop` is set
+  int32_t crop;
   float* q;              // (S*N, 3) or null
   int64_t* coords;       // (S*N, 3)
   int64_t* labels;       // (S*N)
@@ -270,7 +272,10 @@ vote_stage_kernel(const __grid_constant__ StageArgs A) {
     }
     const float qx = quant(x, A.mx, A.dx), qy = quant(y, A.my, A.dy), qz = quant(z, A.mz, A.dz);
     // .to(torch.int64): truncation toward zero (voxel_voting.py:240)
-    const long long cx = static_cast<long long>(qx), cy = static_cast<long long>(qy), cz = static_cast<long long>(qz);
+    long long cx = static_cast<long long>(qx), cy = static_cast<long long>(qy), cz = static_cast<long long>(qz);
+    // the script crops before it quantises: a point outside the open box takes no part in the vote
+    if (A.crop && !(x > A.clo[0] && x < A.chi[0] && y > A.clo[1] && y < A.chi[1] && z > A.clo[2] && z < A.chi[2]))
+      cx = cy = cz = -1;
     const int64_t g = static_cast<int64_t>(s) * A.N + i;
     if (live) A.labels[g] = lab;
     if (A.vec_out && full) {
@@ -650,6 +655,7 @@ int smos_vote_stream(const smos_vote_stream_scan* scans_host, int32_t n_scans, i
 int smos_vote_stage(float* ring_points, uint8_t* ring_pred, int32_t n_slots, int64_t n, int64_t row_floats,
                     const float* new_points, const uint8_t* new_pred, int32_t cur_slot, int32_t hist_slot,
                     float min_x, float min_y, float min_z, float dx, float dy, float dz,
+                    const float* crop_lo_host, const float* crop_hi_host,
                     float* q_out, int64_t* coords_out, int64_t* labels_out, void* stream) {
   if (n_slots <= 0 || n < 0 || row_floats < 3) return SMOS_EINVAL;
   if (n == 0) return SMOS_OK;
@@ -662,6 +668,9 @@ int smos_vote_stage(float* ring_points, uint8_t* ring_pred, int32_t n_slots, int
   A.N = n; A.rs = row_floats; A.S = n_slots; A.cur = cur_slot; A.hist = new_points ? hist_slot : -1;
   A.mx = min_x; A.my = min_y; A.mz = min_z; A.dx = dx; A.dy = dy; A.dz = dz;
   A.q = q_out; A.coords = coords_out; A.labels = labels_out;
+  if ((crop_lo_host == nullptr) != (crop_hi_host == nullptr)) return SMOS_EINVAL;
+  A.crop = crop_lo_host != nullptr ? 1 : 0;
+  for (int k = 0; k < 3; ++k) { A.clo[k] = A.crop ? crop_lo_host[k] : 0.f; A.chi[k] = A.crop ? crop_hi_host[k] : 0.f; }
   A.vec_io = (row_floats == 4 && a16(ring_points) && a16(new_points)) ? 1 : 0;
   A.vec_out = ((n & 3) == 0 && a16(q_out) && a16(coords_out)) ? 1 : 0;
   SMOS_LAUNCH((vote_stage_kernel), smos_ceil_div(n, kStageThreads), kStageThreads, 0, smos_stream(stream), A);

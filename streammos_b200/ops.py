@@ -565,11 +565,13 @@ def quantize(pcds, mins, deltas):
 
 
 def vote_stage(ring_points, ring_pred, mins, deltas, new_points=None, new_pred=None, cur_slot=0, hist_slot=-1,
-               want_q=True):
+               want_q=True, crop=None):
     """Quantize + the two `.to(torch.int64)` casts of voxel_voting.py:234-241 in one kernel, straight from the
     long-term memory ring: ring_points (S, N, r>=3) f32, ring_pred (S, N) u8 -> (q (S*N, 3) f32 or None,
     coords (S*N, 3) int64, labels (S*N,) int64). With new_points / new_pred the ring insert (memory_push) happens in
-    the same kernel first: slot cur_slot moves to hist_slot (if >= 0) and the new scan takes cur_slot."""
+    the same kernel first: slot cur_slot moves to hist_slot (if >= 0) and the new scan takes cur_slot.
+    `crop` = (lo, hi) float thresholds of the open box the script crops the map to before quantising
+    (voxel_voting.py:225-231): points outside it get coords (-1, -1, -1) — no vote, no label."""
     _need_cuda(ring_points, "ring_points")
     _need_f32(ring_points, "ring_points")
     if ring_points.dim() != 3 or not ring_points.is_contiguous() or ring_pred.dtype != torch.uint8 or \
@@ -586,10 +588,12 @@ def vote_stage(ring_points, ring_pred, mins, deltas, new_points=None, new_pred=N
     q = torch.empty((S * N, 3), dtype=torch.float32, device=dev) if want_q else None
     coords = torch.empty((S * N, 3), dtype=torch.int64, device=dev)
     labels = torch.empty((S * N,), dtype=torch.int64, device=dev)
+    lo = (ctypes.c_float * 3)(*[float(v) for v in crop[0]]) if crop is not None else None
+    hi = (ctypes.c_float * 3)(*[float(v) for v in crop[1]]) if crop is not None else None
     with torch.cuda.device(dev):
         rc = _lib.load().smos_vote_stage(_ptr(ring_points), _ptr(ring_pred), S, N, r, _ptr(new_points), _ptr(new_pred),
                                          int(cur_slot), int(hist_slot), float(mins[0]), float(mins[1]), float(mins[2]),
-                                         float(deltas[0]), float(deltas[1]), float(deltas[2]), _ptr(q), _ptr(coords),
+                                         float(deltas[0]), float(deltas[1]), float(deltas[2]), lo, hi, _ptr(q), _ptr(coords),
                                          _ptr(labels), _stream())
     _lib.check(rc, "smos_vote_stage")
     _count(1)

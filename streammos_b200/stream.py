@@ -241,7 +241,8 @@ class HotPath:
 
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
                  batch_plans=False, grids_channels_last=False, overlap_voting=False, branches=False,
-                 ordered_gathers=True, ordered_rv=False, gather_taps=False, fuse_form_batch=True):
+                 ordered_gathers=True, ordered_rv=False, gather_taps=False, fuse_form_batch=True,
+                 instance_branch=True):
         """batch_plans=False (default): every operator is called with the REFERENCE's arguments only
         (VoxelMaxPool(feat, ind, size, scale), BilinearSample(grid, coord)); plans are shared through the plan cache
         exactly as they are under the unmodified reference model. batch_plans=True: the explicit plan API (all five
@@ -251,6 +252,11 @@ class HotPath:
         self.device = torch.device(device)
         self.overlap_voting = overlap_voting
         self.branches = branches and self.device.type == "cuda"
+        # voxel voting (voxel_voting.py) and instance voting (voxel_instance_voting.py) are two independent
+        # post-processing passes over the same local map — separate scripts in the reference. They read the same staged
+        # tensors and write different outputs, so the instance vote runs as a parallel branch (real data flow, unlike
+        # the `branches` experiment above, which exists only because CNN outputs are stand-ins)
+        self.instance_branch = (instance_branch or self.branches) and self.device.type == "cuda"
         self.ordered_gathers, self.ordered_rv = ordered_gathers, ordered_rv
         self.gather_taps = gather_taps and ordered_gathers and point_major and batch_plans
         self.fuse_form_batch = fuse_form_batch
@@ -421,9 +427,9 @@ class HotPath:
         return ops.ms_deform_attn_forward(value2, self.shapes, self.lsi, b.loc[1], b.attn[1], out=self.memory)
 
     def long_term_voting(self, b):
-        """Voxel voting over 8 history scans + the current one, then per-instance votes. The reference functions
-        assume pre-cropped input (voxel_voting.py:225-231); synthetic scans lie inside the crop box and padded points
-        quantise out of range, so no crop is applied here (voting.StreamingVoter implements the script's crop)."""
+        """Voxel voting over 8 history scans + the current one, then per-instance votes. The script crops the local
+        map to fov -/+ eps before it quantises (voxel_voting.py:225-231); the staging kernel applies the same crop
+        (points outside the open box get coords -1: no vote, no label — also what happens to the padded points)."""
         cur = HISTORY
         # raw points of the current frame: loader batches carry them as the first 4 channels of pcds_xyzi
         if hasattr(b, "points"):
@@ -440,17 +446,19 @@ class HotPath:
             # that dies at the cast, so it is not materialised (quantize_staged(want_q=True) returns it: tested)
             q, coords, labels = voting.quantize_staged(self.local_pts, self.local_pred, synthetic.RANGE_X,
                                                        synthetic.RANGE_Y, synthetic.RANGE_Z, self.size, new_points=xyzi,
-                                                       new_pred=b.pred, cur_slot=cur, hist_slot=prev, want_q=False)
+                                                       new_pred=b.pred, cur_slot=cur, hist_slot=prev, want_q=False,
+                                                       crop_eps=1e-4)
             if self.iv_ws is None:
                 self.iv_ws = ops.instance_vote_workspace(N_BOXES, self.device)
-            if self.branches:  # the instance votes do not depend on the voxel votes: a parallel branch
+            if self.instance_branch:  # the instance votes do not depend on the voxel votes: a parallel branch
                 main, (side,) = self._fork(1)
                 with torch.cuda.stream(side):
                     sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi, workspace=self.iv_ws)
             vl = voting.determine_voxel_labels(coords, labels, self.size, num_classes=3)
             point_labels = voting.get_point_labels_from_voxel_labels(coords[cur * n:], vl, self.size)
-            if self.branches:
+            if self.instance_branch:
                 main.wait_stream(side)
+                sums.record_stream(main)  # allocated on the side stream, consumed (D2H) on the main one
             else:
                 sums = ops.instance_vote(pts, labels, self.box_lo, self.box_hi, workspace=self.iv_ws)
             return point_labels, sums

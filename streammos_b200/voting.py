@@ -24,17 +24,24 @@ def Quantize(pcds, range_x=(-40, 62.4), range_y=(-40, 40), range_z=(-3, 5), size
 
 
 def quantize_staged(ring_points, ring_pred, range_x, range_y, range_z, size, new_points=None, new_pred=None,
-                    cur_slot=0, hist_slot=-1, want_q=True):
+                    cur_slot=0, hist_slot=-1, want_q=True, crop_eps=None):
     """The three tensors voxel_voting.py:234-241 builds with `Quantize(...)`, `.to(torch.int64)` and
     `local_map_prediction.to(torch.int64)`, from ONE kernel: (q float32 (P, 3), voxel_coords int64 (P, 3),
     semantic_labels int64 (P,)) for the P = S*N points of a resident long-term memory ring (ring_points (S, N, >=3)
     float32, ring_pred (S, N) uint8). Same values as the three separate calls. With new_points / new_pred the new scan is
     inserted into the ring first (slot cur_slot -> hist_slot, new scan -> cur_slot). `want_q=False` skips the float32
-    tensor (q is None): in the script it is a temporary that dies at the cast (:240), 12 bytes per point of writes."""
+    tensor (q is None): in the script it is a temporary that dies at the cast (:240), 12 bytes per point of writes.
+    `crop_eps` (the script's 1e-4): apply transforms.Crop(fov -/+ eps) of voxel_voting.py:225-231 — a point outside
+    the open box (range_min + eps, range_max - eps) keeps its slot but gets coords (-1, -1, -1), so it casts no vote and
+    reads no voxel label, exactly as if the crop had removed it. None: pre-cropped input, as the bare functions assume."""
     import numpy as np
     mins = (range_x[0], range_y[0], range_z[0])
     deltas = tuple(float(np.float32((r[1] - r[0]) / s)) for r, s in zip((range_x, range_y, range_z), size))
-    return ops.vote_stage(ring_points, ring_pred, mins, deltas, new_points, new_pred, cur_slot, hist_slot, want_q)
+    crop = None
+    if crop_eps is not None:  # thresholds as the float32 comparison of utils/transforms.py:155-157 sees them
+        crop = ([float(np.float32(r[0] + crop_eps)) for r in (range_x, range_y, range_z)],
+                [float(np.float32(r[1] - crop_eps)) for r in (range_x, range_y, range_z)])
+    return ops.vote_stage(ring_points, ring_pred, mins, deltas, new_points, new_pred, cur_slot, hist_slot, want_q, crop)
 
 
 def determine_voxel_labels(voxel_coords, semantic_labels, size, scale=[1, 1], num_classes=None):

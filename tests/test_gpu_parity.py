@@ -681,6 +681,16 @@ def test_vote_stage_equals_quantize_and_casts(S, n, push):
     # want_q=False (what the stream harness uses: the float tensor is a dead temporary in the script): same casts
     q3, coords3, labels3 = voting.quantize_staged(dp, dl, rx, ry, rz, size, want_q=False)
     assert q3 is None and torch.equal(coords3, coords) and torch.equal(labels3, labels)
+    # the script's Crop(fov -/+ 1e-4) in front of Quantize (voxel_voting.py:225-231): points outside the open box
+    # (float32 thresholds, utils/transforms.py:155-157) take no part — coords -1 — all others are untouched
+    _, coords4, labels4 = voting.quantize_staged(dp, dl, rx, ry, rz, size, want_q=False, crop_eps=1e-4)
+    pts4 = want_p.reshape(-1, 4)
+    lo = np.array([np.float32(r[0] + 1e-4) for r in (rx, ry, rz)], np.float32)
+    hi = np.array([np.float32(r[1] - 1e-4) for r in (rx, ry, rz)], np.float32)
+    inside = ((pts4[:, :3] > lo) & (pts4[:, :3] < hi)).all(1)
+    assert pts4.shape[0] < 100 or (inside.any() and (~inside).any())
+    want4 = np.where(inside[:, None], want_q.astype(np.int64), -1)
+    assert np.array_equal(coords4.cpu().numpy(), want4) and torch.equal(labels4, labels)
 
 
 def test_instance_vote_workspace_variant_needs_no_zero_fill():
