@@ -10,11 +10,6 @@
 
 namespace {
 
-constexpr int kGatherThreads = 128;
-#ifndef SMOS_GATHER_MIN_CTAS
-#define SMOS_GATHER_MIN_CTAS 10  // <= 42 registers: the kernel's speed follows the number of resident warps
-#endif
-constexpr int kGatherPts = 32;  // points per CTA
 #ifndef SMOS_GATHER_CPT
 #define SMOS_GATHER_CPT 8
 #endif
@@ -22,51 +17,6 @@ constexpr int kGatherPts = 32;  // points per CTA
 #define SMOS_GATHER_PLANAR_MIN_CTAS 14  // <= 72 registers: room for the 32 loads of a step in flight
 #endif
 constexpr int kCPT = SMOS_GATHER_CPT;  // channels per thread-step in the planar kernel (4 or 8)
-
-// Per-point sampling state shared by all threads of a CTA: the replayed pixel arithmetic costs ~150
-// instructions (two IEEE divisions) and every channel of a point needs the same result, so it is
-// computed ONCE per point by the first 32 threads and broadcast through shared memory. (Recomputing
-// it per channel group made the kernel instruction bound.)
-// ORDERED: slot i of the CTA serves entry p0 + i of a pooling plan's `sorted` list (points grouped by grid cell,
-// out-of-grid points at the tail) instead of point n0 + i. Consecutive slots then sample the same or adjacent
-// cells: in scan order a BEV arc crosses a different image row at almost every point (one 128-byte line per
-// lane and tap), in cell order a warp's taps share one or two lines per channel plane.
-// TAPS: the records were written by the pooling plan builder (same coordinates, grid and scale), one per slot of its
-// cell order: the prologue is a single 48-byte load per slot instead of order entry -> coordinates -> arithmetic.
-template <bool ORDERED, bool TAPS>
-__device__ __forceinline__ void cta_taps(TapsS* s_taps, const float* __restrict__ coord, int32_t b, int32_t n0,
-                                         int32_t N, int64_t co_sb, int64_t co_sn, int64_t co_sd, float sh, float sw,
-                                         int32_t H, int32_t W, const int2* __restrict__ order, int32_t order_hw,
-                                         int64_t order_len, const TapsS* __restrict__ taps) {
-  if (TAPS) {
-    // 32 records x three 128-bit words, one word per thread
-    const int64_t p0 = static_cast<int64_t>(blockIdx.x) * kGatherPts;
-    if (threadIdx.x < kGatherPts * 3) {
-      const int32_t slot = threadIdx.x / 3, w = threadIdx.x - slot * 3;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      const bool live = p0 + slot < order_len;
-      if (live) v = __ldg(reinterpret_cast<const uint4*>(taps + p0 + slot) + w);
-      if (!live && w == 2) v.y = 0xffffffffu;  // n = -1: slot without a point
-      reinterpret_cast<uint4*>(s_taps + slot)[w] = v;
-    }
-    __syncthreads();
-    return;
-  }
-  if (threadIdx.x < kGatherPts) {
-    int32_t n = min(n0 + static_cast<int32_t>(threadIdx.x), N - 1);
-    bool live = n0 + static_cast<int32_t>(threadIdx.x) < N;
-    if (ORDERED) {
-      const int64_t p = static_cast<int64_t>(blockIdx.x) * kGatherPts + threadIdx.x;
-      live = p < order_len;
-      const int2 e = __ldg(order + (live ? p : order_len - 1));
-      n = static_cast<int32_t>(static_cast<uint32_t>(e.x) & 0x7fffffffu);  // bit 31: the plan's run-merge mark
-      b = e.y >= 0 ? e.y / order_hw : -1 - e.y;                            // out-of-grid entries carry -1 - b
-    }
-    const float* cp = coord + b * co_sb + static_cast<int64_t>(n) * co_sn;
-    s_taps[threadIdx.x] = make_taps_record(__ldg(cp), __ldg(cp + co_sd), sh, sw, H, W, live ? n : -1, b);
-  }
-  __syncthreads();
-}
 
 // Per-lane sampling state: slot `slot` of the launch (ORDERED: entry of a pooling plan's `sorted` list over all B*N
 // points; else point `slot` of batch b). Each lane computes (or, with TAPS, loads) the state of ITS point: lanes are
@@ -241,10 +191,19 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
   }
 }
 
-// Channels-last grid (gr_sc == 1, C % 4 == 0): lanes run over channel quads, every tap is a
-// contiguous 16-byte load and a point's taps are four contiguous C*4-byte rows. CTA = 32 points.
+// Channels-last grid (gr_sc == 1, C % 4 == 0): a point's four taps are four contiguous C*4-byte rows, so a lane
+// fetches 16 bytes per tap and 32 lanes cover the taps of 32 / q points at once (q = C / 4 channel quads per point).
+// Same shape as the planar kernel — one independent warp per 32 consecutive slots, no block barrier: the lanes first
+// compute the sampling state of THEIR point (lanes = points) and park it in the warp's slice of shared memory, then
+// the warp walks the points 32 / q at a time (lanes = (point, channel quad)): three 128-bit shared loads for the
+// state, four unconditional 16-byte tap loads, sixteen FMAs and one 16-byte store per lane — the lanes of a point
+// write its row as one contiguous piece, no output staging. Per output element that is a quarter of the planar
+// kernel's load instructions and less than half of its instructions: channels_last feature maps are the layout this
+// operator wants. (The round-1 version of this kernel was a 4-warp CTA sharing 32 points behind two barriers.)
+constexpr int kNhwcWarps = 4;  // independent warps per CTA
+
 template <bool ORDERED, bool TAPS>
-__global__ void __launch_bounds__(kGatherThreads)
+__global__ void __launch_bounds__(kNhwcWarps * 32)
 gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H, int32_t W,
                            int64_t gr_sb, int64_t gr_sh, int64_t gr_sw,
                            const float* __restrict__ coord, int32_t N,
@@ -253,25 +212,34 @@ gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H,
                            const int2* __restrict__ order, int32_t order_hw, int64_t order_len,
                            const TapsS* __restrict__ taps) {
   SMOS_PDL_PROLOGUE();
-  __shared__ TapsS s_taps[kGatherPts];
-  const int32_t n0 = blockIdx.x * kGatherPts;
-  cta_taps<ORDERED, TAPS>(s_taps, coord, blockIdx.z, n0, N, co_sb, co_sn, co_sd, sh, sw, H, W, order, order_hw, order_len,
-                          taps);
+  __shared__ TapsS s_taps[kNhwcWarps][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t slot0 = (static_cast<int64_t>(blockIdx.x) * kNhwcWarps + wid) * 32;
+  if (slot0 >= (ORDERED || TAPS ? order_len : static_cast<int64_t>(N))) return;  // whole warp past the end
+  {
+    TapsS t = lane_taps<ORDERED, TAPS>(slot0 + lane, blockIdx.z, coord, N, co_sb, co_sn, co_sd, sh, sw, H, W, order,
+                                       order_hw, order_len, taps);
+    // pixel offsets -> element offsets inside the batch image (the host checked that they fit 32 bits)
+    t.o_nw = static_cast<int32_t>((t.o_nw / W) * gr_sh + (t.o_nw % W) * gr_sw);
+    t.o_ne = static_cast<int32_t>((t.o_ne / W) * gr_sh + (t.o_ne % W) * gr_sw);
+    t.o_sw = static_cast<int32_t>((t.o_sw / W) * gr_sh + (t.o_sw % W) * gr_sw);
+    t.o_se = static_cast<int32_t>((t.o_se / W) * gr_sh + (t.o_se % W) * gr_sw);
+    s_taps[wid][lane] = t;
+  }
+  __syncwarp();
   const int32_t q = C >> 2;  // channel quads per point
   const bool vec_ok = (o_sc == 1) && ((o_sn & 3) == 0) && ((o_sb & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int32_t i = threadIdx.x; i < kGatherPts * q; i += kGatherThreads) {
-    const int32_t p = i / q, cq = i - p * q;
-    const TapsS t = s_taps[p];
-    const int32_t n = t.n, b = t.b;
-    if (n < 0) break;  // slots without a point are the last ones of the last CTA
-    const float* gq = grid + b * gr_sb + (cq << 2);
-    // unconditional loads from clamped pixels, selected afterwards (see the planar kernel)
-    const float4 l_nw = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_nw / W) * gr_sh + static_cast<int64_t>(t.o_nw % W) * gr_sw));
-    const float4 l_ne = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_ne / W) * gr_sh + static_cast<int64_t>(t.o_ne % W) * gr_sw));
-    const float4 l_sw = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_sw / W) * gr_sh + static_cast<int64_t>(t.o_sw % W) * gr_sw));
-    const float4 l_se = __ldg(reinterpret_cast<const float4*>(gq + static_cast<int64_t>(t.o_se / W) * gr_sh + static_cast<int64_t>(t.o_se % W) * gr_sw));
+  auto one = [&](int32_t p, int32_t cq) {
+    const TapsS t = s_taps[wid][p];
+    const float* gq = grid + t.b * gr_sb + (cq << 2);
+    // unconditional loads from clamped pixels, selected afterwards (see the planar kernel); a slot without a point
+    // (n < 0) still carries valid clamped offsets and b
+    const float4 l_nw = __ldg(reinterpret_cast<const float4*>(gq + t.o_nw));
+    const float4 l_ne = __ldg(reinterpret_cast<const float4*>(gq + t.o_ne));
+    const float4 l_sw = __ldg(reinterpret_cast<const float4*>(gq + t.o_sw));
+    const float4 l_se = __ldg(reinterpret_cast<const float4*>(gq + t.o_se));
     const float4 v_nw = (t.in_mask & 1u) ? l_nw : z, v_ne = (t.in_mask & 2u) ? l_ne : z;
     const float4 v_sw = (t.in_mask & 4u) ? l_sw : z, v_se = (t.in_mask & 8u) ? l_se : z;
     float4 a;
@@ -279,12 +247,23 @@ gather_forward_nhwc_kernel(const float* __restrict__ grid, int32_t C, int32_t H,
     a.y = fmaf(v_se.y, t.w_se, fmaf(v_sw.y, t.w_sw, fmaf(v_ne.y, t.w_ne, fmaf(v_nw.y, t.w_nw, 0.f))));
     a.z = fmaf(v_se.z, t.w_se, fmaf(v_sw.z, t.w_sw, fmaf(v_ne.z, t.w_ne, fmaf(v_nw.z, t.w_nw, 0.f))));
     a.w = fmaf(v_se.w, t.w_se, fmaf(v_sw.w, t.w_sw, fmaf(v_ne.w, t.w_ne, fmaf(v_nw.w, t.w_nw, 0.f))));
-    float* o = out + b * o_sb + static_cast<int64_t>(n) * o_sn + static_cast<int64_t>(cq << 2) * o_sc;
+    if (t.n < 0) return;
+    float* o = out + t.b * o_sb + static_cast<int64_t>(t.n) * o_sn + static_cast<int64_t>(cq << 2) * o_sc;
     if (vec_ok) {
       *reinterpret_cast<float4*>(o) = a;
     } else {
       o[0] = a.x; o[o_sc] = a.y; o[2 * o_sc] = a.z; o[3 * o_sc] = a.w;
     }
+  };
+  if (q <= 32 && (q & (q - 1)) == 0) {  // 32 / q points per step: lane = (point, quad)
+    const int32_t shq = 31 - __clz(q);
+    const int32_t ppi = 32 >> shq;
+    const int32_t p_in = lane >> shq, cq = lane & (q - 1);
+#pragma unroll 2
+    for (int32_t g = 0; g < q; ++g) one(g * ppi + p_in, cq);
+  } else {  // any other channel count: the warp takes the points one by one, lanes over the quads
+    for (int32_t p = 0; p < 32; ++p)
+      for (int32_t cq = lane; cq < q; cq += 32) one(p, cq);
   }
 }
 
@@ -361,12 +340,13 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
   if (B > 65535 || N >= (int64_t(1) << 31) || C >= (1 << 24) || B * N >= (int64_t(1) << 31)) return SMOS_EUNSUPPORTED;
   cudaStream_t st = smos_stream(stream);
   const bool nhwc = (gr_sc == 1) && ((C & 3) == 0) && ((gr_sw & 3) == 0) && ((gr_sh & 3) == 0) &&
-                    ((gr_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+                    ((gr_sb & 3) == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0) &&
+                    (static_cast<int64_t>(H - 1) * gr_sh + static_cast<int64_t>(W - 1) * gr_sw < (int64_t(1) << 31));
   // cell order only pays when a point's channels leave as whole sectors (point-major output rows)
   const bool with_taps = taps != nullptr;  // implies slot (cell) order; the caller checked the output layout
   const bool ordered = (order != nullptr && o_sc == 1 && C > 1) || with_taps;
   const int64_t order_len = B * N;
-  dim3 g(smos_ceil_div(ordered ? order_len : N, kGatherPts), 1, ordered ? 1u : static_cast<unsigned>(B));
+  dim3 g(smos_ceil_div(ordered ? order_len : N, 32 * kNhwcWarps), 1, ordered ? 1u : static_cast<unsigned>(B));
   dim3 gp(smos_ceil_div(ordered ? order_len : N, 32 * kGatherWarps), 1, ordered ? 1u : static_cast<unsigned>(B));
   // one warp = 32 slots x (all channels / split). The split adds warps (latency hiding) at the price of recomputing
   // the sampling state per warp: by default aim at >= 48 resident warps per SM
@@ -383,15 +363,15 @@ static int gather_forward_launch(const float* grid, int64_t B, int64_t C, int32_
   const int32_t Ni = static_cast<int32_t>(N), Ci = static_cast<int32_t>(C);
   if (nhwc) {
     if (with_taps)
-      SMOS_LAUNCH((gather_forward_nhwc_kernel<true, true>), g, kGatherThreads, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
+      SMOS_LAUNCH((gather_forward_nhwc_kernel<true, true>), g, kNhwcWarps * 32, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
                                                                             co_sb, co_sn, co_sd, scale_h, scale_w, out,
                                                                             o_sb, o_sc, o_sn, order, order_hw, order_len, taps);
     else if (ordered)
-      SMOS_LAUNCH((gather_forward_nhwc_kernel<true, false>), g, kGatherThreads, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
+      SMOS_LAUNCH((gather_forward_nhwc_kernel<true, false>), g, kNhwcWarps * 32, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord, Ni,
                                                                              co_sb, co_sn, co_sd, scale_h, scale_w, out,
                                                                              o_sb, o_sc, o_sn, order, order_hw, order_len, nullptr);
     else
-      SMOS_LAUNCH((gather_forward_nhwc_kernel<false, false>), g, kGatherThreads, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord,
+      SMOS_LAUNCH((gather_forward_nhwc_kernel<false, false>), g, kNhwcWarps * 32, 0, st, grid, Ci, H, W, gr_sb, gr_sh, gr_sw, coord,
                                                                               Ni, co_sb, co_sn, co_sd, scale_h, scale_w, out,
                                                                               o_sb, o_sc, o_sn, nullptr, 1, 0, nullptr);
   } else {

@@ -861,7 +861,7 @@ __device__ __forceinline__ void pool_fold_multi(const float* __restrict__ rows, 
 // channel range, so one read of count/start feeds up to C output stores. An occupied cell reads its
 // one row (rows[start]); all row loads of a channel group are issued together. Empty cells store zeros.
 // Every output element is written exactly once with 128-bit stores.
-// FOLD (default): the first `fold_ctas` CTAs of the launch (blockIdx.y == blockIdx.z == 0) are not writers: their
+// FOLD: the first `fold_ctas` CTAs of the launch (blockIdx.z == 0) are not writers: their
 // warps walk the plan's list of multi-piece cells (segments that cross a multiple of 32, reduced as several pieces),
 // fold each cell's piece rows (lanes over channels, 16 rows in flight) and store the C maxima straight into the
 // output; the writer threads skip exactly those cells. This used to be a separate launch between the reduction and
@@ -874,17 +874,20 @@ __global__ void __launch_bounds__(kWriteThreads)
 pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t groups_per_cta,
                   const int32_t* __restrict__ count, const int32_t* __restrict__ start,
                   float* __restrict__ out, int stream_out, const int2* __restrict__ multi,
-                  const int2* __restrict__ sorted, int32_t fold_ctas, int32_t multi_cap, int rule_b) {
+                  const int2* __restrict__ sorted, int32_t fold_ctas, int32_t multi_cap, int rule_b, int32_t tiles_x) {
   SMOS_PDL_PROLOGUE();
   int32_t bx = blockIdx.x;
   if (FOLD) {
     if (bx < fold_ctas) {
-      if (blockIdx.y != 0 || blockIdx.z != 0) return;
+      if (blockIdx.z != 0) return;
       pool_fold_multi(rows, C, hw, count, out, multi, sorted, fold_ctas, multi_cap, bx, rule_b != 0);
       return;
     }
     bx -= fold_ctas;
   }
+  // writer CTAs: (cell tile, channel-group slice) flattened into blockIdx.x so that the fold CTAs exist once per launch
+  const int32_t by = bx / tiles_x;
+  bx -= by * tiles_x;
   const int32_t b = blockIdx.z;
   const bool vec_rows = ((C & 7) == 0);
   constexpr int CPT = VEC4 ? 4 : 1;  // cells per thread
@@ -921,7 +924,7 @@ pool_write_kernel(const float* __restrict__ rows, int32_t C, int32_t hw, int32_t
   }
   const bool any_multi = multi_mask != 0u;
   const int32_t ngroups = (C + kCG - 1) / kCG;
-  const int32_t cg_begin = blockIdx.y * groups_per_cta;
+  const int32_t cg_begin = by * groups_per_cta;
   const int32_t cg_end = min(ngroups, cg_begin + groups_per_cta);
   for (int32_t cg = cg_begin; cg < cg_end; ++cg) {
     const int32_t c0 = cg * kCG;
@@ -1199,7 +1202,8 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
     if (fold_ctas < 1) fold_ctas = 1;
   }
   const int2* multi_list = reinterpret_cast<const int2*>(base + L.off_multi);
-  dim3 grid(gx + fold_ctas, (ngroups + groups_per_cta - 1) / groups_per_cta, static_cast<unsigned>(B));
+  const int32_t gy = (ngroups + groups_per_cta - 1) / groups_per_cta;
+  dim3 grid(static_cast<unsigned>(gx) * gy + fold_ctas, 1, static_cast<unsigned>(B));
   if (stages & SMOS_POOL_STAGE_WRITE) {
     // experiment knob: dynamic shared memory nobody uses caps the resident CTAs per SM of the HBM-bound big writer
     const size_t wsmem = stream_out ? static_cast<size_t>(env_int("SMOS_WRITE_SMEM_KB", 0)) * 1024 : 0;
@@ -1210,7 +1214,7 @@ int smos_voxel_maxpool_forward_stages(const float* pcds_feat, int64_t B, int64_t
     }
 #define SMOS_LAUNCH_WRITE(V, F)                                                                                   \
     SMOS_LAUNCH((pool_write_kernel<V, F>), grid, kWriteThreads, wsmem, st, rows, Ci, hw, groups_per_cta, count, start, \
-                voxel_out, stream_out, multi_list, sorted, fold_ctas, multi_cap, rule_b)
+                voxel_out, stream_out, multi_list, sorted, fold_ctas, multi_cap, rule_b, gx)
     if (vec4 && fold) SMOS_LAUNCH_WRITE(true, true);
     else if (vec4) SMOS_LAUNCH_WRITE(true, false);
     else if (fold) SMOS_LAUNCH_WRITE(false, true);

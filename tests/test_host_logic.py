@@ -137,3 +137,27 @@ def test_gpu_numa_affinity_helpers(tmp_path):
     assert sorted(c for s in shares for c in s) == cpus and all(shares)     # disjoint, complete, never empty
     assert multi.share_of_cpus([5], 3, 4) == [5]
     assert multi.pin_rank_to_gpu(0, 1) is None                                 # single rank: nothing changes
+
+
+def test_resident_window_stream_is_what_the_loader_would_build():
+    """stream.make_host_resident_stream: the RawBatch (host-aligned frames, numpy restatement of the loader steps) and the
+    ResidentRawBatch (raw scans + poses, aligned on the device in the product) describe the same model input — checked
+    here against the C oracle of the loader steps, on the CPU."""
+    import numpy as np
+    from oracle import oracle as O
+    from streammos_b200 import stream, synthetic
+    n, scans = 120000, 3
+    resident, aligned = stream.make_host_resident_stream(2, scans, n, pin=False)
+    for i in range(scans):
+        frames = []
+        for k in range(3):
+            r = resident[(i - k) % scans]
+            raw = r.raw.numpy()[: int(r.meta[0])]
+            pose = np.vstack([resident[i].poses[k].numpy().reshape(3, 4), [0, 0, 0, 1]])
+            frames.append((raw, pose))
+        out, cnt, _ = O.ingest_frames(frames, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, n)
+        assert (cnt < n).all() and (cnt > 0.8 * n).all()
+        assert np.array_equal(out.view(np.uint32), aligned[i].points.numpy().view(np.uint32))
+        assert resident[i].nbytes() < 0.6 * aligned[i].nbytes()  # what crosses PCIe per scan
+    linked = stream.link_window(list(resident))
+    assert linked[0].older == (resident[2], resident[1]) and linked[2].older == (resident[1], resident[0])

@@ -18,18 +18,32 @@ ap.add_argument("--points", type=int, default=120000)
 ap.add_argument("--what", default="step")
 ap.add_argument("--vote-api", default="reference")
 ap.add_argument("--loader", action="store_true", help="start every step from the loader tensors (PointNet stem on device)")
+ap.add_argument("--channel-major-feat", action="store_true",
+                help="hand pool #1 the (B, C, N, 1)-contiguous features of the reference stem instead of point-major ones")
+ap.add_argument("--keep-plans", action="store_true", help="let the plan cache serve the repeated scans (no plan kernels)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 hot = stream.HotPath(dev, a.points, seed=0, branches=False, vote_api=a.vote_api)
-scans = [(stream.make_host_loader_scan if a.loader else stream.make_host_scan)(i, a.points).to(dev) for i in range(4)]
+if a.loader:
+    scans = [stream.make_host_loader_scan(i, a.points).to(dev) for i in range(4)]
+else:
+    scans = [stream.make_host_scan(i, a.points, feat_point_major=not a.channel_major_feat).to(dev) for i in range(4)]
+from streammos_b200 import plan_cache  # noqa: E402
+
+
+def run(i):
+    if not a.keep_plans:  # forget the plans (not what was learned): every step rebuilds them in its three batches
+        plan_cache._entries.clear()
+    fn(scans[i % 4])
+
 fn = {"step": hot.step, "vote": hot.long_term_voting, "proj": hot.projection}[a.what]
 with torch.no_grad():
     for i in range(8):  # the plan cache learns its prefetch batches on the first scans: profile the steady state
-        fn(scans[i % 4])
+        run(i)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for i in range(a.steps):
-            fn(scans[i % 4])
+            run(i)
         torch.cuda.synchronize()
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
