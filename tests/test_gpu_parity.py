@@ -1193,7 +1193,7 @@ def test_step_from_loader_tensors_matches_explicit_inputs():
 
 @pytest.mark.parametrize("use_graphs", [True, False])
 def test_pipeline_matches_serial_step(use_graphs):
-    """ScanPipeline (3 graphs per scan on 3 streams, two scans in flight) == the serial step, scan by scan."""
+    """ScanPipeline (3 graphs per scan, default scans in flight) == the serial step, scan by scan."""
     from streammos_b200 import pipeline, stream
     n, n_buf, n_scans = 20000, 8, 12  # graph replays bake the voting ring slot: buffers = a multiple of 8
     host = [stream.make_host_scan(300 + j, n, pin=False) for j in range(n_buf)]
@@ -1221,6 +1221,35 @@ def test_pipeline_matches_serial_step(use_graphs):
     for i, ((wl, ws), (gl, gs)) in enumerate(zip(want, got)):
         assert torch.equal(wl, gl), "labels differ at scan %d" % i
         assert torch.equal(ws, gs), "instance votes differ at scan %d" % i
+    torch.testing.assert_close(hot.memory, serial.memory, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("in_flight", [2, 4, 8])
+def test_pipeline_with_scans_really_in_flight(in_flight):
+    """Eight scans submitted back to back (no host join in between: up to `in_flight` projections overlap on their own
+    streams, temporal fusion and voting stay ordered by events) give the serial results, scan by scan."""
+    from streammos_b200 import pipeline, stream
+    n, n_buf = 20000, 8
+    host = [stream.make_host_scan(700 + j, n, pin=False) for j in range(n_buf)]
+    serial = stream.HotPath(dev(), n_points=n, seed=4)
+    want = []
+    with torch.no_grad():
+        for i in range(n_buf):
+            labels, sums, _ = serial.step(host[i].to(dev()))
+            want.append((labels.clone(), sums.clone()))
+    hot = stream.HotPath(dev(), n_points=n, seed=4)
+    state0 = (hot.memory.clone(), hot.local_pts.clone(), hot.local_pred.clone())
+    pipe = pipeline.ScanPipeline(hot, [h.to(dev()) for h in host], use_graphs=True, scans_in_flight=in_flight)
+    hot.memory.copy_(state0[0]); hot.local_pts.copy_(state0[1]); hot.local_pred.copy_(state0[2])
+    hot.scan_index = 0
+    torch.cuda.synchronize()
+    for i in range(n_buf):
+        pipe.submit()
+    pipe.join(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    for j, (wl, ws) in enumerate(want):
+        assert torch.equal(wl, pipe.out[j][0]), "labels differ at scan %d" % j
+        assert torch.equal(ws, pipe.out[j][1]), "instance votes differ at scan %d" % j
     torch.testing.assert_close(hot.memory, serial.memory, rtol=0, atol=0)
 
 
