@@ -46,7 +46,7 @@ struct Smem {
   alignas(16) float a2[kC];
   alignas(16) float b2[kC];
   float a0[kCinMax], b0[kCinMax];
-  float4 rows[kComputeThreads / 32][32 * 5];  // per-warp staging of point-major output rows (pitch 5 x 16 bytes)
+  float4 rows[kComputeThreads / 32][32 * 4];  // per-warp staging of point-major output rows (64 bytes per row, swizzled)
   uint64_t full[2];  // operand stage written (one arrival per compute warp)
   uint64_t done[2];  // the stage's MMAs have completed (tcgen05.commit)
   uint32_t tmem_base;
@@ -119,12 +119,23 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
   const int tid = threadIdx.x, wid = tid >> 5;
   const int pt = tid & (kPts - 1), part = tid >> 7;  // my point of the tile, my quarter of the channels
   // ---- one-time setup: parameters, W2 split into its tf32 hi / lo parts, barriers, tensor memory ------------------------
-  for (int i = tid; i < kC * kC; i += kThreads) {
-    const int n = i >> 6, k = i & 63;  // W2[n][k], row = output channel
-    const float v = __ldg(w2 + i);
-    const float hi = tf32_rna(v);  // once per CTA: round to nearest here, the remainder is exact
-    S.b_hi[core_index(n, k)] = hi;
-    S.b_lo[core_index(n, k)] = v - hi;
+  {
+    // all loads of a thread first (8 in flight), then the splits and stores: one round trip instead of eight (the setup
+    // was 5 % of the kernel's stall samples)
+    constexpr int kW2PerThread = (kC * kC + kThreads - 1) / kThreads;
+    float wv[kW2PerThread];
+#pragma unroll
+    for (int u = 0; u < kW2PerThread; ++u) wv[u] = __ldg(w2 + min(tid + u * kThreads, kC * kC - 1));
+#pragma unroll
+    for (int u = 0; u < kW2PerThread; ++u) {
+      const int i = tid + u * kThreads;
+      if (i < kC * kC) {
+        const int n = i >> 6, k = i & 63;  // W2[n][k], row = output channel
+        const float hi = tf32_rna(wv[u]);  // once per CTA: round to nearest here, the remainder is exact
+        S.b_hi[core_index(n, k)] = hi;
+        S.b_lo[core_index(n, k)] = wv[u] - hi;
+      }
+    }
   }
   for (int i = tid; i < kC * kCinMax; i += kThreads) {
     const int c = i / kCinMax, ci = i % kCinMax;
@@ -162,39 +173,46 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
     n0 += stride_n;
     if (n0 >= tiles_per_b * kPts) { n0 -= tiles_per_b * kPts; ++b; }
   };
-  auto fetch = [&](int32_t b, int32_t n0, float (&xr)[KI]) {  // inputs of my point (same arithmetic as point_stem_kernel)
-    const int32_t nn = n0 + pt;
-    const int32_t n = min(nn, N - 1);
+  // Inputs of my point of a tile, in two halves: fetch() only ISSUES the loads (one grid stride ahead, so that they are
+  // in flight during the epilogue of the previous tile), expand() turns them into the layer's inputs at the top of
+  // the tile's own iteration. (With the arithmetic inside fetch() the first multiply waited for the load right
+  // there: 12 % of the kernel's stall samples.) Same arithmetic as point_stem_kernel.
+  auto fetch = [&](int32_t b, int32_t n0, float (&xr)[KI], float4& rawq) {
+    const int32_t n = min(n0 + pt, N - 1);
     if (RAW) {
       const float* p = raw.pts + (static_cast<int64_t>(b) * N + n) * raw.rs;
-      float px, py, pz, pw;
       if (raw.rs == 4 && (reinterpret_cast<uintptr_t>(raw.pts) & 15) == 0) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-        px = q.x; py = q.y; pz = q.z; pw = q.w;
+        rawq = __ldg(reinterpret_cast<const float4*>(p));
       } else {
-        px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2); pw = __ldg(p + 3);
-      }
-      px = __fmul_rn(px, raw.sx);
-      py = __fmul_rn(py, raw.sy);
-      const float qx = __fdiv_rn(__fsub_rn(px, raw.mx), raw.dx);
-      const float qy = __fdiv_rn(__fsub_rn(py, raw.my), raw.dy);
-      const float qz = __fdiv_rn(__fsub_rn(pz, raw.mz), raw.dz);
-      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz));
-      xr[0] = px; xr[1] = py; xr[2] = pz; xr[3] = pw;
-      xr[4] = __fadd_rn(__fsqrt_rn(d2), 1e-12f);
-      xr[5] = __fsub_rn(qx, floorf(qx));
-      xr[6] = __fsub_rn(qy, floorf(qy));
-#pragma unroll
-      for (int ci = 7; ci < KI; ++ci) xr[ci] = 0.f;
-      if (nn < N && part == 0) {
-        float* c = raw.coord + (static_cast<int64_t>(b) * N + n) * 3;
-        c[0] = qx; c[1] = qy; c[2] = qz;
+        rawq = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
       }
       return;
     }
 #pragma unroll
     for (int ci = 0; ci < KI; ++ci)
       xr[ci] = (CIN > 0 ? ci < CIN : ci < Cin) ? __ldg(x + b * x_sb + ci * x_sc + static_cast<int64_t>(n) * x_sn) : 0.f;
+  };
+  auto expand = [&](int32_t b, int32_t n0, float (&xr)[KI], const float4& rawq) {
+    if (!RAW) return;
+    const int32_t nn = n0 + pt;
+    const int32_t n = min(nn, N - 1);
+    const float px = __fmul_rn(rawq.x, raw.sx);
+    const float py = __fmul_rn(rawq.y, raw.sy);
+    const float pz = rawq.z, pw = rawq.w;
+    const float qx = __fdiv_rn(__fsub_rn(px, raw.mx), raw.dx);
+    const float qy = __fdiv_rn(__fsub_rn(py, raw.my), raw.dy);
+    const float qz = __fdiv_rn(__fsub_rn(pz, raw.mz), raw.dz);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz));
+    xr[0] = px; xr[1] = py; xr[2] = pz; xr[3] = pw;
+    xr[4] = __fadd_rn(__fsqrt_rn(d2), 1e-12f);
+    xr[5] = __fsub_rn(qx, floorf(qx));
+    xr[6] = __fsub_rn(qy, floorf(qy));
+#pragma unroll
+    for (int ci = 7; ci < KI; ++ci) xr[ci] = 0.f;
+    if (nn < N && part == 0) {
+      float* c = raw.coord + (static_cast<int64_t>(b) * N + n) * 3;
+      c[0] = qx; c[1] = qy; c[2] = qz;
+    }
   };
   // accumulator of tile `t` (stage s) -> BatchNorm + ReLU -> y
   auto drain = [&](int32_t b, int32_t n0, int s, uint32_t parity) {
@@ -219,17 +237,23 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
       // point-major rows: my 16 channels are 64 contiguous bytes of my point's row. Written straight from the registers,
       // every store instruction would touch 32 rows with 16 bytes each (half sectors: measured 25 of the kernel's 66 us).
       // Through the warp's staging buffer four consecutive lanes write one 64-byte segment: whole sectors only.
+      // Staging layout: row r = 64 contiguous bytes, its 16-byte chunk c at slot c ^ ((r >> 1) & 3). Writes (lane = row,
+      // one chunk index per instruction) and reads (four lanes = the four chunks of a row, eight lanes = two adjacent
+      // rows = 128 contiguous bytes) are both conflict free; the earlier pitch of 80 bytes cost the reads a second
+      // wavefront (ncu: 2x the ideal on the four LDS.128 of the epilogue, 8 % of the kernel's shared-memory wavefronts).
       float4* stg = S.rows[wid];
       const int lane = tid & 31;
 #pragma unroll
-      for (int j = 0; j < kCP / 4; ++j) stg[lane * 5 + j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < kCP / 4; ++j)
+        stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
       const int32_t nw = n0 + (wid & 3) * 32;  // first point of my warp's quarter of the tile
 #pragma unroll
       for (int k = 0; k < kCP / 4; ++k) {
         const int idx = k * 32 + lane, row = idx >> 2, seg = idx & 3;
         if (nw + row < N)
-          *reinterpret_cast<float4*>(y + b * y_sb + static_cast<int64_t>(nw + row) * y_sn + part * kCP + seg * 4) = stg[row * 5 + seg];
+          *reinterpret_cast<float4*>(y + b * y_sb + static_cast<int64_t>(nw + row) * y_sn + part * kCP + seg * 4) =
+              stg[row * 4 + (seg ^ ((row >> 1) & 3))];
       }
       __syncwarp();
     }
@@ -267,14 +291,16 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
   } else {
     // ---- compute warps: layer 1 of tile i, then (while the tensor core works on it) the epilogue of tile i - 1 ------------
     float xr[KI];
+    float4 rawq = make_float4(0.f, 0.f, 0.f, 0.f);
     int32_t t = blockIdx.x;
     int32_t b_cur = t / tiles_per_b, n_cur = (t - b_cur * tiles_per_b) * kPts;  // this tile
     int32_t b_nxt = b_cur, n_nxt = n_cur;                                        // the tile one grid stride ahead
     int32_t b_prev = 0, n_prev = 0;
-    if (t < ntiles) fetch(b_cur, n_cur, xr);
+    if (t < ntiles) fetch(b_cur, n_cur, xr, rawq);
     int32_t it = 0, t_prev = -1;
     for (; t < ntiles; t += gridDim.x, ++it) {
       const int s = it & 1;
+      expand(b_cur, n_cur, xr, rawq);
       {
         float xin[KI];
 #pragma unroll
@@ -317,7 +343,7 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
         }
       }
       advance(b_nxt, n_nxt);
-      if (t + gridDim.x < ntiles) fetch(b_nxt, n_nxt, xr);  // in flight during the epilogue below
+      if (t + gridDim.x < ntiles) fetch(b_nxt, n_nxt, xr, rawq);  // in flight during the epilogue below
       smos_fence_proxy_async();  // my operand stores -> visible to the tensor core (async proxy)
       fence_before_sync();       // and my earlier tcgen05.ld of this stage's accumulator are complete
       __syncwarp();
