@@ -561,7 +561,7 @@ def run_b200(args, world, rank, local):
                 "whole_path": {"algorithmic_bytes_per_scan": ab["total"],
                                "achieved": ab["total"] / (ms_step * 1e-3) / 1e9,
                                "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak,
-                               "note": "pipelined wall time per scan (ms_per_step): kernels of 2 scans in flight overlap"}}
+                               "note": "pipelined wall time per scan (ms_per_step): kernels of %d scans in flight overlap" % args.in_flight}}
     if families:
         # SURVEY 8d's own formula: algorithmic bytes / SUM of the hot-path kernel time (no overlap between families)
         sum_us = sum(f["us_per_scan"] for f in families.values())

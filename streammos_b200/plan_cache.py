@@ -31,7 +31,7 @@ import torch
 
 from . import _lib
 
-CAPACITY = 24  # entries; a scan needs five plans, two scans are in flight, captures leave theirs behind until evicted
+CAPACITY = 48  # entries; a scan needs five plans, four scans are in flight, captures leave theirs behind until evicted
 
 _entries = collections.OrderedDict()   # key -> [coordinate view, version, plan, kind, prefetched-and-unused]
 _history = {}                          # kind -> ordered list of geometries (H, W, sh, sw) seen on tensors of that kind
