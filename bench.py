@@ -449,6 +449,23 @@ def run_b200(args, world, rank, local):
                        "range filter and padding of all T frames (smos_ingest_frames, bit-exact with the loader), Quantize + "
                        "make_point_feat, the PointNet stem, the whole hot path and the D2H of the labels are inside the "
                        "timed region; the copy of scan i+1 overlaps scan i")
+        # (5) as (4), but nothing the loader computed crosses PCIe: SphereQuantize of the current frame on the device too
+        #     (smos_sphere_quantize: floating point, within 1 ulp of the angle of numpy's float32 result — a handful of the
+        #     120 k points change their range-view cell, which is why (4), bit-exact with the loader, stays the headline)
+        hot_s = stream.HotPath(dev, n_points=args.points, seed=rank, point_major=not args.channel_major,
+                               vote_api=args.vote_api, grids_channels_last=args.grids_channels_last, branches=args.branches,
+                               batch_plans=args.explicit_plans, ordered_gathers=not args.no_ordered_gathers,
+                               ordered_rv=args.ordered_rv, gather_taps=args.gather_taps, sphere_on_device=True)
+        host_s, _ = stream.make_host_resident_stream(rank, N_SCANS, args.points, device_sphere=True)
+        devb_s = stream.link_window([h.pack(device=dev) for h in host_s])
+        torch.cuda.synchronize()
+        pipe_s = pipeline.ScanPipeline(hot_s, devb_s, use_graphs=use_graph, scans_in_flight=args.in_flight)
+        e2e_sphere = measure_e2e(pipe_s, host_s, devb_s, side_steps, window=2)
+        e2e_sphere["note"] = ("as the headline, with SphereQuantize of the current frame on the device as well: the host hands "
+                              "over the raw scan, the poses and the stand-ins only (floating-point range-view coordinates, "
+                              "within 1 ulp of the angle of the loader's)")
+        del pipe_s, devb_s, hot_s, host_s
+        e2e["sphere_quantize_on_device"] = e2e_sphere
         e2e["raw_scan_all_frames_from_host"] = e2e_frames
         e2e["loader_tensors"] = e2e_loader
         e2e["hot_path_inputs_over_pcie"] = e2e_feat

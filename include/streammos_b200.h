@@ -288,6 +288,20 @@ int smos_form_batch(const float* points, int64_t T, int64_t N, int64_t row_strid
                     float min_x, float min_y, float min_z, float dx, float dy, float dz,
                     float* pcds_xyzi, float* pcds_coord, void* stream);
 
+/* (next: SURVEY 8f rank 2) utils.SphereQuantize (datasets/utils.py:172-192), the range-view coordinates of form_batch
+ * (datasets/data_StreamMOS.py:481-484): d = sqrt(x*x + y*y + z*z) + 1e-12, phi = phi_hi - arctan2(x, y),
+ * theta = theta_hi - arcsin(z / d), out = (theta / dtheta, phi / dphi), numpy float32 throughout.
+ *   points       : (total, row_stride >= 3) float32 rows x, y, z, ...
+ *   x_sign/y_sign: TTA flip factors (+1 / -1)
+ *   phi_hi, theta_hi : float32(range[1] * pi / 180); dphi, dtheta : float32((hi_rad - lo_rad) / W or H)
+ *   sphere_coord : (total, 2) float32 out (theta_quan, phi_quan), 8-byte aligned
+ * FLOATING POINT, not bit-exact: numpy's float32 arctan2 / arcsin are not correctly rounded and differ between hosts;
+ * here the two angles are evaluated in float64 and rounded to float32 once, all other operations replayed in float32.
+ * Against the reference: |d phi_quan| <= 5e-4 cells, |d theta_quan| <= 5e-5 cells (1 ulp of the angle), identical on
+ * most points; about one point per 120 k scan changes its range-view cell. */
+int smos_sphere_quantize(const float* points, int64_t total, int64_t row_stride, float x_sign, float y_sign,
+                         float phi_hi, float theta_hi, float dphi, float dtheta, float* sphere_coord, void* stream);
+
 /* (next: SURVEY 8f rank 2) Scan ingestion: the loader steps in front of form_batch, per frame of the T-frame window
  * (datasets/data_StreamMOS.py:515-574): utils.Trans (datasets/utils.py:116-126: float64 pose_diff . (x, y, z, 1) ->
  * float32), utils.filter_pcds_mask (:107-113: lo <= p < hi on the aligned point), order-preserving compaction and

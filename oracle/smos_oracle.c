@@ -511,6 +511,37 @@ API void oracle_form_batch(const float* pts, int64_t T, int64_t N, int64_t rs, f
 }
 
 /* ---------------------------------------------------------------------------------------- */
+/* utils.SphereQuantize (datasets/utils.py:172-192), the range-view coordinates of the         */
+/* loader's form_batch (datasets/data_StreamMOS.py:481-484), numpy float32 throughout:         */
+/*   d = sqrt(x**2 + y**2 + z**2) + 1e-12; phi = phi_hi - arctan2(x, y);                        */
+/*   theta = theta_hi - arcsin(z / d); out = (theta / dtheta, phi / dphi).                      */
+/* FLOATING POINT: numpy's float32 arctan2 / arcsin (SVML or libm, by host) are not correctly  */
+/* rounded, so this restatement takes the float64 functions rounded to float32 once — the      */
+/* correctly rounded angle in all but ~1e-9 of the cases — and tests/test_oracle_golden.py      */
+/* bounds its distance to the reference's own output (1 ulp of the angle).                     */
+/* pts (total, rs) -> out (total, 2); c = {phi_hi, theta_hi, dphi, dtheta} as float32.         */
+/* ---------------------------------------------------------------------------------------- */
+API void oracle_sphere_quantize(const float* pts, int64_t total, int64_t rs, float sx, float sy, const float* c,
+                                float* out) {
+  for (int64_t i = 0; i < total; ++i) {
+    const float* p = pts + i * rs;
+    volatile float x = p[0] * sx, y = p[1] * sy, z = p[2];
+    volatile float xx = x * x, yy = y * y, zz = z * z;
+    volatile float s1 = xx + yy;
+    volatile float s2 = s1 + zz;
+    volatile float r = sqrtf(s2);
+    volatile float dist = r + 1e-12f;
+    volatile float q = z / dist;
+    volatile float a_phi = (float)atan2((double)x, (double)y);
+    volatile float a_theta = (float)asin((double)q);
+    volatile float phi = c[0] - a_phi;
+    volatile float theta = c[1] - a_theta;
+    out[2 * i] = theta / c[3];
+    out[2 * i + 1] = phi / c[2];
+  }
+}
+
+/* ---------------------------------------------------------------------------------------- */
 /* Scan ingestion: one frame of the val loader's window,                   */
 /* datasets/data_StreamMOS.py:515-574:                                                         */
 /*   utils.Trans (datasets/utils.py:116-126): pcds_tmp = mat.dot([x, y, z, 1]) in float64      */

@@ -73,6 +73,7 @@ SIGNATURES = {
     "smos_point_stem_forward": (ctypes.c_int, [_vp, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                _vp, _i32, _i32, _vp, _i64, _i64, _i64, _vp]),
     "smos_form_batch": (ctypes.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    "smos_sphere_quantize": (ctypes.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "smos_ingest_workspace_bytes": (_i64, [_i32, _i64, _i64]),
     "smos_ingest_frames": (ctypes.c_int, [ctypes.POINTER(IngestFrame), _i32, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _i64,
                                           _f32, _f32, _vp, _vp, _vp, _vp, _vp]),

@@ -7,9 +7,12 @@
 //                                                                                        diff_x, diff_y)
 // with the TTA flips of form_batch_tta (:495-513) as sign arguments. Every float32 operation of the reference is
 // IEEE-exact and replayed one to one (subtract, divide, multiply, add, sqrt, floor), so the outputs are BIT-EXACT.
-// utils.SphereQuantize (arctan2 / arcsin in numpy float32) is NOT rebuilt here: no device libm matches numpy's
-// results bit for bit, and a 1-ulp difference can move a point across a range-view cell boundary; the range-view
-// coordinates of the current frame (the only ones the model reads, models/StreamMOS.py:99) stay a loader output.
+// utils.SphereQuantize (datasets/utils.py:172-192; arctan2 / arcsin in numpy float32) is a kernel of its own below
+// (smos_sphere_quantize): no device libm matches numpy's float32 arctan2 / arcsin bit for bit (numpy's SVML loops are
+// not correctly rounded and differ between hosts), so that one is a FLOATING-POINT result with a stated tolerance —
+// the two angles are evaluated in float64 and rounded to float32 once (the correctly rounded float32 value in all but
+// ~1e-9 of the cases), every other operation of the reference is replayed in float32. The bit-exact path keeps the
+// range-view coordinates of the current frame (the only ones the model reads, models/StreamMOS.py:99) a loader output.
 #include "common.cuh"
 
 namespace {
@@ -45,7 +48,47 @@ form_batch_kernel(const float* __restrict__ pts, int64_t total, int64_t N, int64
   c[0] = qx; c[1] = qy; c[2] = qz;
 }
 
+// utils.SphereQuantize: (theta_quan, phi_quan) per point. numpy evaluates everything in float32 (the Python-float
+// constants are weak scalars): d = sqrt(x*x + y*y + z*z) + 1e-12; phi = phi_hi - arctan2(x, y); theta = theta_hi -
+// arcsin(z / d); each divided by its float32 step.
+__global__ void __launch_bounds__(256)
+sphere_quantize_kernel(const float* __restrict__ pts, int64_t total, int64_t rs, float sx, float sy, float phi_hi,
+                       float theta_hi, float dphi, float dtheta, float2* __restrict__ out) {
+  SMOS_PDL_PROLOGUE();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= total) return;
+  const float* p = pts + i * rs;
+  float x, y, z;
+  if (rs == 4 && (reinterpret_cast<uintptr_t>(pts) & 15) == 0) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    x = q.x; y = q.y; z = q.z;
+  } else {
+    x = p[0]; y = p[1]; z = p[2];
+  }
+  x = __fmul_rn(x, sx);
+  y = __fmul_rn(y, sy);
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+  const float dist = __fadd_rn(__fsqrt_rn(d2), 1e-12f);
+  const float s = __fdiv_rn(z, dist);
+  const float a_phi = static_cast<float>(atan2(static_cast<double>(x), static_cast<double>(y)));
+  const float a_theta = static_cast<float>(asin(static_cast<double>(s)));
+  const float phi = __fsub_rn(phi_hi, a_phi);
+  const float theta = __fsub_rn(theta_hi, a_theta);
+  out[i] = make_float2(__fdiv_rn(theta, dtheta), __fdiv_rn(phi, dphi));
+}
+
 }  // namespace
+
+extern "C" int smos_sphere_quantize(const float* points, int64_t total, int64_t row_stride, float x_sign, float y_sign,
+                                    float phi_hi, float theta_hi, float dphi, float dtheta, float* sphere_coord,
+                                    void* stream) {
+  if (total < 0 || row_stride < 3 || !(dphi != 0.0f) || !(dtheta != 0.0f)) return SMOS_EINVAL;
+  if (total == 0) return SMOS_OK;
+  if (!points || !sphere_coord || (reinterpret_cast<uintptr_t>(sphere_coord) & 7) != 0) return SMOS_EINVAL;
+  SMOS_LAUNCH((sphere_quantize_kernel), smos_ceil_div(total, 256), 256, 0, smos_stream(stream),
+      points, total, row_stride, x_sign, y_sign, phi_hi, theta_hi, dphi, dtheta, reinterpret_cast<float2*>(sphere_coord));
+  return smos_launch_status();
+}
 
 extern "C" int smos_form_batch(const float* points, int64_t T, int64_t N, int64_t row_stride, float x_sign, float y_sign,
                                float min_x, float min_y, float min_z, float dx, float dy, float dz, float* pcds_xyzi,

@@ -314,6 +314,40 @@ def form_batch(points, range_x, range_y, range_z, size, x_sign=1.0, y_sign=1.0):
     return feat, coord
 
 
+def sphere_constants(phi_range=(-180.0, 180.0), theta_range=(-25.0, 3.0), size=(64, 2048)):
+    """The four float32 constants of utils.SphereQuantize (datasets/utils.py:173-180) as numpy forms them: float64
+    products of the degree bounds, used as weak scalars against float32 arrays -> (phi_hi, theta_hi, dphi, dtheta)."""
+    import numpy as np
+    H, W = size
+    phi_r = (phi_range[0] * np.pi / 180.0, phi_range[1] * np.pi / 180.0)
+    th_r = (theta_range[0] * np.pi / 180.0, theta_range[1] * np.pi / 180.0)
+    dphi = (phi_r[1] - phi_r[0]) / W
+    dth = (th_r[1] - th_r[0]) / H
+    return tuple(float(np.float32(v)) for v in (phi_r[1], th_r[1], dphi, dth))
+
+
+def sphere_quantize(points, phi_range=(-180.0, 180.0), theta_range=(-25.0, 3.0), size=(64, 2048), x_sign=1.0,
+                    y_sign=1.0, out=None):
+    """utils.SphereQuantize (datasets/utils.py:172-192) on the device: points (T, N, >=3) float32 CUDA ->
+    pcds_sphere_coord (T, N, 2, 1) = (theta_quan, phi_quan). Floating point (smos_sphere_quantize): the angles are the
+    float64 arctan2 / arcsin rounded to float32, everything else is the reference's float32 sequence; within 1 ulp of
+    the angle of numpy's result (include/streammos_b200.h states the bound in cells)."""
+    _need_cuda(points, "points")
+    _need_f32(points, "points")
+    assert points.dim() == 3 and points.size(2) >= 3 and points.stride(2) == 1 and points.stride(0) == points.size(1) * points.stride(1)
+    T, N = int(points.size(0)), int(points.size(1))
+    c = sphere_constants(phi_range, theta_range, size)
+    if out is None:
+        out = torch.empty((T, N, 2, 1), dtype=torch.float32, device=points.device)
+    assert out.is_contiguous() and out.numel() == T * N * 2 and out.dtype == torch.float32
+    with torch.cuda.device(points.device):
+        rc = _lib.load().smos_sphere_quantize(_ptr(points), T * N, points.stride(1) if N > 1 else points.size(2),
+                                              float(x_sign), float(y_sign), c[0], c[1], c[2], c[3], _ptr(out), _stream())
+    _lib.check(rc, "smos_sphere_quantize")
+    _count(1)
+    return out
+
+
 def ingest_frames(frames, range_x, range_y, range_z, n_out, pad_xy=-1000.0, pad_z=-4000.0, want_src=False,
                   out=None, workspace=None):
     """The loader steps in front of form_batch on the device (datasets/data_StreamMOS.py:515-574): per frame pose

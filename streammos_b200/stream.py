@@ -163,6 +163,18 @@ class ResidentRawBatch(_FlatBatch):
     older = ()
 
 
+class ResidentScanBatch(_FlatBatch):
+    """ResidentRawBatch without `sphere_cur`: the stream receives NOTHING the loader computed — the raw scan as read from
+    the file, the window's poses and the stand-ins — and the range-view coordinates of the current frame come from
+    smos_sphere_quantize on the ingested frame (HotPath(sphere_on_device=True)). Floating point, not bit-exact with
+    numpy's float32 arctan2 / arcsin (include/streammos_b200.h: within 1 ulp of the angle; a handful of the 120 k
+    points change their range-view cell), which is why the bit-exact ResidentRawBatch stays the default."""
+
+    FIELDS = ("raw", "meta", "poses", "pred", "loc", "attn")
+    coord_rv = None
+    older = ()
+
+
 def link_window(batches, t_frames=3):
     """Scan i of a cyclic list of device batches sees the raw scans of i-1, i-2, ... as the older frames of its window."""
     n = len(batches)
@@ -171,11 +183,12 @@ def link_window(batches, t_frames=3):
     return batches
 
 
-def make_host_resident_stream(seed, n_scans, n_points=120000, t_frames=3, n_cap=None, pin=True):
+def make_host_resident_stream(seed, n_scans, n_points=120000, t_frames=3, n_cap=None, pin=True, device_sphere=False):
     """`n_scans` consecutive scans of ONE synthetic drive, cyclic (scan 0 follows scan n_scans-1): the vehicle moves by
     the same rigid motion every scan, so the window's pose_diff matrices are the same for every scan. Returns
     (resident, raw): ResidentRawBatch per scan, and the RawBatch the HOST would build from the same drive today (its
-    numpy pose alignment + filter + padding of all T frames) — the two describe identical model inputs."""
+    numpy pose alignment + filter + padding of all T frames) — the two describe identical model inputs.
+    device_sphere=True: ResidentScanBatch (no range-view coordinates from the host)."""
     raws = [synthetic.lidar_raw_scan(np.random.default_rng(seed * 7919 + 31 * i)) for i in range(n_scans)]
     n_cap = n_cap or (max(len(r) for r in raws) + 255) // 256 * 256
     diffs = synthetic.stream_pose_diffs(t_frames)
@@ -195,6 +208,8 @@ def make_host_resident_stream(seed, n_scans, n_points=120000, t_frames=3, n_cap=
                              loc=other.loc, attn=other.attn)
         h = RawBatch(points=torch.from_numpy(np.stack(frames)), sphere_cur=torch.from_numpy(sphere.copy()), pred=pred.clone(),
                      loc=other.loc, attn=other.attn)
+        if device_sphere:
+            r = ResidentScanBatch(**{f: getattr(r, f) for f in ResidentScanBatch.FIELDS})
         if pin and torch.cuda.is_available():
             r, h = r.pack(pin=True), h.pack(pin=True)
         resident.append(r)
@@ -242,14 +257,17 @@ class HotPath:
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
                  batch_plans=False, grids_channels_last=False, overlap_voting=False, branches=False,
                  ordered_gathers=True, ordered_rv=False, gather_taps=False, fuse_form_batch=True,
-                 instance_branch=True):
+                 instance_branch=True, sphere_on_device=False):
         """batch_plans=False (default): every operator is called with the REFERENCE's arguments only
         (VoxelMaxPool(feat, ind, size, scale), BilinearSample(grid, coord)); plans are shared through the plan cache
         exactly as they are under the unmodified reference model. batch_plans=True: the explicit plan API (all five
         plans of a scan built by one batch of launches, passed as plan= / order=).
         branches=False (default): one serial chain, the reference's data flow (multi_view_encoder.py:393-417 feeds every
-        stage from the previous one through its CNN blocks)."""
+        stage from the previous one through its CNN blocks).
+        sphere_on_device=True: raw-scan batches get their range-view coordinates from ops.sphere_quantize (SphereQuantize
+        of the loader, floating point) instead of the loader's `sphere_cur`."""
         self.device = torch.device(device)
+        self.sphere_on_device = sphere_on_device
         self.overlap_voting = overlap_voting
         self.branches = branches and self.device.type == "cuda"
         # voxel voting (voxel_voting.py) and instance voting (voxel_instance_voting.py) are two independent
@@ -369,6 +387,9 @@ class HotPath:
             coord_bev = b.coord_bev
             feat = b.feat if hasattr(b, "feat") else self.point_pre(b.pcds_xyzi)
         cur_bev, cur_rv = coord_bev[:1], b.coord_rv
+        if hasattr(b, "points") and (self.sphere_on_device or cur_rv is None):
+            # SphereQuantize of the current frame (the only range-view coordinates the model reads, StreamMOS.py:99)
+            cur_rv = ops.sphere_quantize(b.points[:1], theta_range=synthetic.RV_THETA, size=synthetic.RV_SHAPE)
         # all five pooling plans of the scan depend on the coordinates only: four launches build them all
         if self.batch_plans:
             pl = ops.pool_plan_multi([(coord_bev, (512, 512), (1.0, 1.0)), (cur_rv, (32, 1024), (0.5, 0.5)),

@@ -1075,6 +1075,42 @@ def test_form_batch_golden_and_config_size(golden):
         ops.form_batch(t(s["xyzi"]).cpu(), *rng_, (512, 512, 30))
 
 
+def test_sphere_quantize_golden_and_config_size(golden):
+    """utils.SphereQuantize on the device (smos_sphere_quantize). Floating point: the angles are float64 arctan2 / arcsin
+    rounded to float32, so the kernel and the oracle agree to the last bit (up to a double-rounding case in ~1e-8 of the
+    points) and both sit within 1 ulp of the angle of the reference's numpy output — stated in range-view cells."""
+    from streammos_b200 import ops, synthetic
+    tol_theta, tol_phi = 5e-5, 5e-4
+    g = golden("sphere_a")
+    for tag, (xs, ys) in {"pp": (1, 1), "mp": (-1, 1), "pm": (1, -1)}.items():
+        got = ops.sphere_quantize(t(g["points"][None]), x_sign=xs, y_sign=ys)
+        assert got.shape == (1, 6000, 2, 1)
+        got = got[0, :, :, 0].cpu().numpy()
+        ref = g["sphere_" + tag]
+        d = np.abs(got.astype(np.float64) - ref)
+        assert d[:, 0].max() <= tol_theta and d[:, 1].max() <= tol_phi
+        assert np.array_equal(got[:13], ref[:13]) and np.array_equal(got[5600:], ref[5600:])
+        assert np.array_equal(got, O.sphere_quantize(g["points"], x_sign=xs, y_sign=ys))
+        for s in (1.0, 0.5, 0.25):
+            assert np.array_equal(np.trunc(got * np.float32(s)), np.trunc(ref * np.float32(s)))
+    s = synthetic.make_scan(78, 120000, 3)                                      # config size, all T frames, vs the oracle
+    got = ops.sphere_quantize(t(s["xyzi"]))[..., 0].cpu().numpy()
+    ref = O.sphere_quantize(s["xyzi"])
+    assert (got != ref).mean() < 1e-5 and np.abs(got.astype(np.float64) - ref).max() <= tol_phi
+    # against numpy's own float32 sequence on this host (the loader): the stated bound, and almost no cell changes
+    x, y, z = s["xyzi"][..., 0], s["xyzi"][..., 1], s["xyzi"][..., 2]
+    c = ops.sphere_constants()
+    dist = np.sqrt(x ** 2 + y ** 2 + z ** 2) + np.float32(1e-12)
+    host = np.stack(((np.float32(c[1]) - np.arcsin(z / dist)) / np.float32(c[3]),
+                     (np.float32(c[0]) - np.arctan2(x, y)) / np.float32(c[2])), -1)
+    assert host.dtype == np.float32
+    d = np.abs(got.astype(np.float64) - host)
+    assert d[..., 0].max() <= tol_theta and d[..., 1].max() <= tol_phi
+    assert (np.trunc(got) != np.trunc(host)).any(-1).mean() < 1e-4
+    with pytest.raises(RuntimeError):
+        ops.sphere_quantize(t(s["xyzi"]).cpu())
+
+
 def test_point_stem_tensor_core_variant(golden, monkeypatch):
     """SMOS_STEM_TC=1: layer 2 as 3xTF32 split products on mma.sync. Not bit-identical to the scalar FMA order, but
     inside the same 1e-5 bar against the reference module and the oracle (fixture + config size, raw and loader input)."""
@@ -1328,3 +1364,32 @@ def test_resident_window_step_matches_host_aligned_frames():
             for x, y in zip(pa, pb):
                 assert torch.equal(x, y)
     assert torch.equal(hot_a.memory, hot_b.memory)
+
+
+def test_resident_window_with_device_sphere_quantize():
+    """The same stream with NOTHING from the loader on the host side: the range-view coordinates of the current frame
+    come from smos_sphere_quantize on the ingested frame. Floating point against numpy's float32 arctan2 / arcsin, so the
+    bar is the stated one: coordinates within 1 ulp of the angle (in cells), at most 1e-4 of the points in another
+    range-view cell; everything that does not read range-view coordinates (pool #1, voting, instance votes) identical."""
+    from streammos_b200 import ops, stream, synthetic
+    n, scans = 120000, 3
+    resident, _ = stream.make_host_resident_stream(3, scans, n, pin=False)
+    bare, _ = stream.make_host_resident_stream(3, scans, n, pin=False, device_sphere=True)
+    assert bare[0].nbytes() == resident[0].nbytes() - n * 8 and bare[0].coord_rv is None
+    dres = stream.link_window([b.to(dev()) for b in resident])
+    dbar = stream.link_window([b.to(dev()) for b in bare])
+    hot_a = stream.HotPath(dev(), n, seed=5)
+    hot_b = stream.HotPath(dev(), n, seed=5, sphere_on_device=True)
+    with torch.no_grad():
+        for i in range(scans):
+            la, sa, pa = hot_a.step(dres[i])
+            lb, sb, pb = hot_b.step(dbar[i])
+            assert torch.equal(dres[i].points, dbar[i].points)
+            assert torch.equal(la, lb) and torch.equal(sa, sb) and torch.equal(pa[0], pb[0])
+            got = ops.sphere_quantize(dbar[i].points[:1], theta_range=synthetic.RV_THETA, size=synthetic.RV_SHAPE)
+            d = (got.double() - dres[i].coord_rv.double()).abs()[0, :, :, 0]
+            assert float(d[:, 0].max()) <= 5e-5 and float(d[:, 1].max()) <= 5e-4
+            moved = (torch.trunc(got) != torch.trunc(dres[i].coord_rv)).any(2).float().mean()
+            assert float(moved) < 1e-4
+            for x, y in zip(pa[1:], pb[1:]):  # grids / rows downstream of the range view: a few cells' worth of change
+                assert x.shape == y.shape and float((x != y).float().mean()) < 2e-3

@@ -213,6 +213,29 @@ def test_form_batch_bit_exact(golden):
     assert (g["coord_pp"][..., 0] == 0).any() and (g["coord_pp"] < 0).any()  # lower bound hit, pads out of range
 
 
+# SphereQuantize is a floating-point result (numpy's float32 arctan2 / arcsin are host specific in their last bit):
+# the bar is 1 ulp of the ANGLE, expressed in range-view cells — the same numbers include/streammos_b200.h states
+SPHERE_TOL_THETA, SPHERE_TOL_PHI = 5e-5, 5e-4
+
+
+def test_sphere_quantize_within_one_ulp_of_the_angle(golden):
+    """utils.SphereQuantize (datasets/utils.py:172-192) run by the reference itself vs the float64-angle restatement:
+    coordinates within 1 ulp of the angle (in cells), the axis / origin / padding rows exact, and — on this fixture —
+    no point changes its range-view cell at any of the three grids the model pools into."""
+    g = golden("sphere_a")
+    for tag, (xs, ys) in {"pp": (1, 1), "mp": (-1, 1), "pm": (1, -1)}.items():
+        got = O.sphere_quantize(g["points"], x_sign=xs, y_sign=ys)
+        ref = g["sphere_" + tag]
+        assert got.shape == ref.shape == (6000, 2) and got.dtype == np.float32
+        d = np.abs(got.astype(np.float64) - ref)
+        assert d[:, 0].max() <= SPHERE_TOL_THETA and d[:, 1].max() <= SPHERE_TOL_PHI
+        assert (d == 0).mean() > 0.75                          # most points are identical to the last bit
+        assert np.array_equal(got[:13], ref[:13])              # origin and axis points: exact angles
+        assert np.array_equal(got[5600:], ref[5600:])          # the loader's padding rows
+        for s in (1.0, 0.5, 0.25):                             # cell rule of VoxelMaxPool: int(coord * scale)
+            assert np.array_equal(np.trunc(got * np.float32(s)), np.trunc(ref * np.float32(s)))
+
+
 def _ingest_frames(g):
     return [(g["raw"][t, :int(g["n_raw"][t])], None if np.isnan(g["pose_diff"][t]).any() else g["pose_diff"][t])
             for t in range(len(g["n_raw"]))]

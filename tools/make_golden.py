@@ -9,7 +9,8 @@ What runs, unmodified:
   * voxel_voting.py / voxel_instance_voting.py functions, extracted with `ast` because the scripts run
     argparse at import time (voxel_voting.py:128-136)
   * networks/backbone.py:PointNetStacker(7, 64, pre_bn=True, stack_num=2).eval()   (the stem of models/StreamMOS.py:77)
-  * datasets/utils.py Quantize / SphereQuantize + datasets/data_StreamMOS.py make_point_feat (the loader's form_batch)
+  * datasets/utils.py Quantize / SphereQuantize + datasets/data_StreamMOS.py make_point_feat (the loader's form_batch;
+    SphereQuantize's own output: sphere_a)
 
     python tools/make_golden.py [--ref /root/reference]
 """
@@ -454,6 +455,36 @@ def gen_form_batch(ref, rng):
     return ["form_batch_a"]
 
 
+def gen_sphere(ref, rng):
+    """utils.SphereQuantize (datasets/utils.py:172-192) as the val loader's form_batch calls it
+    (datasets/data_StreamMOS.py:481-484), run by the reference's own function on float32 points: a 64-beam-like cloud,
+    points on the axes (arctan2 at 0, +-pi/2, pi), the sensor origin (dist = 1e-12), the loader's padding rows, and the
+    two TTA sign pairs of form_batch_tta. The outputs are HOST-SPECIFIC in their last bit (numpy's float32 arctan2 /
+    arcsin): the tests bound the distance instead of asking for equality."""
+    du = load_by_path("ref_dutils", os.path.join(ref, "datasets", "utils.py"))
+    N, n_valid = 6000, 5600
+    r = np.abs(rng.standard_normal(N)) * 18.0 + 0.5
+    az = rng.uniform(-np.pi, np.pi, N)
+    el = np.deg2rad(rng.uniform(-25.0, 3.0, N))
+    pts = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el), rng.uniform(0, 1, N)],
+                   -1).astype(np.float32)
+    pts[:8, :3] = 0.0
+    pts[8:16, :3] = np.array([[0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0, 0], [0, -5, -1], [-1e-6, -5, 0.2], [1e-6, -5, 0.2],
+                              [3, 3, -1.5]], np.float32)
+    pts[n_valid:, :] = -1000.0
+    pts[n_valid:, 2] = -4000.0
+    out = {}
+    for tag, (xs, ys) in {"pp": (1, 1), "mp": (-1, 1), "pm": (1, -1)}.items():
+        q = pts.copy()
+        q[:, 0] *= xs
+        q[:, 1] *= ys
+        sph = du.SphereQuantize(q[:, :4], phi_range=(-180.0, 180.0), theta_range=(-25.0, 3.0), size=(64, 2048))
+        assert sph.dtype == np.float32, sph.dtype
+        out["sphere_" + tag] = sph
+    np.savez_compressed(os.path.join(GOLD, "sphere_a.npz"), points=pts, numpy_version=np.array(np.__version__), **out)
+    return ["sphere_a"]
+
+
 def gen_ingest(ref, rng):
     """The val loader's per-frame steps in front of form_batch (datasets/data_StreamMOS.py:515-574) with the
     reference's own utils.Trans and utils.filter_pcds_mask; the compaction and padding lines of __getitem__ (:551-571)
@@ -573,7 +604,7 @@ def main():
     rng = np.random.default_rng(20261018)
     made = []
     single = {"point_stem": (gen_point_stem, 99), "form_batch": (gen_form_batch, 55), "cluster": (gen_cluster, 33),
-              "msda_module": (gen_msda_module, 0), "ingest": (gen_ingest, 66)}
+              "msda_module": (gen_msda_module, 0), "ingest": (gen_ingest, 66), "sphere": (gen_sphere, 44)}
     if a.only in single:
         made += single[a.only][0](a.ref, np.random.default_rng(single[a.only][1]))
         for m in made:
@@ -589,6 +620,7 @@ def main():
     made += gen_form_batch(a.ref, np.random.default_rng(55))
     made += gen_cluster(a.ref, np.random.default_rng(33))
     made += gen_ingest(a.ref, np.random.default_rng(66))
+    made += gen_sphere(a.ref, np.random.default_rng(44))
     made += gen_msda_module(a.ref, None)  # last: it re-seeds torch's generator
     for m in made:
         p = os.path.join(GOLD, m + ".npz")
