@@ -334,8 +334,9 @@ def sphere_quantize(points, phi_range=(-180.0, 180.0), theta_range=(-25.0, 3.0),
     the angle of numpy's result (include/streammos_b200.h states the bound in cells)."""
     _need_cuda(points, "points")
     _need_f32(points, "points")
-    assert points.dim() == 3 and points.size(2) >= 3 and points.stride(2) == 1 and points.stride(0) == points.size(1) * points.stride(1)
+    assert points.dim() == 3 and points.size(2) >= 3 and points.stride(2) == 1
     T, N = int(points.size(0)), int(points.size(1))
+    assert T == 1 or points.stride(0) == N * points.stride(1), "frames must follow each other at one row stride"
     c = sphere_constants(phi_range, theta_range, size)
     if out is None:
         out = torch.empty((T, N, 2, 1), dtype=torch.float32, device=points.device)

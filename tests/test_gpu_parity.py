@@ -1391,5 +1391,7 @@ def test_resident_window_with_device_sphere_quantize():
             assert float(d[:, 0].max()) <= 5e-5 and float(d[:, 1].max()) <= 5e-4
             moved = (torch.trunc(got) != torch.trunc(dres[i].coord_rv)).any(2).float().mean()
             assert float(moved) < 1e-4
-            for x, y in zip(pa[1:], pb[1:]):  # grids / rows downstream of the range view: a few cells' worth of change
-                assert x.shape == y.shape and float((x != y).float().mean()) < 2e-3
+            # downstream of the range view the bilinear gathers sample <= 5e-4 cells off: values move by that times the
+            # local slope everywhere, and by more only where a point changed its cell
+            for x, y in zip(pa[1:], pb[1:]):
+                assert x.shape == y.shape and float(((x - y).abs() > 5e-3).float().mean()) < 2e-3
