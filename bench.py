@@ -366,6 +366,19 @@ def run_b200(args, world, rank, local):
             torch.cuda.synchronize()
             barrier(world)
             ms = max_over_ranks(f0.elapsed_time(f1), world, dev) / nsteps
+            if os.environ.get("SMOS_E2E_PROFILE") and rank == 0:  # concurrency timeline of the same loop (CUPTI)
+                import importlib.util
+                from torch.profiler import ProfilerActivity, profile
+                spec = importlib.util.spec_from_file_location(
+                    "profile_pipeline", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "profile_pipeline.py"))
+                pp = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(pp)
+                torch.cuda.synchronize()
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    e2e_loop(32)
+                    torch.cuda.synchronize()
+                with open(os.environ["SMOS_E2E_PROFILE"], "a") as fh:
+                    pp.analyse(prof, 32, out=fh)
             # host cost of submitting one scan (API calls of e2e_loop): a short burst that fits the launch queue, so the
             # host never waits for the device
             torch.cuda.synchronize()
