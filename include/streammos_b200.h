@@ -347,6 +347,14 @@ int smos_quantize(const float* pcds, int64_t P, int64_t row_stride,
                   float min_x, float min_y, float min_z,
                   float dx, float dy, float dz, float* out, void* stream);
 
+/* The same Quantize with the arithmetic torch applies ON A CUDA DEVICE — where the reference's scripts evaluate it
+ * (voxel_voting.py:218-240): tensor / Python scalar = tensor * float32(1 / scalar) (ATen BinaryDivTrueKernel.cu,
+ * is_cpu_scalar branch). Bit-identical with `(pcds[:, d] - min_d) / delta_d` run by torch on the GPU; differs from
+ * smos_quantize (= numpy / torch-CPU, IEEE division) in the last bit of some quotients. Same arguments. */
+int smos_quantize_rcp(const float* pcds, int64_t P, int64_t row_stride,
+                  float min_x, float min_y, float min_z,
+                  float dx, float dy, float dz, float* out, void* stream);
+
 /* Bytes of scratch for smos_vote_voxel_labels / smos_vote_fused / smos_vote_stream. */
 int64_t smos_vote_workspace_bytes(int64_t P, int32_t X, int32_t Y, int32_t Z, int32_t num_classes);
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "smos_ms_deform_attn_backward": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                                     _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "smos_quantize": (ctypes.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
+    "smos_quantize_rcp": (ctypes.c_int, [_vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "smos_vote_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32]),
     "smos_vote_voxel_labels": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "smos_vote_point_labels": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp]),

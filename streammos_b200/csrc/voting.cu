@@ -186,6 +186,23 @@ quantize_kernel(const float* __restrict__ pcds, int64_t P, int64_t rs, float mx,
   out[i * 3 + 2] = quant(p[2], mz, dz);
 }
 
+// The same expression as torch evaluates it ON A CUDA DEVICE, which is where the reference's scripts run it
+// (voxel_voting.py:218-240): a float tensor divided by a Python scalar becomes a multiplication by the float32
+// reciprocal of the scalar (ATen BinaryDivTrueKernel.cu, the is_cpu_scalar branch: inv_b = 1.0f / float(b), a * inv_b)
+// — one bit away from the IEEE quotient for some inputs, enough to move a point that sits within an ulp of a voxel
+// boundary into the neighbouring voxel. rx / ry / rz are those reciprocals.
+__global__ void __launch_bounds__(kVoteThreads)
+quantize_rcp_kernel(const float* __restrict__ pcds, int64_t P, int64_t rs, float mx, float my, float mz, float rx,
+                    float ry, float rz, float* __restrict__ out) {
+  SMOS_PDL_PROLOGUE();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kVoteThreads + threadIdx.x;
+  if (i >= P) return;
+  const float* p = pcds + i * rs;
+  out[i * 3] = __fmul_rn(__fsub_rn(p[0], mx), rx);
+  out[i * 3 + 1] = __fmul_rn(__fsub_rn(p[1], my), ry);
+  out[i * 3 + 2] = __fmul_rn(__fsub_rn(p[2], mz), rz);
+}
+
 // ---- staging for the reference's int64 voting API (voxel_voting.py:234-241) ----------------------------------
 // The script quantises the local map (Quantize -> float32), casts the result and the predictions to int64
 // (`.to(torch.int64)`, truncation) and hands both to determine_voxel_labels. Here ONE kernel produces all three
@@ -552,6 +569,18 @@ int smos_quantize(const float* pcds, int64_t P, int64_t row_stride, float min_x,
   if (!pcds || !out) return SMOS_EINVAL;
   SMOS_LAUNCH((quantize_kernel), smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, smos_stream(stream), 
       pcds, P, row_stride, min_x, min_y, min_z, dx, dy, dz, out);
+  return smos_launch_status();
+}
+
+int smos_quantize_rcp(const float* pcds, int64_t P, int64_t row_stride, float min_x, float min_y, float min_z, float dx,
+                      float dy, float dz, float* out, void* stream) {
+  if (P < 0 || row_stride < 3 || dx == 0.f || dy == 0.f || dz == 0.f) return SMOS_EINVAL;
+  if (P == 0) return SMOS_OK;
+  if (!pcds || !out) return SMOS_EINVAL;
+  // float32 reciprocals, IEEE division on the host: what `opmath_t(1.0) / b` gives in ATen
+  const volatile float rx = 1.0f / dx, ry = 1.0f / dy, rz = 1.0f / dz;
+  SMOS_LAUNCH((quantize_rcp_kernel), smos_ceil_div(P, kVoteThreads), kVoteThreads, 0, smos_stream(stream),
+      pcds, P, row_stride, min_x, min_y, min_z, static_cast<float>(rx), static_cast<float>(ry), static_cast<float>(rz), out);
   return smos_launch_status();
 }
 

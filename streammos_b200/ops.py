@@ -584,16 +584,21 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
 # ----------------------------------------------------------------------------------------------
 # Voting
 # ----------------------------------------------------------------------------------------------
-def quantize(pcds, mins, deltas):
+def quantize(pcds, mins, deltas, arithmetic="ieee"):
+    """arithmetic="ieee": float32 IEEE division (numpy, torch on the CPU); "torch_cuda": multiplication by the float32
+    reciprocal, bit-identical with torch evaluating the same expression on a CUDA device (smos_quantize_rcp)."""
     _need_cuda(pcds, "pcds")
     _need_f32(pcds, "pcds")
     assert pcds.dim() == 2 and pcds.size(1) >= 3 and pcds.stride(1) == 1
+    if arithmetic not in ("ieee", "torch_cuda"):
+        raise ValueError("arithmetic must be 'ieee' or 'torch_cuda'")
     P = int(pcds.size(0))
     out = torch.empty((P, 3), dtype=torch.float32, device=pcds.device)
+    lib = _lib.load()
+    fn = lib.smos_quantize if arithmetic == "ieee" else lib.smos_quantize_rcp
     with torch.cuda.device(pcds.device):
-        rc = _lib.load().smos_quantize(_ptr(pcds), P, pcds.stride(0) if P > 1 else pcds.size(1), float(mins[0]),
-                                       float(mins[1]), float(mins[2]), float(deltas[0]), float(deltas[1]),
-                                       float(deltas[2]), _ptr(out), _stream())
+        rc = fn(_ptr(pcds), P, pcds.stride(0) if P > 1 else pcds.size(1), float(mins[0]), float(mins[1]), float(mins[2]),
+                float(deltas[0]), float(deltas[1]), float(deltas[2]), _ptr(out), _stream())
     _lib.check(rc, "smos_quantize")
     _count(1)
     return out

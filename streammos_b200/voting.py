@@ -14,13 +14,17 @@ def _dims(size, scale):
     return size[0] // scale_xy, size[1] // scale_xy, size[2] // scale_z
 
 
-def Quantize(pcds, range_x=(-40, 62.4), range_y=(-40, 40), range_z=(-3, 5), size=(512, 512, 20)):
-    """(P, >=3) float32 -> (P, 3) float32 quantised coordinates, (x - min) / d in fp32 with IEEE
-    division (voxel_voting.py:77-91). The caller casts with .to(torch.int64) (truncation)."""
+def Quantize(pcds, range_x=(-40, 62.4), range_y=(-40, 40), range_z=(-3, 5), size=(512, 512, 20), arithmetic="ieee"):
+    """(P, >=3) float32 -> (P, 3) float32 quantised coordinates, (x - min) / d in fp32 (voxel_voting.py:77-91). The
+    caller casts with .to(torch.int64) (truncation).
+    arithmetic="ieee" (default): IEEE division — numpy, torch on the CPU, the oracle, the golden fixtures.
+    arithmetic="torch_cuda": what torch computes for the reference's expression on a CUDA device (tensor / Python scalar
+    = tensor * float32(1 / scalar)), i.e. what voxel_voting.py itself produces when it runs on a GPU; the two differ in
+    the last bit of some quotients (tests/test_gpu_parity.py checks this mode against torch on the device)."""
     dx = (range_x[1] - range_x[0]) / size[0]
     dy = (range_y[1] - range_y[0]) / size[1]
     dz = (range_z[1] - range_z[0]) / size[2]
-    return ops.quantize(pcds, (range_x[0], range_y[0], range_z[0]), (dx, dy, dz))
+    return ops.quantize(pcds, (range_x[0], range_y[0], range_z[0]), (dx, dy, dz), arithmetic)
 
 
 def quantize_staged(ring_points, ring_pred, range_x, range_y, range_z, size, new_points=None, new_pred=None,

@@ -1075,6 +1075,32 @@ def test_form_batch_golden_and_config_size(golden):
         ops.form_batch(t(s["xyzi"]).cpu(), *rng_, (512, 512, 30))
 
 
+def test_quantize_torch_cuda_arithmetic_matches_torch_on_the_device():
+    """the reference's voting scripts evaluate Quantize on CUDA tensors (voxel_voting.py:218-240),
+    where torch turns `tensor / python_scalar` into a multiplication by the float32 reciprocal. arithmetic="torch_cuda"
+    reproduces THAT bit for bit (checked against torch itself on this device, with the reference's three lines,
+    voxel_voting.py:86-88); the default "ieee" mode is numpy's / torch-CPU's division and equals the oracle."""
+    from streammos_b200 import synthetic, voting
+    rx, ry, rz, size = (-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0), (512, 512, 30)
+    pts = np.concatenate([synthetic.make_scan(70 + i, 120000, 1)["xyzi"][0] for i in range(9)])     # the 9-scan local map
+    pcds = t(pts)
+    dx, dy, dz = (rx[1] - rx[0]) / size[0], (ry[1] - ry[0]) / size[1], (rz[1] - rz[0]) / size[2]
+    ref = torch.stack(((pcds[:, 0] - rx[0]) / dx, (pcds[:, 1] - ry[0]) / dy, (pcds[:, 2] - rz[0]) / dz), dim=-1)
+    got = voting.Quantize(pcds, rx, ry, rz, size, arithmetic="torch_cuda")
+    assert torch.equal(got, ref)
+    assert torch.equal(got.to(torch.int64), ref.to(torch.int64))
+    ieee = voting.Quantize(pcds, rx, ry, rz, size)
+    assert np.array_equal(ieee.cpu().numpy(), O.quantize(pts, rx, ry, rz, size))
+    cpu = torch.from_numpy(pts)
+    ref_cpu = torch.stack(((cpu[:, 0] - rx[0]) / dx, (cpu[:, 1] - ry[0]) / dy, (cpu[:, 2] - rz[0]) / dz), dim=-1)
+    assert torch.equal(ieee.cpu(), ref_cpu)                      # torch on the CPU divides
+    diff = (ieee != got).any(1)
+    assert 0 < int(diff.sum())                                   # the two arithmetics are not the same function ...
+    assert bool(((ieee - got).abs() <= 2.0 ** -22 * ieee.abs().clamp(min=1e-30)).all())   # ... but at most an ulp or two apart
+    with pytest.raises(ValueError):
+        voting.Quantize(pcds, rx, ry, rz, size, arithmetic="fast")
+
+
 def test_sphere_quantize_golden_and_config_size(golden):
     """utils.SphereQuantize on the device (smos_sphere_quantize). Floating point: the angles are float64 arctan2 / arcsin
     rounded to float32, so the kernel and the oracle agree to the last bit (up to a double-rounding case in ~1e-8 of the
