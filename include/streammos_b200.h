@@ -274,8 +274,9 @@ int smos_point_stem_forward(const float* x, int64_t B, int32_t Cin, int64_t N,
 /* (E, next: SURVEY 8f rank 2, exact part) model input tensors from raw scans. */
 /* Replaces utils.Quantize (datasets/utils.py:151-169) + make_point_feat        */
 /* (datasets/data_StreamMOS.py:25-50) inside the loader's form_batch (:471-493) */
-/* and the TTA flips of form_batch_tta (:495-513). SphereQuantize stays on the  */
-/* host (numpy's float32 arctan2 / arcsin cannot be matched bit for bit).       */
+/* and the TTA flips of form_batch_tta (:495-513). SphereQuantize is a separate, */
+/* floating-point entry below (numpy's arctan2 / arcsin cannot be matched bit    */
+/* for bit).                                                                     */
 /* ------------------------------------------------------------------------- */
 
 /*   points     : (T*N, row_stride>=4) float32 raw x, y, z, intensity of T frames (range filtered, padded)
