@@ -337,6 +337,18 @@ int smos_point_stem_forward_raw(const float* points, int64_t T, int64_t N, int64
                                 const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
                                 float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn, void* stream);
 
+/* The same call with a cap on the kernel's persistent CTAs (one per SM; 0 = all SMs). A scheduling hint, results are
+ * identical: the stem is latency bound and holds its SM (165 KB of shared memory) against every other kernel, so a
+ * stream that keeps several scans in flight runs it on ~60 % of the SMs and lets the HBM-bound kernels of the
+ * neighbouring scans have the rest (measured: +3-4 % end to end); a caller that runs one kernel at a time wants 0. */
+int smos_point_stem_forward_raw_capped(const float* points, int64_t T, int64_t N, int64_t row_stride,
+                                float x_sign, float y_sign, float min_x, float min_y, float min_z,
+                                float dx, float dy, float dz,
+                                const float* bn0_alpha, const float* bn0_beta, const float* w1,
+                                const float* bn1_alpha, const float* bn1_beta, const float* w2,
+                                const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
+                                float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn, int32_t max_ctas, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* (C) Long-term-memory voting.                                               */
 /* ------------------------------------------------------------------------- */

@@ -81,6 +81,9 @@ SIGNATURES = {
     "smos_point_stem_forward_raw": (ctypes.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32,
                                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64,
                                                    _i64, _vp]),
+    "smos_point_stem_forward_raw_capped": (ctypes.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32,
+                                                          _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp,
+                                                          _i64, _i64, _i64, _i32, _vp]),
     "smos_vote_stage": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32,
                                        ctypes.POINTER(_f32), ctypes.POINTER(_f32), _vp, _vp, _vp, _vp]),
     "smos_memory_push": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -289,8 +289,8 @@ static int stem_launch(const float* x, int64_t B, int32_t Cin, int64_t N, int64_
                        const StemRaw& raw, const float* bn0_alpha, const float* bn0_beta, const float* w1,
                        const float* bn1_alpha, const float* bn1_beta, const float* w2, const float* bn2_alpha,
                        const float* bn2_beta, int32_t C1, int32_t C2, float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn,
-                       void* stream) {
-  if (B <= 0 || N < 0 || Cin <= 0) return SMOS_EINVAL;
+                       void* stream, int32_t max_ctas = 0) {
+  if (B <= 0 || N < 0 || Cin <= 0 || max_ctas < 0) return SMOS_EINVAL;
   if (N == 0) return SMOS_OK;
   if ((!x && !raw.pts) || !w1 || !bn1_alpha || !bn1_beta || !w2 || !bn2_alpha || !bn2_beta || !y) return SMOS_EINVAL;
   if ((bn0_alpha == nullptr) != (bn0_beta == nullptr)) return SMOS_EINVAL;
@@ -313,7 +313,12 @@ static int stem_launch(const float* x, int64_t B, int32_t Cin, int64_t N, int64_
     static std::atomic<unsigned long long> opted{0};                                                                  \
     if (cudaError_t e = smos_smem_opt_in(kern, opted, static_cast<int>(sizeof(umma_stem::Smem) + 128)); e != cudaSuccess) \
       return static_cast<int>(e);                                                                                     \
-    const int64_t want = SMOS_SM_COUNT; /* 165 KB of shared memory: one persistent CTA per SM */                      \
+    /* 165 KB of shared memory: one persistent CTA per SM. max_ctas (or SMOS_STEM_CTAS=n) leaves SMs to the kernels of  \
+       the other scans in flight: the stem is latency bound (10 % of the DRAM rate) and blocks its SM for everything  \
+       else, so a pipelined stream runs it on ~60 % of the SMs */                                        \
+    int64_t want = SMOS_SM_COUNT;                                                                                     \
+    const int cap = max_ctas > 0 ? max_ctas : smos_env_int("SMOS_STEM_CTAS", 0);                                      \
+    if (cap > 0 && cap < want) want = cap;                                                                            \
     dim3 grid(static_cast<unsigned>(ntiles < want ? ntiles : want));                                                  \
     SMOS_LAUNCH((kern), grid, umma_stem::kThreads, sizeof(umma_stem::Smem) + 128, st, x, Cin, Ni, Bi, x_sb, x_sc, x_sn, \
                 raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, y, y_sb, y_sc, y_sn);     \
@@ -367,8 +372,22 @@ extern "C" int smos_point_stem_forward_raw(const float* points, int64_t T, int64
                                            const float* bn2_alpha, const float* bn2_beta, int32_t C1, int32_t C2,
                                            float* pcds_coord, float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn,
                                            void* stream) {
+  return smos_point_stem_forward_raw_capped(points, T, N, row_stride, x_sign, y_sign, min_x, min_y, min_z, dx, dy, dz,
+                                            bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta, C1, C2,
+                                            pcds_coord, y, y_sb, y_sc, y_sn, 0, stream);
+}
+
+// The same call with the number of persistent CTAs capped (a scheduling hint: results are identical).
+extern "C" int smos_point_stem_forward_raw_capped(const float* points, int64_t T, int64_t N, int64_t row_stride,
+                                                  float x_sign, float y_sign, float min_x, float min_y, float min_z,
+                                                  float dx, float dy, float dz, const float* bn0_alpha,
+                                                  const float* bn0_beta, const float* w1, const float* bn1_alpha,
+                                                  const float* bn1_beta, const float* w2, const float* bn2_alpha,
+                                                  const float* bn2_beta, int32_t C1, int32_t C2, float* pcds_coord,
+                                                  float* y, int64_t y_sb, int64_t y_sc, int64_t y_sn, int32_t max_ctas,
+                                                  void* stream) {
   if (!points || !pcds_coord) return SMOS_EINVAL;
   StemRaw raw = {points, row_stride, x_sign, y_sign, min_x, min_y, min_z, dx, dy, dz, pcds_coord};
   return stem_launch(nullptr, T, 7, N, 0, 0, 0, raw, bn0_alpha, bn0_beta, w1, bn1_alpha, bn1_beta, w2, bn2_alpha, bn2_beta,
-                     C1, C2, y, y_sb, y_sc, y_sn, stream);
+                     C1, C2, y, y_sb, y_sc, y_sn, stream, max_ctas);
 }

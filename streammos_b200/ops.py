@@ -451,9 +451,10 @@ def point_stem_forward(x, bn0, w1, bn1, w2, bn2, out=None, point_major_out=False
 
 
 def point_stem_forward_raw(points, range_x, range_y, range_z, size, bn0, w1, bn1, w2, bn2, x_sign=1.0, y_sign=1.0,
-                           point_major_out=False):
+                           point_major_out=False, max_ctas=0):
     """form_batch + point_stem_forward in one kernel: points (T, N, >=4) float32 CUDA raw scans ->
-    (features (T, 64, N, 1), pcds_coord (T, N, 3, 1)); bit-identical to the two separate calls."""
+    (features (T, 64, N, 1), pcds_coord (T, N, 3, 1)); bit-identical to the two separate calls.
+    max_ctas > 0 caps the persistent CTAs of the kernel (scheduling hint for pipelined streams, same results)."""
     import numpy as np
     _need_cuda(points, "points")
     _need_f32(points, "points")
@@ -478,11 +479,11 @@ def point_stem_forward_raw(points, range_x, range_y, range_z, size, bn0, w1, bn1
     out = _stem_out(T, C2, N, points.device, point_major_out)
     coord = torch.empty((T, N, 3, 1), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
-        rc = _lib.load().smos_point_stem_forward_raw(
+        rc = _lib.load().smos_point_stem_forward_raw_capped(
             _ptr(points), T, N, points.stride(1) if N > 1 else points.size(2), float(x_sign), float(y_sign),
             float(range_x[0]), float(range_y[0]), float(range_z[0]), d[0], d[1], d[2], _ptr(a0), _ptr(b0), _ptr(w1),
             _ptr(a1), _ptr(b1), _ptr(w2), _ptr(a2), _ptr(b2), C1, C2, _ptr(coord), _ptr(out), out.stride(0), out.stride(1),
-            out.stride(2), _stream())
+            out.stride(2), int(max_ctas), _stream())
     _lib.check(rc, "smos_point_stem_forward_raw")
     _count(1)
     return out, coord

@@ -38,6 +38,11 @@ class ScanPipeline:
         self.v_done = [torch.cuda.Event() for _ in range(self.n)]
         self.submitted = 0
         hot.overlap_voting = False
+        # several scans in flight: the latency-bound PointNet stem (raw-scan batches) leaves ~40 % of the SMs to the
+        # HBM-bound kernels of the neighbouring scans (measured on B200, end to end: 148 CTAs 3426-3446 scans/s,
+        # 84-96 CTAs 3484-3597); SMOS_PIPE_STEM_SHARE overrides
+        if scans_in_flight > 1 and getattr(hot, "stem_sm_share", None) == 1.0:
+            hot.stem_sm_share = float(os.environ.get("SMOS_PIPE_STEM_SHARE", "0.61"))
         with torch.no_grad():
             # eager warm-up of every buffer / ring slot (also allocates persistent scratch outside capture)
             for j in range(self.n):

@@ -257,7 +257,7 @@ class HotPath:
     def __init__(self, device, n_points=120000, seed=0, point_major=True, vote_api="reference",
                  batch_plans=False, grids_channels_last=False, overlap_voting=False, branches=False,
                  ordered_gathers=True, ordered_rv=False, gather_taps=False, fuse_form_batch=True,
-                 instance_branch=True, sphere_on_device=False):
+                 instance_branch=True, sphere_on_device=False, stem_sm_share=1.0):
         """batch_plans=False (default): every operator is called with the REFERENCE's arguments only
         (VoxelMaxPool(feat, ind, size, scale), BilinearSample(grid, coord)); plans are shared through the plan cache
         exactly as they are under the unmodified reference model. batch_plans=True: the explicit plan API (all five
@@ -268,6 +268,10 @@ class HotPath:
         of the loader, floating point) instead of the loader's `sphere_cur`."""
         self.device = torch.device(device)
         self.sphere_on_device = sphere_on_device
+        # share of the SMs the persistent PointNet-stem kernel may take (raw-scan batches). 1.0 = one CTA per SM, right
+        # for a stream that runs one kernel at a time; a pipelined stream (ScanPipeline) sets ~0.6: the stem is latency
+        # bound and holds its SMs against every other kernel, the HBM-bound kernels of the neighbouring scans use the rest
+        self.stem_sm_share = stem_sm_share
         self.overlap_voting = overlap_voting
         self.branches = branches and self.device.type == "cuda"
         # voxel voting (voxel_voting.py) and instance voting (voxel_instance_voting.py) are two independent
@@ -376,9 +380,13 @@ class HotPath:
                                                     self.n_points, synthetic.PAD_XY, synthetic.PAD_Z)
         if hasattr(b, "points"):      # raw scan: Quantize + make_point_feat on the device, then the stem
             if self.fuse_form_batch:  # one kernel: raw points -> 64-channel features + quantised coordinates
+                cap = 0
+                if self.stem_sm_share < 1.0:
+                    cap = max(1, int(round(self.stem_sm_share *
+                                           torch.cuda.get_device_properties(self.device).multi_processor_count)))
                 feat, coord = ops.point_stem_forward_raw(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z,
                                                          self.size, *self.stem.fused_parameters(),
-                                                         point_major_out=self.point_major)
+                                                         point_major_out=self.point_major, max_ctas=cap)
             else:
                 feat7, coord = ops.form_batch(b.points, synthetic.RANGE_X, synthetic.RANGE_Y, synthetic.RANGE_Z, self.size)
                 feat = self.point_pre(feat7)

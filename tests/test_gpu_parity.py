@@ -1189,6 +1189,21 @@ def test_point_stem_from_raw_points_equals_form_batch_then_stem(golden, path, mo
                                    rtol=1e-5, atol=2e-3)
 
 
+def test_point_stem_cta_cap_is_a_scheduling_hint_only(golden):
+    """smos_point_stem_forward_raw_capped: any cap on the persistent CTAs gives the bits of the uncapped launch."""
+    from streammos_b200 import ops, synthetic
+    g = golden("point_stem_a")
+    bn0, w1, bn1, w2, bn2 = _stem_params(g)
+    tt = lambda pair: (t(pair[0]), t(pair[1]))
+    rng_ = ((-50.0, 50.0), (-50.0, 50.0), (-4.0, 2.0))
+    pts = t(synthetic.make_scan(9, 120000, 3)["xyzi"])
+    args = (pts, *rng_, (512, 512, 30), tt(bn0), t(w1), tt(bn1), t(w2), tt(bn2))
+    y0, c0 = ops.point_stem_forward_raw(*args, point_major_out=True)
+    for cap in (1, 37, 90, 147, 100000):
+        y, c = ops.point_stem_forward_raw(*args, point_major_out=True, max_ctas=cap)
+        assert torch.equal(y, y0) and torch.equal(c, c0), cap
+
+
 def test_step_from_raw_scan_matches_step_from_loader_tensors():
     """RawBatch (Quantize + make_point_feat on the device) and LoaderBatch (done by the host) give the same step."""
     from streammos_b200 import stream
