@@ -456,8 +456,9 @@ def run_b200(args, world, rank, local):
         e2e = measure_e2e(pipe_w, host_w, devb_w, args.steps, window=2)
         clocks = sampler.stop() if rank == 0 else None  # sampled across the timed regions
         e2e["note"] = ("host buffers = the NEW raw scan as read from the file (own sensor frame, no filter, no padding) + the "
-                       "pose_diff matrices of the T = 3 window + range-view coordinates of the current frame (SphereQuantize "
-                       "stays on the host) + predicted labels and attention samples as stand-ins for network "
+                       "pose_diff matrices of the T = 3 window + range-view coordinates of the current frame (the loader's "
+                       "SphereQuantize output, so that every input is bit-exact; sphere_quantize_on_device computes them on "
+                       "the GPU too) + predicted labels and attention samples as stand-ins for network "
                        "intermediates; ONE H2D copy per scan. The two older raw scans stay resident in HBM; pose alignment, "
                        "range filter and padding of all T frames (smos_ingest_frames, bit-exact with the loader), Quantize + "
                        "make_point_feat, the PointNet stem, the whole hot path and the D2H of the labels are inside the "
