@@ -161,3 +161,29 @@ def test_resident_window_stream_is_what_the_loader_would_build():
         assert resident[i].nbytes() < 0.6 * aligned[i].nbytes()  # what crosses PCIe per scan
     linked = stream.link_window(list(resident))
     assert linked[0].older == (resident[2], resident[1]) and linked[2].older == (resident[1], resident[0])
+
+
+def test_sphere_quantize_host_side():
+    """ops.sphere_constants forms the four float32 constants of utils.SphereQuantize (datasets/utils.py:173-180) as numpy
+    does; the oracle's restatement is within 1 ulp of the angle of a plain numpy float32 evaluation of the reference's
+    lines on this host; the stream variant without host range-view coordinates carries exactly 8 bytes per point less."""
+    import numpy as np
+    from oracle import oracle as O
+    from streammos_b200 import ops, stream, synthetic
+    phi_hi, theta_hi, dphi, dtheta = ops.sphere_constants((-180.0, 180.0), synthetic.RV_THETA, synthetic.RV_SHAPE)
+    assert phi_hi == float(np.float32(np.pi)) and theta_hi == float(np.float32(3.0 * np.pi / 180.0))
+    assert dphi == float(np.float32(2 * np.pi / 2048)) and dtheta == float(np.float32((28.0 * np.pi / 180.0) / 64))
+    pts = synthetic.make_scan(5, 20000, 1)["xyzi"][0]
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    d = np.sqrt(x ** 2 + y ** 2 + z ** 2) + 1e-12                      # the reference's lines, numpy float32
+    host = np.stack(((np.float32(theta_hi) - np.arcsin(z / d)) / np.float32(dtheta),
+                     (np.float32(phi_hi) - np.arctan2(x, y)) / np.float32(dphi)), -1)
+    assert host.dtype == np.float32
+    got = O.sphere_quantize(pts, theta_range=synthetic.RV_THETA, size=synthetic.RV_SHAPE)
+    diff = np.abs(got.astype(np.float64) - host)
+    assert diff[:, 0].max() <= 5e-5 and diff[:, 1].max() <= 5e-4 and (diff == 0).mean() > 0.75
+    full, _ = stream.make_host_resident_stream(2, 1, 120000, pin=False)
+    bare, _ = stream.make_host_resident_stream(2, 1, 120000, pin=False, device_sphere=True)
+    assert isinstance(bare[0], stream.ResidentScanBatch) and bare[0].coord_rv is None
+    assert full[0].nbytes() - bare[0].nbytes() == 120000 * 8
+    assert torch.equal(full[0].raw, bare[0].raw) and torch.equal(full[0].poses, bare[0].poses)
