@@ -201,7 +201,8 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
     const float pz = rawq.z, pw = rawq.w;
     const float qx = __fdiv_rn(__fsub_rn(px, raw.mx), raw.dx);
     const float qy = __fdiv_rn(__fsub_rn(py, raw.my), raw.dy);
-    const float qz = __fdiv_rn(__fsub_rn(pz, raw.mz), raw.dz);
+    // (the third quotient only feeds the coordinate output: one of the four threads of a point computes it)
+    const float qz = part == 0 ? __fdiv_rn(__fsub_rn(pz, raw.mz), raw.dz) : 0.f;
     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz));
     xr[0] = px; xr[1] = py; xr[2] = pz; xr[3] = pw;
     xr[4] = __fadd_rn(__fsqrt_rn(d2), 1e-12f);
@@ -216,7 +217,7 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
   };
   // accumulator of tile `t` (stage s) -> BatchNorm + ReLU -> y
   auto drain = [&](int32_t b, int32_t n0, int s, uint32_t parity) {
-    smos_mbar_wait(&S.done[s], parity);  // the tile's 24 MMAs have completed
+    smos_mbar_wait_sleepy(&S.done[s], parity);  // the tile's 24 MMAs have completed
     fence_after_sync();
     const int32_t n = n0 + pt;
     // warp w may touch TMEM lanes 32 * (w % 4) ...: exactly the 32 points of its quarter of the tile
@@ -248,12 +249,24 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
         stg[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
       const int32_t nw = n0 + (wid & 3) * 32;  // first point of my warp's quarter of the tile
+      // lane l moves chunk l & 3 of rows (l >> 2) + 8 k: one base pointer per tile, a constant step per store, and the
+      // staged chunks fetched together before the first store (the stores used to wait on their LDS one by one)
+      const int r0 = lane >> 2, seg = lane & 3;
+      float* yb = y + b * y_sb + static_cast<int64_t>(nw + r0) * y_sn + part * kCP + seg * 4;
+      const int64_t step = 8 * y_sn;
+      float4 o[kCP / 4];
 #pragma unroll
       for (int k = 0; k < kCP / 4; ++k) {
-        const int idx = k * 32 + lane, row = idx >> 2, seg = idx & 3;
-        if (nw + row < N)
-          *reinterpret_cast<float4*>(y + b * y_sb + static_cast<int64_t>(nw + row) * y_sn + part * kCP + seg * 4) =
-              stg[row * 4 + (seg ^ ((row >> 1) & 3))];
+        const int row = r0 + 8 * k;
+        o[k] = stg[row * 4 + (seg ^ ((row >> 1) & 3))];
+      }
+      if (nw + 32 <= N) {
+#pragma unroll
+        for (int k = 0; k < kCP / 4; ++k) *reinterpret_cast<float4*>(yb + k * step) = o[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < kCP / 4; ++k)
+          if (nw + r0 + 8 * k < N) *reinterpret_cast<float4*>(yb + k * step) = o[k];
       }
       __syncwarp();
     }
@@ -274,7 +287,7 @@ point_stem_umma_kernel(const float* __restrict__ x, int32_t Cin, int32_t N, int3
       int32_t it = 0;
       for (int32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int s = it & 1;
-        smos_mbar_wait(&S.full[s], static_cast<uint32_t>((it >> 1) & 1));
+        smos_mbar_wait_sleepy(&S.full[s], static_cast<uint32_t>((it >> 1) & 1));
         fence_after_sync();
         const uint32_t d = tmem + static_cast<uint32_t>(s * kC);
         const uint64_t dah0 = smem_desc(S.a_hi[s]), dal0 = smem_desc(S.a_lo[s]);
