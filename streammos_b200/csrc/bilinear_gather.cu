@@ -41,7 +41,9 @@ __device__ __forceinline__ TapsS lane_taps(int64_t slot, int32_t b, const float*
     live = slot < order_len;
     const int2 e = __ldg(order + (live ? slot : order_len - 1));
     n = static_cast<int32_t>(static_cast<uint32_t>(e.x) & 0x7fffffffu);  // bit 31: the plan's run-merge mark
-    b = e.y >= 0 ? e.y / order_hw : -1 - e.y;                            // out-of-grid entries carry -1 - b
+    // out-of-grid entries carry -1 - b; a single batch (order_len == N, the streaming case) needs no division — the
+    // quotient sat on the chain order entry -> coordinates of every warp
+    b = e.y >= 0 ? (order_len == static_cast<int64_t>(N) ? 0 : e.y / order_hw) : -1 - e.y;
   } else {
     live = slot < N;
     n = static_cast<int32_t>(live ? slot : N - 1);
@@ -180,13 +182,29 @@ gather_forward_planar_kernel(const float* __restrict__ grid, int32_t C, int32_t 
     const int64_t my_row = n >= 0 ? (b * o_sb + static_cast<int64_t>(n) * o_sn) : -1;
     const bool pow2 = (q & (q - 1)) == 0;
     const int32_t shq = 31 - __clz(q);
-    for (int32_t i = lane; i < 32 * q; i += 32) {
-      const int32_t p = pow2 ? (i >> shq) : i / q;
-      const int32_t j = i - p * q;
-      const int64_t rb = __shfl_sync(0xffffffffu, my_row, p);
-      if (rb < 0) continue;
-      const float4 r = *reinterpret_cast<const float4*>(s_out + p * ld_s + (j << 2));
-      *reinterpret_cast<float4*>(out + rb + c_lo + (j << 2)) = r;
+    if (pow2 && q <= 32) {
+      // q pieces per row, 32 / q rows per step: a lane keeps its piece index, only the row advances — one shuffle, one
+      // shared load and one store per step on pointers that move by constants (the generic loop below recomputed row,
+      // piece and both addresses for every piece: a fifth of the kernel's instructions)
+      const int32_t rpi = 32 >> shq, pr = lane >> shq, j4 = (lane & (q - 1)) << 2;
+      const float* sp = s_out + pr * ld_s + j4;
+      float* gp = out + c_lo + j4;
+      const int32_t sstep = rpi * ld_s;
+#pragma unroll 4
+      for (int32_t it = 0; it < q; ++it) {
+        const int64_t rb = __shfl_sync(0xffffffffu, my_row, it * rpi + pr);
+        const float4 r = *reinterpret_cast<const float4*>(sp + it * sstep);
+        if (rb >= 0) *reinterpret_cast<float4*>(gp + rb) = r;
+      }
+    } else {
+      for (int32_t i = lane; i < 32 * q; i += 32) {
+        const int32_t p = i / q;
+        const int32_t j = i - p * q;
+        const int64_t rb = __shfl_sync(0xffffffffu, my_row, p);
+        if (rb < 0) continue;
+        const float4 r = *reinterpret_cast<const float4*>(s_out + p * ld_s + (j << 2));
+        *reinterpret_cast<float4*>(out + rb + c_lo + (j << 2)) = r;
+      }
     }
   }
 }
